@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — advection-operator throughput (GDoF/s) on B200, BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one application  dst = M^-1 A(src)  of the 3D3V degree-3 FP64 advection operator
+(the loop body of performance/operators_advection_01.likwid.cc:205-239) on a Cartesian periodic
+phase-space lattice with 8^6 cells = 1 073 741 824 DoFs per GPU (BASELINE.json configs[1],
+performance/operators_advection_01/node_level_basic.json) and synthetic data (sin*cos wave
+sampled at the GLL nodes, velocity (1, .15, -.05, .1, -.15, .5), SkewFactor 0.5).
+
+  value       GDoF/s with src/dst resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e         the same metric through hd_advection_apply_host on pinned HOST buffers: H2D of src and
+              D2H of dst inside the timed region (N=1: rank 0's 8 GiB + 8 GiB per step)
+  roofline    algorithmic 16 B/DoF (read src once + write dst once) over the measured
+              kernel time against MEASURED_PEAKS.json's copy bandwidth
+  cpu_baseline  the CPU restatement of the reference's literal ECL algorithm (oracle/, "port") on
+              the host cores, on a bounded sample (4^6-cell lattice of the same discretisation)
+  --impl reference   times only that CPU restatement (the hyper.deal binary itself cannot be built
+              here: deal.II and MPI are absent)
+
+N > 1: weak scaling, one brick of 8^6 cells per GPU; the lattice is doubled along x_2, x_1, x_0
+(examples/advection/performance/weak.py:95-101 doubles the x-directions first) and the bricks
+exchange ghost faces over NCCL each step (pack -> send/recv -> apply), all inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VELOCITY = (1.0, 0.15, -0.05, 0.1, -0.15, 0.5)
+SKEW = 0.5
+DEGREE = 3
+CELLS_PER_DIR = 8
+BYTES_PER_DOF = 16.0  # FP64: read src + write dst
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel_name):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_name)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(seconds_hint=15.0):
+    """CPU restatement of the reference's ECL kernel (oracle/hd_oracle.cpp), all host cores, on a
+    4^6-cell 3D3V k=3 lattice (same discretisation, 1/64 of the cells)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    cores = os.cpu_count() or 1
+    nc = (4,) * 6
+    mesh = O.Mesh(3, 3, nc, (0.0,) * 6, (1.0,) * 6, (True,) * 6)
+    orc = O.Oracle(mesh, DEGREE, skew=SKEW, velocity=VELOCITY, nthreads=cores)
+    src = orc.interpolate(O.hyperrectangle_exact, 0.0)
+    dst = np.zeros_like(src)
+    orc.apply(src, dst=dst)  # warm-up (also builds the library)
+    t0, n = time.perf_counter(), 0
+    while True:
+        orc.apply(src, dst=dst)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > seconds_hint or n >= 50:
+            break
+    return {"value": orc.ndofs * n / el / 1e9, "unit": "GDoF/s", "cores": cores, "kind": "port", "sample": "%d applies of the 4^6-cell (%.1fM DoF) 3D3V k=3 lattice, %d threads" % (n, orc.ndofs / 1e6, cores), "seconds": el}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    import numpy as np
+
+    from oracle import oracle as O
+
+    cores = os.cpu_count() or 1
+    nc = (4,) * 6
+    mesh = O.Mesh(3, 3, nc, (0.0,) * 6, (1.0,) * 6, (True,) * 6)
+    orc = O.Oracle(mesh, DEGREE, skew=SKEW, velocity=VELOCITY, nthreads=cores)
+    src = orc.interpolate(O.hyperrectangle_exact, 0.0)
+    dst = np.zeros_like(src)
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.apply(src, dst=dst)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.apply(src, dst=dst)
+    el = time.perf_counter() - t0
+    v = orc.ndofs * steps / el / 1e9
+    sample = "each step = one apply on a 4^6-cell (%.1fM DoF) 3D3V k=3 lattice, %d threads; CPU restatement of hyper.deal's ECL kernel (the hyper.deal binary needs deal.II+MPI, absent)" % (orc.ndofs / 1e6, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "advection operator throughput (3D3V, k=3, FP64)", "value": v, "unit": "GDoF/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": "3D3V k=3 FP64 advection apply, Cartesian periodic, skew 0.5 (CPU sample: 4^6 cells)"},
+        "cpu_baseline": {"value": v, "unit": "GDoF/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def brick_layout(world, rank):
+    """Weak scaling: 8^6 cells per GPU; GPUs form a px2 x px1 x px0 grid over the x-directions."""
+    p = [1, 1, 1]
+    w, d = world, 2
+    while w > 1:
+        p[d] *= 2
+        w //= 2
+        d = (d - 1) % 3
+    coords = [0, 0, 0]
+    r = rank
+    for d in range(3):
+        coords[d] = r % p[d]
+        r //= p[d]
+    return p, coords
+
+
+def neighbour_rank(p, coords, d, delta):
+    c = list(coords)
+    c[d] = (c[d] + delta) % p[d]
+    return c[0] + p[0] * (c[1] + p[1] * c[2])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cells", type=int, default=CELLS_PER_DIR, help="cells per direction per GPU (default 8 = the BASELINE workload)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fused 3D3V kernel")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hyperdeal_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    p, coords = brick_layout(world, rank)
+    nloc = [args.cells] * 6
+    nglob = [args.cells * (p[d] if d < 3 else 1) for d in range(6)]
+    off = [coords[d] * args.cells if d < 3 else 0 for d in range(6)]
+    side_kind = [[api.SIDE_GHOST if (d < 3 and p[d] > 1) else api.SIDE_PERIODIC_LOCAL] * 2 for d in range(6)]
+    ctx = api.Context(local_rank)
+    mf = api.MatrixFree(ctx, 3, 3, DEGREE, nloc, (0.0,) * 6, (1.0,) * 6, n_cells_global=nglob, cell_offset=off, side_kind=side_kind)
+    op = api.AdvectionOperation(mf, VELOCITY, SKEW)
+    op.set_kernel(args.kernel)
+    n_dofs = mf.n_dofs
+    src = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
+    dst = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
+    api.VectorTools.interpolate(mf, src.data_ptr(), api.FN_HYPERRECTANGLE, 0.0)
+    dst.zero_()
+    halo = mf.halo_total
+    send = torch.empty(max(halo, 1), dtype=torch.float64, device="cuda")
+    ghost = torch.zeros(max(halo, 1), dtype=torch.float64, device="cuda")
+
+    def exchange():
+        if world == 1:
+            return
+        mf.halo_pack(src.data_ptr(), send.data_ptr())
+        ops = []
+        for d in range(3):
+            if p[d] == 1:
+                continue
+            for side in range(2):
+                o, n = mf.halo_offset(d, side), mf.ghost_size(d, side)
+                peer = neighbour_rank(p, coords, d, +1 if side else -1)
+                # my boundary layer on `side` becomes the peer's ghost on its opposite side
+                ops.append(dist.P2POp(dist.isend, send[o : o + n], peer, tag=2 * d + side))
+                ops.append(dist.P2POp(dist.irecv, ghost[o : o + n], peer, tag=2 * d + (1 - side)))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def step():
+        exchange()
+        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = op.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        exchange()
+        ctx.timer_start()
+        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
+        kernel_ms.append(ctx.timer_stop() if world == 1 else 0.0)
+    ev1.record()
+    barrier()
+    if world > 1:
+        # per-launch kernel time is only sampled at N=1 (timer_stop synchronises); re-time one launch
+        ctx.timer_start()
+        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
+        kernel_ms = [ctx.timer_stop()]
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = op.launch_count - launches0 - (1 if world > 1 else 0)
+    value = n_dofs * world * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer entry point (N=1 semantics per rank)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        h_src = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
+        h_dst = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
+        h_src.copy_(src)
+        e_steps = max(1, min(args.steps, 3))
+        op.apply_host_ptr(h_dst.data_ptr(), h_src.data_ptr(), 0.0)  # warm-up (allocates staging)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            op.apply_host_ptr(h_dst.data_ptr(), h_src.data_ptr(), 0.0)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        e2e = {"value": n_dofs * e_steps / el / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": n_dofs * 8, "d2h_bytes_per_step": n_dofs * 8, "steps": e_steps,
+               "checksum": float(h_dst[:: max(1, n_dofs // 4096)].sum())}
+        del h_src, h_dst
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = n_dofs * BYTES_PER_DOF / (k_ms * 1e-3) / 1e9
+        name = op.kernel_name
+        out = {
+            "metric": "advection operator throughput (3D3V, k=3, FP64)", "value": value, "unit": "GDoF/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D3V k=3 FP64 advection apply, Cartesian periodic, %d^6 cells (%.3g DoFs) per GPU, skew 0.5, ECL" % (args.cells, n_dofs),
+                       "cells_global": nglob, "gpu_grid_x": p, "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
+                       "kernel": name},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": n_dofs * BYTES_PER_DOF, "kernel_ms": k_ms},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if not args.no_cpu and world == 1:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

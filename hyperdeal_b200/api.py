@@ -1,0 +1,325 @@
+"""ctypes binding of libhdgpu.so (include/hyperdeal_b200.h) for the Python-side plumbing:
+tests, bench.py and the torch.distributed launcher.  The product host layer is the C++ shim in
+hyperdeal_b200/cpp/; this module only forwards to the same C ABI and never computes anything
+itself.  If the library or a CUDA device is missing every call raises — there is no CPU
+fallback (the CPU oracle lives in oracle/ and is test infrastructure only).
+
+Class and method names follow the reference:
+  MatrixFree            hyperdeal::MatrixFree             (matrix_free/matrix_free.h:39)
+  AdvectionOperation    hyperdeal::advection::AdvectionOperation (operators/advection/advection_operation.h:56)
+  LowStorageRungeKuttaIntegrator                           (base/time_integrators.h:48)
+  VectorTools.interpolate / norm_and_error                 (numerics/vector_tools.h:88, :151)
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_void_p
+
+import numpy as np
+
+HD_MAX_DIM = 6
+HD_F64, HD_F32 = 0, 1
+SIDE_PERIODIC_LOCAL, SIDE_GHOST, SIDE_DIRICHLET, SIDE_DIRICHLET_HOM = 0, 1, 2, 3
+FN_ZERO, FN_HYPERRECTANGLE = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhdgpu.so")
+
+EXPORTS = [
+    "hd_last_error", "hd_version", "hd_context_create", "hd_context_destroy", "hd_context_set_stream",
+    "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
+    "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
+    "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_host", "hd_advection_set_kernel",
+    "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
+    "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
+    "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
+    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_timer_start", "hd_timer_stop",
+]
+
+
+class MeshDesc(ctypes.Structure):
+    _fields_ = [
+        ("dim_x", c_int), ("dim_v", c_int), ("degree", c_int), ("n_points", c_int), ("collocation", c_int),
+        ("number_type", c_int),
+        ("left", c_double * HD_MAX_DIM), ("right", c_double * HD_MAX_DIM),
+        ("n_cells_global", c_int * HD_MAX_DIM), ("n_cells", c_int * HD_MAX_DIM), ("cell_offset", c_int * HD_MAX_DIM),
+        ("side_kind", (c_int * 2) * HD_MAX_DIM),
+    ]
+
+
+class HdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libhdgpu.so (built in-tree by hyperdeal_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HdError(f"{LIB_PATH} is missing: run `python -m hyperdeal_b200.build` (needs nvcc); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    L.hd_last_error.restype = c_char_p
+    L.hd_advection_kernel_name.restype = c_char_p
+    L.hd_advection_kernel_name.argtypes = [c_void_p]
+    for name in ("hd_mesh_n_dofs", "hd_mesh_n_cells", "hd_halo_total", "hd_advection_launch_count"):
+        getattr(L, name).restype = c_int64
+        getattr(L, name).argtypes = [c_void_p]
+    for name in ("hd_mesh_ghost_size", "hd_halo_offset"):
+        getattr(L, name).restype = c_int64
+        getattr(L, name).argtypes = [c_void_p, c_int, c_int]
+    L.hd_context_create.argtypes = [c_int, POINTER(c_void_p)]
+    L.hd_context_destroy.argtypes = [c_void_p]
+    L.hd_context_set_stream.argtypes = [c_void_p, c_void_p]
+    L.hd_context_synchronize.argtypes = [c_void_p]
+    L.hd_device_count.argtypes = [POINTER(c_int)]
+    L.hd_mesh_create.argtypes = [c_void_p, POINTER(MeshDesc), POINTER(c_void_p)]
+    L.hd_mesh_destroy.argtypes = [c_void_p]
+    L.hd_mesh_dofs_per_cell.argtypes = [c_void_p]
+    L.hd_mesh_basis.argtypes = [c_void_p, c_int, c_void_p]
+    L.hd_vector_alloc.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
+    L.hd_vector_free.argtypes = [c_void_p, c_void_p]
+    L.hd_vector_copy_in.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
+    L.hd_vector_copy_out.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
+    L.hd_vector_zero.argtypes = [c_void_p, c_void_p]
+    L.hd_vector_copy.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.hd_advection_create.argtypes = [c_void_p, c_double, POINTER(c_double), POINTER(c_void_p)]
+    L.hd_advection_destroy.argtypes = [c_void_p]
+    L.hd_advection_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double]
+    L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
+    L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
+    L.hd_advection_set_dirichlet_values.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64]
+    L.hd_advection_set_dirichlet_builtin.argtypes = [c_void_p, c_int]
+    L.hd_halo_pack.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.hd_lsrk_create.argtypes = [c_void_p, c_char_p, POINTER(c_void_p)]
+    L.hd_lsrk_destroy.argtypes = [c_void_p]
+    L.hd_lsrk_n_stages.argtypes = [c_void_p]
+    L.hd_lsrk_coefficients.argtypes = [c_void_p, c_int, c_void_p]
+    L.hd_lsrk_stage_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
+    L.hd_lsrk_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
+    L.hd_interpolate_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double]
+    L.hd_norm_and_error_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double, POINTER(c_double)]
+    L.hd_timer_start.argtypes = [c_void_p]
+    L.hd_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise HdError("libhdgpu: %s (code %d)" % (lib().hd_last_error().decode(), rc))
+    return rc
+
+
+class Context:
+    """One GPU + stream (stands in for the (comm, comm_sm) pair, matrix_free.h:108)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = c_void_p()
+        _check(lib().hd_context_create(device, byref(self._h)))
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream: int):
+        _check(lib().hd_context_set_stream(self._h, c_void_p(stream)))
+
+    def synchronize(self):
+        _check(lib().hd_context_synchronize(self._h))
+
+    def timer_start(self):
+        _check(lib().hd_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = c_double()
+        _check(lib().hd_timer_stop(self._h, byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._h:
+            lib().hd_context_destroy(self._h)
+            self._h = c_void_p()
+
+
+class MatrixFree:
+    """Cartesian phase-space lattice + basis (hyperdeal::MatrixFree::reinit, matrix_free.templates.h:862)."""
+
+    def __init__(self, ctx: Context, dim_x, dim_v, degree, n_cells, left, right, periodic=True, n_points=None, collocation=False,
+                 dtype=np.float64, n_cells_global=None, cell_offset=None, side_kind=None):
+        dim = dim_x + dim_v
+        self.ctx, self.dim_x, self.dim_v, self.dim, self.degree = ctx, dim_x, dim_v, dim, degree
+        self.dtype = np.dtype(dtype)
+        d = MeshDesc()
+        d.dim_x, d.dim_v, d.degree = dim_x, dim_v, degree
+        d.n_points = n_points if n_points is not None else degree + 1
+        d.collocation = int(bool(collocation))
+        d.number_type = HD_F64 if self.dtype == np.float64 else HD_F32
+        if isinstance(periodic, bool):
+            periodic = (periodic,) * dim
+        for i in range(HD_MAX_DIM):
+            d.left[i] = left[i] if i < dim else 0.0
+            d.right[i] = right[i] if i < dim else 1.0
+            d.n_cells[i] = n_cells[i] if i < dim else 1
+            d.n_cells_global[i] = (n_cells_global[i] if n_cells_global is not None else n_cells[i]) if i < dim else 1
+            d.cell_offset[i] = (cell_offset[i] if cell_offset is not None else 0) if i < dim else 0
+            for s in range(2):
+                if side_kind is not None and i < dim:
+                    d.side_kind[i][s] = side_kind[i][s]
+                else:
+                    d.side_kind[i][s] = SIDE_PERIODIC_LOCAL if (i >= dim or periodic[i]) else SIDE_DIRICHLET
+        self.desc = d
+        self.n_cells = tuple(n_cells[:dim])
+        self._h = c_void_p()
+        _check(lib().hd_mesh_create(ctx._h, byref(d), byref(self._h)))
+        self.n_dofs = lib().hd_mesh_n_dofs(self._h)
+        self.n_cells_total = lib().hd_mesh_n_cells(self._h)
+        self.dofs_per_cell = lib().hd_mesh_dofs_per_cell(self._h)
+        self.halo_total = lib().hd_halo_total(self._h)
+
+    # -- initialize_dof_vector (matrix_free.templates.h:1369)
+    def initialize_dof_vector(self, do_ghosts=False) -> int:
+        p = c_void_p()
+        _check(lib().hd_vector_alloc(self._h, int(do_ghosts), byref(p)))
+        return p.value
+
+    def free_vector(self, ptr: int):
+        _check(lib().hd_vector_free(self._h, c_void_p(ptr)))
+
+    def copy_in(self, ptr: int, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        _check(lib().hd_vector_copy_in(self._h, c_void_p(ptr), host.ctypes.data_as(c_void_p), host.size))
+
+    def copy_out(self, ptr: int, n: int | None = None) -> np.ndarray:
+        out = np.empty(self.n_dofs if n is None else n, dtype=self.dtype)
+        _check(lib().hd_vector_copy_out(self._h, c_void_p(ptr), out.ctypes.data_as(c_void_p), out.size))
+        return out
+
+    def basis(self, which: int) -> np.ndarray:
+        n = _check(lib().hd_mesh_basis(self._h, which, None))
+        out = np.empty(n)
+        _check(lib().hd_mesh_basis(self._h, which, out.ctypes.data_as(c_void_p)))
+        return out
+
+    def halo_offset(self, d, side):
+        return lib().hd_halo_offset(self._h, d, side)
+
+    def ghost_size(self, d, side):
+        return lib().hd_mesh_ghost_size(self._h, d, side)
+
+    def halo_pack(self, src_ptr: int, send_ptr: int):
+        _check(lib().hd_halo_pack(self._h, c_void_p(src_ptr), c_void_p(send_ptr)))
+
+    def close(self):
+        if self._h:
+            lib().hd_mesh_destroy(self._h)
+            self._h = c_void_p()
+
+
+class AdvectionOperation:
+    """advection::AdvectionOperation with ConstantVelocityFieldView (advection_operation.h:56-209)."""
+
+    def __init__(self, matrix_free: MatrixFree, velocity, skew_factor: float = 0.0):
+        self.mf = matrix_free
+        v = (c_double * HD_MAX_DIM)(*([float(x) for x in velocity] + [0.0] * (HD_MAX_DIM - len(velocity))))
+        self._h = c_void_p()
+        _check(lib().hd_advection_create(matrix_free._h, float(skew_factor), v, byref(self._h)))
+
+    def apply(self, dst: int, src: int, time: float = 0.0, ghosts: int | None = None):
+        """dst = M^-1 A(src, time); dst/src are device pointers (advection_operation.h:137)."""
+        _check(lib().hd_advection_apply(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts or 0), float(time)))
+
+    def apply_host(self, dst: np.ndarray, src: np.ndarray, time: float = 0.0):
+        assert dst.flags.c_contiguous and src.flags.c_contiguous
+        _check(lib().hd_advection_apply_host(self._h, dst.ctypes.data_as(c_void_p), src.ctypes.data_as(c_void_p), float(time)))
+
+    def apply_host_ptr(self, dst_ptr: int, src_ptr: int, time: float = 0.0):
+        _check(lib().hd_advection_apply_host(self._h, c_void_p(dst_ptr), c_void_p(src_ptr), float(time)))
+
+    def set_kernel(self, which: int):
+        _check(lib().hd_advection_set_kernel(self._h, which))
+
+    @property
+    def kernel_name(self) -> str:
+        return lib().hd_advection_kernel_name(self._h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return lib().hd_advection_launch_count(self._h)
+
+    def set_dirichlet_builtin(self, fn_id: int):
+        _check(lib().hd_advection_set_dirichlet_builtin(self._h, fn_id))
+
+    def set_dirichlet_values(self, d: int, side: int, g: np.ndarray):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        _check(lib().hd_advection_set_dirichlet_values(self._h, d, side, g.ctypes.data_as(c_void_p), g.size))
+
+    def close(self):
+        if self._h:
+            lib().hd_advection_destroy(self._h)
+            self._h = c_void_p()
+
+
+class LowStorageRungeKuttaIntegrator:
+    """base/time_integrators.h:48; perform_time_step uses the fused device path (hd_lsrk_step)."""
+
+    def __init__(self, matrix_free: MatrixFree, vec_Ki: int, vec_Ti: int, rk_type: str = "rk45"):
+        self.mf, self.Ki, self.Ti = matrix_free, vec_Ki, vec_Ti
+        self._h = c_void_p()
+        _check(lib().hd_lsrk_create(matrix_free._h, rk_type.encode(), byref(self._h)))
+
+    def n_stages(self) -> int:
+        return lib().hd_lsrk_n_stages(self._h)
+
+    def coefficients(self):
+        s = self.n_stages()
+        b, a = np.empty(s), np.empty(max(s - 1, 1))
+        lib().hd_lsrk_coefficients(self._h, 0, b.ctypes.data_as(c_void_p))
+        lib().hd_lsrk_coefficients(self._h, 1, a.ctypes.data_as(c_void_p))
+        return b, a[: s - 1]
+
+    def perform_time_step(self, solution: int, current_time: float, time_step: float, op):
+        """op: an AdvectionOperation (fused device path) or a callable op(src, dst, time) on device
+        pointers (unfused path, the reference's std::function signature, time_integrators.h:66-72)."""
+        if isinstance(op, AdvectionOperation):
+            _check(lib().hd_lsrk_step(self._h, op._h, c_void_p(solution), c_void_p(self.Ki), c_void_p(self.Ti), float(current_time), float(time_step)))
+            return
+        b, a = self.coefficients()
+        L, mf = lib(), self.mf
+        _check(L.hd_vector_copy(mf._h, c_void_p(self.Ti), c_void_p(solution)))  # only_Ti_is_ghosted branch
+        sum_prev_b = 0.0
+        for stage in range(len(b)):
+            c = 0.0
+            if stage > 0:
+                c = sum_prev_b + a[stage - 1]
+                sum_prev_b += b[stage - 1]
+            op(self.Ti, self.Ki, current_time + c * time_step)
+            fa = 0.0 if stage == len(b) - 1 else a[stage] * time_step
+            _check(L.hd_lsrk_stage_update(mf._h, c_void_p(solution), c_void_p(self.Ti), c_void_p(self.Ki), b[stage] * time_step, fa))
+
+    def close(self):
+        if self._h:
+            lib().hd_lsrk_destroy(self._h)
+            self._h = c_void_p()
+
+
+class VectorTools:
+    @staticmethod
+    def interpolate(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):
+        _check(lib().hd_interpolate_builtin(matrix_free._h, c_void_p(vec), fn_id, float(time)))
+
+    @staticmethod
+    def norm_and_error_sums(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):
+        out = (c_double * 2)()
+        _check(lib().hd_norm_and_error_builtin(matrix_free._h, c_void_p(vec), fn_id, float(time), out))
+        return out[0], out[1]
+
+    @staticmethod
+    def norm_and_error(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):
+        n2, e2 = VectorTools.norm_and_error_sums(matrix_free, vec, fn_id, time)
+        return math.sqrt(n2), math.sqrt(e2)

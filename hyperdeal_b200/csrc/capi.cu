@@ -1,0 +1,998 @@
+// C ABI of libhdgpu.so (see include/hyperdeal_b200.h for the contract and the reference
+// members each entry point replaces).
+#include <cstring>
+#include <new>
+
+#include "hd_internal.h"
+
+namespace hd
+{
+  static thread_local std::string g_error;
+
+  int
+  fail(int code, const std::string &msg)
+  {
+    g_error = msg;
+    return code;
+  }
+} // namespace hd
+
+// ------------------------------------------------------------------------------------------
+// small device kernels: LSRK update, halo pack, interpolate, norms
+// ------------------------------------------------------------------------------------------
+namespace
+{
+  // perform_stage update loops, base/time_integrators.templates.h:117-132
+  template <typename T>
+  __global__ void
+  k_stage_update(T *__restrict__ sol, T *__restrict__ ti, const T *__restrict__ K, T b, T a, long long n)
+  {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      {
+        const T k = K[i], s = sol[i];
+        sol[i] = s + b * k;
+        if (a != T(0))
+          ti[i] = s + a * k;
+      }
+  }
+
+  struct LatticeParams
+  {
+    int       dim, n, nq;
+    int       ncell[HD_MAX_DIM], cell_offset[HD_MAX_DIM];
+    double    left[HD_MAX_DIM], h[HD_MAX_DIM];
+    long long nd, ncells;
+  };
+
+  // pack loop of export_to_ghosted_array_start, matrix_free/vector_partitioner.h:1443-1460
+  template <typename T>
+  __global__ void
+  k_halo_pack(const T *__restrict__ src, T *__restrict__ send, LatticeParams lp, int dir, int side, long long off, long long count)
+  {
+    const long long nf       = lp.nd / lp.n;
+    long long       stride_d = 1;
+    for (int e = 0; e < dir; ++e)
+      stride_d *= lp.n;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gstride)
+      {
+        const long long fc = i / nf, fo = i - fc * nf;
+        // face cell -> cell
+        long long r = fc, cell = 0, m = 1;
+        for (int e = 0; e < lp.dim; ++e)
+          {
+            int ce;
+            if (e == dir)
+              ce = side ? lp.ncell[e] - 1 : 0;
+            else
+              {
+                ce = int(r % lp.ncell[e]);
+                r /= lp.ncell[e];
+              }
+            cell += ce * m;
+            m *= lp.ncell[e];
+          }
+        const long long lo = fo % stride_d, hi = fo / stride_d;
+        const long long o  = (hi * lp.n + (side ? lp.n - 1 : 0)) * stride_d + lo;
+        send[off + i]      = src[cell * lp.nd + o];
+      }
+  }
+
+  __device__ double
+  builtin_value(int fn_id, int dim, const double *x, double t)
+  {
+    if (fn_id == HD_FN_HYPERRECTANGLE)
+      {
+        // examples/advection/cases/hyperrectangle.h:46-57
+        const double adv[6] = {1.0, 0.15, -0.05, 0.0, 0.0, 0.0};
+        const double PI     = 3.14159265358979323846;
+        double       r      = sin(2.0 * (x[0] - t * adv[0]) * PI);
+        for (int d = 1; d < dim; ++d)
+          r *= cos(2.0 * (x[d] - t * adv[d]) * PI);
+        return r;
+      }
+    return 0.0;
+  }
+
+  // VectorTools::interpolate, numerics/vector_tools.h:88-137
+  template <typename T>
+  __global__ void
+  k_interpolate(T *__restrict__ vec, LatticeParams lp, const double *__restrict__ nodes, int fn_id, double time)
+  {
+    const long long total   = lp.nd * lp.ncells;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride)
+      {
+        long long cell = i / lp.nd, o = i - cell * lp.nd;
+        double    x[HD_MAX_DIM];
+        for (int d = 0; d < lp.dim; ++d)
+          {
+            const int c = int(cell % lp.ncell[d]);
+            cell /= lp.ncell[d];
+            const int id = int(o % lp.n);
+            o /= lp.n;
+            x[d] = lp.left[d] + lp.h[d] * ((c + lp.cell_offset[d]) + nodes[id]);
+          }
+        vec[i] = T(builtin_value(fn_id, lp.dim, x, time));
+      }
+  }
+
+  // VectorTools::norm_and_error, numerics/vector_tools.h:151-220: one CTA per cell, S sweeps in
+  // shared memory (double), then sum over the quadrature points.
+  template <typename T>
+  __global__ void
+  k_norm_error(const T *__restrict__ vec, LatticeParams lp, const double *__restrict__ basis, int fn_id, double time, double *__restrict__ out)
+  {
+    extern __shared__ double sm[];
+    const int     dim = lp.dim, n = lp.n, nq = lp.nq;
+    const double *xq = basis + n, *w = xq + nq, *S = w + nq;
+    int           mx = n > nq ? n : nq;
+    long long     cap = 1;
+    for (int d = 0; d < dim; ++d)
+      cap *= mx;
+    double *        A = sm, *B = sm + cap;
+    const long long cell = blockIdx.x;
+    for (long long i = threadIdx.x; i < lp.nd; i += blockDim.x)
+      A[i] = double(vec[cell * lp.nd + i]);
+    __syncthreads();
+    double *in = A, *outb = B;
+    for (int d = 0; d < dim; ++d)
+      {
+        long long stride = 1;
+        for (int e = 0; e < d; ++e)
+          stride *= nq;
+        long long outer = 1;
+        for (int e = d + 1; e < dim; ++e)
+          outer *= n;
+        const long long total = outer * nq * stride;
+        for (long long i = threadIdx.x; i < total; i += blockDim.x)
+          {
+            const long long lo = i % stride, rest = i / stride, q = rest % nq, o = rest / nq;
+            double          acc = 0;
+            for (int k = 0; k < n; ++k)
+              acc += S[q * n + k] * in[(o * n + k) * stride + lo];
+            outb[i] = acc;
+          }
+        __syncthreads();
+        double *t = in;
+        in        = outb;
+        outb      = t;
+      }
+    long long nqd = 1;
+    for (int d = 0; d < dim; ++d)
+      nqd *= nq;
+    int       c[HD_MAX_DIM];
+    long long r = cell;
+    for (int d = 0; d < dim; ++d)
+      {
+        c[d] = int(r % lp.ncell[d]);
+        r /= lp.ncell[d];
+      }
+    double s_norm = 0, s_err = 0;
+    for (long long i = threadIdx.x; i < nqd; i += blockDim.x)
+      {
+        long long rr = i;
+        double    x[HD_MAX_DIM], jxw = 1;
+        for (int d = 0; d < dim; ++d)
+          {
+            const int q = int(rr % nq);
+            rr /= nq;
+            x[d] = lp.left[d] + lp.h[d] * ((c[d] + lp.cell_offset[d]) + xq[q]);
+            jxw *= lp.h[d] * w[q];
+          }
+        const double u = in[i];
+        const double f = builtin_value(fn_id, dim, x, time);
+        s_norm += u * u * jxw;
+        s_err += (u - f) * (u - f) * jxw;
+      }
+    // block reduction
+    __shared__ double red[2][32];
+    for (int off = 16; off > 0; off >>= 1)
+      {
+        s_norm += __shfl_down_sync(0xffffffffu, s_norm, off);
+        s_err += __shfl_down_sync(0xffffffffu, s_err, off);
+      }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+      {
+        red[0][wid] = s_norm;
+        red[1][wid] = s_err;
+      }
+    __syncthreads();
+    if (wid == 0)
+      {
+        const int nw = (blockDim.x + 31) / 32;
+        s_norm       = lane < nw ? red[0][lane] : 0.0;
+        s_err        = lane < nw ? red[1][lane] : 0.0;
+        for (int off = 16; off > 0; off >>= 1)
+          {
+            s_norm += __shfl_down_sync(0xffffffffu, s_norm, off);
+            s_err += __shfl_down_sync(0xffffffffu, s_err, off);
+          }
+        if (lane == 0)
+          {
+            atomicAdd(out + 0, s_norm);
+            atomicAdd(out + 1, s_err);
+          }
+      }
+  }
+
+  LatticeParams
+  lattice(const hd_mesh *m)
+  {
+    LatticeParams lp;
+    lp.dim = m->dim;
+    lp.n   = m->n;
+    lp.nq  = m->nq;
+    for (int d = 0; d < HD_MAX_DIM; ++d)
+      {
+        lp.ncell[d]       = d < m->dim ? m->d.n_cells[d] : 1;
+        lp.cell_offset[d] = d < m->dim ? m->d.cell_offset[d] : 0;
+        lp.left[d]        = m->d.left[d];
+        lp.h[d]           = m->h[d];
+      }
+    lp.nd     = m->nd;
+    lp.ncells = m->ncells;
+    return lp;
+  }
+
+  unsigned
+  grid_for(const hd_context *ctx, long long n, int threads)
+  {
+    long long blocks = (n + threads - 1) / threads;
+    long long cap    = (long long)ctx->sm_count * 16;
+    if (blocks > cap)
+      blocks = cap;
+    if (blocks < 1)
+      blocks = 1;
+    return (unsigned)blocks;
+  }
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *
+hd_last_error(void)
+{
+  return hd::g_error.c_str();
+}
+
+int
+hd_version(void)
+{
+  return 100;
+}
+
+int
+hd_device_count(int *count)
+{
+  HD_REQUIRE(count, "null argument");
+  *count = 0;
+  HD_CUDA(cudaGetDeviceCount(count));
+  return HD_OK;
+}
+
+int
+hd_context_create(int device, hd_context **out)
+{
+  HD_REQUIRE(out, "null argument");
+  int count = 0;
+  HD_CUDA(cudaGetDeviceCount(&count));
+  if (count == 0)
+    return hd::fail(HD_ERR_CUDA, "no CUDA device: libhdgpu has no CPU fallback");
+  HD_REQUIRE(device >= 0 && device < count, "device index out of range");
+  HD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return hd::fail(HD_ERR_CUDA, "libhdgpu is built for sm_100a (Blackwell) only");
+  hd_context *ctx = new (std::nothrow) hd_context;
+  HD_REQUIRE(ctx, "out of memory");
+  ctx->device     = device;
+  ctx->sm_count   = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  HD_CUDA(cudaEventCreate(&ctx->ev0));
+  HD_CUDA(cudaEventCreate(&ctx->ev1));
+  *out = ctx;
+  return HD_OK;
+}
+
+int
+hd_context_destroy(hd_context *ctx)
+{
+  if (!ctx)
+    return HD_OK;
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  delete ctx;
+  return HD_OK;
+}
+
+int
+hd_context_set_stream(hd_context *ctx, void *stream)
+{
+  HD_REQUIRE(ctx, "null context");
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  return HD_OK;
+}
+
+int
+hd_context_synchronize(hd_context *ctx)
+{
+  HD_REQUIRE(ctx, "null context");
+  HD_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_timer_start(hd_context *ctx)
+{
+  HD_REQUIRE(ctx, "null context");
+  HD_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_timer_stop(hd_context *ctx, double *ms)
+{
+  HD_REQUIRE(ctx && ms, "null argument");
+  HD_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  HD_CUDA(cudaEventSynchronize(ctx->ev1));
+  float f = 0;
+  HD_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+  return HD_OK;
+}
+
+// ---- mesh ---------------------------------------------------------------------------------
+int
+hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
+{
+  HD_REQUIRE(ctx && desc && out, "null argument");
+  const int dim = desc->dim_x + desc->dim_v;
+  HD_REQUIRE(desc->dim_x >= 1 && desc->dim_x <= 3 && desc->dim_v >= 1 && desc->dim_v <= 3, "dim_x and dim_v must be in 1..3");
+  HD_REQUIRE(desc->degree >= 1 && desc->degree <= 5, "degree must be in 1..5");
+  HD_REQUIRE(desc->n_points >= desc->degree + 1 && desc->n_points <= 8, "n_points must be in degree+1..8");
+  HD_REQUIRE(desc->number_type == HD_F64 || desc->number_type == HD_F32, "number_type");
+  HD_REQUIRE(!desc->collocation || desc->n_points == desc->degree + 1, "collocation requires n_points == degree+1");
+  hd_mesh *m = new (std::nothrow) hd_mesh;
+  HD_REQUIRE(m, "out of memory");
+  m->ctx       = ctx;
+  m->d         = *desc;
+  m->dim       = dim;
+  m->n         = desc->degree + 1;
+  m->nq        = desc->n_points;
+  m->elem_size = desc->number_type == HD_F64 ? 8 : 4;
+  m->nd        = 1;
+  m->ncells    = 1;
+  for (int d = 0; d < HD_MAX_DIM; ++d)
+    {
+      m->h[d] = 1.0;
+      for (int s = 0; s < 2; ++s)
+        m->ghost_off[d][s] = m->ghost_cnt[d][s] = 0;
+    }
+  for (int d = 0; d < dim; ++d)
+    {
+      if (!(desc->n_cells[d] >= 1 && desc->n_cells_global[d] >= desc->n_cells[d] && desc->cell_offset[d] >= 0 &&
+            desc->cell_offset[d] + desc->n_cells[d] <= desc->n_cells_global[d] && desc->right[d] > desc->left[d]))
+        {
+          delete m;
+          return hd::fail(HD_ERR_INVALID, "inconsistent cell counts / domain in hd_mesh_desc");
+        }
+      for (int s = 0; s < 2; ++s)
+        if (desc->side_kind[d][s] < 0 || desc->side_kind[d][s] > HD_SIDE_DIRICHLET_HOM)
+          {
+            delete m;
+            return hd::fail(HD_ERR_INVALID, "bad side_kind");
+          }
+      m->nd *= m->n;
+      m->ncells *= desc->n_cells[d];
+      // same expression as the oracle / the reference's subdivided_hyper_rectangle
+      m->h[d] = (desc->right[d] - desc->left[d]) / desc->n_cells_global[d];
+    }
+  m->nf    = m->nd / m->n;
+  m->ndofs = m->nd * m->ncells;
+  int64_t off = 0;
+  for (int d = 0; d < dim; ++d)
+    for (int s = 0; s < 2; ++s)
+      {
+        m->ghost_off[d][s] = off;
+        if (desc->side_kind[d][s] == HD_SIDE_GHOST)
+          {
+            m->ghost_cnt[d][s] = (m->ncells / desc->n_cells[d]) * m->nf;
+            off += m->ghost_cnt[d][s];
+            m->has_ghosts = true;
+          }
+      }
+  m->ghost_total = off;
+  try
+    {
+      m->basis.init(desc->degree, desc->n_points, desc->collocation != 0);
+    }
+  catch (const std::exception &e)
+    {
+      delete m;
+      return hd::fail(HD_ERR_INVALID, e.what());
+    }
+  // device basis block: nodes[n], xq[nq], w[nq], S[nq*n], Sinv[n*nq]
+  std::vector<double> hb;
+  for (auto v : m->basis.nodes)
+    hb.push_back((double)v);
+  for (auto v : m->basis.xq)
+    hb.push_back((double)v);
+  for (auto v : m->basis.w)
+    hb.push_back((double)v);
+  for (auto v : m->basis.S)
+    hb.push_back((double)v);
+  for (auto v : m->basis.Sinv)
+    hb.push_back((double)v);
+  HD_CUDA(cudaSetDevice(ctx->device));
+  HD_CUDA(cudaMalloc(&m->d_basis, hb.size() * sizeof(double)));
+  HD_CUDA(cudaMemcpy(m->d_basis, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  HD_CUDA(cudaMalloc(&m->d_reduce, 2 * sizeof(double)));
+  *out = m;
+  return HD_OK;
+}
+
+int
+hd_mesh_destroy(hd_mesh *m)
+{
+  if (!m)
+    return HD_OK;
+  cudaFree(m->d_basis);
+  cudaFree(m->d_reduce);
+  delete m;
+  return HD_OK;
+}
+
+int64_t
+hd_mesh_n_dofs(const hd_mesh *m)
+{
+  return m ? m->ndofs : 0;
+}
+int64_t
+hd_mesh_n_cells(const hd_mesh *m)
+{
+  return m ? m->ncells : 0;
+}
+int
+hd_mesh_dofs_per_cell(const hd_mesh *m)
+{
+  return m ? (int)m->nd : 0;
+}
+int64_t
+hd_mesh_ghost_size(const hd_mesh *m, int dir, int side)
+{
+  if (!m || dir < 0 || dir >= m->dim || side < 0 || side > 1)
+    return 0;
+  return m->ghost_cnt[dir][side];
+}
+int64_t
+hd_halo_offset(const hd_mesh *m, int dir, int side)
+{
+  if (!m || dir < 0 || dir >= m->dim || side < 0 || side > 1)
+    return 0;
+  return m->ghost_off[dir][side];
+}
+int64_t
+hd_halo_total(const hd_mesh *m)
+{
+  return m ? m->ghost_total : 0;
+}
+
+int
+hd_mesh_basis(const hd_mesh *m, int which, double *out)
+{
+  HD_REQUIRE(m, "null mesh");
+  const std::vector<hd::LD> *v = nullptr;
+  switch (which)
+    {
+      case 0:
+        v = &m->basis.nodes;
+        break;
+      case 1:
+        v = &m->basis.xq;
+        break;
+      case 2:
+        v = &m->basis.w;
+        break;
+      case 3:
+        v = &m->basis.S;
+        break;
+      case 4:
+        v = &m->basis.D;
+        break;
+      case 5:
+        v = &m->basis.Sinv;
+        break;
+      default:
+        return hd::fail(HD_ERR_INVALID, "hd_mesh_basis: which must be 0..5");
+    }
+  if (out)
+    for (size_t i = 0; i < v->size(); ++i)
+      out[i] = (double)(*v)[i];
+  return (int)v->size();
+}
+
+// ---- vectors -------------------------------------------------------------------------------
+int
+hd_vector_alloc(hd_mesh *m, int do_ghosts, void **ptr)
+{
+  HD_REQUIRE(m && ptr, "null argument");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t bytes = (size_t)(m->ndofs + (do_ghosts ? m->ghost_total : 0)) * m->elem_size;
+  HD_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+  HD_CUDA(cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_vector_free(hd_mesh *m, void *ptr)
+{
+  HD_REQUIRE(m, "null mesh");
+  HD_CUDA(cudaFree(ptr));
+  return HD_OK;
+}
+
+int
+hd_vector_copy_in(hd_mesh *m, void *ptr, const void *host, int64_t n)
+{
+  HD_REQUIRE(m && ptr && host && n >= 0, "bad argument");
+  HD_CUDA(cudaMemcpyAsync(ptr, host, (size_t)n * m->elem_size, cudaMemcpyHostToDevice, m->ctx->stream));
+  HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_vector_copy_out(hd_mesh *m, const void *ptr, void *host, int64_t n)
+{
+  HD_REQUIRE(m && ptr && host && n >= 0, "bad argument");
+  HD_CUDA(cudaMemcpyAsync(host, ptr, (size_t)n * m->elem_size, cudaMemcpyDeviceToHost, m->ctx->stream));
+  HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_vector_zero(hd_mesh *m, void *ptr)
+{
+  HD_REQUIRE(m && ptr, "bad argument");
+  HD_CUDA(cudaMemsetAsync(ptr, 0, (size_t)m->ndofs * m->elem_size, m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_vector_copy(hd_mesh *m, void *dst, const void *src)
+{
+  HD_REQUIRE(m && dst && src, "bad argument");
+  HD_CUDA(cudaMemcpyAsync(dst, src, (size_t)m->ndofs * m->elem_size, cudaMemcpyDeviceToDevice, m->ctx->stream));
+  return HD_OK;
+}
+
+// ---- advection operator ---------------------------------------------------------------------
+} // extern "C"
+namespace
+{
+  template <typename T, int N>
+  void
+  fill_coef(const hd_advection *op, std::vector<unsigned char> &blob)
+  {
+    const int dim = op->mesh->dim;
+    blob.assign(sizeof(DirCoef<T, N>) * dim, 0);
+    DirCoef<T, N> *c = reinterpret_cast<DirCoef<T, N> *>(blob.data());
+    for (int d = 0; d < dim; ++d)
+      {
+        for (int v = 0; v < 4; ++v)
+          for (int i = 0; i < N * N; ++i)
+            c[d].C[v][i] = T(op->hC[d][v][i]);
+        for (int i = 0; i < N; ++i)
+          {
+            c[d].L0[i] = T(op->hL0[d][i]);
+            c[d].L1[i] = T(op->hL1[d][i]);
+          }
+      }
+  }
+} // namespace
+extern "C" {
+
+int
+hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advection **out)
+{
+  HD_REQUIRE(m && velocity && out, "null argument");
+  hd_advection *op = new (std::nothrow) hd_advection;
+  HD_REQUIRE(op, "out of memory");
+  op->mesh = m;
+  op->skew = skew;
+  for (int d = 0; d < HD_MAX_DIM; ++d)
+    {
+      op->a[d]       = d < m->dim ? velocity[d] : 0.0;
+      op->nb_mask[d] = 0;
+      for (int s = 0; s < 2; ++s)
+        {
+          op->d_g[d][s]     = nullptr;
+          op->g_count[d][s] = 0;
+        }
+    }
+  hd::Basis1D &b = m->basis;
+  b.set_skew((hd::LD)skew);
+  const int           n = m->n;
+  std::vector<double> lifts((size_t)m->dim * 2 * n, 0.0);
+  for (int d = 0; d < m->dim; ++d)
+    {
+      std::vector<hd::LD> C[4], L0, L1;
+      b.direction_matrices((hd::LD)velocity[d], (hd::LD)m->h[d], (hd::LD)skew, C, L0, L1);
+      for (int v = 0; v < 4; ++v)
+        {
+          op->hC[d][v].resize(n * n);
+          for (int i = 0; i < n * n; ++i)
+            op->hC[d][v][i] = (double)C[v][i];
+        }
+      op->hL0[d].resize(n);
+      op->hL1[d].resize(n);
+      bool any0 = false, any1 = false;
+      for (int i = 0; i < n; ++i)
+        {
+          op->hL0[d][i] = (double)L0[i];
+          op->hL1[d][i] = (double)L1[i];
+          any0 |= (L0[i] != 0);
+          any1 |= (L1[i] != 0);
+          lifts[(size_t)(2 * d + 0) * n + i] = (double)(2 * L0[i]);
+          lifts[(size_t)(2 * d + 1) * n + i] = (double)(2 * L1[i]);
+        }
+      op->nb_mask[d] = (any0 ? 1 : 0) | (any1 ? 2 : 0);
+    }
+  std::vector<unsigned char> blob;
+  const bool                 f64 = m->d.number_type == HD_F64;
+  switch (n)
+    {
+      case 2:
+        f64 ? fill_coef<double, 2>(op, blob) : fill_coef<float, 2>(op, blob);
+        break;
+      case 3:
+        f64 ? fill_coef<double, 3>(op, blob) : fill_coef<float, 3>(op, blob);
+        break;
+      case 4:
+        f64 ? fill_coef<double, 4>(op, blob) : fill_coef<float, 4>(op, blob);
+        break;
+      case 5:
+        f64 ? fill_coef<double, 5>(op, blob) : fill_coef<float, 5>(op, blob);
+        break;
+      case 6:
+        f64 ? fill_coef<double, 6>(op, blob) : fill_coef<float, 6>(op, blob);
+        break;
+      default:
+        delete op;
+        return hd::fail(HD_ERR_UNSUPPORTED, "degree must be in 1..5");
+    }
+  // layout: [DirCoef block, padded to 8 bytes][double lifts[dim][2][n]]
+  op->coef_bytes = (blob.size() + 7) / 8 * 8;
+  blob.resize(op->coef_bytes + lifts.size() * sizeof(double));
+  std::memcpy(blob.data() + op->coef_bytes, lifts.data(), lifts.size() * sizeof(double));
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  HD_CUDA(cudaMalloc(&op->d_coef, blob.size()));
+  HD_CUDA(cudaMemcpy(op->d_coef, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  *out = op;
+  return HD_OK;
+}
+
+int
+hd_advection_destroy(hd_advection *op)
+{
+  if (!op)
+    return HD_OK;
+  hd::fast6d_release(op);
+  cudaFree(op->d_coef);
+  cudaFree(op->d_stage_src);
+  cudaFree(op->d_stage_dst);
+  for (int d = 0; d < HD_MAX_DIM; ++d)
+    for (int s = 0; s < 2; ++s)
+      cudaFree(op->d_g[d][s]);
+  delete op;
+  return HD_OK;
+}
+
+int
+hd_advection_set_kernel(hd_advection *op, int which)
+{
+  HD_REQUIRE(op && which >= 0 && which <= 2, "bad argument");
+  if (which == 2 && !hd::fast6d_supported(op))
+    return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
+  op->kernel_choice = which;
+  return HD_OK;
+}
+
+const char *
+hd_advection_kernel_name(const hd_advection *op)
+{
+  return op ? op->last_kernel : "none";
+}
+
+int64_t
+hd_advection_launch_count(const hd_advection *op)
+{
+  return op ? op->launches : 0;
+}
+
+static int
+apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu)
+{
+  HD_REQUIRE(op && src && (dst || fu.enabled), "null argument");
+  HD_REQUIRE(dst != src, "dst and src must not alias (ECL reads neighbours of src)");
+  hd_mesh *m = op->mesh;
+  HD_REQUIRE(!m->has_ghosts || ghosts, "mesh has HD_SIDE_GHOST sides but no ghost buffer was passed");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  int  rc;
+  bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  if (fast)
+    rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu);
+  else
+    rc = hd::launch_generic(op, dst, src, ghosts, time, fu);
+  if (rc != HD_OK)
+    return rc;
+  bool any_dirichlet = false;
+  for (int d = 0; d < m->dim; ++d)
+    for (int s = 0; s < 2; ++s)
+      any_dirichlet |= (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET);
+  if (any_dirichlet)
+    return hd::launch_dirichlet_source(op, dst, time, fu);
+  return HD_OK;
+}
+
+int
+hd_advection_apply(hd_advection *op, void *dst, const void *src, const void *ghosts, double time)
+{
+  FusedUpdate fu;
+  return apply_impl(op, dst, src, ghosts, time, fu);
+}
+
+int
+hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time)
+{
+  HD_REQUIRE(op && dst_host && src_host, "null argument");
+  hd_mesh *m = op->mesh;
+  HD_REQUIRE(!m->has_ghosts, "hd_advection_apply_host is for single-GPU meshes");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t bytes = (size_t)m->ndofs * m->elem_size;
+  if (!op->d_stage_src)
+    {
+      HD_CUDA(cudaMalloc(&op->d_stage_src, bytes));
+      HD_CUDA(cudaMalloc(&op->d_stage_dst, bytes));
+    }
+  HD_CUDA(cudaMemcpyAsync(op->d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, m->ctx->stream));
+  FusedUpdate fu;
+  int         rc = apply_impl(op, op->d_stage_dst, op->d_stage_src, nullptr, time, fu);
+  if (rc != HD_OK)
+    return rc;
+  HD_CUDA(cudaMemcpyAsync(dst_host, op->d_stage_dst, bytes, cudaMemcpyDeviceToHost, m->ctx->stream));
+  HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_advection_set_dirichlet_values(hd_advection *op, int dir, int side, const double *g, int64_t n)
+{
+  HD_REQUIRE(op && g, "null argument");
+  hd_mesh *m = op->mesh;
+  HD_REQUIRE(dir >= 0 && dir < m->dim && side >= 0 && side <= 1, "bad (dir, side)");
+  HD_REQUIRE(m->d.side_kind[dir][side] == HD_SIDE_DIRICHLET, "side is not an inhomogeneous Dirichlet boundary");
+  int64_t nqf = 1;
+  for (int e = 0; e < m->dim - 1; ++e)
+    nqf *= m->nq;
+  const int64_t expect = (m->ncells / m->d.n_cells[dir]) * nqf;
+  HD_REQUIRE(n == expect, "wrong number of boundary values");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  if (!op->d_g[dir][side])
+    HD_CUDA(cudaMalloc(&op->d_g[dir][side], (size_t)n * sizeof(double)));
+  op->g_count[dir][side] = n;
+  HD_CUDA(cudaMemcpyAsync(op->d_g[dir][side], g, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_advection_set_dirichlet_builtin(hd_advection *op, int fn_id)
+{
+  HD_REQUIRE(op && (fn_id == HD_FN_ZERO || fn_id == HD_FN_HYPERRECTANGLE), "bad argument");
+  op->dirichlet_fn = fn_id;
+  return HD_OK;
+}
+
+// ---- halo -----------------------------------------------------------------------------------
+int
+hd_halo_pack(hd_mesh *m, const void *src, void *send)
+{
+  HD_REQUIRE(m && src, "null argument");
+  if (!m->has_ghosts)
+    return HD_OK;
+  HD_REQUIRE(send, "null send buffer");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const LatticeParams lp = lattice(m);
+  for (int d = 0; d < m->dim; ++d)
+    for (int s = 0; s < 2; ++s)
+      {
+        const long long cnt = m->ghost_cnt[d][s];
+        if (cnt == 0)
+          continue;
+        const unsigned g = grid_for(m->ctx, cnt, 256);
+        if (m->d.number_type == HD_F64)
+          k_halo_pack<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(send), lp, d, s, m->ghost_off[d][s], cnt);
+        else
+          k_halo_pack<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(send), lp, d, s, m->ghost_off[d][s], cnt);
+        HD_CUDA(cudaGetLastError());
+      }
+  return HD_OK;
+}
+
+// ---- LSRK -----------------------------------------------------------------------------------
+int
+hd_lsrk_create(hd_mesh *m, const char *type, hd_lsrk **out)
+{
+  HD_REQUIRE(m && type && out, "null argument");
+  hd_lsrk *rk = new (std::nothrow) hd_lsrk;
+  HD_REQUIRE(rk, "out of memory");
+  rk->mesh             = m;
+  const std::string t  = type;
+  auto &            bi = rk->bi;
+  auto &            ai = rk->ai;
+  // Kennedy, Carpenter, Lewis (2000) low-storage schemes; base/time_integrators.templates.h:34-86
+  if (t == "rk33")
+    {
+      bi = {0.245170287303492, 0.184896052186740, 0.569933660509768};
+      ai = {0.755726351946097, 0.386954477304099};
+    }
+  else if (t == "rk45")
+    {
+      bi = {1153189308089. / 22510343858157., 1772645290293. / 4653164025191., -1672844663538. / 4480602732383., 2114624349019. / 3568978502595., 5198255086312. / 14908931495163.};
+      ai = {970286171893. / 4311952581923., 6584761158862. / 12103376702013., 2251764453980. / 15575788980749., 26877169314380. / 34165994151039.};
+    }
+  else if (t == "rk47")
+    {
+      bi = {0.0941840925477795334, 0.149683694803496998, 0.285204742060440058, -0.122201846148053668, 0.0605151571191401122, 0.345986987898399296, 0.186627171718797670};
+      ai = {0.241566650129646868 + bi[0], 0.0423866513027719953 + bi[1], 0.215602732678803776 + bi[2], 0.232328007537583987 + bi[3], 0.256223412574146438 + bi[4], 0.0978694102142697230 + bi[5]};
+    }
+  else if (t == "rk59")
+    {
+      bi = {2274579626619. / 23610510767302., 693987741272. / 12394497460941., -347131529483. / 15096185902911., 1144057200723. / 32081666971178., 1562491064753. / 11797114684756., 13113619727965. / 44346030145118., 393957816125. / 7825732611452., 720647959663. / 6565743875477., 3559252274877. / 14424734981077.};
+      ai = {1107026461565. / 5417078080134., 38141181049399. / 41724347789894., 493273079041. / 11940823631197., 1851571280403. / 6147804934346., 11782306865191. / 62590030070788., 9452544825720. / 13648368537481., 4435885630781. / 26285702406235., 2357909744247. / 11371140753790.};
+    }
+  else
+    {
+      delete rk;
+      return hd::fail(HD_ERR_UNSUPPORTED, "LSRK type must be rk33, rk45, rk47 or rk59");
+    }
+  *out = rk;
+  return HD_OK;
+}
+
+int
+hd_lsrk_destroy(hd_lsrk *rk)
+{
+  if (!rk)
+    return HD_OK;
+  cudaFree(rk->d_ti2);
+  delete rk;
+  return HD_OK;
+}
+
+int
+hd_lsrk_n_stages(const hd_lsrk *rk)
+{
+  return rk ? (int)rk->bi.size() : 0;
+}
+
+int
+hd_lsrk_coefficients(const hd_lsrk *rk, int which, double *out)
+{
+  HD_REQUIRE(rk && out && (which == 0 || which == 1), "bad argument");
+  const auto &v = which == 0 ? rk->bi : rk->ai;
+  for (size_t i = 0; i < v.size(); ++i)
+    out[i] = v[i];
+  return (int)v.size();
+}
+
+int
+hd_lsrk_stage_update(hd_mesh *m, void *sol, void *ti, const void *K, double b, double a)
+{
+  HD_REQUIRE(m && sol && K && (ti || a == 0.0), "null argument");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const unsigned g = grid_for(m->ctx, m->ndofs, 256);
+  if (m->d.number_type == HD_F64)
+    k_stage_update<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<double *>(sol), static_cast<double *>(ti), static_cast<const double *>(K), b, a, m->ndofs);
+  else
+    k_stage_update<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<float *>(sol), static_cast<float *>(ti), static_cast<const float *>(K), (float)b, (float)a, m->ndofs);
+  HD_CUDA(cudaGetLastError());
+  return HD_OK;
+}
+
+int
+hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *vec_Ti, double t, double dt)
+{
+  HD_REQUIRE(rk && op && solution && vec_Ki && vec_Ti, "null argument");
+  hd_mesh *m = rk->mesh;
+  HD_REQUIRE(m == op->mesh, "integrator and operator belong to different meshes");
+  HD_REQUIRE(!m->has_ghosts, "hd_lsrk_step is for single-GPU meshes; drive stages with hd_lsrk_stage_update otherwise");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t bytes = (size_t)m->ndofs * m->elem_size;
+  // Fused path: the operator's epilogue does the stage update, so K is never stored and each
+  // stage streams Ti (read), solution (read+write) and the next Ti (write) once.  The next Ti
+  // must not overwrite the Ti the neighbours still read: ping-pong between vec_Ti and vec_Ki
+  // (vec_Ki is free because K never materialises).
+  // only_Ti_is_ghosted branch (time_integrators.templates.h:142-156): Ti <- solution
+  HD_CUDA(cudaMemcpyAsync(vec_Ti, solution, bytes, cudaMemcpyDeviceToDevice, m->ctx->stream));
+  void * cur = vec_Ti, *nxt = vec_Ki;
+  double sum_prev_b = 0.0;
+  const int S = (int)rk->bi.size();
+  for (int stage = 0; stage < S; ++stage)
+    {
+      double c = 0.0;
+      if (stage > 0)
+        {
+          c = sum_prev_b + rk->ai[stage - 1];
+          sum_prev_b += rk->bi[stage - 1];
+        }
+      FusedUpdate fu;
+      fu.enabled = 1;
+      fu.sol     = solution;
+      fu.ti_next = nxt;
+      fu.fb      = rk->bi[stage] * dt;
+      fu.fa      = (stage == S - 1) ? 0.0 : rk->ai[stage] * dt;
+      int rc     = apply_impl(op, nullptr, cur, nullptr, t + c * dt, fu);
+      if (rc != HD_OK)
+        return rc;
+      void *tmp = cur;
+      cur       = nxt;
+      nxt       = tmp;
+    }
+  return HD_OK;
+}
+
+// ---- VectorTools ------------------------------------------------------------------------------
+int
+hd_interpolate_builtin(hd_mesh *m, void *vec, int fn_id, double time)
+{
+  HD_REQUIRE(m && vec, "null argument");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const LatticeParams lp = lattice(m);
+  const unsigned      g  = grid_for(m->ctx, m->ndofs, 256);
+  if (m->d.number_type == HD_F64)
+    k_interpolate<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<double *>(vec), lp, m->d_basis, fn_id, time);
+  else
+    k_interpolate<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<float *>(vec), lp, m->d_basis, fn_id, time);
+  HD_CUDA(cudaGetLastError());
+  return HD_OK;
+}
+
+int
+hd_norm_and_error_builtin(hd_mesh *m, const void *vec, int fn_id, double time, double out[2])
+{
+  HD_REQUIRE(m && vec && out, "null argument");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const LatticeParams lp = lattice(m);
+  int                 mx = m->n > m->nq ? m->n : m->nq;
+  size_t              cap = 1;
+  for (int d = 0; d < m->dim; ++d)
+    cap *= mx;
+  const size_t smem = 2 * cap * sizeof(double);
+  if (smem > m->ctx->smem_optin)
+    return hd::fail(HD_ERR_UNSUPPORTED, "norm_and_error: cell does not fit into shared memory");
+  HD_CUDA(cudaMemsetAsync(m->d_reduce, 0, 2 * sizeof(double), m->ctx->stream));
+  if (m->d.number_type == HD_F64)
+    {
+      if (smem > 48 * 1024)
+        HD_CUDA(cudaFuncSetAttribute(k_norm_error<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_norm_error<double><<<(unsigned)m->ncells, 256, smem, m->ctx->stream>>>(static_cast<const double *>(vec), lp, m->d_basis, fn_id, time, m->d_reduce);
+    }
+  else
+    {
+      if (smem > 48 * 1024)
+        HD_CUDA(cudaFuncSetAttribute(k_norm_error<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_norm_error<float><<<(unsigned)m->ncells, 256, smem, m->ctx->stream>>>(static_cast<const float *>(vec), lp, m->d_basis, fn_id, time, m->d_reduce);
+    }
+  HD_CUDA(cudaGetLastError());
+  HD_CUDA(cudaMemcpyAsync(out, m->d_reduce, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return HD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,122 @@
+// Internal declarations shared by the translation units of libhdgpu.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/hyperdeal_b200.h"
+#include "basis.hpp"
+
+#define HD_CUDA(call)                                                                              \
+  do                                                                                               \
+    {                                                                                              \
+      cudaError_t e_ = (call);                                                                     \
+      if (e_ != cudaSuccess)                                                                       \
+        return hd::fail(HD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    }                                                                                              \
+  while (0)
+
+#define HD_REQUIRE(cond, msg)                                                                      \
+  do                                                                                               \
+    {                                                                                              \
+      if (!(cond))                                                                                 \
+        return hd::fail(HD_ERR_INVALID, std::string(msg) + " (" #cond ")");                        \
+    }                                                                                              \
+  while (0)
+
+namespace hd
+{
+  int fail(int code, const std::string &msg);
+}
+
+struct hd_context
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  int          sm_count = 0;
+  size_t       smem_optin = 0;
+};
+
+struct hd_mesh
+{
+  hd_context * ctx = nullptr;
+  hd_mesh_desc d;
+  int          dim = 0, n = 0, nq = 0;
+  int64_t      nd = 0;     // DoFs per cell  n^dim
+  int64_t      nf = 0;     // DoFs per face  n^(dim-1)
+  int64_t      ncells = 0; // local cells
+  int64_t      ndofs  = 0; // local DoFs
+  double       h[HD_MAX_DIM];
+  hd::Basis1D  basis;
+  size_t       elem_size = 8;
+  int64_t      ghost_off[HD_MAX_DIM][2];
+  int64_t      ghost_cnt[HD_MAX_DIM][2];
+  int64_t      ghost_total = 0;
+  bool         has_ghosts  = false;
+  // device copies (double) of nodes[n], xq[nq], w[nq], S[nq*n]
+  double *d_basis = nullptr;
+  double *d_reduce = nullptr; // 2 doubles for norm reductions
+};
+
+// per-direction collapsed matrices as uploaded to the device (T = Number)
+template <typename T, int N>
+struct DirCoef
+{
+  T C[4][N * N];
+  T L0[N];
+  T L1[N];
+};
+
+struct hd_advection
+{
+  hd_mesh *   mesh = nullptr;
+  double      skew = 0;
+  double      a[HD_MAX_DIM];
+  void *      d_coef      = nullptr; // DirCoef<T,N>[dim]
+  size_t      coef_bytes  = 0;
+  int         nb_mask[HD_MAX_DIM]; // bit0: lower neighbour trace needed, bit1: upper
+  int         kernel_choice = 0;
+  const char *last_kernel   = "none";
+  int64_t     launches      = 0;
+  // host copies of the collapsed matrices in double (for the specialised kernels)
+  std::vector<double> hC[HD_MAX_DIM][4], hL0[HD_MAX_DIM], hL1[HD_MAX_DIM];
+  // Dirichlet data
+  int     dirichlet_fn = -1;                    // built-in id or -1
+  double *d_g[HD_MAX_DIM][2];                   // device g at face quadrature points (double)
+  int64_t g_count[HD_MAX_DIM][2];
+  // staging for apply_host
+  void *  d_stage_src = nullptr, *d_stage_dst = nullptr;
+  // fast-kernel private state (tensor maps etc.)
+  void *fast_state = nullptr;
+};
+
+struct hd_lsrk
+{
+  hd_mesh *           mesh = nullptr;
+  std::vector<double> bi, ai;
+  void *              d_ti2 = nullptr; // second Ti register for the fused path
+};
+
+// optional fused LSRK epilogue:  K = (M^-1 A src);  sol += fb*K;  if (fa != 0) ti_next = sol_old + fa*K
+struct FusedUpdate
+{
+  void * sol     = nullptr;
+  void * ti_next = nullptr;
+  double fb = 0, fa = 0;
+  int    enabled = 0;
+};
+
+namespace hd
+{
+  // kernels_generic.cu
+  int launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
+  // kernel_fast6d.cu
+  bool fast6d_supported(const hd_advection *op);
+  int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
+  void fast6d_release(hd_advection *op);
+  // dirichlet source term (kernels_generic.cu)
+  int launch_dirichlet_source(hd_advection *op, void *dst, double time, const FusedUpdate &fu);
+} // namespace hd

@@ -1,0 +1,213 @@
+/* hyperdeal_b200.h — C ABI of libhdgpu.so, the B200 (sm_100a) implementation of
+ * hyper.deal's advection hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, plain pointers and sizes,
+ * int status codes and a thread-local error string.  The reference has no FFI of
+ * its own (it is a header-only C++ template library), so every entry point cites the
+ * reference C++ member it stands in for (paths relative to the hyper.deal source
+ * tree).  The header-only C++ shim in hyperdeal_b200/cpp/ re-creates those classes
+ * (hyperdeal::MatrixFree, advection::AdvectionOperation,
+ * LowStorageRungeKuttaIntegrator, VectorTools, ...) on top of these calls, see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns HD_OK (0) or a negative error code; hd_last_error()
+ *    gives the message of the last failure on the calling thread.
+ *  - "device pointer" arguments are raw CUDA device addresses of this process'
+ *    current device; "host" arguments are ordinary host memory.
+ *  - all kernels are enqueued on the context's stream (hd_context_set_stream) and
+ *    are asynchronous; only the *_host, copy_out, norm and timing calls synchronise.
+ *  - DoF vector layout (identical to the reference, matrix_free.templates.h:553-562,
+ *    shape_info.h:126-146): cells back to back, local cell id lexicographic with
+ *    direction 0 (x_0) fastest and v_last slowest; inside a cell (k+1)^dim nodal
+ *    values at the Gauss-Lobatto points, x_0 fastest.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with HD_ERR_CUDA.
+ */
+#ifndef HYPERDEAL_B200_H
+#define HYPERDEAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_MAX_DIM 6
+
+enum
+{
+  HD_OK              = 0,
+  HD_ERR_INVALID     = -1, /* bad argument / unsupported configuration */
+  HD_ERR_CUDA        = -2, /* CUDA runtime or driver failure (incl. no device) */
+  HD_ERR_UNSUPPORTED = -3  /* valid in the reference but not implemented here */
+};
+
+/* Number type of the DoF vectors (the reference's template parameter `Number`). */
+enum
+{
+  HD_F64 = 0,
+  HD_F32 = 1
+};
+
+/* Face neighbour kind on the lower/upper side of the LOCAL brick in one direction. */
+enum
+{
+  HD_SIDE_PERIODIC_LOCAL = 0, /* neighbour is the opposite end of this brick           */
+  HD_SIDE_GHOST          = 1, /* neighbour lives on another GPU: read the ghost buffer */
+  HD_SIDE_DIRICHLET      = 2, /* domain boundary, u+ = -u- + 2 g  (BoundaryType::DirichletInhomogenous,
+                                 operators/advection/boundary_descriptor.h:31-37)     */
+  HD_SIDE_DIRICHLET_HOM  = 3  /* domain boundary, u+ = -u-        (DirichletHomogenous) */
+};
+
+/* Built-in analytic fields (evaluated on the device). */
+enum
+{
+  HD_FN_ZERO           = 0,
+  HD_FN_HYPERRECTANGLE = 1 /* sin(2 pi (x0 - a0 t)) prod cos(2 pi (xd - ad t)), a = (1, .15, -.05, 0, 0, 0);
+                              examples/advection/cases/hyperrectangle.h:29-66 */
+};
+
+typedef struct hd_context   hd_context;
+typedef struct hd_mesh      hd_mesh;
+typedef struct hd_advection hd_advection;
+typedef struct hd_lsrk      hd_lsrk;
+
+/* Description of the Cartesian phase-space lattice owned by this process.
+ * Replaces the two dealii::Triangulation/dealii::MatrixFree objects handed to
+ * hyperdeal::MatrixFree::reinit (matrix_free/matrix_free.templates.h:862-1235) for the
+ * mesh class the hot path is specified on (subdivided_hyper_rectangle,
+ * grid/grid_generator.cc:235).  Directions 0..dim_x-1 are x, dim_x..dim_x+dim_v-1 are v. */
+typedef struct hd_mesh_desc
+{
+  int    dim_x, dim_v;
+  int    degree;      /* k; FE_DGQ(k) on Gauss-Lobatto nodes                                */
+  int    n_points;    /* 1-D quadrature points n_q (k+1 unless over-integration)            */
+  int    collocation; /* 1: Gauss-Lobatto quadrature (DoCollocation), requires n_q == k+1   */
+  int    number_type; /* HD_F64 / HD_F32                                                    */
+  double left[HD_MAX_DIM], right[HD_MAX_DIM]; /* GLOBAL domain                              */
+  int    n_cells_global[HD_MAX_DIM];          /* GLOBAL cells per direction                 */
+  int    n_cells[HD_MAX_DIM];                 /* cells of the LOCAL brick per direction     */
+  int    cell_offset[HD_MAX_DIM];             /* first global cell of the local brick       */
+  int    side_kind[HD_MAX_DIM][2];            /* HD_SIDE_* for the lower/upper brick side   */
+} hd_mesh_desc;
+
+/* ---- errors ------------------------------------------------------------------------- */
+const char *hd_last_error(void);
+int         hd_version(void);
+
+/* ---- context: device + stream ------------------------------------------------------- */
+/* Stands in for the (comm, comm_sm) pair of hyperdeal::MatrixFree's constructor
+ * (matrix_free/matrix_free.h:108): one context per process = one GPU. */
+int hd_context_create(int device, hd_context **out);
+int hd_context_destroy(hd_context *ctx);
+/* `stream` is a cudaStream_t (0 = legacy default stream). */
+int hd_context_set_stream(hd_context *ctx, void *stream);
+int hd_context_synchronize(hd_context *ctx);
+int hd_device_count(int *count);
+
+/* ---- mesh / matrix-free data -------------------------------------------------------- */
+/* hyperdeal::MatrixFree::reinit (matrix_free.templates.h:862). */
+int     hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out);
+int     hd_mesh_destroy(hd_mesh *mesh);
+int64_t hd_mesh_n_dofs(const hd_mesh *mesh);        /* owned DoFs of this brick           */
+int64_t hd_mesh_n_cells(const hd_mesh *mesh);
+int     hd_mesh_dofs_per_cell(const hd_mesh *mesh);
+/* number of ghost values behind side (dir, side): n_face_cells * (k+1)^(dim-1), 0 if the
+ * side is not HD_SIDE_GHOST  (vector_partitioner.h:916-945). */
+int64_t hd_mesh_ghost_size(const hd_mesh *mesh, int dir, int side);
+/* 1-D basis data the reference takes from dealii ShapeInfo (fe_evaluation_cell.h:93-95):
+ * which: 0 GLL nodes[n], 1 quad points[nq], 2 quad weights[nq], 3 S[nq*n], 4 D[nq*nq],
+ * 5 Sinv[n*nq]; returns the number of doubles written (out may be NULL to query). */
+int hd_mesh_basis(const hd_mesh *mesh, int which, double *out);
+
+/* ---- DoF vectors ---------------------------------------------------------------------- */
+/* hyperdeal::MatrixFree::initialize_dof_vector (matrix_free.templates.h:1369-1413): owned
+ * range + (if do_ghosts) ghost-face region, zero-initialised, on the device.  The returned
+ * device pointer is what every *_ptr entry point takes; free with hd_vector_free. */
+int hd_vector_alloc(hd_mesh *mesh, int do_ghosts, void **device_ptr);
+int hd_vector_free(hd_mesh *mesh, void *device_ptr);
+int hd_vector_copy_in(hd_mesh *mesh, void *device_ptr, const void *host, int64_t n_values);
+int hd_vector_copy_out(hd_mesh *mesh, const void *device_ptr, void *host, int64_t n_values);
+int hd_vector_zero(hd_mesh *mesh, void *device_ptr);
+/* dst = src for the owned range (device to device). */
+int hd_vector_copy(hd_mesh *mesh, void *dst, const void *src);
+
+/* ---- advection operator ---------------------------------------------------------------- */
+/* advection::AdvectionOperation::reinit (operators/advection/advection_operation.h:98) with a
+ * ConstantVelocityFieldView (operators/advection/velocity_field_view.h:69) and the SkewFactor of
+ * AdvectionOperationParamters (advection_operation_parameters.h:29-41).
+ * velocity[dim]: constant transport direction (x components first, then v). */
+int hd_advection_create(hd_mesh *mesh, double skew_factor, const double *velocity, hd_advection **out);
+int hd_advection_destroy(hd_advection *op);
+
+/* AdvectionOperation::apply(dst, src, time) (advection_operation.h:137): dst = M^-1 A(src, time)
+ * for the owned cells; dst is overwritten (ECL semantics, advection_operation.h:562).
+ * src/dst: device pointers with the vector layout above; they must not alias.
+ * ghosts: device pointer to the ghost-face values of src filled by the halo exchange
+ * (layout: hd_halo_offset), or NULL when no side is HD_SIDE_GHOST. */
+int hd_advection_apply(hd_advection *op, void *dst, const void *src, const void *ghosts, double time);
+/* Same call on HOST buffers: copies src in, applies, copies dst out (used for the end-to-end
+ * timing and by hosts that keep their vectors in host memory). */
+int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time);
+/* Select the kernel: 0 = automatic (fastest available), 1 = generic kernel, 2 = fused 3D3V k=3 kernel. */
+int hd_advection_set_kernel(hd_advection *op, int which);
+/* Name of the kernel the last apply launched (for logs and tests). */
+const char *hd_advection_kernel_name(const hd_advection *op);
+/* number of kernel launches issued by this operator so far */
+int64_t hd_advection_launch_count(const hd_advection *op);
+/* Inhomogeneous Dirichlet data (BoundaryDescriptor::dirichlet_bc, boundary_descriptor.h:42-76 with
+ * MatrixFreeTools::evaluate_scalar_function, matrix_free/tools.h:31): g sampled by the host at the
+ * face quadrature points of every boundary face of side (dir, side) for the stage time; values are
+ * ordered face-cell major (lexicographic over the other directions' local cells), then the
+ * n_q^(dim-1) face quadrature points, lowest direction fastest. */
+int hd_advection_set_dirichlet_values(hd_advection *op, int dir, int side, const double *g_host, int64_t n_values);
+/* Use a built-in analytic field as Dirichlet data, evaluated on the device at the stage time. */
+int hd_advection_set_dirichlet_builtin(hd_advection *op, int fn_id);
+
+/* ---- ghost faces (multi-GPU) ------------------------------------------------------------ */
+/* VectorDataExchange::Contiguous::export_to_ghosted_array_start (matrix_free/vector_partitioner.h:1387,
+ * pack loop :1443-1460): gather the nodal face layers of `src` that neighbouring bricks need into
+ * the contiguous send buffer.  Segment (dir, side) of the SEND buffer holds this brick's own
+ * boundary layer on that side; the matching segment of the neighbour's GHOST buffer is
+ * (dir, 1-side).  Transport between GPUs (NCCL send/recv or peer copies) is done by the caller
+ * between hd_halo_pack and hd_advection_apply. */
+int     hd_halo_pack(hd_mesh *mesh, const void *src, void *send_buffer);
+int64_t hd_halo_offset(const hd_mesh *mesh, int dir, int side); /* offset (values) of a segment  */
+int64_t hd_halo_total(const hd_mesh *mesh);                     /* total values of all segments  */
+
+/* ---- low-storage Runge-Kutta ----------------------------------------------------------- */
+/* LowStorageRungeKuttaIntegrator (base/time_integrators.h:48, coefficients
+ * base/time_integrators.templates.h:34-86). type: "rk33" | "rk45" | "rk47" | "rk59". */
+int hd_lsrk_create(hd_mesh *mesh, const char *type, hd_lsrk **out);
+int hd_lsrk_destroy(hd_lsrk *rk);
+int hd_lsrk_n_stages(const hd_lsrk *rk);
+/* coefficients: which 0 = b_i [n_stages], 1 = a_i [n_stages-1] */
+int hd_lsrk_coefficients(const hd_lsrk *rk, int which, double *out);
+/* One stage update with an externally computed K (perform_stage, time_integrators.templates.h:103-138):
+ *   solution += b*K ; if (a != 0) next_Ti = solution_old + a*K        (b, a already multiplied by dt) */
+int hd_lsrk_stage_update(hd_mesh *mesh, void *solution, void *next_Ti, const void *K, double b, double a);
+/* perform_time_step (time_integrators.templates.h:93-184) with the advection operator as `op`:
+ * all stages on the device; uses the fused operator+update kernel when available.  Ki and Ti
+ * are the two registers the reference's constructor takes; for single-GPU meshes only. */
+int hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *vec_Ti, double t, double dt);
+
+/* ---- VectorTools ------------------------------------------------------------------------ */
+/* VectorTools::interpolate (numerics/vector_tools.h:88): nodal values at the GLL points. */
+int hd_interpolate_builtin(hd_mesh *mesh, void *vec, int fn_id, double time);
+/* VectorTools::norm_and_error (numerics/vector_tools.h:151): out[0] = sum u_h^2 JxW,
+ * out[1] = sum (u_h - f)^2 JxW over the OWNED cells at the quadrature points (the caller
+ * all-reduces over GPUs and takes the square roots, vector_tools.h:212-219). */
+int hd_norm_and_error_builtin(hd_mesh *mesh, const void *vec, int fn_id, double time, double out[2]);
+
+/* ---- timing ----------------------------------------------------------------------------- */
+/* CUDA-event timing on the context's stream (the device-side counterpart of hyperdeal::Timers,
+ * base/timers.h:36): returns milliseconds between the two calls. */
+int hd_timer_start(hd_context *ctx);
+int hd_timer_stop(hd_context *ctx, double *milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
