@@ -219,3 +219,35 @@ def test_errors_are_reported(api, ctx):
         op.set_kernel(2)  # the 3D3V kernel does not cover 1D1V
     with pytest.raises(api.HdError):
         api.MatrixFree(ctx, 4, 1, 3, (1,) * 5, (0,) * 5, (1,) * 5)
+
+
+# ------------------------------------------------------------------------------------------
+# the pipelined 3D3V k=3 kernel (kernel_fast6d.cu)
+FAST_CASES = [
+    # cells                 velocity                                 skew
+    ((2, 2, 2, 2, 2, 2), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5),
+    ((3, 2, 1, 2, 2, 3), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.0),   # ragged, a direction with one cell
+    ((4, 1, 2, 3, 1, 2), (-1.0, -0.15, 0.05, -0.1, 0.15, -0.5), 0.5),  # all signs flipped: descending walk
+    ((2, 3, 2, 1, 2, 2), (0.0, 0.3, 0.0, 0.0, -0.2, 0.0), 0.5),       # zero components: inactive directions
+    ((1, 1, 1, 1, 1, 1), (0.4, -0.3, 0.2, -0.1, 0.6, 0.7), 1.0),      # single cell
+    ((5, 2, 2, 2, 2, 2), (0.0, 0.0, 0.0, 0.0, 0.0, 0.9), 0.0),
+    ((8, 4, 2, 2, 2, 2), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5),   # more rows than SMs would take at once
+]
+
+
+@pytest.mark.parametrize("nc,vel,skew", FAST_CASES)
+def test_fast_kernel_matches_oracle(api, ctx, nc, vel, skew):
+    rel, name = _run(api, ctx, 3, 3, nc, 3, skew=skew, vel=vel, kernel=2)
+    assert name == "advect_3d3v_k3"
+    assert rel <= TOL64, rel
+
+
+def test_auto_selects_fast_kernel(api, ctx):
+    rel, name = _run(api, ctx, 3, 3, (2, 2, 2, 2, 2, 2), 3, skew=0.5, kernel=0)
+    assert name == "advect_3d3v_k3" and rel <= TOL64
+
+
+def test_fast_kernel_many_rows(api, ctx):
+    """4^6 cells: every CTA walks several rows, all ring/parity phases wrap many times."""
+    rel, name = _run(api, ctx, 3, 3, (4, 4, 4, 4, 4, 4), 3, skew=0.5, kernel=2)
+    assert name == "advect_3d3v_k3" and rel <= TOL64
