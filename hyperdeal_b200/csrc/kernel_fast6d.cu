@@ -4,25 +4,26 @@
 //   dst_cell = sum_{d=0..5} (I x .. C_d .. x I) u_cell + L_d(i_d) * trace_d(upwind neighbour)
 // i.e. advection_operation.h:221-566 for Cartesian cells and a constant velocity, 30 DFMA per DoF.
 //
-// How it is mapped onto one SM (one persistent CTA per SM, 5 warps):
-//   warp 4      producer: TMA (cp.async.bulk.tensor, 128B/32B swizzle) brings the next cell
-//               (32 KiB) and the upwind face layers of directions 1 and 5 (8 KiB each) into a
-//               3-stage shared-memory ring; it also issues L2 prefetches for the face layers of
-//               directions 2,3,4 and gathers the direction-0 trace of the first cell of a row.
+// How it is mapped onto one SM (one persistent CTA per SM, 6 warps, mbarrier-only pipeline):
+//   warp 4      cell producer: takes rows of cells (along x_0) from a global atomic counter — so the
+//               148 CTAs sweep the lattice as one compact window and neighbour faces are still in L2
+//               — and TMA-loads (cp.async.bulk.tensor, 128B swizzle) each cell (32 KiB) into a 3-deep
+//               ring, the upwind face layers of directions 1 and 5 into a 2-deep ring, and gathers the
+//               direction-0 trace of the first cell of a row with cp.async.
+//   warp 5      face producer for round 2: TMA-loads the upwind face layers of directions 2,3,4
+//               (8 KiB each, from src or from the ghost buffer) into a 3-slot ring.
 //   warps 0,1   round 1: thread (i2,i3,i4) owns the 4x4x4 sub-tensor over (i0,i1,i5); 64 FP64
-//               accumulators in registers, u streamed plane by plane from shared memory; does
-//               directions 0,1,5.  The direction-0 neighbour trace never touches memory: the CTA
-//               walks a row of cells along x_0 in upwind order and the thread keeps the previous
-//               cell's end layer in 16 registers.  Result -> shared "partial" buffer (2-deep).
+//               accumulators in registers, u streamed plane by plane from shared memory; directions
+//               0,1,5.  The direction-0 neighbour trace never touches memory inside a row: cells are
+//               walked in upwind order and the thread keeps the previous cell's end layer in 16
+//               registers.  Result -> shared "partial" buffer (2-deep).
 //   warps 2,3   round 2, one cell behind: thread (i0,i1,i5) owns the sub-tensor over (i2,i3,i4);
-//               accumulators start from round 1's partial sums, directions 2,3,4, face layers read
-//               with coalesced loads through L2, then coalesced 128 B-per-half-warp stores to
-//               dst — or the fused LSRK update (sol += b dt K, Ti' = sol_old + a dt K,
-//               time_integrators.templates.h:117-132) so K is never written.
-// All (k+1)x(k+1) matrices sit in the kernel-parameter constant bank and are used as immediate
-// DFMA operands.  Synchronisation is mbarrier-only (no __syncthreads in the steady state).
+//               accumulators start from round 1's partial sums, directions 2,3,4, then coalesced
+//               128 B-per-half-warp stores to dst — or the fused LSRK update (sol += b dt K,
+//               Ti' = sol_old + a dt K, time_integrators.templates.h:117-132) so K is never written.
+// All (k+1)x(k+1) matrices sit in the kernel-parameter constant bank (uniform-register DFMA operands).
 //
-// Shared memory: 3 x (32 + 8 + 8) KiB ring + 2 x 32 KiB partials + 8 KiB trace + barriers = 216 KiB.
+// Shared memory: 3x32 (cells) + 2x16 (faces 1,5) + 2x32 (partials) + 3x8 (faces 2,3,4) + 8 (trace) KiB.
 // Algorithmic traffic 16 B/DoF (fused: 32 B/DoF); see DESIGN.md §4 for the roofline budget.
 #include <cuda.h>
 
@@ -32,22 +33,28 @@
 
 namespace
 {
-  constexpr int CELL      = 4096; // doubles per cell
-  constexpr int STAGES    = 3;
-  constexpr int THREADS   = 160;
-  constexpr int U_BYTES   = 32768;
-  constexpr int F_BYTES   = 8192;
-  constexpr int STAGE_BYTES = U_BYTES + 2 * F_BYTES;
-  constexpr int ACC_OFF   = STAGES * STAGE_BYTES;      // 147456
-  constexpr int T0_OFF    = ACC_OFF + 2 * U_BYTES;     // 212992
-  constexpr int BAR_OFF   = T0_OFF + F_BYTES;          // 221184
-  constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;     // + alignment slack
+  constexpr int CELL       = 4096; // doubles per cell
+  constexpr int STAGES     = 3;
+  constexpr int THREADS    = 192;
+  constexpr int U_BYTES    = 32768;
+  constexpr int F_BYTES    = 8192;
+  constexpr int R1F_OFF    = STAGES * U_BYTES;       // 98304
+  constexpr int ACC_OFF    = R1F_OFF + 2 * 2 * F_BYTES; // 131072
+  constexpr int R2F_OFF    = ACC_OFF + 2 * U_BYTES;  // 196608
+  constexpr int T0_OFF     = R2F_OFF + 3 * F_BYTES;  // 221184
+  constexpr int INFO_OFF   = T0_OFF + F_BYTES;       // 229376
+  constexpr int BAR_OFF    = INFO_OFF + 128;
+  constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + alignment slack
 
   struct FastCoef
   {
     double C[6][16]; // C_d[i*4+j]
     double L[6][4];  // lifting vector of the upwind face (0 if a_d == 0)
   };
+
+  // (k+1)x(k+1) matrices of the current launch; DFMA reads them through the constant bank.
+  // Uploaded stream-ordered before every launch (launches of one device serialise on the context stream).
+  __constant__ FastCoef cf;
 
   struct FastParams
   {
@@ -58,11 +65,19 @@ namespace
     int           up_delta[6];  // -1: upwind neighbour is the lower cell, +1: the upper one, 0: none
     int           up_kind[6];   // HD_SIDE_* of the brick side the upwind neighbour may lie behind
     long long     ghost_off[6]; // ghost segment of that side
-    long long     nrows;
+    int           nrows;
+    int *         counters; // [0] next row, [1] finished CTAs (self-resetting)
     double *      sol;
     double *      ti_next;
     double        fb, fa;
     int           pass; // 0 all rows, 1 rows that need no ghost data, 2 rows that need ghost data
+  };
+
+  struct CellInfo // 32 bytes, one per cell-ring stage
+  {
+    int cell; // -1: end of work
+    int c[6];
+    int first; // first cell of a row
   };
 
   // ---------------------------------------------------------------- PTX wrappers
@@ -114,9 +129,20 @@ namespace
                  : "memory");
   }
   __device__ __forceinline__ void
-  prefetch_l2(const void *p)
+  bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
   {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_8(uint32_t dst, const void *src)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_arrive_noinc(uint32_t bar)
+  {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
   }
   __device__ __forceinline__ double2
   lds128(uint32_t addr)
@@ -132,29 +158,17 @@ namespace
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
   }
+  __device__ __forceinline__ int4
+  lds_int4(uint32_t addr)
+  {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+  }
   __device__ __forceinline__ void
   sts128(uint32_t addr, double a, double b)
   {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-  }
-
-  // walk state shared by the three roles: every role enumerates the same (row, cell) sequence
-  struct Walk
-  {
-    int       c[6];
-    long long cell;
-  };
-
-  __device__ __forceinline__ void
-  row_coords(const FastParams &p, long long row, int (&c)[6])
-  {
-    long long r = row;
-#pragma unroll
-    for (int d = 1; d < 6; ++d)
-      {
-        c[d] = int(r % p.ncell[d]);
-        r /= p.ncell[d];
-      }
   }
 
   __device__ __forceinline__ long long
@@ -219,7 +233,8 @@ namespace
 
   template <bool FUSED>
   __global__ void __launch_bounds__(THREADS, 1)
-    k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ FastCoef cf, const FastParams p)
+    k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
+                     const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const FastParams p)
   {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw  = smem_u32(smem_raw);
@@ -227,11 +242,15 @@ namespace
     unsigned char *gbase = smem_raw + (base - raw);
     const uint32_t bar0 = base + BAR_OFF;
     // barrier slots
-    auto fullU   = [&](int s) { return bar0 + 8 * s; };
-    auto emptyU  = [&](int s) { return bar0 + 24 + 8 * s; };
-    auto accFull = [&](int a) { return bar0 + 48 + 8 * a; };
-    auto accEmpty = [&](int a) { return bar0 + 64 + 8 * a; };
-    const uint32_t t0Full = bar0 + 80, t0Empty = bar0 + 88;
+    auto fullU    = [&](int s) { return bar0 + 8 * s; };         // 0..2
+    auto emptyU   = [&](int s) { return bar0 + 24 + 8 * s; };    // 3..5
+    auto r1fFull  = [&](int f) { return bar0 + 48 + 8 * f; };    // 6..7
+    auto r1fEmpty = [&](int f) { return bar0 + 64 + 8 * f; };    // 8..9
+    auto accFull  = [&](int a) { return bar0 + 80 + 8 * a; };    // 10..11
+    auto accEmpty = [&](int a) { return bar0 + 96 + 8 * a; };    // 12..13
+    auto r2fFull  = [&](int j) { return bar0 + 112 + 8 * j; };   // 14..16
+    auto r2fEmpty = [&](int j) { return bar0 + 136 + 8 * j; };   // 17..19
+    const uint32_t t0Full = bar0 + 160, t0Empty = bar0 + 168;
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
@@ -243,9 +262,13 @@ namespace
           {
             mbar_init(fullU(s), 1);
             mbar_init(emptyU(s), 128);
+            mbar_init(r2fFull(s), 1);
+            mbar_init(r2fEmpty(s), 64);
           }
         for (int a = 0; a < 2; ++a)
           {
+            mbar_init(r1fFull(a), 1);
+            mbar_init(r1fEmpty(a), 64);
             mbar_init(accFull(a), 64);
             mbar_init(accEmpty(a), 64);
           }
@@ -256,108 +279,174 @@ namespace
       }
     __syncthreads();
 
-    const int  n0       = p.ncell[0];
-    const bool act0     = p.up_delta[0] != 0;
-    const bool act1     = p.up_delta[1] != 0;
-    const bool act5     = p.up_delta[5] != 0;
-    const bool descend  = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
+    const int  n0      = p.ncell[0];
+    const bool act0    = p.up_delta[0] != 0;
+    const bool act1    = p.up_delta[1] != 0;
+    const bool act5    = p.up_delta[5] != 0;
+    const bool r1faces = act1 || act5;
+    const bool descend = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
 
     if (warp == 4)
       {
-        // ======================================================================= producer
+        // ======================================================================= cell producer
         if (lane == 0)
           {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
           }
-        const uint32_t tx_bytes = U_BYTES + (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
-        long long      k        = 0; // cell sequence number of this CTA
-        long long      nrow_seq = 0; // row sequence number of this CTA
-        for (long long row = blockIdx.x; row < p.nrows; row += gridDim.x)
+        const uint32_t f_bytes  = (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
+        int            k        = 0; // cell sequence number of this CTA
+        int            nrow_seq = 0; // row sequence number of this CTA
+        for (;;)
           {
+            int row = 0;
+            if (lane == 0)
+              row = atomicAdd(p.counters, 1);
+            row = __shfl_sync(0xffffffffu, row, 0);
+            if (row >= p.nrows)
+              break;
             int c[6];
-            row_coords(p, row, c);
-            c[0] = 0;
+            {
+              int r = row;
+#pragma unroll
+              for (int d = 1; d < 6; ++d)
+                {
+                  c[d] = r % p.ncell[d];
+                  r /= p.ncell[d];
+                }
+            }
+            c[0] = descend ? n0 - 1 : 0;
             if (!row_selected(p, c))
               continue;
+            // direction-0 trace of the upwind neighbour of the first cell of the row (asynchronous gather)
+            if (act0)
+              {
+                mbar_wait(t0Empty, uint32_t(nrow_seq & 1) ^ 1u);
+                const uint32_t t0 = base + T0_OFF;
+                if (needs_ghost(p, c, 0))
+                  {
+                    const double *g = p.ghost + p.ghost_off[0] + face_cell(p, c, 0) * 1024;
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j)
+                      cp_async_8(t0 + 8u * (lane + 32 * j), g + lane + 32 * j);
+                  }
+                else
+                  {
+                    const long long nb = upwind_cell(p, c, 0);
+                    const double *  g  = p.src + nb * CELL + (p.up_delta[0] < 0 ? 3 : 0);
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j)
+                      cp_async_8(t0 + 8u * (lane + 32 * j), g + 4 * (lane + 32 * j));
+                  }
+                cp_async_arrive_noinc(t0Full);
+              }
             for (int step = 0; step < n0; ++step, ++k)
               {
-                c[0]                = descend ? n0 - 1 - step : step;
+                c[0]                 = descend ? n0 - 1 - step : step;
                 const long long cell = cell_index(p, c);
-                const int       s    = int(k % STAGES);
-                const uint32_t  ph   = uint32_t((k / STAGES) & 1);
-                mbar_wait(emptyU(s), ph ^ 1u);
+                const int       s    = k % STAGES;
+                mbar_wait(emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
                 if (lane == 0)
                   {
-                    const uint32_t dstU = base + s * STAGE_BYTES;
-                    mbar_expect_tx(fullU(s), tx_bytes);
+                    int *info = reinterpret_cast<int *>(gbase + INFO_OFF + 32 * s);
+                    info[0]   = int(cell);
+#pragma unroll
+                    for (int d = 0; d < 6; ++d)
+                      info[1 + d] = c[d];
+                    info[7]             = (step == 0) ? 1 : 0;
+                    const uint32_t dstU = base + s * U_BYTES;
+                    mbar_expect_tx(fullU(s), U_BYTES);
 #pragma unroll
                     for (int piece = 0; piece < 4; ++piece)
                       tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), fullU(s));
-                    if (act1)
+                  }
+                if (r1faces)
+                  {
+                    const int f = k & 1;
+                    mbar_wait(r1fEmpty(f), uint32_t((k >> 1) & 1) ^ 1u);
+                    if (lane == 0)
                       {
-                        const long long nb = upwind_cell(p, c, 1);
-                        tma_load_3d(dstU + U_BYTES, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(nb * 256), fullU(s));
-                      }
-                    if (act5)
-                      {
-                        const long long nb = upwind_cell(p, c, 5);
-                        tma_load_2d(dstU + U_BYTES + F_BYTES, &mapU, 0, int(nb * 256 + (p.up_delta[5] < 0 ? 192 : 0)), fullU(s));
+                        const uint32_t dstF = base + R1F_OFF + f * 2 * F_BYTES;
+                        mbar_expect_tx(r1fFull(f), f_bytes);
+                        if (act1)
+                          {
+                            const long long nb = upwind_cell(p, c, 1);
+                            tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(nb * 256), r1fFull(f));
+                          }
+                        if (act5)
+                          {
+                            const long long nb = upwind_cell(p, c, 5);
+                            tma_load_2d(dstF + F_BYTES, &mapU, 0, int(nb * 256 + (p.up_delta[5] < 0 ? 192 : 0)), r1fFull(f));
+                          }
                       }
                   }
-                // L2 prefetch of the face layers round 2 reads with plain loads (directions 2,3,4)
+              }
+            ++nrow_seq;
+          }
+        // end marker
+        {
+          const int s = k % STAGES;
+          mbar_wait(emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
+          if (lane == 0)
+            {
+              int *info = reinterpret_cast<int *>(gbase + INFO_OFF + 32 * s);
+              info[0]   = -1;
+              mbar_arrive(fullU(s));
+              // the last CTA to finish re-arms the row counter for the next launch
+              __threadfence();
+              const int done = atomicAdd(p.counters + 1, 1);
+              if (done == int(gridDim.x) - 1)
+                {
+                  p.counters[0] = 0;
+                  p.counters[1] = 0;
+                  __threadfence();
+                }
+            }
+        }
+      }
+    else if (warp == 5)
+      {
+        // ======================================================================= face producer for round 2
+        if (lane == 0)
+          {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
+            for (int k = 0;; ++k)
+              {
+                const int s = k % STAGES;
+                mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
+                const int *info = reinterpret_cast<const int *>(gbase + INFO_OFF + 32 * s);
+                if (info[0] < 0)
+                  break;
+                int c[6];
 #pragma unroll
-                for (int d = 2; d <= 4; ++d)
+                for (int d = 0; d < 6; ++d)
+                  c[d] = info[1 + d];
+#pragma unroll
+                for (int j = 2; j >= 0; --j)
                   {
+                    const int d = 2 + j;
                     if (p.up_delta[d] == 0)
                       continue;
-                    const double *fb;
+                    mbar_wait(r2fEmpty(j), uint32_t(k & 1) ^ 1u);
+                    const uint32_t dstF = base + R2F_OFF + j * F_BYTES;
+                    mbar_expect_tx(r2fFull(j), F_BYTES);
                     if (needs_ghost(p, c, d))
-                      {
-                        fb = p.ghost + p.ghost_off[d] + face_cell(p, c, d) * 1024;
-#pragma unroll
-                        for (int r = 0; r < 2; ++r)
-                          prefetch_l2(fb + (lane + 32 * r) * 16);
-                      }
+                      bulk_load_1d(dstF, p.ghost + p.ghost_off[d] + face_cell(p, c, d) * 1024, F_BYTES, r2fFull(j));
                     else
                       {
                         const long long nb    = upwind_cell(p, c, d);
                         const int       layer = p.up_delta[d] < 0 ? 3 : 0;
-                        const int       lo_n  = 1 << (2 * (d - 2)); // 4^(d-2) lines below digit d
-                        fb                    = p.src + nb * CELL;
-#pragma unroll
-                        for (int r = 0; r < 2; ++r)
-                          {
-                            const int l = lane + 32 * r, lo = l % lo_n, hi = l / lo_n;
-                            prefetch_l2(fb + (lo + lo_n * (layer + 4 * hi)) * 16);
-                          }
+                        if (d == 2)
+                          tma_load_3d(dstF, &mapT2, 0, layer, int(nb * 64), r2fFull(j));
+                        else if (d == 3)
+                          tma_load_3d(dstF, &mapT3, 0, layer, int(nb * 16), r2fFull(j));
+                        else
+                          tma_load_3d(dstF, &mapT4, 0, layer, int(nb * 4), r2fFull(j));
                       }
-                  }
-                // direction-0 trace of the neighbour of the first cell of the row
-                if (step == 0 && act0)
-                  {
-                    const uint32_t tph = uint32_t(nrow_seq & 1);
-                    mbar_wait(t0Empty, tph ^ 1u);
-                    double *t0 = reinterpret_cast<double *>(gbase + T0_OFF);
-                    if (needs_ghost(p, c, 0))
-                      {
-                        const double *g = p.ghost + p.ghost_off[0] + face_cell(p, c, 0) * 1024;
-#pragma unroll 8
-                        for (int j = 0; j < 32; ++j)
-                          t0[lane + 32 * j] = __ldg(g + lane + 32 * j);
-                      }
-                    else
-                      {
-                        const long long nb = upwind_cell(p, c, 0);
-                        const double *  g  = p.src + nb * CELL + (p.up_delta[0] < 0 ? 3 : 0);
-#pragma unroll 8
-                        for (int j = 0; j < 32; ++j)
-                          t0[lane + 32 * j] = __ldg(g + 4 * (lane + 32 * j));
-                      }
-                    mbar_arrive(t0Full);
                   }
               }
-            ++nrow_seq;
           }
       }
     else if (warp < 2)
@@ -366,131 +455,139 @@ namespace
         const int      t    = tid;          // (i2,i3,i4)
         const uint32_t sw   = uint32_t(t & 7);
         const uint32_t rowU = uint32_t(t) * 128u;
-        double         carry[4][4]; // [i5][i1]
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            carry[a][b] = 0.0;
-        long long k = 0, nrow_seq = 0;
-        for (long long row = blockIdx.x; row < p.nrows; row += gridDim.x)
+        int nrow_seq = 0;
+        for (int k = 0;; ++k)
           {
-            int c[6];
-            row_coords(p, row, c);
-            c[0] = 0;
-            if (!row_selected(p, c))
-              continue;
-            for (int step = 0; step < n0; ++step, ++k)
+            const int      s  = k % STAGES;
+            const int      f  = k & 1;
+            const uint32_t pf = uint32_t((k >> 1) & 1);
+            const uint32_t ub = base + s * U_BYTES;
+            mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
+            const int4 inf = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
+            const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
+            if (cellid < 0)
+              break;
+            // direction-0 trace of the upwind neighbour: the end layer of the previous cell of the row, read
+            // from that cell's ring stage (still resident: round 2 works on it), or the gathered trace at a row start
+            const bool from_t0 = inf.w != 0;
+            if (from_t0 && act0)
               {
-                const int      s  = int(k % STAGES);
-                const uint32_t ph = uint32_t((k / STAGES) & 1);
-                const int      a  = int(k & 1);
-                const uint32_t pa = uint32_t((k >> 1) & 1);
-                const uint32_t ub = base + s * STAGE_BYTES;
-                if (step == 0 && act0)
-                  {
-                    mbar_wait(t0Full, uint32_t(nrow_seq & 1));
-                    const uint32_t tb = base + T0_OFF + uint32_t(t) * 32u;
-#pragma unroll
-                    for (int j5 = 0; j5 < 4; ++j5)
-                      {
-                        const double2 v0 = lds128(tb + j5 * 2048), v1 = lds128(tb + j5 * 2048 + 16);
-                        carry[j5][0] = v0.x;
-                        carry[j5][1] = v0.y;
-                        carry[j5][2] = v1.x;
-                        carry[j5][3] = v1.y;
-                      }
-                    mbar_arrive(t0Empty);
-                  }
-                mbar_wait(fullU(s), ph);
+                mbar_wait(t0Full, uint32_t(nrow_seq & 1));
+                ++nrow_seq;
+              }
+            const uint32_t pb  = base + ((k + STAGES - 1) % STAGES) * U_BYTES + rowU + (descend ? 0u : 8u);
+            const uint32_t t0b = base + T0_OFF + uint32_t(t) * 32u;
+            if (r1faces)
+              mbar_wait(r1fFull(f), pf);
+            const uint32_t fbuf = base + R1F_OFF + f * 2 * F_BYTES;
 
-                double acc[4][4][4]; // [i5][i1][i0]
+            double acc[4][4][4]; // [i5][i1][i0]
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < 4; ++x)
 #pragma unroll
-                  for (int y = 0; y < 4; ++y)
+              for (int y = 0; y < 4; ++y)
 #pragma unroll
-                    for (int z = 0; z < 4; ++z)
-                      acc[x][y][z] = 0.0;
+                for (int z = 0; z < 4; ++z)
+                  acc[x][y][z] = 0.0;
 
 #pragma unroll
-                for (int j5 = 0; j5 < 4; ++j5)
+            for (int j5 = 0; j5 < 4; ++j5)
+              {
+                double P[4][4]; // [i1][i0]
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
                   {
-                    double P[4][4]; // [i1][i0]
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                      {
-                        const double2 v        = lds128(ub + rowU + j5 * 8192 + ((uint32_t(ch) ^ sw) << 4));
-                        P[ch >> 1][(ch & 1) * 2]     = v.x;
-                        P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
-                      }
-                    double t1v[4] = {0.0, 0.0, 0.0, 0.0};
-                    if (act1)
-                      {
-                        const uint32_t r32 = uint32_t(t) + 64u * j5;
-                        const uint32_t fl  = (r32 >> 2) & 1u;
-                        const uint32_t tb  = ub + U_BYTES + r32 * 32u;
-                        const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
-                        t1v[0] = v0.x;
-                        t1v[1] = v0.y;
-                        t1v[2] = v1.x;
-                        t1v[3] = v1.y;
-                      }
-#pragma unroll
-                    for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-                      for (int i0 = 0; i0 < 4; ++i0)
-                        {
-                          double v = acc[j5][i1][i0];
-#pragma unroll
-                          for (int j = 0; j < 4; ++j)
-                            v = fma(cf.C[0][i0 * 4 + j], P[i1][j], v);
-#pragma unroll
-                          for (int j = 0; j < 4; ++j)
-                            v = fma(cf.C[1][i1 * 4 + j], P[j][i0], v);
-                          v = fma(cf.L[0][i0], carry[j5][i1], v);
-                          v = fma(cf.L[1][i1], t1v[i0], v);
-                          acc[j5][i1][i0] = v;
-                        }
-#pragma unroll
-                    for (int i5 = 0; i5 < 4; ++i5)
-#pragma unroll
-                      for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-                        for (int i0 = 0; i0 < 4; ++i0)
-                          acc[i5][i1][i0] = fma(cf.C[5][i5 * 4 + j5], P[i1][i0], acc[i5][i1][i0]);
-#pragma unroll
-                    for (int i1 = 0; i1 < 4; ++i1)
-                      carry[j5][i1] = descend ? P[i1][0] : P[i1][3];
+                    const double2 v              = lds128(ub + rowU + j5 * 8192 + ((uint32_t(ch) ^ sw) << 4));
+                    P[ch >> 1][(ch & 1) * 2]     = v.x;
+                    P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
                   }
-                if (act5)
+                double cv[4] = {0.0, 0.0, 0.0, 0.0};
+                if (act0)
                   {
-                    const uint32_t tb = ub + U_BYTES + F_BYTES + rowU;
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
+                    if (from_t0)
                       {
-                        const double2 v  = lds128(tb + ((uint32_t(ch) ^ sw) << 4));
-                        const int     i1 = ch >> 1, i0 = (ch & 1) * 2;
+                        const double2 v0 = lds128(t0b + j5 * 2048), v1 = lds128(t0b + j5 * 2048 + 16);
+                        cv[0] = v0.x;
+                        cv[1] = v0.y;
+                        cv[2] = v1.x;
+                        cv[3] = v1.y;
+                      }
+                    else
+                      {
 #pragma unroll
-                        for (int i5 = 0; i5 < 4; ++i5)
-                          {
-                            acc[i5][i1][i0]     = fma(cf.L[5][i5], v.x, acc[i5][i1][i0]);
-                            acc[i5][i1][i0 + 1] = fma(cf.L[5][i5], v.y, acc[i5][i1][i0 + 1]);
-                          }
+                        for (int i1 = 0; i1 < 4; ++i1)
+                          cv[i1] = lds64(pb + j5 * 8192 + ((uint32_t(2 * i1 + (descend ? 0 : 1)) ^ sw) << 4));
                       }
                   }
-                mbar_arrive(emptyU(s));
-                // partial sums -> shared (same swizzle as u)
-                mbar_wait(accEmpty(a), pa ^ 1u);
-                const uint32_t ab = base + ACC_OFF + a * U_BYTES + rowU;
+                double t1v[4] = {0.0, 0.0, 0.0, 0.0};
+                if (act1)
+                  {
+                    const uint32_t r32 = uint32_t(t) + 64u * j5;
+                    const uint32_t fl  = (r32 >> 2) & 1u;
+                    const uint32_t tb  = fbuf + r32 * 32u;
+                    const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
+                    t1v[0] = v0.x;
+                    t1v[1] = v0.y;
+                    t1v[2] = v1.x;
+                    t1v[3] = v1.y;
+                  }
+#pragma unroll
+                for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+                  for (int i0 = 0; i0 < 4; ++i0)
+                    {
+                      double v = acc[j5][i1][i0];
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v = fma(cf.C[0][i0 * 4 + j], P[i1][j], v);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v = fma(cf.C[1][i1 * 4 + j], P[j][i0], v);
+                      v = fma(cf.L[0][i0], cv[i1], v);
+                      v = fma(cf.L[1][i1], t1v[i0], v);
+                      acc[j5][i1][i0] = v;
+                    }
 #pragma unroll
                 for (int i5 = 0; i5 < 4; ++i5)
 #pragma unroll
-                  for (int ch = 0; ch < 8; ++ch)
-                    sts128(ab + i5 * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[i5][ch >> 1][(ch & 1) * 2], acc[i5][ch >> 1][(ch & 1) * 2 + 1]);
-                mbar_arrive(accFull(a));
+                  for (int i1 = 0; i1 < 4; ++i1)
+#pragma unroll
+                    for (int i0 = 0; i0 < 4; ++i0)
+                      acc[i5][i1][i0] = fma(cf.C[5][i5 * 4 + j5], P[i1][i0], acc[i5][i1][i0]);
               }
-            ++nrow_seq;
+            // release the PREVIOUS cell's stage (its end layer was this cell's direction-0 trace)
+            if (k > 0)
+              mbar_arrive(emptyU((k + STAGES - 1) % STAGES));
+            if (from_t0 && act0)
+              mbar_arrive(t0Empty);
+            if (act5)
+              {
+                const uint32_t tb = fbuf + F_BYTES + rowU;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                  {
+                    const double2 v  = lds128(tb + ((uint32_t(ch) ^ sw) << 4));
+                    const int     i1 = ch >> 1, i0 = (ch & 1) * 2;
+#pragma unroll
+                    for (int i5 = 0; i5 < 4; ++i5)
+                      {
+                        acc[i5][i1][i0]     = fma(cf.L[5][i5], v.x, acc[i5][i1][i0]);
+                        acc[i5][i1][i0 + 1] = fma(cf.L[5][i5], v.y, acc[i5][i1][i0 + 1]);
+                      }
+                  }
+              }
+            if (r1faces)
+              mbar_arrive(r1fEmpty(f));
+            // partial sums -> shared (same swizzle as u)
+            const int a = k & 1;
+            mbar_wait(accEmpty(a), pf ^ 1u);
+            const uint32_t ab = base + ACC_OFF + a * U_BYTES + rowU;
+#pragma unroll
+            for (int i5 = 0; i5 < 4; ++i5)
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch)
+                sts128(ab + i5 * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[i5][ch >> 1][(ch & 1) * 2], acc[i5][ch >> 1][(ch & 1) * 2 + 1]);
+            mbar_arrive(accFull(a));
           }
       }
     else
@@ -499,219 +596,158 @@ namespace
         const int      tt  = tid - 64;
         const int      cc  = tt & 15; // (i0,i1)
         const int      i5  = tt >> 4;
-        const uint32_t col = uint32_t(cc >> 1);
+        const uint32_t col = uint32_t(cc >> 1) << 4;
         const uint32_t sub = uint32_t(cc & 1) * 8u;
-        // swizzled column offsets for row & 7 = 0..7
-        uint32_t xoff[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          xoff[q] = ((col ^ uint32_t(q)) << 4) + sub;
-        const uint32_t rowbase = uint32_t(i5) * 8192u; // row = q + 64 i5
-        long long      k       = 0;
-        for (long long row = blockIdx.x; row < p.nrows; row += gridDim.x)
+        const uint32_t rowbase = uint32_t(i5) * 8192u + sub; // row = q + 64 i5
+        const uint32_t fcol    = base + R2F_OFF + 8u * uint32_t(cc + 256 * i5);
+        for (int k = 0;; ++k)
           {
-            int c[6];
-            row_coords(p, row, c);
-            c[0] = 0;
-            if (!row_selected(p, c))
-              continue;
-            for (int step = 0; step < n0; ++step, ++k)
-              {
-                c[0]                 = descend ? n0 - 1 - step : step;
-                const long long cell = cell_index(p, c);
-                const int       s    = int(k % STAGES);
-                const uint32_t  ph   = uint32_t((k / STAGES) & 1);
-                const int       a    = int(k & 1);
-                const uint32_t  pa   = uint32_t((k >> 1) & 1);
-                const uint32_t  ub   = base + s * STAGE_BYTES + rowbase;
-                const uint32_t  ab   = base + ACC_OFF + a * U_BYTES + rowbase;
+            const int      s  = k % STAGES;
+            const int      a  = k & 1;
+            const uint32_t pa = uint32_t((k >> 1) & 1);
+            const uint32_t pk = uint32_t(k & 1);
+            const uint32_t ub = base + s * U_BYTES + rowbase;
+            const uint32_t ab = base + ACC_OFF + a * U_BYTES + rowbase;
+            mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
+            const int cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
+            if (cellid < 0)
+              break;
 
-                // face sources (uniform per cell): base pointer and strides of the two free tile indices
-                const double *fptr[3];
-                int           fsA[3], fsB[3];
+            mbar_wait(accFull(a), pa);
+            double acc[4][4][4]; // [i4][i3][i2]
 #pragma unroll
-                for (int d = 2; d <= 4; ++d)
-                  {
-                    const int e = d - 2;
-                    if (p.up_delta[d] == 0)
-                      {
-                        fptr[e] = nullptr;
-                        fsA[e] = fsB[e] = 0;
-                        continue;
-                      }
-                    if (needs_ghost(p, c, d))
-                      {
-                        fptr[e] = p.ghost + p.ghost_off[d] + face_cell(p, c, d) * 1024 + cc + 256 * i5;
-                        fsA[e]  = 16;
-                        fsB[e]  = 64;
-                      }
-                    else
-                      {
-                        const long long nb    = upwind_cell(p, c, d);
-                        const int       layer = p.up_delta[d] < 0 ? 3 : 0;
-                        fptr[e]               = p.src + nb * CELL + cc + 1024 * i5 + layer * (16 << (2 * e));
-                        fsA[e]                = d == 2 ? 64 : 16;
-                        fsB[e]                = d == 4 ? 64 : 256;
-                      }
-                  }
+            for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+              for (int i3 = 0; i3 < 4; ++i3)
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2)
+                  acc[i4][i3][i2] = lds64(ab + uint32_t(i2 + 4 * i3 + 16 * i4) * 128u + (col ^ (uint32_t((i2 + 4 * i3) & 7) << 4)));
 
-                mbar_wait(fullU(s), ph);
-                mbar_wait(accFull(a), pa);
-                double acc[4][4][4]; // [i4][i3][i2]
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              {
+                double P[4][4]; // [i3][i2]
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3)
+#pragma unroll
+                  for (int i2 = 0; i2 < 4; ++i2)
+                    P[i3][i2] = lds64(ub + uint32_t(i2 + 4 * i3 + 16 * j4) * 128u + (col ^ (uint32_t((i2 + 4 * i3) & 7) << 4)));
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3)
+#pragma unroll
+                  for (int i2 = 0; i2 < 4; ++i2)
+                    {
+                      double v = acc[j4][i3][i2];
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v = fma(cf.C[2][i2 * 4 + j], P[i3][j], v);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v = fma(cf.C[3][i3 * 4 + j], P[j][i2], v);
+                      acc[j4][i3][i2] = v;
+                    }
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
                   for (int i3 = 0; i3 < 4; ++i3)
 #pragma unroll
                     for (int i2 = 0; i2 < 4; ++i2)
-                      acc[i4][i3][i2] = lds64(ab + uint32_t(i2 + 4 * i3 + 16 * i4) * 128u + xoff[(i2 + 4 * i3) & 7]);
-                mbar_arrive(accEmpty(a));
+                      acc[i4][i3][i2] = fma(cf.C[4][i4 * 4 + j4], P[i3][i2], acc[i4][i3][i2]);
+                if (j4 == 0)
+                  mbar_arrive(accEmpty(a)); // every partial sum has been consumed into the accumulators
+              }
+            mbar_arrive(emptyU(s));
 
-                double fv[16];
-                // batch 0: direction 4 (longest reuse distance -> issued first)
-                if (fptr[2])
+            // neighbour traces of directions 4, 3, 2 from the face ring (face dof order: digit d removed)
+            if (p.up_delta[4] != 0)
+              {
+                mbar_wait(r2fFull(2), pk);
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3)
                   {
+                    double fv[4];
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2)
+                      fv[i2] = lds64(fcol + 2 * F_BYTES + 128u * uint32_t(i2 + 4 * i3));
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+                      for (int i2 = 0; i2 < 4; ++i2)
+                        acc[i4][i3][i2] = fma(cf.L[4][i4], fv[i2], acc[i4][i3][i2]);
+                  }
+                mbar_arrive(r2fEmpty(2));
+              }
+            if (p.up_delta[3] != 0)
+              {
+                mbar_wait(r2fFull(1), pk);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4)
+                  {
+                    double fv[4];
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2)
+                      fv[i2] = lds64(fcol + 1 * F_BYTES + 128u * uint32_t(i2 + 4 * i4));
 #pragma unroll
                     for (int i3 = 0; i3 < 4; ++i3)
 #pragma unroll
                       for (int i2 = 0; i2 < 4; ++i2)
-                        fv[i3 * 4 + i2] = __ldg(fptr[2] + i2 * fsA[2] + i3 * fsB[2]);
+                        acc[i4][i3][i2] = fma(cf.L[3][i3], fv[i2], acc[i4][i3][i2]);
                   }
-                else
+                mbar_arrive(r2fEmpty(1));
+              }
+            if (p.up_delta[2] != 0)
+              {
+                mbar_wait(r2fFull(0), pk);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4)
                   {
+                    double fv[4];
+#pragma unroll
+                    for (int i3 = 0; i3 < 4; ++i3)
+                      fv[i3] = lds64(fcol + 128u * uint32_t(i3 + 4 * i4));
+#pragma unroll
+                    for (int i3 = 0; i3 < 4; ++i3)
+#pragma unroll
+                      for (int i2 = 0; i2 < 4; ++i2)
+                        acc[i4][i3][i2] = fma(cf.L[2][i2], fv[i3], acc[i4][i3][i2]);
+                  }
+                mbar_arrive(r2fEmpty(0));
+              }
+
+            // epilogue: coalesced stores (a half-warp writes 128 contiguous bytes)
+            const long long g = (long long)cellid * CELL + cc + 1024 * i5;
+            if (FUSED)
+              {
+                const double *solr = p.sol + g;
+                double *      solw = p.sol + g;
+                double *      tiw  = p.ti_next + g;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4)
+                  {
+                    double sv[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                      fv[q] = 0.0;
-                  }
-
+                      sv[q] = solr[(q + 16 * i4) * 16];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4)
-                  {
-                    double P[4][4]; // [i3][i2]
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                      for (int i2 = 0; i2 < 4; ++i2)
-                        P[i3][i2] = lds64(ub + uint32_t(i2 + 4 * i3 + 16 * j4) * 128u + xoff[(i2 + 4 * i3) & 7]);
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                      for (int i2 = 0; i2 < 4; ++i2)
-                        {
-                          double v = acc[j4][i3][i2];
-#pragma unroll
-                          for (int j = 0; j < 4; ++j)
-                            v = fma(cf.C[2][i2 * 4 + j], P[i3][j], v);
-#pragma unroll
-                          for (int j = 0; j < 4; ++j)
-                            v = fma(cf.C[3][i3 * 4 + j], P[j][i2], v);
-                          acc[j4][i3][i2] = v;
-                        }
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                      for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2)
-                          acc[i4][i3][i2] = fma(cf.C[4][i4 * 4 + j4], P[i3][i2], acc[i4][i3][i2]);
-
-                    if (j4 == 0)
+                    for (int q = 0; q < 16; ++q)
                       {
-                        // consume direction 4, fetch direction 3
-#pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                          for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                            for (int i2 = 0; i2 < 4; ++i2)
-                              acc[i4][i3][i2] = fma(cf.L[4][i4], fv[i3 * 4 + i2], acc[i4][i3][i2]);
-                        if (fptr[1])
-                          {
-#pragma unroll
-                            for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                              for (int i2 = 0; i2 < 4; ++i2)
-                                fv[i4 * 4 + i2] = __ldg(fptr[1] + i2 * fsA[1] + i4 * fsB[1]);
-                          }
-                        else
-                          {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                              fv[q] = 0.0;
-                          }
-                      }
-                    if (j4 == 1)
-                      {
-#pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                          for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                            for (int i2 = 0; i2 < 4; ++i2)
-                              acc[i4][i3][i2] = fma(cf.L[3][i3], fv[i4 * 4 + i2], acc[i4][i3][i2]);
-                        if (fptr[0])
-                          {
-#pragma unroll
-                            for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                              for (int i3 = 0; i3 < 4; ++i3)
-                                fv[i4 * 4 + i3] = __ldg(fptr[0] + i3 * fsA[0] + i4 * fsB[0]);
-                          }
-                        else
-                          {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                              fv[q] = 0.0;
-                          }
-                      }
-                    if (j4 == 2)
-                      {
-#pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                          for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                            for (int i2 = 0; i2 < 4; ++i2)
-                              acc[i4][i3][i2] = fma(cf.L[2][i2], fv[i4 * 4 + i3], acc[i4][i3][i2]);
+                        const double kv          = acc[i4][q >> 2][q & 3];
+                        solw[(q + 16 * i4) * 16] = fma(p.fb, kv, sv[q]);
+                        if (p.fa != 0.0)
+                          tiw[(q + 16 * i4) * 16] = fma(p.fa, kv, sv[q]);
                       }
                   }
-                mbar_arrive(emptyU(s));
-
-                // epilogue: coalesced stores (a half-warp writes 128 contiguous bytes)
-                const long long g = cell * CELL + cc + 1024 * i5;
-                if (FUSED)
-                  {
-                    const double *solr = p.sol + g;
-                    double *      solw = p.sol + g;
-                    double *      tiw  = p.ti_next + g;
+              }
+            else
+              {
+                double *out = p.dst + g;
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4)
-                      {
-                        double sv[16];
+                for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                          sv[q] = solr[(q + 16 * i4) * 16];
+                  for (int i3 = 0; i3 < 4; ++i3)
 #pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                          {
-                            const double kv = acc[i4][q >> 2][q & 3];
-                            solw[(q + 16 * i4) * 16] = fma(p.fb, kv, sv[q]);
-                            if (p.fa != 0.0)
-                              tiw[(q + 16 * i4) * 16] = fma(p.fa, kv, sv[q]);
-                          }
-                      }
-                  }
-                else
-                  {
-                    double *out = p.dst + g;
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                      for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2)
-                          out[(i2 + 4 * i3 + 16 * i4) * 16] = acc[i4][i3][i2];
-                  }
+                    for (int i2 = 0; i2 < 4; ++i2)
+                      out[(i2 + 4 * i3 + 16 * i4) * 16] = acc[i4][i3][i2];
               }
           }
       }
@@ -723,18 +759,36 @@ namespace
 
   struct Maps
   {
-    CUtensorMap u, t1;
+    CUtensorMap u, t1, t2, t3, t4;
   };
 
   struct FastState
   {
-    EncodeTiledFn                 encode = nullptr;
-    std::map<const void *, Maps>  cache;
-    bool                          attr_set[2] = {false, false};
+    EncodeTiledFn                encode = nullptr;
+    std::map<const void *, Maps> cache;
+    bool                         attr_set[2] = {false, false};
+    int *                        d_counters  = nullptr;
   };
 
   int
-  get_maps(hd_advection *op, const void *src, Maps **out)
+  encode_face_map(FastState *st, CUtensorMap *m, const void *src, cuuint64_t ncells, int d)
+  {
+    // face layer of direction d: view src as [hi = 4^(5-d) * ncells][4][lo = 4^d], box = (lo, 1, 4^(5-d))
+    const cuuint64_t lo = 1ull << (2 * d), hi = 1ull << (2 * (5 - d));
+    cuuint64_t       gdim[3] = {lo, 4, hi * ncells};
+    cuuint64_t       gstr[2] = {lo * 8, lo * 32};
+    cuuint32_t       box[3]  = {(cuuint32_t)lo, 1, (cuuint32_t)hi};
+    cuuint32_t       estr[3] = {1, 1, 1};
+    CUresult         r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            d == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(face " + std::to_string(d) + ") failed with code " + std::to_string((int)r));
+    return HD_OK;
+  }
+
+  int
+  get_state(hd_advection *op, FastState **out)
   {
     FastState *st = static_cast<FastState *>(op->fast_state);
     if (!st)
@@ -751,17 +805,29 @@ namespace
           return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
         st->encode = reinterpret_cast<EncodeTiledFn>(fn);
       }
+    if (!st->d_counters)
+      {
+        HD_CUDA(cudaMalloc(&st->d_counters, 2 * sizeof(int)));
+        HD_CUDA(cudaMemset(st->d_counters, 0, 2 * sizeof(int)));
+      }
+    *out = st;
+    return HD_OK;
+  }
+
+  int
+  get_maps(hd_advection *op, FastState *st, const void *src, Maps **out)
+  {
     auto it = st->cache.find(src);
     if (it == st->cache.end())
       {
         if (st->cache.size() > 64)
           st->cache.clear();
-        Maps            m;
-        const hd_mesh * mesh  = op->mesh;
-        const cuuint64_t rows = (cuuint64_t)mesh->ncells * 256;
+        Maps             m;
+        const hd_mesh *  mesh   = op->mesh;
+        const cuuint64_t ncells = (cuuint64_t)mesh->ncells;
         {
           // cell data as rows of 16 doubles (one (i0,i1) plane), 128B swizzle, boxes of 64 rows
-          cuuint64_t gdim[2] = {16, rows};
+          cuuint64_t gdim[2] = {16, ncells * 256};
           cuuint64_t gstr[1] = {128};
           cuuint32_t box[2]  = {16, 64};
           cuuint32_t estr[2] = {1, 1};
@@ -770,17 +836,15 @@ namespace
           if (r != CUDA_SUCCESS)
             return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(u) failed with code " + std::to_string((int)r));
         }
-        {
-          // direction-1 face layer: [rows][i1][i0], box = one i1 layer of all 256 rows of a cell, 32B swizzle
-          cuuint64_t gdim[3] = {4, 4, rows};
-          cuuint64_t gstr[2] = {32, 128};
-          cuuint32_t box[3]  = {4, 1, 256};
-          cuuint32_t estr[3] = {1, 1, 1};
-          CUresult   r = st->encode(&m.t1, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (r != CUDA_SUCCESS)
-            return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(t1) failed with code " + std::to_string((int)r));
-        }
+        int rc;
+        if ((rc = encode_face_map(st, &m.t1, src, ncells, 1)) != HD_OK)
+          return rc;
+        if ((rc = encode_face_map(st, &m.t2, src, ncells, 2)) != HD_OK)
+          return rc;
+        if ((rc = encode_face_map(st, &m.t3, src, ncells, 3)) != HD_OK)
+          return rc;
+        if ((rc = encode_face_map(st, &m.t4, src, ncells, 4)) != HD_OK)
+          return rc;
         it = st->cache.emplace(src, m).first;
       }
     *out = &it->second;
@@ -804,7 +868,7 @@ namespace hd
           const int kind = m->d.side_kind[d][s];
           if (kind == HD_SIDE_DIRICHLET || kind == HD_SIDE_DIRICHLET_HOM)
             return false;
-          // ghost faces are read by round 2's plain loads (directions 2,3,4) and the direction-0 gather
+          // ghost faces: directions 2,3,4 (bulk copies of round 2's face ring) and the direction-0 gather
           if (kind == HD_SIDE_GHOST && (d == 1 || d == 5))
             return false;
         }
@@ -814,24 +878,28 @@ namespace hd
   int
   launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
   {
-    hd_mesh *m = op->mesh;
-    Maps *   maps;
-    int      rc = get_maps(op, src, &maps);
+    hd_mesh *  m = op->mesh;
+    FastState *st;
+    int        rc = get_state(op, &st);
     if (rc != HD_OK)
       return rc;
-    FastCoef   cf;
+    Maps *maps;
+    rc = get_maps(op, st, src, &maps);
+    if (rc != HD_OK)
+      return rc;
+    FastCoef   cfh;
     FastParams p;
-    p.src   = static_cast<const double *>(src);
-    p.dst   = static_cast<double *>(dst);
-    p.ghost = static_cast<const double *>(ghosts);
-    p.nrows = 1;
+    p.src       = static_cast<const double *>(src);
+    p.dst       = static_cast<double *>(dst);
+    p.ghost     = static_cast<const double *>(ghosts);
+    long long nrows = 1;
     for (int d = 0; d < 6; ++d)
       {
         p.ncell[d] = m->d.n_cells[d];
         if (d > 0)
-          p.nrows *= p.ncell[d];
+          nrows *= p.ncell[d];
         for (int i = 0; i < 16; ++i)
-          cf.C[d][i] = op->hC[d][0][i];
+          cfh.C[d][i] = op->hC[d][0][i];
         // upwind side: L0 (lower neighbour) is non-zero for a_d > 0, L1 (upper) for a_d < 0
         const bool lo = (op->nb_mask[d] & 1) != 0, hi = (op->nb_mask[d] & 2) != 0;
         p.up_delta[d]  = lo ? -1 : (hi ? +1 : 0);
@@ -839,15 +907,16 @@ namespace hd
         p.up_kind[d]   = m->d.side_kind[d][side];
         p.ghost_off[d] = m->ghost_off[d][side];
         for (int i = 0; i < 4; ++i)
-          cf.L[d][i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
+          cfh.L[d][i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
       }
-    p.sol     = static_cast<double *>(fu.sol);
-    p.ti_next = static_cast<double *>(fu.ti_next);
-    p.fb      = fu.fb;
-    p.fa      = fu.fa;
-    p.pass    = 0;
-    FastState *st   = static_cast<FastState *>(op->fast_state);
-    const int  fidx = fu.enabled ? 1 : 0;
+    p.nrows    = (int)nrows;
+    p.counters = st->d_counters;
+    p.sol      = static_cast<double *>(fu.sol);
+    p.ti_next  = static_cast<double *>(fu.ti_next);
+    p.fb       = fu.fb;
+    p.fa       = fu.fa;
+    p.pass     = 0;
+    const int fidx = fu.enabled ? 1 : 0;
     if (!st->attr_set[fidx])
       {
         if (fu.enabled)
@@ -856,11 +925,12 @@ namespace hd
           HD_CUDA(cudaFuncSetAttribute(k_advect_3d3v_k3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         st->attr_set[fidx] = true;
       }
-    long long grid = p.nrows < m->ctx->sm_count ? p.nrows : m->ctx->sm_count;
+    HD_CUDA(cudaMemcpyToSymbolAsync(cf, &cfh, sizeof(FastCoef), 0, cudaMemcpyHostToDevice, m->ctx->stream));
+    long long grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
     if (fu.enabled)
-      k_advect_3d3v_k3<true><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, cf, p);
+      k_advect_3d3v_k3<true><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p);
     else
-      k_advect_3d3v_k3<false><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, cf, p);
+      k_advect_3d3v_k3<false><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = fu.enabled ? "advect_3d3v_k3_fused_lsrk" : "advect_3d3v_k3";
@@ -870,7 +940,10 @@ namespace hd
   void
   fast6d_release(hd_advection *op)
   {
-    delete static_cast<FastState *>(op->fast_state);
+    FastState *st = static_cast<FastState *>(op->fast_state);
+    if (st)
+      cudaFree(st->d_counters);
+    delete st;
     op->fast_state = nullptr;
   }
 } // namespace hd
