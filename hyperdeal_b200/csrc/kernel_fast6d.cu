@@ -46,10 +46,14 @@ namespace
   constexpr int BAR_OFF    = INFO_OFF + 128;
   constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + alignment slack
 
+  struct RoleCoef // matrices of one round: in-plane directions A, B and the plane direction C
+  {
+    double A[16], B[16], C[16]; // [i*4+j]
+    double LA[4], LB[4], LC[4]; // lifting vector of the upwind face (0 if a_d == 0)
+  };
   struct FastCoef
   {
-    double C[6][16]; // C_d[i*4+j]
-    double L[6][4];  // lifting vector of the upwind face (0 if a_d == 0)
+    RoleCoef r[2]; // round 1: directions (0,1 | 5), round 2: (2,3 | 4)
   };
 
   // (k+1)x(k+1) matrices of the current launch; DFMA reads them through the constant bank.
@@ -229,6 +233,328 @@ namespace
       if (e != d)
         fc = fc * p.ncell[e] + c[e];
     return fc;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // Compute warps.  Round ROLE works on directions (A,B | C) = (0,1 | 5) resp. (2,3 | 4) of its 4x4x4 tile:
+  //     acc[c][b][a] += sum_j CA[a][j] P[b][j] + sum_j CB[b][j] P[j][a] + LA[a] fa[b] + LB[b] fb[a]   (plane c)
+  //     acc[c'][b][a] += CC[c'][c] P[b][a]   for all c',         acc[c][b][a] += LC[c] fc[b][a]   (at the end)
+  // The plane loop is NOT unrolled: its body (224 DFMA) is the whole FP64 core, ~7 KiB of code per round,
+  // so both rounds stay resident in the SM's instruction cache (the fully unrolled form, 2 x 25 KiB,
+  // spent 30-45 % of its issue slots waiting for instruction fetch: profiles/r01b).
+  template <int ROLE, bool FUSED>
+  __device__ __forceinline__ void
+  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const uint32_t bar0, const int tid)
+  {
+    auto fullU    = [&](int s) { return bar0 + 8 * s; };
+    auto emptyU   = [&](int s) { return bar0 + 24 + 8 * s; };
+    auto r1fFull  = [&](int f) { return bar0 + 48 + 8 * f; };
+    auto r1fEmpty = [&](int f) { return bar0 + 64 + 8 * f; };
+    auto accFull  = [&](int a) { return bar0 + 80 + 8 * a; };
+    auto accEmpty = [&](int a) { return bar0 + 96 + 8 * a; };
+    auto r2fFull  = [&](int j) { return bar0 + 112 + 8 * j; };
+    auto r2fEmpty = [&](int j) { return bar0 + 136 + 8 * j; };
+    const uint32_t t0Full = bar0 + 160, t0Empty = bar0 + 168;
+    const bool     act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
+    const bool     r1faces = act1 || act5;
+    const bool     descend = p.up_delta[0] > 0;
+    constexpr int  role = ROLE;
+    const RoleCoef &rc  = cf.r[ROLE];
+    const int       t    = tid & 63;
+    // round-1 addressing: thread (i2,i3,i4) = row t of each i5 block, 16 contiguous (swizzled) doubles
+    const uint32_t sw   = uint32_t(t & 7);
+    const uint32_t rowU = uint32_t(t) * 128u;
+    // round-2 addressing: thread (i0,i1,i5) = column cc of the rows (i2,i3,i4) + 64 i5
+    const int      cc      = t & 15;
+    const int      i5      = t >> 4;
+    const uint32_t col     = uint32_t(cc >> 1) << 4;
+    const uint32_t rowbase = uint32_t(i5) * 8192u + uint32_t(cc & 1) * 8u;
+    const uint32_t fcol    = base + R2F_OFF + 8u * uint32_t(cc + 256 * i5);
+    const bool     actA = role ? (p.up_delta[2] != 0) : act0;
+    const bool     actB = role ? (p.up_delta[3] != 0) : act1;
+    const bool     actC = role ? (p.up_delta[4] != 0) : act5;
+    int            nrow_seq = 0;
+
+    for (int k = 0;; ++k)
+      {
+        const int      s  = k % STAGES;
+        const int      f  = k & 1; // face-ring slot (round 1) / partial buffer (both)
+        const uint32_t pf = uint32_t((k >> 1) & 1);
+        const uint32_t pk = uint32_t(k & 1);
+        const uint32_t ub = base + s * U_BYTES;
+        mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
+        const int4 inf = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
+        const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
+        if (cellid < 0)
+          break;
+
+        double acc[4][4][4]; // [c][b][a]
+        // ---- prologue
+        const bool from_t0 = (role == 0) && inf.w != 0;
+        uint32_t   pb = 0, t0b = 0, fbuf = 0, ab;
+        if (role == 0)
+          {
+            // direction-0 trace of the upwind neighbour: the end layer of the previous cell of the row, read
+            // from that cell's ring stage (still resident: round 2 works on it), or the gathered trace at a row start
+            if (from_t0 && act0)
+              {
+                mbar_wait(t0Full, uint32_t(nrow_seq & 1));
+                ++nrow_seq;
+              }
+            pb  = base + ((k + STAGES - 1) % STAGES) * U_BYTES + rowU + (descend ? 0u : 8u);
+            t0b = base + T0_OFF + uint32_t(t) * 32u;
+            if (r1faces)
+              mbar_wait(r1fFull(f), pf);
+            fbuf = base + R1F_OFF + f * 2 * F_BYTES;
+            ab   = base + ACC_OFF + f * U_BYTES + rowU;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+              for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int z = 0; z < 4; ++z)
+                  acc[x][y][z] = 0.0;
+          }
+        else
+          {
+            ab = base + ACC_OFF + f * U_BYTES + rowbase;
+            mbar_wait(accFull(f), pf);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  acc[c][b][a] = lds64(ab + uint32_t(a + 4 * b + 16 * c) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
+            if (actA)
+              mbar_wait(r2fFull(0), pk);
+            if (actB)
+              mbar_wait(r2fFull(1), pk);
+          }
+
+        // ---- planes (rolled: the body below is the whole FP64 core, ~7 KiB of code, re-used 4x per cell)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c)
+          {
+            double P[4][4]; // [b][a]
+            double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
+            if (role == 0)
+              {
+                const uint32_t up = ub + rowU + uint32_t(c) * 8192u;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                  {
+                    const double2 v              = lds128(up + ((uint32_t(ch) ^ sw) << 4));
+                    P[ch >> 1][(ch & 1) * 2]     = v.x;
+                    P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
+                  }
+                if (actA)
+                  {
+                    if (from_t0)
+                      {
+                        const double2 v0 = lds128(t0b + c * 2048), v1 = lds128(t0b + c * 2048 + 16);
+                        fa[0] = v0.x;
+                        fa[1] = v0.y;
+                        fa[2] = v1.x;
+                        fa[3] = v1.y;
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          fa[b] = lds64(pb + uint32_t(c) * 8192u + ((uint32_t(2 * b + (descend ? 0 : 1)) ^ sw) << 4));
+                      }
+                  }
+                if (actB)
+                  {
+                    const uint32_t r32 = uint32_t(t) + 64u * uint32_t(c);
+                    const uint32_t fl  = (r32 >> 2) & 1u;
+                    const uint32_t tb  = fbuf + r32 * 32u;
+                    const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
+                    fb[0] = v0.x;
+                    fb[1] = v0.y;
+                    fb[2] = v1.x;
+                    fb[3] = v1.y;
+                  }
+              }
+            else
+              {
+                const uint32_t up = ub + rowbase + uint32_t(c) * 2048u;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    P[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
+                if (actA)
+                  {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                      fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(c));
+                  }
+                if (actB)
+                  {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(c));
+                  }
+              }
+            // FP64 core
+            const double cc0 = rc.C[0 + c], cc1 = rc.C[4 + c], cc2 = rc.C[8 + c], cc3 = rc.C[12 + c];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              {
+                double q[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  {
+                    double v = rc.A[a * 4 + 0] * P[b][0];
+#pragma unroll
+                    for (int j = 1; j < 4; ++j)
+                      v = fma(rc.A[a * 4 + j], P[b][j], v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      v = fma(rc.B[b * 4 + j], P[j][a], v);
+                    v    = fma(rc.LA[a], fa[b], v);
+                    v    = fma(rc.LB[b], fb[a], v);
+                    q[a] = v;
+                    const double pv = P[b][a];
+                    acc[0][b][a]    = fma(cc0, pv, acc[0][b][a]);
+                    acc[1][b][a]    = fma(cc1, pv, acc[1][b][a]);
+                    acc[2][b][a]    = fma(cc2, pv, acc[2][b][a]);
+                    acc[3][b][a]    = fma(cc3, pv, acc[3][b][a]);
+                  }
+                // the in-plane part belongs to plane c: one uniform branch per row keeps register indices static
+                switch (c)
+                  {
+                    case 0:
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        acc[0][b][a] += q[a];
+                      break;
+                    case 1:
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        acc[1][b][a] += q[a];
+                      break;
+                    case 2:
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        acc[2][b][a] += q[a];
+                      break;
+                    default:
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        acc[3][b][a] += q[a];
+                      break;
+                  }
+              }
+            if (c == 0 && role != 0)
+              mbar_arrive(accEmpty(f)); // every partial sum has been consumed into the accumulators
+          }
+
+        // ---- releases + face of direction C
+        if (role == 0)
+          {
+            // release the PREVIOUS cell's stage (its end layer was this cell's direction-0 trace)
+            if (k > 0)
+              mbar_arrive(emptyU((k + STAGES - 1) % STAGES));
+            if (from_t0 && act0)
+              mbar_arrive(t0Empty);
+          }
+        else
+          {
+            mbar_arrive(emptyU(s));
+            if (actA)
+              mbar_arrive(r2fEmpty(0));
+            if (actB)
+              mbar_arrive(r2fEmpty(1));
+            if (actC)
+              mbar_wait(r2fFull(2), pk);
+          }
+        if (actC)
+          {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              {
+                double fc[4];
+                if (role == 0)
+                  {
+                    const uint32_t tb = fbuf + F_BYTES + rowU;
+                    const double2  v0 = lds128(tb + ((uint32_t(2 * b) ^ sw) << 4)), v1 = lds128(tb + ((uint32_t(2 * b + 1) ^ sw) << 4));
+                    fc[0] = v0.x;
+                    fc[1] = v0.y;
+                    fc[2] = v1.x;
+                    fc[3] = v1.y;
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      fc[a] = lds64(fcol + 2 * F_BYTES + 128u * uint32_t(a + 4 * b));
+                  }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    acc[c][b][a] = fma(rc.LC[c], fc[a], acc[c][b][a]);
+              }
+          }
+
+        // ---- epilogue
+        if (role == 0)
+          {
+            if (r1faces)
+              mbar_arrive(r1fEmpty(f));
+            // partial sums -> shared (same swizzle as u)
+            mbar_wait(accEmpty(f), pf ^ 1u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch)
+                sts128(ab + c * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[c][ch >> 1][(ch & 1) * 2], acc[c][ch >> 1][(ch & 1) * 2 + 1]);
+            mbar_arrive(accFull(f));
+          }
+        else
+          {
+            if (actC)
+              mbar_arrive(r2fEmpty(2));
+            // coalesced stores (a half-warp writes 128 contiguous bytes)
+            const long long g = (long long)cellid * CELL + cc + 1024 * i5;
+            if (FUSED)
+              {
+                const double *solr = p.sol + g;
+                double *      solw = p.sol + g;
+                double *      tiw  = p.ti_next + g;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  {
+                    double sv[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                      sv[q] = solr[(q + 16 * c) * 16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                      {
+                        const double kv         = acc[c][q >> 2][q & 3];
+                        solw[(q + 16 * c) * 16] = fma(p.fb, kv, sv[q]);
+                        if (p.fa != 0.0)
+                          tiw[(q + 16 * c) * 16] = fma(p.fa, kv, sv[q]);
+                      }
+                  }
+              }
+            else
+              {
+                double *out = p.dst + g;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      out[(a + 4 * b + 16 * c) * 16] = acc[c][b][a];
+              }
+          }
+      }
   }
 
   template <bool FUSED>
@@ -450,307 +776,9 @@ namespace
           }
       }
     else if (warp < 2)
-      {
-        // ======================================================================= round 1: directions 0, 1, 5
-        const int      t    = tid;          // (i2,i3,i4)
-        const uint32_t sw   = uint32_t(t & 7);
-        const uint32_t rowU = uint32_t(t) * 128u;
-        int nrow_seq = 0;
-        for (int k = 0;; ++k)
-          {
-            const int      s  = k % STAGES;
-            const int      f  = k & 1;
-            const uint32_t pf = uint32_t((k >> 1) & 1);
-            const uint32_t ub = base + s * U_BYTES;
-            mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
-            const int4 inf = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
-            const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
-            if (cellid < 0)
-              break;
-            // direction-0 trace of the upwind neighbour: the end layer of the previous cell of the row, read
-            // from that cell's ring stage (still resident: round 2 works on it), or the gathered trace at a row start
-            const bool from_t0 = inf.w != 0;
-            if (from_t0 && act0)
-              {
-                mbar_wait(t0Full, uint32_t(nrow_seq & 1));
-                ++nrow_seq;
-              }
-            const uint32_t pb  = base + ((k + STAGES - 1) % STAGES) * U_BYTES + rowU + (descend ? 0u : 8u);
-            const uint32_t t0b = base + T0_OFF + uint32_t(t) * 32u;
-            if (r1faces)
-              mbar_wait(r1fFull(f), pf);
-            const uint32_t fbuf = base + R1F_OFF + f * 2 * F_BYTES;
-
-            double acc[4][4][4]; // [i5][i1][i0]
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-              for (int y = 0; y < 4; ++y)
-#pragma unroll
-                for (int z = 0; z < 4; ++z)
-                  acc[x][y][z] = 0.0;
-
-#pragma unroll
-            for (int j5 = 0; j5 < 4; ++j5)
-              {
-                double P[4][4]; // [i1][i0]
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                  {
-                    const double2 v              = lds128(ub + rowU + j5 * 8192 + ((uint32_t(ch) ^ sw) << 4));
-                    P[ch >> 1][(ch & 1) * 2]     = v.x;
-                    P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
-                  }
-                double cv[4] = {0.0, 0.0, 0.0, 0.0};
-                if (act0)
-                  {
-                    if (from_t0)
-                      {
-                        const double2 v0 = lds128(t0b + j5 * 2048), v1 = lds128(t0b + j5 * 2048 + 16);
-                        cv[0] = v0.x;
-                        cv[1] = v0.y;
-                        cv[2] = v1.x;
-                        cv[3] = v1.y;
-                      }
-                    else
-                      {
-#pragma unroll
-                        for (int i1 = 0; i1 < 4; ++i1)
-                          cv[i1] = lds64(pb + j5 * 8192 + ((uint32_t(2 * i1 + (descend ? 0 : 1)) ^ sw) << 4));
-                      }
-                  }
-                double t1v[4] = {0.0, 0.0, 0.0, 0.0};
-                if (act1)
-                  {
-                    const uint32_t r32 = uint32_t(t) + 64u * j5;
-                    const uint32_t fl  = (r32 >> 2) & 1u;
-                    const uint32_t tb  = fbuf + r32 * 32u;
-                    const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
-                    t1v[0] = v0.x;
-                    t1v[1] = v0.y;
-                    t1v[2] = v1.x;
-                    t1v[3] = v1.y;
-                  }
-#pragma unroll
-                for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-                  for (int i0 = 0; i0 < 4; ++i0)
-                    {
-                      double v = acc[j5][i1][i0];
-#pragma unroll
-                      for (int j = 0; j < 4; ++j)
-                        v = fma(cf.C[0][i0 * 4 + j], P[i1][j], v);
-#pragma unroll
-                      for (int j = 0; j < 4; ++j)
-                        v = fma(cf.C[1][i1 * 4 + j], P[j][i0], v);
-                      v = fma(cf.L[0][i0], cv[i1], v);
-                      v = fma(cf.L[1][i1], t1v[i0], v);
-                      acc[j5][i1][i0] = v;
-                    }
-#pragma unroll
-                for (int i5 = 0; i5 < 4; ++i5)
-#pragma unroll
-                  for (int i1 = 0; i1 < 4; ++i1)
-#pragma unroll
-                    for (int i0 = 0; i0 < 4; ++i0)
-                      acc[i5][i1][i0] = fma(cf.C[5][i5 * 4 + j5], P[i1][i0], acc[i5][i1][i0]);
-              }
-            // release the PREVIOUS cell's stage (its end layer was this cell's direction-0 trace)
-            if (k > 0)
-              mbar_arrive(emptyU((k + STAGES - 1) % STAGES));
-            if (from_t0 && act0)
-              mbar_arrive(t0Empty);
-            if (act5)
-              {
-                const uint32_t tb = fbuf + F_BYTES + rowU;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                  {
-                    const double2 v  = lds128(tb + ((uint32_t(ch) ^ sw) << 4));
-                    const int     i1 = ch >> 1, i0 = (ch & 1) * 2;
-#pragma unroll
-                    for (int i5 = 0; i5 < 4; ++i5)
-                      {
-                        acc[i5][i1][i0]     = fma(cf.L[5][i5], v.x, acc[i5][i1][i0]);
-                        acc[i5][i1][i0 + 1] = fma(cf.L[5][i5], v.y, acc[i5][i1][i0 + 1]);
-                      }
-                  }
-              }
-            if (r1faces)
-              mbar_arrive(r1fEmpty(f));
-            // partial sums -> shared (same swizzle as u)
-            const int a = k & 1;
-            mbar_wait(accEmpty(a), pf ^ 1u);
-            const uint32_t ab = base + ACC_OFF + a * U_BYTES + rowU;
-#pragma unroll
-            for (int i5 = 0; i5 < 4; ++i5)
-#pragma unroll
-              for (int ch = 0; ch < 8; ++ch)
-                sts128(ab + i5 * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[i5][ch >> 1][(ch & 1) * 2], acc[i5][ch >> 1][(ch & 1) * 2 + 1]);
-            mbar_arrive(accFull(a));
-          }
-      }
+      compute_round<0, FUSED>(p, base, gbase, bar0, tid);
     else
-      {
-        // ======================================================================= round 2: directions 2, 3, 4 + store
-        const int      tt  = tid - 64;
-        const int      cc  = tt & 15; // (i0,i1)
-        const int      i5  = tt >> 4;
-        const uint32_t col = uint32_t(cc >> 1) << 4;
-        const uint32_t sub = uint32_t(cc & 1) * 8u;
-        const uint32_t rowbase = uint32_t(i5) * 8192u + sub; // row = q + 64 i5
-        const uint32_t fcol    = base + R2F_OFF + 8u * uint32_t(cc + 256 * i5);
-        for (int k = 0;; ++k)
-          {
-            const int      s  = k % STAGES;
-            const int      a  = k & 1;
-            const uint32_t pa = uint32_t((k >> 1) & 1);
-            const uint32_t pk = uint32_t(k & 1);
-            const uint32_t ub = base + s * U_BYTES + rowbase;
-            const uint32_t ab = base + ACC_OFF + a * U_BYTES + rowbase;
-            mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
-            const int cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
-            if (cellid < 0)
-              break;
-
-            mbar_wait(accFull(a), pa);
-            double acc[4][4][4]; // [i4][i3][i2]
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-              for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                for (int i2 = 0; i2 < 4; ++i2)
-                  acc[i4][i3][i2] = lds64(ab + uint32_t(i2 + 4 * i3 + 16 * i4) * 128u + (col ^ (uint32_t((i2 + 4 * i3) & 7) << 4)));
-
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              {
-                double P[4][4]; // [i3][i2]
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                  for (int i2 = 0; i2 < 4; ++i2)
-                    P[i3][i2] = lds64(ub + uint32_t(i2 + 4 * i3 + 16 * j4) * 128u + (col ^ (uint32_t((i2 + 4 * i3) & 7) << 4)));
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                  for (int i2 = 0; i2 < 4; ++i2)
-                    {
-                      double v = acc[j4][i3][i2];
-#pragma unroll
-                      for (int j = 0; j < 4; ++j)
-                        v = fma(cf.C[2][i2 * 4 + j], P[i3][j], v);
-#pragma unroll
-                      for (int j = 0; j < 4; ++j)
-                        v = fma(cf.C[3][i3 * 4 + j], P[j][i2], v);
-                      acc[j4][i3][i2] = v;
-                    }
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                  for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2)
-                      acc[i4][i3][i2] = fma(cf.C[4][i4 * 4 + j4], P[i3][i2], acc[i4][i3][i2]);
-                if (j4 == 0)
-                  mbar_arrive(accEmpty(a)); // every partial sum has been consumed into the accumulators
-              }
-            mbar_arrive(emptyU(s));
-
-            // neighbour traces of directions 4, 3, 2 from the face ring (face dof order: digit d removed)
-            if (p.up_delta[4] != 0)
-              {
-                mbar_wait(r2fFull(2), pk);
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3)
-                  {
-                    double fv[4];
-#pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2)
-                      fv[i2] = lds64(fcol + 2 * F_BYTES + 128u * uint32_t(i2 + 4 * i3));
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                      for (int i2 = 0; i2 < 4; ++i2)
-                        acc[i4][i3][i2] = fma(cf.L[4][i4], fv[i2], acc[i4][i3][i2]);
-                  }
-                mbar_arrive(r2fEmpty(2));
-              }
-            if (p.up_delta[3] != 0)
-              {
-                mbar_wait(r2fFull(1), pk);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4)
-                  {
-                    double fv[4];
-#pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2)
-                      fv[i2] = lds64(fcol + 1 * F_BYTES + 128u * uint32_t(i2 + 4 * i4));
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                      for (int i2 = 0; i2 < 4; ++i2)
-                        acc[i4][i3][i2] = fma(cf.L[3][i3], fv[i2], acc[i4][i3][i2]);
-                  }
-                mbar_arrive(r2fEmpty(1));
-              }
-            if (p.up_delta[2] != 0)
-              {
-                mbar_wait(r2fFull(0), pk);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4)
-                  {
-                    double fv[4];
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3)
-                      fv[i3] = lds64(fcol + 128u * uint32_t(i3 + 4 * i4));
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                      for (int i2 = 0; i2 < 4; ++i2)
-                        acc[i4][i3][i2] = fma(cf.L[2][i2], fv[i3], acc[i4][i3][i2]);
-                  }
-                mbar_arrive(r2fEmpty(0));
-              }
-
-            // epilogue: coalesced stores (a half-warp writes 128 contiguous bytes)
-            const long long g = (long long)cellid * CELL + cc + 1024 * i5;
-            if (FUSED)
-              {
-                const double *solr = p.sol + g;
-                double *      solw = p.sol + g;
-                double *      tiw  = p.ti_next + g;
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4)
-                  {
-                    double sv[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                      sv[q] = solr[(q + 16 * i4) * 16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                      {
-                        const double kv          = acc[i4][q >> 2][q & 3];
-                        solw[(q + 16 * i4) * 16] = fma(p.fb, kv, sv[q]);
-                        if (p.fa != 0.0)
-                          tiw[(q + 16 * i4) * 16] = fma(p.fa, kv, sv[q]);
-                      }
-                  }
-              }
-            else
-              {
-                double *out = p.dst + g;
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4)
-#pragma unroll
-                  for (int i3 = 0; i3 < 4; ++i3)
-#pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2)
-                      out[(i2 + 4 * i3 + 16 * i4) * 16] = acc[i4][i3][i2];
-              }
-          }
-      }
+      compute_round<1, FUSED>(p, base, gbase, bar0, tid);
   }
 
   // ------------------------------------------------------------------------------- host side
@@ -898,8 +926,11 @@ namespace hd
         p.ncell[d] = m->d.n_cells[d];
         if (d > 0)
           nrows *= p.ncell[d];
+        const int role = (d >= 2 && d <= 4) ? 1 : 0;
+        double *  Cd   = (d == 0 || d == 2) ? cfh.r[role].A : ((d == 1 || d == 3) ? cfh.r[role].B : cfh.r[role].C);
+        double *  Ld   = (d == 0 || d == 2) ? cfh.r[role].LA : ((d == 1 || d == 3) ? cfh.r[role].LB : cfh.r[role].LC);
         for (int i = 0; i < 16; ++i)
-          cfh.C[d][i] = op->hC[d][0][i];
+          Cd[i] = op->hC[d][0][i];
         // upwind side: L0 (lower neighbour) is non-zero for a_d > 0, L1 (upper) for a_d < 0
         const bool lo = (op->nb_mask[d] & 1) != 0, hi = (op->nb_mask[d] & 2) != 0;
         p.up_delta[d]  = lo ? -1 : (hi ? +1 : 0);
@@ -907,7 +938,7 @@ namespace hd
         p.up_kind[d]   = m->d.side_kind[d][side];
         p.ghost_off[d] = m->ghost_off[d][side];
         for (int i = 0; i < 4; ++i)
-          cfh.L[d][i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
+          Ld[i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
       }
     p.nrows    = (int)nrows;
     p.counters = st->d_counters;
