@@ -35,7 +35,7 @@ namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
   constexpr int STAGES     = 3;
-  constexpr int THREADS    = 192;
+  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
   constexpr int R1F_OFF    = STAGES * U_BYTES;       // 98304
@@ -236,15 +236,19 @@ namespace
   }
 
   // ---------------------------------------------------------------------------------------------
-  // Compute warps.  Round ROLE works on directions (A,B | C) = (0,1 | 5) resp. (2,3 | 4) of its 4x4x4 tile:
-  //     acc[c][b][a] += sum_j CA[a][j] P[b][j] + sum_j CB[b][j] P[j][a] + LA[a] fa[b] + LB[b] fb[a]   (plane c)
-  //     acc[c'][b][a] += CC[c'][c] P[b][a]   for all c',         acc[c][b][a] += LC[c] fc[b][a]   (at the end)
-  // The plane loop is NOT unrolled: its body (224 DFMA) is the whole FP64 core, ~7 KiB of code per round,
-  // so both rounds stay resident in the SM's instruction cache (the fully unrolled form, 2 x 25 KiB,
-  // spent 30-45 % of its issue slots waiting for instruction fetch: profiles/r01b).
+  // Compute warps (4 per round; every SM sub-partition hosts one warp of each round so that the FP64
+  // pipe always has a second instruction stream to issue from).
+  // Round ROLE works on directions (A,B | C) = (0,1 | 5) resp. (2,3 | 4).  A 4x4x4 tile [c][b][a] is shared
+  // by two threads: thread half h owns the output planes c = 2h, 2h+1 (32 accumulators) and streams all four
+  // source planes s:
+  //     acc[c][b][a] += CC[c][s] P_s[b][a]                                                       (every s)
+  //     acc[s][b][a] += sum_j CA[a][j] P_s[b][j] + sum_j CB[b][j] P_s[j][a] + LA[a] fa[b] + LB[b] fb[a]   (s in own half)
+  //     acc[c][b][a] += LC[c] fc[b][a]                                                           (at the end)
+  // The plane loop is NOT unrolled: both rounds' FP64 cores stay resident in the instruction cache (the fully
+  // unrolled form, 2 x 25 KiB, lost 30-45 % of its issue slots to instruction fetch: profiles/r01b).
   template <int ROLE, bool FUSED>
   __device__ __forceinline__ void
-  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const uint32_t bar0, const int tid)
+  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const uint32_t bar0, const int tid_in_role)
   {
     auto fullU    = [&](int s) { return bar0 + 8 * s; };
     auto emptyU   = [&](int s) { return bar0 + 24 + 8 * s; };
@@ -254,13 +258,21 @@ namespace
     auto accEmpty = [&](int a) { return bar0 + 96 + 8 * a; };
     auto r2fFull  = [&](int j) { return bar0 + 112 + 8 * j; };
     auto r2fEmpty = [&](int j) { return bar0 + 136 + 8 * j; };
-    const uint32_t t0Full = bar0 + 160, t0Empty = bar0 + 168;
-    const bool     act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
-    const bool     r1faces = act1 || act5;
-    const bool     descend = p.up_delta[0] > 0;
-    constexpr int  role = ROLE;
-    const RoleCoef &rc  = cf.r[ROLE];
-    const int       t    = tid & 63;
+    const uint32_t  t0Full = bar0 + 160, t0Empty = bar0 + 168;
+    const bool      act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
+    const bool      r1faces = act1 || act5;
+    const bool      descend = p.up_delta[0] > 0;
+    constexpr int   role    = ROLE;
+    const RoleCoef &rc      = cf.r[ROLE];
+    const int       lane    = tid_in_role & 31;
+    const int       h       = tid_in_role >> 6; // which half of the planes (warp-uniform)
+    const int       t       = tid_in_role & 63;
+    // one lane per warp signals the consumer-release barriers (after __syncwarp: all lanes' reads are done)
+    auto release = [&](uint32_t bar) {
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(bar);
+    };
     // round-1 addressing: thread (i2,i3,i4) = row t of each i5 block, 16 contiguous (swizzled) doubles
     const uint32_t sw   = uint32_t(t & 7);
     const uint32_t rowU = uint32_t(t) * 128u;
@@ -283,12 +295,12 @@ namespace
         const uint32_t pk = uint32_t(k & 1);
         const uint32_t ub = base + s * U_BYTES;
         mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
-        const int4 inf = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
+        const int4 inf    = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
         const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
         if (cellid < 0)
           break;
 
-        double acc[4][4][4]; // [c][b][a]
+        double acc[2][4][4]; // [c - 2h][b][a]
         // ---- prologue
         const bool from_t0 = (role == 0) && inf.w != 0;
         uint32_t   pb = 0, t0b = 0, fbuf = 0, ab;
@@ -306,9 +318,9 @@ namespace
             if (r1faces)
               mbar_wait(r1fFull(f), pf);
             fbuf = base + R1F_OFF + f * 2 * F_BYTES;
-            ab   = base + ACC_OFF + f * U_BYTES + rowU;
+            ab   = base + ACC_OFF + f * U_BYTES + rowU + uint32_t(h) * 16384u;
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < 2; ++x)
 #pragma unroll
               for (int y = 0; y < 4; ++y)
 #pragma unroll
@@ -317,30 +329,30 @@ namespace
           }
         else
           {
-            ab = base + ACC_OFF + f * U_BYTES + rowbase;
+            ab = base + ACC_OFF + f * U_BYTES + rowbase + uint32_t(h) * 4096u; // rows (a + 4b + 16 (2h + cl)) + 64 i5
             mbar_wait(accFull(f), pf);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int cl = 0; cl < 2; ++cl)
 #pragma unroll
               for (int b = 0; b < 4; ++b)
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
-                  acc[c][b][a] = lds64(ab + uint32_t(a + 4 * b + 16 * c) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
+                  acc[cl][b][a] = lds64(ab + uint32_t(a + 4 * b + 16 * cl) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
             if (actA)
               mbar_wait(r2fFull(0), pk);
             if (actB)
               mbar_wait(r2fFull(1), pk);
           }
+        const double lc0 = rc.LC[2 * h], lc1 = rc.LC[2 * h + 1];
 
-        // ---- planes (rolled: the body below is the whole FP64 core, ~7 KiB of code, re-used 4x per cell)
+        // ---- source planes (rolled)
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c)
+        for (int sp = 0; sp < 4; ++sp)
           {
             double P[4][4]; // [b][a]
-            double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
             if (role == 0)
               {
-                const uint32_t up = ub + rowU + uint32_t(c) * 8192u;
+                const uint32_t up = ub + rowU + uint32_t(sp) * 8192u;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch)
                   {
@@ -348,108 +360,111 @@ namespace
                     P[ch >> 1][(ch & 1) * 2]     = v.x;
                     P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
                   }
-                if (actA)
-                  {
-                    if (from_t0)
-                      {
-                        const double2 v0 = lds128(t0b + c * 2048), v1 = lds128(t0b + c * 2048 + 16);
-                        fa[0] = v0.x;
-                        fa[1] = v0.y;
-                        fa[2] = v1.x;
-                        fa[3] = v1.y;
-                      }
-                    else
-                      {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                          fa[b] = lds64(pb + uint32_t(c) * 8192u + ((uint32_t(2 * b + (descend ? 0 : 1)) ^ sw) << 4));
-                      }
-                  }
-                if (actB)
-                  {
-                    const uint32_t r32 = uint32_t(t) + 64u * uint32_t(c);
-                    const uint32_t fl  = (r32 >> 2) & 1u;
-                    const uint32_t tb  = fbuf + r32 * 32u;
-                    const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
-                    fb[0] = v0.x;
-                    fb[1] = v0.y;
-                    fb[2] = v1.x;
-                    fb[3] = v1.y;
-                  }
               }
             else
               {
-                const uint32_t up = ub + rowbase + uint32_t(c) * 2048u;
+                const uint32_t up = ub + rowbase + uint32_t(sp) * 2048u;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
 #pragma unroll
                   for (int a = 0; a < 4; ++a)
                     P[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
-                if (actA)
-                  {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                      fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(c));
-                  }
-                if (actB)
-                  {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                      fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(c));
-                  }
               }
-            // FP64 core
-            const double cc0 = rc.C[0 + c], cc1 = rc.C[4 + c], cc2 = rc.C[8 + c], cc3 = rc.C[12 + c];
+            // cross-plane sweep into the two own output planes
+            const double c0 = rc.C[(2 * h) * 4 + sp], c1 = rc.C[(2 * h + 1) * 4 + sp];
 #pragma unroll
             for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                {
+                  acc[0][b][a] = fma(c0, P[b][a], acc[0][b][a]);
+                  acc[1][b][a] = fma(c1, P[b][a], acc[1][b][a]);
+                }
+            // in-plane sweeps: only for the planes this thread owns
+            if ((sp >> 1) == h)
               {
-                double q[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
+                double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
+                if (role == 0)
                   {
-                    double v = rc.A[a * 4 + 0] * P[b][0];
+                    if (actA)
+                      {
+                        if (from_t0)
+                          {
+                            const double2 v0 = lds128(t0b + sp * 2048), v1 = lds128(t0b + sp * 2048 + 16);
+                            fa[0] = v0.x;
+                            fa[1] = v0.y;
+                            fa[2] = v1.x;
+                            fa[3] = v1.y;
+                          }
+                        else
+                          {
 #pragma unroll
-                    for (int j = 1; j < 4; ++j)
-                      v = fma(rc.A[a * 4 + j], P[b][j], v);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      v = fma(rc.B[b * 4 + j], P[j][a], v);
-                    v    = fma(rc.LA[a], fa[b], v);
-                    v    = fma(rc.LB[b], fb[a], v);
-                    q[a] = v;
-                    const double pv = P[b][a];
-                    acc[0][b][a]    = fma(cc0, pv, acc[0][b][a]);
-                    acc[1][b][a]    = fma(cc1, pv, acc[1][b][a]);
-                    acc[2][b][a]    = fma(cc2, pv, acc[2][b][a]);
-                    acc[3][b][a]    = fma(cc3, pv, acc[3][b][a]);
+                            for (int b = 0; b < 4; ++b)
+                              fa[b] = lds64(pb + uint32_t(sp) * 8192u + ((uint32_t(2 * b + (descend ? 0 : 1)) ^ sw) << 4));
+                          }
+                      }
+                    if (actB)
+                      {
+                        const uint32_t r32 = uint32_t(t) + 64u * uint32_t(sp);
+                        const uint32_t fl  = (r32 >> 2) & 1u;
+                        const uint32_t tb  = fbuf + r32 * 32u;
+                        const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
+                        fb[0] = v0.x;
+                        fb[1] = v0.y;
+                        fb[2] = v1.x;
+                        fb[3] = v1.y;
+                      }
                   }
-                // the in-plane part belongs to plane c: one uniform branch per row keeps register indices static
-                switch (c)
+                else
                   {
-                    case 0:
+                    if (actA)
+                      {
 #pragma unroll
-                      for (int a = 0; a < 4; ++a)
-                        acc[0][b][a] += q[a];
-                      break;
-                    case 1:
+                        for (int b = 0; b < 4; ++b)
+                          fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(sp));
+                      }
+                    if (actB)
+                      {
 #pragma unroll
-                      for (int a = 0; a < 4; ++a)
-                        acc[1][b][a] += q[a];
-                      break;
-                    case 2:
+                        for (int a = 0; a < 4; ++a)
+                          fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(sp));
+                      }
+                  }
 #pragma unroll
-                      for (int a = 0; a < 4; ++a)
-                        acc[2][b][a] += q[a];
-                      break;
-                    default:
+                for (int b = 0; b < 4; ++b)
+                  {
+                    double q[4];
 #pragma unroll
-                      for (int a = 0; a < 4; ++a)
-                        acc[3][b][a] += q[a];
-                      break;
+                    for (int a = 0; a < 4; ++a)
+                      {
+                        double v = rc.A[a * 4 + 0] * P[b][0];
+#pragma unroll
+                        for (int j = 1; j < 4; ++j)
+                          v = fma(rc.A[a * 4 + j], P[b][j], v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                          v = fma(rc.B[b * 4 + j], P[j][a], v);
+                        v    = fma(rc.LA[a], fa[b], v);
+                        v    = fma(rc.LB[b], fb[a], v);
+                        q[a] = v;
+                      }
+                    // one uniform branch per row keeps the register indices static
+                    if (sp & 1)
+                      {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                          acc[1][b][a] += q[a];
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                          acc[0][b][a] += q[a];
+                      }
                   }
               }
-            if (c == 0 && role != 0)
-              mbar_arrive(accEmpty(f)); // every partial sum has been consumed into the accumulators
+            if (sp == 0 && role != 0)
+              release(accEmpty(f)); // every partial sum has been consumed into the accumulators
           }
 
         // ---- releases + face of direction C
@@ -457,17 +472,17 @@ namespace
           {
             // release the PREVIOUS cell's stage (its end layer was this cell's direction-0 trace)
             if (k > 0)
-              mbar_arrive(emptyU((k + STAGES - 1) % STAGES));
+              release(emptyU((k + STAGES - 1) % STAGES));
             if (from_t0 && act0)
-              mbar_arrive(t0Empty);
+              release(t0Empty);
           }
         else
           {
-            mbar_arrive(emptyU(s));
+            release(emptyU(s));
             if (actA)
-              mbar_arrive(r2fEmpty(0));
+              release(r2fEmpty(0));
             if (actB)
-              mbar_arrive(r2fEmpty(1));
+              release(r2fEmpty(1));
             if (actC)
               mbar_wait(r2fFull(2), pk);
           }
@@ -493,10 +508,11 @@ namespace
                       fc[a] = lds64(fcol + 2 * F_BYTES + 128u * uint32_t(a + 4 * b));
                   }
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                  for (int a = 0; a < 4; ++a)
-                    acc[c][b][a] = fma(rc.LC[c], fc[a], acc[c][b][a]);
+                for (int a = 0; a < 4; ++a)
+                  {
+                    acc[0][b][a] = fma(lc0, fc[a], acc[0][b][a]);
+                    acc[1][b][a] = fma(lc1, fc[a], acc[1][b][a]);
+                  }
               }
           }
 
@@ -504,41 +520,41 @@ namespace
         if (role == 0)
           {
             if (r1faces)
-              mbar_arrive(r1fEmpty(f));
+              release(r1fEmpty(f));
             // partial sums -> shared (same swizzle as u)
             mbar_wait(accEmpty(f), pf ^ 1u);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int cl = 0; cl < 2; ++cl)
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch)
-                sts128(ab + c * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[c][ch >> 1][(ch & 1) * 2], acc[c][ch >> 1][(ch & 1) * 2 + 1]);
-            mbar_arrive(accFull(f));
+                sts128(ab + cl * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[cl][ch >> 1][(ch & 1) * 2], acc[cl][ch >> 1][(ch & 1) * 2 + 1]);
+            release(accFull(f));
           }
         else
           {
             if (actC)
-              mbar_arrive(r2fEmpty(2));
+              release(r2fEmpty(2));
             // coalesced stores (a half-warp writes 128 contiguous bytes)
-            const long long g = (long long)cellid * CELL + cc + 1024 * i5;
+            const long long g = (long long)cellid * CELL + cc + 1024 * i5 + 512 * h;
             if (FUSED)
               {
                 const double *solr = p.sol + g;
                 double *      solw = p.sol + g;
                 double *      tiw  = p.ti_next + g;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int cl = 0; cl < 2; ++cl)
                   {
                     double sv[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                      sv[q] = solr[(q + 16 * c) * 16];
+                      sv[q] = solr[(q + 16 * cl) * 16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
                       {
-                        const double kv         = acc[c][q >> 2][q & 3];
-                        solw[(q + 16 * c) * 16] = fma(p.fb, kv, sv[q]);
+                        const double kv          = acc[cl][q >> 2][q & 3];
+                        solw[(q + 16 * cl) * 16] = fma(p.fb, kv, sv[q]);
                         if (p.fa != 0.0)
-                          tiw[(q + 16 * c) * 16] = fma(p.fa, kv, sv[q]);
+                          tiw[(q + 16 * cl) * 16] = fma(p.fa, kv, sv[q]);
                       }
                   }
               }
@@ -546,12 +562,12 @@ namespace
               {
                 double *out = p.dst + g;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int cl = 0; cl < 2; ++cl)
 #pragma unroll
                   for (int b = 0; b < 4; ++b)
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
-                      out[(a + 4 * b + 16 * c) * 16] = acc[c][b][a];
+                      out[(a + 4 * b + 16 * cl) * 16] = acc[cl][b][a];
               }
           }
       }
@@ -587,19 +603,19 @@ namespace
         for (int s = 0; s < STAGES; ++s)
           {
             mbar_init(fullU(s), 1);
-            mbar_init(emptyU(s), 128);
+            mbar_init(emptyU(s), 8);
             mbar_init(r2fFull(s), 1);
-            mbar_init(r2fEmpty(s), 64);
+            mbar_init(r2fEmpty(s), 4);
           }
         for (int a = 0; a < 2; ++a)
           {
             mbar_init(r1fFull(a), 1);
-            mbar_init(r1fEmpty(a), 64);
-            mbar_init(accFull(a), 64);
-            mbar_init(accEmpty(a), 64);
+            mbar_init(r1fEmpty(a), 4);
+            mbar_init(accFull(a), 4);
+            mbar_init(accEmpty(a), 4);
           }
         mbar_init(t0Full, 32);
-        mbar_init(t0Empty, 64);
+        mbar_init(t0Empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
@@ -612,7 +628,7 @@ namespace
     const bool r1faces = act1 || act5;
     const bool descend = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
 
-    if (warp == 4)
+    if (warp == 8)
       {
         // ======================================================================= cell producer
         if (lane == 0)
@@ -730,7 +746,7 @@ namespace
             }
         }
       }
-    else if (warp == 5)
+    else if (warp == 9)
       {
         // ======================================================================= face producer for round 2
         if (lane == 0)
@@ -775,10 +791,10 @@ namespace
               }
           }
       }
-    else if (warp < 2)
+    else if (warp < 4)
       compute_round<0, FUSED>(p, base, gbase, bar0, tid);
     else
-      compute_round<1, FUSED>(p, base, gbase, bar0, tid);
+      compute_round<1, FUSED>(p, base, gbase, bar0, tid - 128);
   }
 
   // ------------------------------------------------------------------------------- host side
