@@ -24,9 +24,12 @@
 // All (k+1)x(k+1) matrices sit in the kernel-parameter constant bank (uniform-register DFMA operands).
 //
 // Shared memory: 3x32 (cells) + 2x16 (faces 1,5) + 2x32 (partials) + 3x8 (faces 2,3,4) + 8 (trace) KiB.
+// The shallow shared-memory ring is fed from L2: the producer prefetches (cp.async.bulk.prefetch.L2) the
+// cell PREFETCH_DIST cells ahead and its direction-4/5 face layers, so TMA loads see L2 latency, not DRAM's.
 // Algorithmic traffic 16 B/DoF (fused: 32 B/DoF); see DESIGN.md §4 for the roofline budget.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 
 #include "hd_internal.h"
@@ -35,12 +38,13 @@ namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
   constexpr int STAGES     = 3;
+  constexpr int PREFETCH_DIST = 0; // cells of explicit L2 lookahead per CTA (measured: 0 is best, profiles/r01_prefetch_sweep.txt)
   constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
   constexpr int R1F_OFF    = STAGES * U_BYTES;       // 98304
   constexpr int ACC_OFF    = R1F_OFF + 2 * 2 * F_BYTES; // 131072
-  constexpr int R2F_OFF    = ACC_OFF + 2 * U_BYTES;  // 196608
+  constexpr int R2F_OFF    = ACC_OFF + 2 * U_BYTES;
   constexpr int T0_OFF     = R2F_OFF + 3 * F_BYTES;  // 221184
   constexpr int INFO_OFF   = T0_OFF + F_BYTES;       // 229376
   constexpr int BAR_OFF    = INFO_OFF + 128;
@@ -75,6 +79,7 @@ namespace
     double *      ti_next;
     double        fb, fa;
     int           pass; // 0 all rows, 1 rows that need no ghost data, 2 rows that need ghost data
+    int           prefetch_dist; // cells of L2 lookahead (0 = off)
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -137,6 +142,11 @@ namespace
   {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+  }
+  __device__ __forceinline__ void
+  prefetch_l2_bulk(const void *src, uint32_t bytes)
+  {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
   }
   __device__ __forceinline__ void
   cp_async_8(uint32_t dst, const void *src)
@@ -251,14 +261,14 @@ namespace
   compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const uint32_t bar0, const int tid_in_role)
   {
     auto fullU    = [&](int s) { return bar0 + 8 * s; };
-    auto emptyU   = [&](int s) { return bar0 + 24 + 8 * s; };
-    auto r1fFull  = [&](int f) { return bar0 + 48 + 8 * f; };
-    auto r1fEmpty = [&](int f) { return bar0 + 64 + 8 * f; };
-    auto accFull  = [&](int a) { return bar0 + 80 + 8 * a; };
-    auto accEmpty = [&](int a) { return bar0 + 96 + 8 * a; };
-    auto r2fFull  = [&](int j) { return bar0 + 112 + 8 * j; };
-    auto r2fEmpty = [&](int j) { return bar0 + 136 + 8 * j; };
-    const uint32_t  t0Full = bar0 + 160, t0Empty = bar0 + 168;
+    auto emptyU   = [&](int s) { return bar0 + 32 + 8 * s; };
+    auto r1fFull  = [&](int f) { return bar0 + 64 + 8 * f; };
+    auto r1fEmpty = [&](int f) { return bar0 + 80 + 8 * f; };
+    auto r2fFull  = [&](int j) { return bar0 + 96 + 8 * j; };
+    auto r2fEmpty = [&](int j) { return bar0 + 120 + 8 * j; };
+    auto accFull  = [&](int a) { return bar0 + 144 + 8 * a; };
+    auto accEmpty = [&](int a) { return bar0 + 160 + 8 * a; };
+    const uint32_t  t0Full = bar0 + 176, t0Empty = bar0 + 184;
     const bool      act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
     const bool      r1faces = act1 || act5;
     const bool      descend = p.up_delta[0] > 0;
@@ -346,30 +356,35 @@ namespace
         const double lc0 = rc.LC[2 * h], lc1 = rc.LC[2 * h + 1];
 
         // ---- source planes (rolled)
+        // (own planes first: the in-plane faces are released after two of the four iterations)
+        auto load_plane = [&](double(&Q)[4][4], int spl) {
+          if (role == 0)
+            {
+              const uint32_t up = ub + rowU + uint32_t(spl) * 8192u;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch)
+                {
+                  const double2 v              = lds128(up + ((uint32_t(ch) ^ sw) << 4));
+                  Q[ch >> 1][(ch & 1) * 2]     = v.x;
+                  Q[ch >> 1][(ch & 1) * 2 + 1] = v.y;
+                }
+            }
+          else
+            {
+              const uint32_t up = ub + rowbase + uint32_t(spl) * 2048u;
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  Q[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
+            }
+        };
 #pragma unroll 1
-        for (int sp = 0; sp < 4; ++sp)
+        for (int it = 0; it < 4; ++it)
           {
-            double P[4][4]; // [b][a]
-            if (role == 0)
-              {
-                const uint32_t up = ub + rowU + uint32_t(sp) * 8192u;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                  {
-                    const double2 v              = lds128(up + ((uint32_t(ch) ^ sw) << 4));
-                    P[ch >> 1][(ch & 1) * 2]     = v.x;
-                    P[ch >> 1][(ch & 1) * 2 + 1] = v.y;
-                  }
-              }
-            else
-              {
-                const uint32_t up = ub + rowbase + uint32_t(sp) * 2048u;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                  for (int a = 0; a < 4; ++a)
-                    P[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
-              }
+            const int sp = (it + 2 * h) & 3;
+            double    P[4][4]; // [b][a]
+            load_plane(P, sp);
             // cross-plane sweep into the two own output planes
             const double c0 = rc.C[(2 * h) * 4 + sp], c1 = rc.C[(2 * h + 1) * 4 + sp];
 #pragma unroll
@@ -463,8 +478,16 @@ namespace
                       }
                   }
               }
-            if (sp == 0 && role != 0)
+            if (it == 0 && role != 0)
               release(accEmpty(f)); // every partial sum has been consumed into the accumulators
+            if (it == 1 && role != 0)
+              {
+                // in-plane faces of directions 2 and 3 are done: let the face producer refill them for the next cell
+                if (actA)
+                  release(r2fEmpty(0));
+                if (actB)
+                  release(r2fEmpty(1));
+              }
           }
 
         // ---- releases + face of direction C
@@ -479,10 +502,6 @@ namespace
         else
           {
             release(emptyU(s));
-            if (actA)
-              release(r2fEmpty(0));
-            if (actB)
-              release(r2fEmpty(1));
             if (actC)
               mbar_wait(r2fFull(2), pk);
           }
@@ -584,15 +603,15 @@ namespace
     unsigned char *gbase = smem_raw + (base - raw);
     const uint32_t bar0 = base + BAR_OFF;
     // barrier slots
-    auto fullU    = [&](int s) { return bar0 + 8 * s; };         // 0..2
-    auto emptyU   = [&](int s) { return bar0 + 24 + 8 * s; };    // 3..5
-    auto r1fFull  = [&](int f) { return bar0 + 48 + 8 * f; };    // 6..7
-    auto r1fEmpty = [&](int f) { return bar0 + 64 + 8 * f; };    // 8..9
-    auto accFull  = [&](int a) { return bar0 + 80 + 8 * a; };    // 10..11
-    auto accEmpty = [&](int a) { return bar0 + 96 + 8 * a; };    // 12..13
-    auto r2fFull  = [&](int j) { return bar0 + 112 + 8 * j; };   // 14..16
-    auto r2fEmpty = [&](int j) { return bar0 + 136 + 8 * j; };   // 17..19
-    const uint32_t t0Full = bar0 + 160, t0Empty = bar0 + 168;
+    auto fullU    = [&](int s) { return bar0 + 8 * s; };
+    auto emptyU   = [&](int s) { return bar0 + 32 + 8 * s; };
+    auto r1fFull  = [&](int f) { return bar0 + 64 + 8 * f; };
+    auto r1fEmpty = [&](int f) { return bar0 + 80 + 8 * f; };
+    auto r2fFull  = [&](int j) { return bar0 + 96 + 8 * j; };
+    auto r2fEmpty = [&](int j) { return bar0 + 120 + 8 * j; };
+    auto accFull  = [&](int a) { return bar0 + 144 + 8 * a; };
+    auto accEmpty = [&](int a) { return bar0 + 160 + 8 * a; };
+    const uint32_t t0Full = bar0 + 176, t0Empty = bar0 + 184;
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
@@ -604,8 +623,11 @@ namespace
           {
             mbar_init(fullU(s), 1);
             mbar_init(emptyU(s), 8);
-            mbar_init(r2fFull(s), 1);
-            mbar_init(r2fEmpty(s), 4);
+          }
+        for (int j = 0; j < 3; ++j)
+          {
+            mbar_init(r2fFull(j), 1);
+            mbar_init(r2fEmpty(j), 4);
           }
         for (int a = 0; a < 2; ++a)
           {
@@ -639,27 +661,44 @@ namespace
         const uint32_t f_bytes  = (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
         int            k        = 0; // cell sequence number of this CTA
         int            nrow_seq = 0; // row sequence number of this CTA
-        for (;;)
-          {
-            int row = 0;
-            if (lane == 0)
-              row = atomicAdd(p.counters, 1);
-            row = __shfl_sync(0xffffffffu, row, 0);
-            if (row >= p.nrows)
-              break;
-            int c[6];
+        // rows come from a global counter (in lattice order, so the CTAs sweep the lattice as one compact
+        // window); one row of lookahead feeds the L2 prefetcher
+        auto fetch_row = [&](int (&cr)[6]) -> bool {
+          for (;;)
             {
+              int row = 0;
+              if (lane == 0)
+                row = atomicAdd(p.counters, 1);
+              row = __shfl_sync(0xffffffffu, row, 0);
+              if (row >= p.nrows)
+                return false;
               int r = row;
 #pragma unroll
               for (int d = 1; d < 6; ++d)
                 {
-                  c[d] = r % p.ncell[d];
+                  cr[d] = r % p.ncell[d];
                   r /= p.ncell[d];
                 }
+              cr[0] = descend ? n0 - 1 : 0;
+              if (row_selected(p, cr))
+                return true;
             }
-            c[0] = descend ? n0 - 1 : 0;
-            if (!row_selected(p, c))
-              continue;
+        };
+        // L2 prefetch of a cell and of the face layers that are not already L2-resident through their
+        // owners (directions 4 and 5 have the longest reuse distances)
+        auto prefetch_cell = [&](const int (&cp)[6]) {
+          if (lane == 0)
+            prefetch_l2_bulk(p.src + cell_index(p, cp) * CELL, U_BYTES);
+          else if (lane == 1 && act5 && !needs_ghost(p, cp, 5))
+            prefetch_l2_bulk(p.src + upwind_cell(p, cp, 5) * CELL + (p.up_delta[5] < 0 ? 3072 : 0), F_BYTES);
+          else if (lane >= 2 && lane < 6 && p.up_delta[4] != 0 && !needs_ghost(p, cp, 4))
+            prefetch_l2_bulk(p.src + upwind_cell(p, cp, 4) * CELL + (p.up_delta[4] < 0 ? 768 : 0) + 1024 * (lane - 2), 2048);
+        };
+        int  c[6], cn[6];
+        bool have = fetch_row(c);
+        while (have)
+          {
+            const bool have_next = fetch_row(cn);
             // direction-0 trace of the upwind neighbour of the first cell of the row (asynchronous gather)
             if (act0)
               {
@@ -684,6 +723,27 @@ namespace
               }
             for (int step = 0; step < n0; ++step, ++k)
               {
+                // L2 prefetch PREFETCH_DIST cells ahead (this row, or the beginning of the next one)
+                {
+                  const int ps = step + p.prefetch_dist;
+                  if (p.prefetch_dist == 0)
+                    {
+                    }
+                  else if (ps < n0)
+                    {
+                      int cp[6];
+#pragma unroll
+                      for (int d = 1; d < 6; ++d)
+                        cp[d] = c[d];
+                      cp[0] = descend ? n0 - 1 - ps : ps;
+                      prefetch_cell(cp);
+                    }
+                  else if (have_next && ps - n0 < n0)
+                    {
+                      cn[0] = descend ? n0 - 1 - (ps - n0) : ps - n0;
+                      prefetch_cell(cn);
+                    }
+                }
                 c[0]                 = descend ? n0 - 1 - step : step;
                 const long long cell = cell_index(p, c);
                 const int       s    = k % STAGES;
@@ -724,6 +784,11 @@ namespace
                   }
               }
             ++nrow_seq;
+            have = have_next;
+#pragma unroll
+            for (int d = 0; d < 6; ++d)
+              c[d] = cn[d];
+            c[0] = descend ? n0 - 1 : 0; // (cn[0] was moved by the prefetcher)
           }
         // end marker
         {
@@ -963,6 +1028,10 @@ namespace hd
     p.fb       = fu.fb;
     p.fa       = fu.fa;
     p.pass     = 0;
+    {
+      const char *e   = getenv("HD_PREFETCH_DIST"); // tuning knob
+      p.prefetch_dist = e ? atoi(e) : PREFETCH_DIST;
+    }
     const int fidx = fu.enabled ? 1 : 0;
     if (!st->attr_set[fidx])
       {
