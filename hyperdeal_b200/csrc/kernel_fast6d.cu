@@ -42,13 +42,13 @@ namespace
   constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
-  constexpr int R1F_OFF    = STAGES * U_BYTES;       // 98304
-  constexpr int ACC_OFF    = R1F_OFF + 2 * 2 * F_BYTES; // 131072
-  constexpr int R2F_OFF    = ACC_OFF + 2 * U_BYTES;
-  constexpr int T0_OFF     = R2F_OFF + 3 * F_BYTES;  // 221184
-  constexpr int INFO_OFF   = T0_OFF + F_BYTES;       // 229376
+  constexpr int R1F_OFF    = STAGES * U_BYTES;          // 98304: 2 slots x (direction 1, direction 5)
+  constexpr int ACC_OFF    = R1F_OFF + 2 * 2 * F_BYTES; // 131072: round 1's partial sums (one cell)
+  constexpr int R2F_OFF    = ACC_OFF + U_BYTES;         // 163840: 2 slots x (directions 2, 3, 4)
+  constexpr int T0_OFF     = R2F_OFF + 2 * 3 * F_BYTES; // 212992
+  constexpr int INFO_OFF   = T0_OFF + F_BYTES;          // 221184
   constexpr int BAR_OFF    = INFO_OFF + 128;
-  constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // + alignment slack
+  constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;      // + alignment slack
 
   struct RoleCoef // matrices of one round: in-plane directions A, B and the plane direction C
   {
@@ -245,30 +245,40 @@ namespace
     return fc;
   }
 
+  // mbarrier slots (8 bytes each, 256 bytes reserved at BAR_OFF)
+  struct Bars
+  {
+    uint32_t b;
+    __device__ __forceinline__ uint32_t fullU(int s) const { return b + 8 * s; }            // cell stage s has landed
+    __device__ __forceinline__ uint32_t emptyU(int s) const { return b + 32 + 8 * s; }      // 8 compute warps + face producer are done with it
+    __device__ __forceinline__ uint32_t r1fFull(int f) const { return b + 64 + 8 * f; }     // faces of directions 1,5
+    __device__ __forceinline__ uint32_t r1fEmpty(int f) const { return b + 80 + 8 * f; }
+    __device__ __forceinline__ uint32_t r2fFull(int f, int j) const { return b + 96 + 8 * (3 * f + j); } // face of direction 2+j
+    __device__ __forceinline__ uint32_t r2fEmpty(int f, int j) const { return b + 144 + 8 * (3 * f + j); }
+    __device__ __forceinline__ uint32_t accFull() const { return b + 192; }                 // round 1's partial sums are in shared memory
+    __device__ __forceinline__ uint32_t accEmpty() const { return b + 200; }
+    __device__ __forceinline__ uint32_t t0Full() const { return b + 208; }                  // direction-0 trace of a row start
+    __device__ __forceinline__ uint32_t t0Empty() const { return b + 216; }
+    __device__ __forceinline__ uint32_t infoFull(int s) const { return b + 224 + 8 * s; }   // CellInfo of stage s is written
+  };
+
   // ---------------------------------------------------------------------------------------------
   // Compute warps (4 per round; every SM sub-partition hosts one warp of each round so that the FP64
-  // pipe always has a second instruction stream to issue from).
+  // pipe always has a second instruction stream to issue from).  Both rounds work on the SAME cell at the
+  // same time (a ring stage lives for one cell time, so the 3-stage ring gives two cells of load lookahead).
   // Round ROLE works on directions (A,B | C) = (0,1 | 5) resp. (2,3 | 4).  A 4x4x4 tile [c][b][a] is shared
   // by two threads: thread half h owns the output planes c = 2h, 2h+1 (32 accumulators) and streams all four
   // source planes s:
   //     acc[c][b][a] += CC[c][s] P_s[b][a]                                                       (every s)
   //     acc[s][b][a] += sum_j CA[a][j] P_s[b][j] + sum_j CB[b][j] P_s[j][a] + LA[a] fa[b] + LB[b] fb[a]   (s in own half)
   //     acc[c][b][a] += LC[c] fc[b][a]                                                           (at the end)
+  // Round 1 hands its sums to round 2 through one shared-memory buffer; round 2 adds them in its epilogue.
   // The plane loop is NOT unrolled: both rounds' FP64 cores stay resident in the instruction cache (the fully
   // unrolled form, 2 x 25 KiB, lost 30-45 % of its issue slots to instruction fetch: profiles/r01b).
   template <int ROLE, bool FUSED>
   __device__ __forceinline__ void
-  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const uint32_t bar0, const int tid_in_role)
+  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const Bars bars, const int tid_in_role)
   {
-    auto fullU    = [&](int s) { return bar0 + 8 * s; };
-    auto emptyU   = [&](int s) { return bar0 + 32 + 8 * s; };
-    auto r1fFull  = [&](int f) { return bar0 + 64 + 8 * f; };
-    auto r1fEmpty = [&](int f) { return bar0 + 80 + 8 * f; };
-    auto r2fFull  = [&](int j) { return bar0 + 96 + 8 * j; };
-    auto r2fEmpty = [&](int j) { return bar0 + 120 + 8 * j; };
-    auto accFull  = [&](int a) { return bar0 + 144 + 8 * a; };
-    auto accEmpty = [&](int a) { return bar0 + 160 + 8 * a; };
-    const uint32_t  t0Full = bar0 + 176, t0Empty = bar0 + 184;
     const bool      act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
     const bool      r1faces = act1 || act5;
     const bool      descend = p.up_delta[0] > 0;
@@ -291,67 +301,60 @@ namespace
     const int      i5      = t >> 4;
     const uint32_t col     = uint32_t(cc >> 1) << 4;
     const uint32_t rowbase = uint32_t(i5) * 8192u + uint32_t(cc & 1) * 8u;
-    const uint32_t fcol    = base + R2F_OFF + 8u * uint32_t(cc + 256 * i5);
     const bool     actA = role ? (p.up_delta[2] != 0) : act0;
     const bool     actB = role ? (p.up_delta[3] != 0) : act1;
     const bool     actC = role ? (p.up_delta[4] != 0) : act5;
+    // partial-sum buffer (same swizzle as u): round 1 writes rows t, round 2 reads column cc
+    const uint32_t ab = role == 0 ? base + ACC_OFF + rowU + uint32_t(h) * 16384u : base + ACC_OFF + rowbase + uint32_t(h) * 4096u;
     int            nrow_seq = 0;
+    // round 1: the direction-0 trace a cell needs is the end layer of the previous cell of the row, i.e. values this
+    // very thread held in its planes: keep them in registers (own planes only)
+    double tr[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
 
     for (int k = 0;; ++k)
       {
         const int      s  = k % STAGES;
-        const int      f  = k & 1; // face-ring slot (round 1) / partial buffer (both)
+        const int      f  = k & 1; // face-ring slot
         const uint32_t pf = uint32_t((k >> 1) & 1);
         const uint32_t pk = uint32_t(k & 1);
         const uint32_t ub = base + s * U_BYTES;
-        mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
+        mbar_wait(bars.fullU(s), uint32_t((k / STAGES) & 1));
         const int4 inf    = lds_int4(base + INFO_OFF + 32 * s + 16); // c[3], c[4], c[5], first
         const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
         if (cellid < 0)
           break;
 
         double acc[2][4][4]; // [c - 2h][b][a]
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+              acc[x][y][z] = 0.0;
         // ---- prologue
-        const bool from_t0 = (role == 0) && inf.w != 0;
-        uint32_t   pb = 0, t0b = 0, fbuf = 0, ab;
+        const bool     from_t0 = (role == 0) && inf.w != 0;
+        uint32_t       t0b = 0, fbuf = 0;
+        const uint32_t fcol = base + R2F_OFF + uint32_t(f) * (3u * F_BYTES) + 8u * uint32_t(cc + 256 * i5);
         if (role == 0)
           {
-            // direction-0 trace of the upwind neighbour: the end layer of the previous cell of the row, read
-            // from that cell's ring stage (still resident: round 2 works on it), or the gathered trace at a row start
+            // direction-0 trace of the upwind neighbour at a row start: gathered by the producer
             if (from_t0 && act0)
               {
-                mbar_wait(t0Full, uint32_t(nrow_seq & 1));
+                mbar_wait(bars.t0Full(), uint32_t(nrow_seq & 1));
                 ++nrow_seq;
               }
-            pb  = base + ((k + STAGES - 1) % STAGES) * U_BYTES + rowU + (descend ? 0u : 8u);
             t0b = base + T0_OFF + uint32_t(t) * 32u;
             if (r1faces)
-              mbar_wait(r1fFull(f), pf);
+              mbar_wait(bars.r1fFull(f), pf);
             fbuf = base + R1F_OFF + f * 2 * F_BYTES;
-            ab   = base + ACC_OFF + f * U_BYTES + rowU + uint32_t(h) * 16384u;
-#pragma unroll
-            for (int x = 0; x < 2; ++x)
-#pragma unroll
-              for (int y = 0; y < 4; ++y)
-#pragma unroll
-                for (int z = 0; z < 4; ++z)
-                  acc[x][y][z] = 0.0;
           }
         else
           {
-            ab = base + ACC_OFF + f * U_BYTES + rowbase + uint32_t(h) * 4096u; // rows (a + 4b + 16 (2h + cl)) + 64 i5
-            mbar_wait(accFull(f), pf);
-#pragma unroll
-            for (int cl = 0; cl < 2; ++cl)
-#pragma unroll
-              for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                  acc[cl][b][a] = lds64(ab + uint32_t(a + 4 * b + 16 * cl) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
             if (actA)
-              mbar_wait(r2fFull(0), pk);
+              mbar_wait(bars.r2fFull(f, 0), pf);
             if (actB)
-              mbar_wait(r2fFull(1), pk);
+              mbar_wait(bars.r2fFull(f, 1), pf);
           }
         const double lc0 = rc.LC[2 * h], lc1 = rc.LC[2 * h + 1];
 
@@ -395,8 +398,8 @@ namespace
                   acc[0][b][a] = fma(c0, P[b][a], acc[0][b][a]);
                   acc[1][b][a] = fma(c1, P[b][a], acc[1][b][a]);
                 }
-            // in-plane sweeps: only for the planes this thread owns
-            if ((sp >> 1) == h)
+            // in-plane sweeps: only for the planes this thread owns (it = 0, 1)
+            if (it < 2)
               {
                 double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
                 if (role == 0)
@@ -411,11 +414,30 @@ namespace
                             fa[2] = v1.x;
                             fa[3] = v1.y;
                           }
+                        else if (it == 0)
+                          {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                              fa[b] = tr[0][b];
+                          }
                         else
                           {
 #pragma unroll
                             for (int b = 0; b < 4; ++b)
-                              fa[b] = lds64(pb + uint32_t(sp) * 8192u + ((uint32_t(2 * b + (descend ? 0 : 1)) ^ sw) << 4));
+                              fa[b] = tr[1][b];
+                          }
+                        // this cell's end layer is the next cell's trace (uniform branches keep the indices static)
+                        if (it == 0)
+                          {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                              tr[0][b] = descend ? P[b][0] : P[b][3];
+                          }
+                        else
+                          {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                              tr[1][b] = descend ? P[b][0] : P[b][3];
                           }
                       }
                     if (actB)
@@ -464,7 +486,7 @@ namespace
                         q[a] = v;
                       }
                     // one uniform branch per row keeps the register indices static
-                    if (sp & 1)
+                    if (it == 1)
                       {
 #pragma unroll
                         for (int a = 0; a < 4; ++a)
@@ -478,32 +500,27 @@ namespace
                       }
                   }
               }
-            if (it == 0 && role != 0)
-              release(accEmpty(f)); // every partial sum has been consumed into the accumulators
             if (it == 1 && role != 0)
               {
-                // in-plane faces of directions 2 and 3 are done: let the face producer refill them for the next cell
+                // in-plane faces of directions 2 and 3 are done: let the face producer refill this slot
                 if (actA)
-                  release(r2fEmpty(0));
+                  release(bars.r2fEmpty(f, 0));
                 if (actB)
-                  release(r2fEmpty(1));
+                  release(bars.r2fEmpty(f, 1));
               }
           }
 
-        // ---- releases + face of direction C
+        // ---- the cell stage is free (both rounds read it at the same time), then the face of direction C
+        release(bars.emptyU(s));
         if (role == 0)
           {
-            // release the PREVIOUS cell's stage (its end layer was this cell's direction-0 trace)
-            if (k > 0)
-              release(emptyU((k + STAGES - 1) % STAGES));
             if (from_t0 && act0)
-              release(t0Empty);
+              release(bars.t0Empty());
           }
         else
           {
-            release(emptyU(s));
             if (actC)
-              mbar_wait(r2fFull(2), pk);
+              mbar_wait(bars.r2fFull(f, 2), pf);
           }
         if (actC)
           {
@@ -539,20 +556,30 @@ namespace
         if (role == 0)
           {
             if (r1faces)
-              release(r1fEmpty(f));
-            // partial sums -> shared (same swizzle as u)
-            mbar_wait(accEmpty(f), pf ^ 1u);
+              release(bars.r1fEmpty(f));
+            // partial sums -> shared (same swizzle as u), once round 2 has taken the previous cell's
+            mbar_wait(bars.accEmpty(), pk ^ 1u);
 #pragma unroll
             for (int cl = 0; cl < 2; ++cl)
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch)
                 sts128(ab + cl * 8192 + ((uint32_t(ch) ^ sw) << 4), acc[cl][ch >> 1][(ch & 1) * 2], acc[cl][ch >> 1][(ch & 1) * 2 + 1]);
-            release(accFull(f));
+            release(bars.accFull());
           }
         else
           {
             if (actC)
-              release(r2fEmpty(2));
+              release(bars.r2fEmpty(f, 2));
+            // add round 1's sums
+            mbar_wait(bars.accFull(), pk);
+#pragma unroll
+            for (int cl = 0; cl < 2; ++cl)
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  acc[cl][b][a] += lds64(ab + uint32_t(a + 4 * b + 16 * cl) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
+            release(bars.accEmpty());
             // coalesced stores (a half-warp writes 128 contiguous bytes)
             const long long g = (long long)cellid * CELL + cc + 1024 * i5 + 512 * h;
             if (FUSED)
@@ -601,17 +628,7 @@ namespace
     const uint32_t raw  = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char *gbase = smem_raw + (base - raw);
-    const uint32_t bar0 = base + BAR_OFF;
-    // barrier slots
-    auto fullU    = [&](int s) { return bar0 + 8 * s; };
-    auto emptyU   = [&](int s) { return bar0 + 32 + 8 * s; };
-    auto r1fFull  = [&](int f) { return bar0 + 64 + 8 * f; };
-    auto r1fEmpty = [&](int f) { return bar0 + 80 + 8 * f; };
-    auto r2fFull  = [&](int j) { return bar0 + 96 + 8 * j; };
-    auto r2fEmpty = [&](int j) { return bar0 + 120 + 8 * j; };
-    auto accFull  = [&](int a) { return bar0 + 144 + 8 * a; };
-    auto accEmpty = [&](int a) { return bar0 + 160 + 8 * a; };
-    const uint32_t t0Full = bar0 + 176, t0Empty = bar0 + 184;
+    const Bars     bars{base + BAR_OFF};
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
@@ -621,23 +638,24 @@ namespace
       {
         for (int s = 0; s < STAGES; ++s)
           {
-            mbar_init(fullU(s), 1);
-            mbar_init(emptyU(s), 8);
+            mbar_init(bars.fullU(s), 1);
+            mbar_init(bars.emptyU(s), 9); // 8 compute warps + the face producer (it reads the CellInfo)
+            mbar_init(bars.infoFull(s), 1);
           }
-        for (int j = 0; j < 3; ++j)
+        for (int f = 0; f < 2; ++f)
           {
-            mbar_init(r2fFull(j), 1);
-            mbar_init(r2fEmpty(j), 4);
+            mbar_init(bars.r1fFull(f), 1);
+            mbar_init(bars.r1fEmpty(f), 4);
+            for (int j = 0; j < 3; ++j)
+              {
+                mbar_init(bars.r2fFull(f, j), 1);
+                mbar_init(bars.r2fEmpty(f, j), 4);
+              }
           }
-        for (int a = 0; a < 2; ++a)
-          {
-            mbar_init(r1fFull(a), 1);
-            mbar_init(r1fEmpty(a), 4);
-            mbar_init(accFull(a), 4);
-            mbar_init(accEmpty(a), 4);
-          }
-        mbar_init(t0Full, 32);
-        mbar_init(t0Empty, 4);
+        mbar_init(bars.accFull(), 4);
+        mbar_init(bars.accEmpty(), 4);
+        mbar_init(bars.t0Full(), 32);
+        mbar_init(bars.t0Empty(), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
@@ -702,7 +720,7 @@ namespace
             // direction-0 trace of the upwind neighbour of the first cell of the row (asynchronous gather)
             if (act0)
               {
-                mbar_wait(t0Empty, uint32_t(nrow_seq & 1) ^ 1u);
+                mbar_wait(bars.t0Empty(), uint32_t(nrow_seq & 1) ^ 1u);
                 const uint32_t t0 = base + T0_OFF;
                 if (needs_ghost(p, c, 0))
                   {
@@ -719,7 +737,7 @@ namespace
                     for (int j = 0; j < 32; ++j)
                       cp_async_8(t0 + 8u * (lane + 32 * j), g + 4 * (lane + 32 * j));
                   }
-                cp_async_arrive_noinc(t0Full);
+                cp_async_arrive_noinc(bars.t0Full());
               }
             for (int step = 0; step < n0; ++step, ++k)
               {
@@ -747,7 +765,7 @@ namespace
                 c[0]                 = descend ? n0 - 1 - step : step;
                 const long long cell = cell_index(p, c);
                 const int       s    = k % STAGES;
-                mbar_wait(emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
+                mbar_wait(bars.emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
                 if (lane == 0)
                   {
                     int *info = reinterpret_cast<int *>(gbase + INFO_OFF + 32 * s);
@@ -756,29 +774,30 @@ namespace
                     for (int d = 0; d < 6; ++d)
                       info[1 + d] = c[d];
                     info[7]             = (step == 0) ? 1 : 0;
+                    mbar_arrive(bars.infoFull(s)); // (release: the face producer may start on this cell's faces now)
                     const uint32_t dstU = base + s * U_BYTES;
-                    mbar_expect_tx(fullU(s), U_BYTES);
+                    mbar_expect_tx(bars.fullU(s), U_BYTES);
 #pragma unroll
                     for (int piece = 0; piece < 4; ++piece)
-                      tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), fullU(s));
+                      tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), bars.fullU(s));
                   }
                 if (r1faces)
                   {
                     const int f = k & 1;
-                    mbar_wait(r1fEmpty(f), uint32_t((k >> 1) & 1) ^ 1u);
+                    mbar_wait(bars.r1fEmpty(f), uint32_t((k >> 1) & 1) ^ 1u);
                     if (lane == 0)
                       {
                         const uint32_t dstF = base + R1F_OFF + f * 2 * F_BYTES;
-                        mbar_expect_tx(r1fFull(f), f_bytes);
+                        mbar_expect_tx(bars.r1fFull(f), f_bytes);
                         if (act1)
                           {
                             const long long nb = upwind_cell(p, c, 1);
-                            tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(nb * 256), r1fFull(f));
+                            tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(nb * 256), bars.r1fFull(f));
                           }
                         if (act5)
                           {
                             const long long nb = upwind_cell(p, c, 5);
-                            tma_load_2d(dstF + F_BYTES, &mapU, 0, int(nb * 256 + (p.up_delta[5] < 0 ? 192 : 0)), r1fFull(f));
+                            tma_load_2d(dstF + F_BYTES, &mapU, 0, int(nb * 256 + (p.up_delta[5] < 0 ? 192 : 0)), bars.r1fFull(f));
                           }
                       }
                   }
@@ -793,12 +812,13 @@ namespace
         // end marker
         {
           const int s = k % STAGES;
-          mbar_wait(emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
+          mbar_wait(bars.emptyU(s), uint32_t((k / STAGES) & 1) ^ 1u);
           if (lane == 0)
             {
               int *info = reinterpret_cast<int *>(gbase + INFO_OFF + 32 * s);
               info[0]   = -1;
-              mbar_arrive(fullU(s));
+              mbar_arrive(bars.infoFull(s));
+              mbar_arrive(bars.fullU(s));
               // the last CTA to finish re-arms the row counter for the next launch
               __threadfence();
               const int done = atomicAdd(p.counters + 1, 1);
@@ -822,44 +842,46 @@ namespace
             for (int k = 0;; ++k)
               {
                 const int s = k % STAGES;
-                mbar_wait(fullU(s), uint32_t((k / STAGES) & 1));
-                const int *info = reinterpret_cast<const int *>(gbase + INFO_OFF + 32 * s);
+                const int f = k & 1;
+                mbar_wait(bars.infoFull(s), uint32_t((k / STAGES) & 1));
+                const volatile int *info = reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
                 if (info[0] < 0)
                   break;
                 int c[6];
 #pragma unroll
                 for (int d = 0; d < 6; ++d)
                   c[d] = info[1 + d];
+                mbar_arrive(bars.emptyU(s)); // the CellInfo is in registers
 #pragma unroll
                 for (int j = 2; j >= 0; --j)
                   {
                     const int d = 2 + j;
                     if (p.up_delta[d] == 0)
                       continue;
-                    mbar_wait(r2fEmpty(j), uint32_t(k & 1) ^ 1u);
-                    const uint32_t dstF = base + R2F_OFF + j * F_BYTES;
-                    mbar_expect_tx(r2fFull(j), F_BYTES);
+                    mbar_wait(bars.r2fEmpty(f, j), uint32_t((k >> 1) & 1) ^ 1u);
+                    const uint32_t dstF = base + R2F_OFF + (3 * f + j) * F_BYTES;
+                    mbar_expect_tx(bars.r2fFull(f, j), F_BYTES);
                     if (needs_ghost(p, c, d))
-                      bulk_load_1d(dstF, p.ghost + p.ghost_off[d] + face_cell(p, c, d) * 1024, F_BYTES, r2fFull(j));
+                      bulk_load_1d(dstF, p.ghost + p.ghost_off[d] + face_cell(p, c, d) * 1024, F_BYTES, bars.r2fFull(f, j));
                     else
                       {
                         const long long nb    = upwind_cell(p, c, d);
                         const int       layer = p.up_delta[d] < 0 ? 3 : 0;
                         if (d == 2)
-                          tma_load_3d(dstF, &mapT2, 0, layer, int(nb * 64), r2fFull(j));
+                          tma_load_3d(dstF, &mapT2, 0, layer, int(nb * 64), bars.r2fFull(f, j));
                         else if (d == 3)
-                          tma_load_3d(dstF, &mapT3, 0, layer, int(nb * 16), r2fFull(j));
+                          tma_load_3d(dstF, &mapT3, 0, layer, int(nb * 16), bars.r2fFull(f, j));
                         else
-                          tma_load_3d(dstF, &mapT4, 0, layer, int(nb * 4), r2fFull(j));
+                          tma_load_3d(dstF, &mapT4, 0, layer, int(nb * 4), bars.r2fFull(f, j));
                       }
                   }
               }
           }
       }
     else if (warp < 4)
-      compute_round<0, FUSED>(p, base, gbase, bar0, tid);
+      compute_round<0, FUSED>(p, base, gbase, bars, tid);
     else
-      compute_round<1, FUSED>(p, base, gbase, bar0, tid - 128);
+      compute_round<1, FUSED>(p, base, gbase, bars, tid - 128);
   }
 
   // ------------------------------------------------------------------------------- host side
