@@ -22,7 +22,8 @@ sampled at the GLL nodes, velocity (1, .15, -.05, .1, -.15, .5), SkewFactor 0.5)
 
 N > 1: weak scaling, one brick of 8^6 cells per GPU; the lattice is doubled along x_2, x_1, x_0
 (examples/advection/performance/weak.py:95-101 doubles the x-directions first) and the bricks
-exchange ghost faces over NCCL each step (pack -> send/recv -> apply), all inside the timed region.
+exchange the upwind ghost faces over NCCL each step (pack -> send/recv overlapped with the interior cells
+-> boundary-layer cells), all inside the timed region.
 """
 from __future__ import annotations
 
@@ -165,28 +166,6 @@ def run_reference(args, rank):
     }))
 
 
-def brick_layout(world, rank):
-    """Weak scaling: 8^6 cells per GPU; GPUs form a px2 x px1 x px0 grid over the x-directions."""
-    p = [1, 1, 1]
-    w, d = world, 2
-    while w > 1:
-        p[d] *= 2
-        w //= 2
-        d = (d - 1) % 3
-    coords = [0, 0, 0]
-    r = rank
-    for d in range(3):
-        coords[d] = r % p[d]
-        r //= p[d]
-    return p, coords
-
-
-def neighbour_rank(p, coords, d, delta):
-    c = list(coords)
-    c[d] = (c[d] + delta) % p[d]
-    return c[0] + p[0] * (c[1] + p[1] * c[2])
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=CELLS_PER_DIR, help="cells per direction per GPU (default 8 = the BASELINE workload)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fused 3D3V kernel")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: direct peer-memory stores over NVLink (default) or NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -219,13 +199,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    p, coords = brick_layout(world, rank)
-    nloc = [args.cells] * 6
-    nglob = [args.cells * (p[d] if d < 3 else 1) for d in range(6)]
-    off = [coords[d] * args.cells if d < 3 else 0 for d in range(6)]
-    side_kind = [[api.SIDE_GHOST if (d < 3 and p[d] > 1) else api.SIDE_PERIODIC_LOCAL] * 2 for d in range(6)]
+    from hyperdeal_b200.partition import BrickPartition, HaloExchange
+
+    part = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 0))
+    nglob, p = list(part.n_cells_global), list(part.grid)
     ctx = api.Context(local_rank)
-    mf = api.MatrixFree(ctx, 3, 3, DEGREE, nloc, (0.0,) * 6, (1.0,) * 6, n_cells_global=nglob, cell_offset=off, side_kind=side_kind)
+    mf = api.MatrixFree(ctx, 3, 3, DEGREE, part.n_cells, (0.0,) * 6, (1.0,) * 6, n_cells_global=part.n_cells_global, cell_offset=part.cell_offset, side_kind=part.side_kind)
     op = api.AdvectionOperation(mf, VELOCITY, SKEW)
     op.set_kernel(args.kernel)
     n_dofs = mf.n_dofs
@@ -234,29 +213,57 @@ def main():
     api.VectorTools.interpolate(mf, src.data_ptr(), api.FN_HYPERRECTANGLE, 0.0)
     dst.zero_()
     halo = mf.halo_total
-    send = torch.empty(max(halo, 1), dtype=torch.float64, device="cuda")
-    ghost = torch.zeros(max(halo, 1), dtype=torch.float64, device="cuda")
+    send = torch.empty(max(halo, 16), dtype=torch.float64, device="cuda")
+    ghost = torch.zeros(max(halo, 16), dtype=torch.float64, device="cuda")
+    offsets = {(d, s): mf.halo_offset(d, s) for d in range(6) for s in range(2)}
+    sizes = {(d, s): mf.ghost_size(d, s) for d in range(6) for s in range(2)}
+    # upwind flux: only the inflow ghost side of every cut direction is read -> only that one is exchanged
+    exch = HaloExchange(part, offsets, sizes, op.ghost_sides())
+    send_mask = exch.send_mask()
+    halo_bytes = exch.bytes_per_exchange[0] * 8
 
-    def exchange():
-        if world == 1:
-            return
-        mf.halo_pack(src.data_ptr(), send.data_ptr())
-        ops = []
-        for d in range(3):
-            if p[d] == 1:
-                continue
-            for side in range(2):
-                o, n = mf.halo_offset(d, side), mf.ghost_size(d, side)
-                peer = neighbour_rank(p, coords, d, +1 if side else -1)
-                # my boundary layer on `side` becomes the peer's ghost on its opposite side
-                ops.append(dist.P2POp(dist.isend, send[o : o + n], peer, tag=2 * d + side))
-                ops.append(dist.P2POp(dist.irecv, ghost[o : o + n], peer, tag=2 * d + (1 - side)))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    # N > 1: direct NVLink variant (pack kernel stores into the neighbours' ghost buffers) unless --halo nccl
+    peer, halo_mode = None, "none"
+    if world > 1:
+        halo_mode = "nccl"
+        if args.halo == "peer":
+            from hyperdeal_b200.partition import PeerHaloExchange
+
+            try:
+                peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local_rank))
+                halo_mode = "peer"
+            except Exception as e:  # symmetric memory unavailable on this box: NCCL send/recv
+                if rank == 0:
+                    sys.stderr.write("bench: peer-memory halo unavailable (%s: %s), using NCCL send/recv\n" % (type(e).__name__, e))
+            ok = torch.tensor([1 if peer is not None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                peer, halo_mode = None, "nccl"
+    main_stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream() if world > 1 else None
+    ev_src, ev_halo = torch.cuda.Event(), torch.cuda.Event()
 
     def step():
-        exchange()
-        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
+        """one operator application; N > 1: start the halo (side stream) -> interior cells -> halo arrived -> boundary cells
+        (the reference's overlapping levels, matrix_free.templates.h:1516-1566)"""
+        if world == 1:
+            op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
+            return
+        ev_src.record(main_stream)
+        side_stream.wait_event(ev_src)
+        ctx.set_stream(side_stream.cuda_stream)
+        with torch.cuda.stream(side_stream):
+            if peer is not None:
+                g = peer.start(mf, src.data_ptr())
+            else:
+                mf.halo_pack(src.data_ptr(), send.data_ptr(), send_mask=send_mask)
+                HaloExchange.finish(exch.start(send, ghost))
+                g = ghost
+            ev_halo.record(side_stream)
+        ctx.set_stream(main_stream.cuda_stream)
+        op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_INTERIOR)
+        main_stream.wait_event(ev_halo)
+        op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
 
     def barrier():
         if world > 1:
@@ -274,23 +281,27 @@ def main():
     kernel_ms = []
     ev0.record()
     for _ in range(args.steps):
-        exchange()
-        ctx.timer_start()
-        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
-        kernel_ms.append(ctx.timer_stop() if world == 1 else 0.0)
+        if world == 1:
+            ctx.timer_start()
+            step()
+            kernel_ms.append(ctx.timer_stop())
+        else:
+            step()
     ev1.record()
     barrier()
+    launches = op.launch_count - launches0
     if world > 1:
-        # per-launch kernel time is only sampled at N=1 (timer_stop synchronises); re-time one launch
+        # per-launch kernel time for the roofline entry: one un-split launch on this rank's brick (outside the timed region)
         ctx.timer_start()
-        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr() if halo else None)
+        op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr())
         kernel_ms = [ctx.timer_stop()]
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    launches = op.launch_count - launches0 - (1 if world > 1 else 0)
+    if world > 1:
+        launches += args.steps * sum(send_mask)  # pack kernels
     value = n_dofs * world * args.steps / (total_ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer entry point (N=1 semantics per rank)
@@ -321,7 +332,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D3V k=3 FP64 advection apply, Cartesian periodic, %d^6 cells (%.3g DoFs) per GPU, skew 0.5, ECL" % (args.cells, n_dofs),
-                       "cells_global": nglob, "gpu_grid_x": p, "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
+                       "cells_global": nglob, "gpu_grid": p, "halo_bytes_sent_per_gpu_per_step": halo_bytes, "halo": halo_mode, "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
                        "kernel": name},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": n_dofs * BYTES_PER_DOF, "kernel_ms": k_ms},

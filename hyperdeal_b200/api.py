@@ -23,6 +23,7 @@ HD_MAX_DIM = 6
 HD_F64, HD_F32 = 0, 1
 SIDE_PERIODIC_LOCAL, SIDE_GHOST, SIDE_DIRICHLET, SIDE_DIRICHLET_HOM = 0, 1, 2, 3
 FN_ZERO, FN_HYPERRECTANGLE = 0, 1
+PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhdgpu.so")
@@ -32,9 +33,9 @@ EXPORTS = [
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_host", "hd_advection_set_kernel",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
-    "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
+    "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
     "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_timer_start", "hd_timer_stop",
 ]
@@ -92,6 +93,9 @@ def lib():
     L.hd_advection_create.argtypes = [c_void_p, c_double, POINTER(c_double), POINTER(c_void_p)]
     L.hd_advection_destroy.argtypes = [c_void_p]
     L.hd_advection_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double]
+    L.hd_advection_apply_part.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int]
+    L.hd_advection_ghost_sides.argtypes = [c_void_p, POINTER(c_int)]
+    L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p)]
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
     L.hd_advection_set_dirichlet_values.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64]
@@ -212,8 +216,14 @@ class MatrixFree:
     def ghost_size(self, d, side):
         return lib().hd_mesh_ghost_size(self._h, d, side)
 
-    def halo_pack(self, src_ptr: int, send_ptr: int):
-        _check(lib().hd_halo_pack(self._h, c_void_p(src_ptr), c_void_p(send_ptr)))
+    def halo_pack(self, src_ptr: int, send_ptr: int, send_mask=None, peer_dst=None):
+        """send_mask / peer_dst: sequences of 2*HD_MAX_DIM entries indexed 2*dir+side (hd_halo_pack_ex)."""
+        if send_mask is None and peer_dst is None:
+            _check(lib().hd_halo_pack(self._h, c_void_p(src_ptr), c_void_p(send_ptr)))
+            return
+        mask = (c_int * (2 * HD_MAX_DIM))(*[int(x) for x in send_mask]) if send_mask is not None else None
+        dst = (c_void_p * (2 * HD_MAX_DIM))(*[c_void_p(x or 0) for x in peer_dst]) if peer_dst is not None else None
+        _check(lib().hd_halo_pack_ex(self._h, c_void_p(src_ptr), c_void_p(send_ptr or 0), mask, dst))
 
     def close(self):
         if self._h:
@@ -233,6 +243,16 @@ class AdvectionOperation:
     def apply(self, dst: int, src: int, time: float = 0.0, ghosts: int | None = None):
         """dst = M^-1 A(src, time); dst/src are device pointers (advection_operation.h:137)."""
         _check(lib().hd_advection_apply(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts or 0), float(time)))
+
+    def apply_part(self, dst: int, src: int, time: float, ghosts: int | None, part: int):
+        """PART_INTERIOR (no ghost data read) / PART_BOUNDARY / PART_ALL: hd_advection_apply_part."""
+        _check(lib().hd_advection_apply_part(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts or 0), float(time), int(part)))
+
+    def ghost_sides(self):
+        """needed[2*dir+side]: which ghost sides the operator reads (upwind sides only)."""
+        out = (c_int * (2 * HD_MAX_DIM))()
+        _check(lib().hd_advection_ghost_sides(self._h, out))
+        return list(out)
 
     def apply_host(self, dst: np.ndarray, src: np.ndarray, time: float = 0.0):
         assert dst.flags.c_contiguous and src.flags.c_contiguous

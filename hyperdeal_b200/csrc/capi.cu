@@ -45,37 +45,62 @@ namespace
     long long nd, ncells;
   };
 
-  // pack loop of export_to_ghosted_array_start, matrix_free/vector_partitioner.h:1443-1460
-  template <typename T>
+  // pack loop of export_to_ghosted_array_start, matrix_free/vector_partitioner.h:1443-1460: gather the nodal face layer
+  // `side` of direction `dir` of every boundary cell into a contiguous segment.  One thread moves VEC consecutive values
+  // (16 bytes whenever the layer is contiguous over at least that much, i.e. for dir >= 1); `out` may be a peer-mapped
+  // pointer (the neighbour GPU's ghost segment): the stores then go over NVLink directly.
+  template <typename T, int VEC>
   __global__ void
-  k_halo_pack(const T *__restrict__ src, T *__restrict__ send, LatticeParams lp, int dir, int side, long long off, long long count)
+  k_halo_pack(const T *__restrict__ src, T *__restrict__ out, LatticeParams lp, int dir, int side, long long count)
   {
+    struct alignas(sizeof(T) * VEC) Chunk
+    {
+      T v[VEC];
+    };
     const long long nf       = lp.nd / lp.n;
     long long       stride_d = 1;
     for (int e = 0; e < dir; ++e)
       stride_d *= lp.n;
     const long long gstride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gstride)
+    const long long nchunks = count / VEC;
+    constexpr int   UNROLL  = 4; // independent loads in flight per thread (NVLink / strided-HBM latency)
+    for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < nchunks; c0 += UNROLL * gstride)
       {
-        const long long fc = i / nf, fo = i - fc * nf;
-        // face cell -> cell
-        long long r = fc, cell = 0, m = 1;
-        for (int e = 0; e < lp.dim; ++e)
+        Chunk     v[UNROLL];
+        long long dsti[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
           {
-            int ce;
-            if (e == dir)
-              ce = side ? lp.ncell[e] - 1 : 0;
-            else
+            const long long ci = c0 + u * gstride;
+            dsti[u]            = -1;
+            if (ci >= nchunks)
+              continue;
+            const long long i  = ci * VEC;
+            const long long fc = i / nf, fo = i - fc * nf;
+            // face cell -> cell
+            long long r = fc, cell = 0, m = 1;
+            for (int e = 0; e < lp.dim; ++e)
               {
-                ce = int(r % lp.ncell[e]);
-                r /= lp.ncell[e];
+                int ce;
+                if (e == dir)
+                  ce = side ? lp.ncell[e] - 1 : 0;
+                else
+                  {
+                    ce = int(r % lp.ncell[e]);
+                    r /= lp.ncell[e];
+                  }
+                cell += ce * m;
+                m *= lp.ncell[e];
               }
-            cell += ce * m;
-            m *= lp.ncell[e];
+            const long long lo = fo % stride_d, hi = fo / stride_d;
+            const long long o  = (hi * lp.n + (side ? lp.n - 1 : 0)) * stride_d + lo;
+            v[u]               = *reinterpret_cast<const Chunk *>(src + cell * lp.nd + o);
+            dsti[u]            = i;
           }
-        const long long lo = fo % stride_d, hi = fo / stride_d;
-        const long long o  = (hi * lp.n + (side ? lp.n - 1 : 0)) * stride_d + lo;
-        send[off + i]      = src[cell * lp.nd + o];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (dsti[u] >= 0)
+            *reinterpret_cast<Chunk *>(out + dsti[u]) = v[u];
       }
   }
 
@@ -715,8 +740,9 @@ hd_advection_launch_count(const hd_advection *op)
 }
 
 static int
-apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu)
+apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part = HD_PART_ALL)
 {
+  HD_REQUIRE(part == HD_PART_ALL || part == HD_PART_INTERIOR || part == HD_PART_BOUNDARY, "bad part");
   HD_REQUIRE(op && src && (dst || fu.enabled), "null argument");
   HD_REQUIRE(dst != src, "dst and src must not alias (ECL reads neighbours of src)");
   hd_mesh *m = op->mesh;
@@ -725,11 +751,18 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
   int  rc;
   bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (fast)
-    rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu);
+    rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu, part);
   else
-    rc = hd::launch_generic(op, dst, src, ghosts, time, fu);
+    {
+      // the generic kernel has no interior/boundary split: everything runs in the boundary part
+      if (part == HD_PART_INTERIOR)
+        return HD_OK;
+      rc = hd::launch_generic(op, dst, src, ghosts, time, fu);
+    }
   if (rc != HD_OK)
     return rc;
+  if (part == HD_PART_INTERIOR)
+    return HD_OK;
   bool any_dirichlet = false;
   for (int d = 0; d < m->dim; ++d)
     for (int s = 0; s < 2; ++s)
@@ -744,6 +777,13 @@ hd_advection_apply(hd_advection *op, void *dst, const void *src, const void *gho
 {
   FusedUpdate fu;
   return apply_impl(op, dst, src, ghosts, time, fu);
+}
+
+int
+hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, int part)
+{
+  FusedUpdate fu;
+  return apply_impl(op, dst, src, ghosts, time, fu, part);
 }
 
 int
@@ -800,27 +840,70 @@ hd_advection_set_dirichlet_builtin(hd_advection *op, int fn_id)
 
 // ---- halo -----------------------------------------------------------------------------------
 int
-hd_halo_pack(hd_mesh *m, const void *src, void *send)
+hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, void *const *peer_dst)
 {
   HD_REQUIRE(m && src, "null argument");
   if (!m->has_ghosts)
     return HD_OK;
-  HD_REQUIRE(send, "null send buffer");
   HD_CUDA(cudaSetDevice(m->ctx->device));
   const LatticeParams lp = lattice(m);
   for (int d = 0; d < m->dim; ++d)
     for (int s = 0; s < 2; ++s)
       {
         const long long cnt = m->ghost_cnt[d][s];
-        if (cnt == 0)
+        if (cnt == 0 || (send_mask && !send_mask[2 * d + s]))
           continue;
-        const unsigned g = grid_for(m->ctx, cnt, 256);
+        void *out = peer_dst ? peer_dst[2 * d + s] : nullptr;
+        if (!out)
+          {
+            HD_REQUIRE(send, "null send buffer");
+            out = static_cast<char *>(send) + (size_t)m->ghost_off[d][s] * m->elem_size;
+          }
+        // 16-byte chunks if the layer is contiguous over that much and everything is aligned
+        long long stride_d = 1;
+        for (int e = 0; e < d; ++e)
+          stride_d *= m->n;
+        const int  vec   = int(16 / m->elem_size);
+        const bool wide  = (stride_d % vec == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (m->nd % vec == 0);
+        // one 128-thread CTA per SM (64 registers per thread): small enough to run beside the persistent operator
+        // kernel, so that packing (and the NVLink stores of the direct variant) overlaps with the interior cells
+        constexpr int PT = 128;
+        unsigned      g  = grid_for(m->ctx, ((wide ? cnt / vec : cnt) + 3) / 4, PT);
+        if (g > (unsigned)m->ctx->sm_count)
+          g = (unsigned)m->ctx->sm_count;
         if (m->d.number_type == HD_F64)
-          k_halo_pack<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(send), lp, d, s, m->ghost_off[d][s], cnt);
+          {
+            if (wide)
+              k_halo_pack<double, 2><<<g, PT, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, cnt);
+            else
+              k_halo_pack<double, 1><<<g, PT, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, cnt);
+          }
         else
-          k_halo_pack<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(send), lp, d, s, m->ghost_off[d][s], cnt);
+          {
+            if (wide)
+              k_halo_pack<float, 4><<<g, PT, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, cnt);
+            else
+              k_halo_pack<float, 1><<<g, PT, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, cnt);
+          }
         HD_CUDA(cudaGetLastError());
       }
+  return HD_OK;
+}
+
+int
+hd_halo_pack(hd_mesh *m, const void *src, void *send)
+{
+  return hd_halo_pack_ex(m, src, send, nullptr, nullptr);
+}
+
+int
+hd_advection_ghost_sides(const hd_advection *op, int *needed)
+{
+  HD_REQUIRE(op && needed, "null argument");
+  const hd_mesh *m = op->mesh;
+  for (int d = 0; d < HD_MAX_DIM; ++d)
+    for (int s = 0; s < 2; ++s)
+      needed[2 * d + s] = (d < m->dim && m->d.side_kind[d][s] == HD_SIDE_GHOST && ((op->nb_mask[d] >> s) & 1)) ? 1 : 0;
   return HD_OK;
 }
 

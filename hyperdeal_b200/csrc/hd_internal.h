@@ -115,7 +115,7 @@ namespace hd
   int launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);
-  int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
+  int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part);
   void fast6d_release(hd_advection *op);
   // dirichlet source term (kernels_generic.cu)
   int launch_dirichlet_source(hd_advection *op, void *dst, double time, const FusedUpdate &fu);

@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <map>
 
 #include "hd_internal.h"
@@ -38,7 +39,6 @@ namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
   constexpr int STAGES     = 3;
-  constexpr int PREFETCH_DIST = 0; // cells of explicit L2 lookahead per CTA (measured: 0 is best, profiles/r01_prefetch_sweep.txt)
   constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
@@ -79,7 +79,6 @@ namespace
     double *      ti_next;
     double        fb, fa;
     int           pass; // 0 all rows, 1 rows that need no ghost data, 2 rows that need ghost data
-    int           prefetch_dist; // cells of L2 lookahead (0 = off)
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -144,11 +143,6 @@ namespace
                  : "memory");
   }
   __device__ __forceinline__ void
-  prefetch_l2_bulk(const void *src, uint32_t bytes)
-  {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-  }
-  __device__ __forceinline__ void
   cp_async_8(uint32_t dst, const void *src)
   {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -202,18 +196,6 @@ namespace
     if (p.up_delta[d] == 0 || p.up_kind[d] != HD_SIDE_GHOST)
       return false;
     return p.up_delta[d] < 0 ? (c[d] == 0) : (c[d] == p.ncell[d] - 1);
-  }
-
-  __device__ __forceinline__ bool
-  row_selected(const FastParams &p, const int (&c)[6])
-  {
-    if (p.pass == 0)
-      return true;
-    bool g = false;
-#pragma unroll
-    for (int d = 1; d < 6; ++d)
-      g |= needs_ghost(p, c, d);
-    return p.pass == 1 ? !g : g;
   }
 
   // upwind neighbour cell (inside the brick, possibly wrapped); only valid if !needs_ghost
@@ -622,7 +604,8 @@ namespace
   template <bool FUSED>
   __global__ void __launch_bounds__(THREADS, 1)
     k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
-                     const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const FastParams p)
+                     const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ CUtensorMap mapG1,
+                     const __grid_constant__ CUtensorMap mapG5, const FastParams p)
   {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw  = smem_u32(smem_raw);
@@ -677,11 +660,15 @@ namespace
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
           }
         const uint32_t f_bytes  = (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
+        const bool     ghost0   = act0 && p.up_kind[0] == HD_SIDE_GHOST;
         int            k        = 0; // cell sequence number of this CTA
         int            nrow_seq = 0; // row sequence number of this CTA
-        // rows come from a global counter (in lattice order, so the CTAs sweep the lattice as one compact
-        // window); one row of lookahead feeds the L2 prefetcher
-        auto fetch_row = [&](int (&cr)[6]) -> bool {
+        // Rows come from a global counter in lattice order, so the CTAs sweep the lattice as one compact window.
+        // A row is walked in upwind order over the steps [sb, se).  With ghost faces the work is split into an
+        // interior pass that needs no ghost data (overlapped with the halo exchange) and a boundary pass, the
+        // reference's overlapping levels (matrix_free.templates.h:1516-1566): a row whose directions 1..5 need no
+        // ghosts is interior, except for its upwind-most cell if direction 0 is cut.
+        auto fetch_row = [&](int (&cr)[6], int &sb, int &se) -> bool {
           for (;;)
             {
               int row = 0;
@@ -697,29 +684,37 @@ namespace
                   cr[d] = r % p.ncell[d];
                   r /= p.ncell[d];
                 }
-              cr[0] = descend ? n0 - 1 : 0;
-              if (row_selected(p, cr))
+              cr[0]    = 0;
+              bool g15 = false;
+#pragma unroll
+              for (int d = 1; d < 6; ++d)
+                g15 |= needs_ghost(p, cr, d);
+              sb = 0;
+              se = n0;
+              if (p.pass == 1)
+                {
+                  if (g15)
+                    continue;
+                  if (ghost0)
+                    sb = 1;
+                }
+              else if (p.pass == 2 && !g15)
+                {
+                  if (!ghost0)
+                    continue;
+                  se = 1;
+                }
+              if (sb < se)
                 return true;
             }
         };
-        // L2 prefetch of a cell and of the face layers that are not already L2-resident through their
-        // owners (directions 4 and 5 have the longest reuse distances)
-        auto prefetch_cell = [&](const int (&cp)[6]) {
-          if (lane == 0)
-            prefetch_l2_bulk(p.src + cell_index(p, cp) * CELL, U_BYTES);
-          else if (lane == 1 && act5 && !needs_ghost(p, cp, 5))
-            prefetch_l2_bulk(p.src + upwind_cell(p, cp, 5) * CELL + (p.up_delta[5] < 0 ? 3072 : 0), F_BYTES);
-          else if (lane >= 2 && lane < 6 && p.up_delta[4] != 0 && !needs_ghost(p, cp, 4))
-            prefetch_l2_bulk(p.src + upwind_cell(p, cp, 4) * CELL + (p.up_delta[4] < 0 ? 768 : 0) + 1024 * (lane - 2), 2048);
-        };
-        int  c[6], cn[6];
-        bool have = fetch_row(c);
-        while (have)
+        int c[6], sb = 0, se = 0;
+        while (fetch_row(c, sb, se))
           {
-            const bool have_next = fetch_row(cn);
-            // direction-0 trace of the upwind neighbour of the first cell of the row (asynchronous gather)
+            // direction-0 trace of the upwind neighbour of the first cell of the walk (asynchronous gather)
             if (act0)
               {
+                c[0] = descend ? n0 - 1 - sb : sb;
                 mbar_wait(bars.t0Empty(), uint32_t(nrow_seq & 1) ^ 1u);
                 const uint32_t t0 = base + T0_OFF;
                 if (needs_ghost(p, c, 0))
@@ -739,29 +734,8 @@ namespace
                   }
                 cp_async_arrive_noinc(bars.t0Full());
               }
-            for (int step = 0; step < n0; ++step, ++k)
+            for (int step = sb; step < se; ++step, ++k)
               {
-                // L2 prefetch PREFETCH_DIST cells ahead (this row, or the beginning of the next one)
-                {
-                  const int ps = step + p.prefetch_dist;
-                  if (p.prefetch_dist == 0)
-                    {
-                    }
-                  else if (ps < n0)
-                    {
-                      int cp[6];
-#pragma unroll
-                      for (int d = 1; d < 6; ++d)
-                        cp[d] = c[d];
-                      cp[0] = descend ? n0 - 1 - ps : ps;
-                      prefetch_cell(cp);
-                    }
-                  else if (have_next && ps - n0 < n0)
-                    {
-                      cn[0] = descend ? n0 - 1 - (ps - n0) : ps - n0;
-                      prefetch_cell(cn);
-                    }
-                }
                 c[0]                 = descend ? n0 - 1 - step : step;
                 const long long cell = cell_index(p, c);
                 const int       s    = k % STAGES;
@@ -773,7 +747,7 @@ namespace
 #pragma unroll
                     for (int d = 0; d < 6; ++d)
                       info[1 + d] = c[d];
-                    info[7]             = (step == 0) ? 1 : 0;
+                    info[7]             = (step == sb) ? 1 : 0;
                     mbar_arrive(bars.infoFull(s)); // (release: the face producer may start on this cell's faces now)
                     const uint32_t dstU = base + s * U_BYTES;
                     mbar_expect_tx(bars.fullU(s), U_BYTES);
@@ -791,23 +765,22 @@ namespace
                         mbar_expect_tx(bars.r1fFull(f), f_bytes);
                         if (act1)
                           {
-                            const long long nb = upwind_cell(p, c, 1);
-                            tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(nb * 256), bars.r1fFull(f));
+                            if (needs_ghost(p, c, 1)) // ghost segment viewed as rows of 4 doubles (same 32 B swizzle)
+                              tma_load_2d(dstF, &mapG1, 0, int((p.ghost_off[1] + face_cell(p, c, 1) * 1024) >> 2), bars.r1fFull(f));
+                            else
+                              tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(upwind_cell(p, c, 1) * 256), bars.r1fFull(f));
                           }
                         if (act5)
                           {
-                            const long long nb = upwind_cell(p, c, 5);
-                            tma_load_2d(dstF + F_BYTES, &mapU, 0, int(nb * 256 + (p.up_delta[5] < 0 ? 192 : 0)), bars.r1fFull(f));
+                            if (needs_ghost(p, c, 5)) // ghost segment viewed as rows of 16 doubles (128 B swizzle)
+                              tma_load_2d(dstF + F_BYTES, &mapG5, 0, int((p.ghost_off[5] + face_cell(p, c, 5) * 1024) >> 4), bars.r1fFull(f));
+                            else
+                              tma_load_2d(dstF + F_BYTES, &mapU, 0, int(upwind_cell(p, c, 5) * 256 + (p.up_delta[5] < 0 ? 192 : 0)), bars.r1fFull(f));
                           }
                       }
                   }
               }
             ++nrow_seq;
-            have = have_next;
-#pragma unroll
-            for (int d = 0; d < 6; ++d)
-              c[d] = cn[d];
-            c[0] = descend ? n0 - 1 : 0; // (cn[0] was moved by the prefetcher)
           }
         // end marker
         {
@@ -892,11 +865,16 @@ namespace
   {
     CUtensorMap u, t1, t2, t3, t4;
   };
+  struct GhostMaps
+  {
+    CUtensorMap g1, g5;
+  };
 
   struct FastState
   {
     EncodeTiledFn                encode = nullptr;
     std::map<const void *, Maps> cache;
+    std::map<const void *, GhostMaps> ghost_cache;
     bool                         attr_set[2] = {false, false};
     int *                        d_counters  = nullptr;
   };
@@ -981,6 +959,47 @@ namespace
     *out = &it->second;
     return HD_OK;
   }
+
+  // ghost buffer viewed as rows of 4 doubles (direction-1 faces, 32 B swizzle like mapT1) and as rows of 16 doubles
+  // (direction-5 faces, 128 B swizzle like mapU); a ghost face of one cell is 1024 contiguous doubles
+  int
+  get_ghost_maps(hd_advection *op, FastState *st, const void *ghosts, GhostMaps **out)
+  {
+    auto it = st->ghost_cache.find(ghosts);
+    if (it == st->ghost_cache.end())
+      {
+        if (st->ghost_cache.size() > 64)
+          st->ghost_cache.clear();
+        GhostMaps m;
+        std::memset(&m, 0, sizeof(m));
+        const cuuint64_t total = (cuuint64_t)op->mesh->ghost_total;
+        if (ghosts && total > 0)
+          {
+            cuuint32_t estr[2] = {1, 1};
+            {
+              cuuint64_t gdim[2] = {4, total / 4};
+              cuuint64_t gstr[1] = {32};
+              cuuint32_t box[2]  = {4, 256};
+              CUresult   r = st->encode(&m.g1, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(ghosts), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+              if (r != CUDA_SUCCESS)
+                return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(ghost 1) failed with code " + std::to_string((int)r));
+            }
+            {
+              cuuint64_t gdim[2] = {16, total / 16};
+              cuuint64_t gstr[1] = {128};
+              cuuint32_t box[2]  = {16, 64};
+              CUresult   r = st->encode(&m.g5, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(ghosts), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+              if (r != CUDA_SUCCESS)
+                return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(ghost 5) failed with code " + std::to_string((int)r));
+            }
+          }
+        it = st->ghost_cache.emplace(ghosts, m).first;
+      }
+    *out = &it->second;
+    return HD_OK;
+  }
 } // namespace
 
 namespace hd
@@ -999,15 +1018,12 @@ namespace hd
           const int kind = m->d.side_kind[d][s];
           if (kind == HD_SIDE_DIRICHLET || kind == HD_SIDE_DIRICHLET_HOM)
             return false;
-          // ghost faces: directions 2,3,4 (bulk copies of round 2's face ring) and the direction-0 gather
-          if (kind == HD_SIDE_GHOST && (d == 1 || d == 5))
-            return false;
         }
     return true;
   }
 
   int
-  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
+  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu, int part)
   {
     hd_mesh *  m = op->mesh;
     FastState *st;
@@ -1016,6 +1032,12 @@ namespace hd
       return rc;
     Maps *maps;
     rc = get_maps(op, st, src, &maps);
+    if (rc != HD_OK)
+      return rc;
+    GhostMaps *gmaps;
+    if (ghosts && (reinterpret_cast<uintptr_t>(ghosts) & 127) != 0)
+      return hd::fail(HD_ERR_INVALID, "the ghost buffer must be 128-byte aligned");
+    rc = get_ghost_maps(op, st, ghosts, &gmaps);
     if (rc != HD_OK)
       return rc;
     FastCoef   cfh;
@@ -1049,11 +1071,7 @@ namespace hd
     p.ti_next  = static_cast<double *>(fu.ti_next);
     p.fb       = fu.fb;
     p.fa       = fu.fa;
-    p.pass     = 0;
-    {
-      const char *e   = getenv("HD_PREFETCH_DIST"); // tuning knob
-      p.prefetch_dist = e ? atoi(e) : PREFETCH_DIST;
-    }
+    p.pass     = part; // 0 all cells, 1 interior (no ghost data needed), 2 boundary layer
     const int fidx = fu.enabled ? 1 : 0;
     if (!st->attr_set[fidx])
       {
@@ -1066,9 +1084,9 @@ namespace hd
     HD_CUDA(cudaMemcpyToSymbolAsync(cf, &cfh, sizeof(FastCoef), 0, cudaMemcpyHostToDevice, m->ctx->stream));
     long long grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
     if (fu.enabled)
-      k_advect_3d3v_k3<true><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p);
+      k_advect_3d3v_k3<true><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
     else
-      k_advect_3d3v_k3<false><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p);
+      k_advect_3d3v_k3<false><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = fu.enabled ? "advect_3d3v_k3_fused_lsrk" : "advect_3d3v_k3";

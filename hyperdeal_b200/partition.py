@@ -1,0 +1,198 @@
+"""Phase-space partition across the GPUs of one box and the ghost-face exchange between the bricks.
+
+Host-side plumbing only (torch.distributed: NCCL on GPUs, gloo in the CPU tests); the data movement on the device
+is done by libhdgpu (hd_halo_pack[_ex], hd_advection_apply[_part]).
+
+Reference counterparts:
+  * process grid PartitionX x PartitionV of the drivers (performance/util/driver.h:79-126,
+    examples/advection/performance/weak.py:95-101 doubles the x-directions first) -> ``BrickPartition``:
+    a Cartesian brick decomposition with one entry per direction;
+  * VectorDataExchange::Contiguous::export_to_ghosted_array_start/finish
+    (matrix_free/vector_partitioner.h:1387-1592): pack, MPI_Isend/Irecv per neighbour, wait -> ``HaloExchange``:
+    one grouped batch of send/recv pairs per operator application, started before the interior cells and
+    finished before the boundary-layer cells.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+SIDE_PERIODIC_LOCAL, SIDE_GHOST = 0, 1
+
+
+class BrickPartition:
+    """world ranks -> p[0] x ... x p[dim-1] grid of bricks; rank = lexicographic index, direction 0 fastest."""
+
+    def __init__(self, world: int, rank: int, n_cells_local, split_order=(2, 1, 0), grid=None):
+        self.world, self.rank = int(world), int(rank)
+        self.dim = len(n_cells_local)
+        self.n_cells = tuple(int(c) for c in n_cells_local)
+        if grid is None:
+            # powers of two are spread over split_order round-robin (weak scaling: x_2, x_1, x_0, x_2, ...)
+            grid = [1] * self.dim
+            w, i = self.world, 0
+            while w > 1:
+                if w % 2:
+                    raise ValueError("world size must be a power of two unless an explicit grid is given")
+                grid[split_order[i % len(split_order)]] *= 2
+                w //= 2
+                i += 1
+        self.grid = tuple(int(g) for g in grid)
+        n = 1
+        for g in self.grid:
+            n *= g
+        if n != self.world:
+            raise ValueError("grid %r does not match world size %d" % (self.grid, self.world))
+        self.coords = self.coords_of(self.rank)
+        self.n_cells_global = tuple(c * g for c, g in zip(self.n_cells, self.grid))
+        self.cell_offset = tuple(c * k for c, k in zip(self.n_cells, self.coords))
+        # a direction cut into several bricks has ghost sides; an uncut periodic direction wraps inside the brick
+        self.side_kind = [[SIDE_GHOST if g > 1 else SIDE_PERIODIC_LOCAL] * 2 for g in self.grid]
+
+    def coords_of(self, rank: int):
+        c, r = [], rank
+        for g in self.grid:
+            c.append(r % g)
+            r //= g
+        return tuple(c)
+
+    def rank_of(self, coords) -> int:
+        r, m = 0, 1
+        for c, g in zip(coords, self.grid):
+            r += (c % g) * m
+            m *= g
+        return r
+
+    def neighbour(self, d: int, side: int) -> int:
+        """rank owning the brick behind side (d, side) (periodic wrap)."""
+        c = list(self.coords)
+        c[d] += 1 if side else -1
+        return self.rank_of(c)
+
+
+def ghost_layout(n_cells_local, dofs_1d: int, side_kind):
+    """Offsets/sizes (in values) of the ghost segments, ordered (direction, side) — the layout of hd_halo_offset /
+    hd_mesh_ghost_size (include/hyperdeal_b200.h), i.e. n_face_cells * (k+1)^(dim-1) values per ghost side."""
+    dim = len(n_cells_local)
+    ncells = 1
+    for c in n_cells_local:
+        ncells *= c
+    nf = dofs_1d ** (dim - 1)
+    off, sizes, offsets = 0, {}, {}
+    for d in range(dim):
+        for s in range(2):
+            offsets[(d, s)] = off
+            if side_kind[d][s] == SIDE_GHOST:
+                sizes[(d, s)] = (ncells // n_cells_local[d]) * nf
+                off += sizes[(d, s)]
+            else:
+                sizes[(d, s)] = 0
+    return offsets, sizes, off
+
+
+@dataclass
+class _Msg:
+    d: int
+    side: int  # my side the message belongs to (send: my boundary layer; recv: my ghost side)
+    peer: int
+    offset: int
+    size: int
+
+
+class HaloExchange:
+    """Ghost-face exchange plan of one brick.
+
+    needed[2*d+side] (optional) = the operator reads ghost side (d, side); with the upwind flux only the inflow side of
+    every direction is read (hd_advection_ghost_sides), which halves the traffic.  All ranks must pass the same mask.
+    """
+
+    def __init__(self, part: BrickPartition, offsets, sizes, needed=None):
+        self.part = part
+        self.sends, self.recvs = [], []
+        for d in range(part.dim):
+            if part.grid[d] == 1:
+                continue
+            # my boundary layer `side` fills the ghost side (1 - side) of the neighbour behind it
+            for side in (0, 1):
+                if needed is None or needed[2 * d + (1 - side)]:
+                    self.sends.append(_Msg(d, side, part.neighbour(d, side), offsets[(d, side)], sizes[(d, side)]))
+            # Receives are posted upper side first: NCCL matches the messages of one pair of ranks by order, and when
+            # a direction is cut in two the same peer is both neighbours — its first send (its lower layer) is my
+            # upper ghost.
+            for side in (1, 0):
+                if needed is None or needed[2 * d + side]:
+                    self.recvs.append(_Msg(d, side, part.neighbour(d, side), offsets[(d, side)], sizes[(d, side)]))
+
+    def send_mask(self, max_dim: int = 6):
+        m = [0] * (2 * max_dim)
+        for s in self.sends:
+            m[2 * s.d + s.side] = 1
+        return m
+
+    @property
+    def bytes_per_exchange(self):
+        return sum(s.size for s in self.sends), sum(r.size for r in self.recvs)
+
+    def start(self, send, ghost, group=None):
+        """Post all sends/receives (send, ghost: 1-D tensors holding the packed layers / the ghost segments)."""
+        import torch.distributed as dist
+
+        ops = []
+        for s in self.sends:
+            ops.append(dist.P2POp(dist.isend, send[s.offset : s.offset + s.size], s.peer, group=group, tag=2 * s.d + s.side))
+        for r in self.recvs:
+            # the sender tagged the message with ITS side = the opposite of my ghost side
+            ops.append(dist.P2POp(dist.irecv, ghost[r.offset : r.offset + r.size], r.peer, group=group, tag=2 * r.d + (1 - r.side)))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(works):
+        for w in works:
+            w.wait()
+
+
+class PeerHaloExchange:
+    """Direct variant for one NVLink/NVSwitch box: the pack kernel (hd_halo_pack_ex) stores every boundary layer
+    straight into the neighbour GPU's ghost segment through peer-mapped pointers — pack and transport are ONE kernel
+    whose stores travel over NVLink — followed by a device-side barrier.  This is the B200 counterpart of the
+    reference's MPI-3 shared-memory window, where ranks of one node read each other's vector directly
+    (matrix_free/vector_partitioner.h:552-640 `sync`, :1387-1460).
+
+    Ghost buffers are symmetric-memory allocations (torch.distributed._symmetric_memory) and double-buffered: step n
+    writes into buffer n % 2, so one barrier per step is enough (a rank can only start writing buffer n % 2 again after
+    its neighbour has passed the barrier of step n + 1, i.e. after that neighbour's boundary pass of step n).
+
+    Requires equal bricks on all ranks (same ghost layout everywhere).
+    """
+
+    def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.part = part
+        group = group if group is not None else dist.group.WORLD
+        n = max(int(total), 16)
+        self.ghosts = [symm.empty(n, dtype=torch.float64, device=device) for _ in range(2)]
+        for g in self.ghosts:
+            g.zero_()
+        self.handles = [symm.rendezvous(g, group) for g in self.ghosts]
+        plan = HaloExchange(part, offsets, sizes, needed)
+        self.mask = plan.send_mask(max_dim)
+        self.bytes_sent = plan.bytes_per_exchange[0] * 8
+        self.peer_dst = []
+        for h in self.handles:
+            ptrs = [0] * (2 * max_dim)
+            for s in plan.sends:
+                # my boundary layer (d, side) is the ghost segment (d, 1 - side) of the neighbour behind that side
+                ptrs[2 * s.d + s.side] = int(h.buffer_ptrs[s.peer]) + 8 * offsets[(s.d, 1 - s.side)]
+            self.peer_dst.append(ptrs)
+        self.step = 0
+
+    def start(self, mf, src_ptr: int):
+        """Pack-and-store into the neighbours, then signal; call on the stream the pack should run on.
+        Returns the ghost tensor the boundary pass of this step has to read."""
+        b = self.step % 2
+        self.step += 1
+        mf.halo_pack(src_ptr, None, send_mask=self.mask, peer_dst=self.peer_dst[b])
+        self.handles[b].barrier(channel=0)
+        return self.ghosts[b]

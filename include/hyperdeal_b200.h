@@ -148,6 +148,24 @@ int hd_advection_destroy(hd_advection *op);
  * ghosts: device pointer to the ghost-face values of src filled by the halo exchange
  * (layout: hd_halo_offset), or NULL when no side is HD_SIDE_GHOST. */
 int hd_advection_apply(hd_advection *op, void *dst, const void *src, const void *ghosts, double time);
+/* The same operator in two parts, so that the ghost-face exchange overlaps with cell work — the reference's
+ * overlapping levels (MatrixFree::loop_cell_centric, matrix_free.templates.h:1516-1566: cells without remote faces
+ * run between export_to_ghosted_array_start and _finish, the others after):
+ *   HD_PART_INTERIOR  cells that read no ghost data (may run while the halo is in flight; `ghosts` is not read)
+ *   HD_PART_BOUNDARY  the remaining cells (after the halo has arrived)
+ *   HD_PART_ALL       both (what hd_advection_apply does)
+ * INTERIOR followed by BOUNDARY writes every owned cell of dst exactly once. */
+enum
+{
+  HD_PART_ALL      = 0,
+  HD_PART_INTERIOR = 1,
+  HD_PART_BOUNDARY = 2
+};
+int hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, int part);
+/* needed[2*dir+side] = 1 if the operator reads ghost side (dir, side): with the upwind flux only the inflow side
+ * of a direction is read (beta_f = 0 on the outflow side, advection_operation.h:459-467 for a constant velocity), so
+ * the exchange can skip the other one.  needed has 2*HD_MAX_DIM entries. */
+int hd_advection_ghost_sides(const hd_advection *op, int *needed);
 /* Same call on HOST buffers: copies src in, applies, copies dst out (used for the end-to-end
  * timing and by hosts that keep their vectors in host memory). */
 int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time);
@@ -174,6 +192,11 @@ int hd_advection_set_dirichlet_builtin(hd_advection *op, int fn_id);
  * (dir, 1-side).  Transport between GPUs (NCCL send/recv or peer copies) is done by the caller
  * between hd_halo_pack and hd_advection_apply. */
 int     hd_halo_pack(hd_mesh *mesh, const void *src, void *send_buffer);
+/* Selective / direct variant: send_mask[2*dir+side] (NULL = all) selects the boundary layers to pack;
+ * peer_dst[2*dir+side] (NULL or entry NULL = the send buffer segment) is a device pointer the layer is written to
+ * instead — e.g. the peer-mapped address of the neighbour GPU's ghost segment (dir, 1-side), in which case the pack
+ * kernel's stores travel over NVLink and no separate transport step is needed (the caller synchronises the GPUs). */
+int     hd_halo_pack_ex(hd_mesh *mesh, const void *src, void *send_buffer, const int *send_mask, void *const *peer_dst);
 int64_t hd_halo_offset(const hd_mesh *mesh, int dir, int side); /* offset (values) of a segment  */
 int64_t hd_halo_total(const hd_mesh *mesh);                     /* total values of all segments  */
 

@@ -130,8 +130,9 @@ def test_vector_tools_reference_output(api, ctx):
     assert 3.9 < math.log2(errs[0] / errs[1]) < 4.1 and 3.9 < math.log2(errs[1] / errs[2]) < 4.1
 
 
-@pytest.mark.parametrize("split_dir,kernel", [(0, 1), (2, 1), (5, 1), (0, 2), (2, 2), (3, 2), (4, 2)])
-def test_two_bricks_with_ghost_faces(api, ctx, split_dir, kernel):
+@pytest.mark.parametrize("split_dir,kernel,parts", [(0, 1, False), (2, 1, False), (5, 1, False), (0, 2, False), (1, 2, False), (2, 2, False), (3, 2, False), (4, 2, False), (5, 2, False),
+                                                    (0, 2, True), (1, 2, True), (2, 2, True), (4, 2, True), (5, 2, True), (2, 1, True)])
+def test_two_bricks_with_ghost_faces(api, ctx, split_dir, kernel, parts):
     """Partition the lattice into two bricks along one direction, exchange packed faces by hand and
     compare with the unpartitioned operator (the ghost path of matrix_free/vector_partitioner.h)."""
     dx, dv, k = 3, 3, 3
@@ -175,10 +176,23 @@ def test_two_bricks_with_ghost_faces(api, ctx, split_dir, kernel):
             # bricks on a periodic direction both of my neighbours are the other brick
             o_ot = other["mf"].halo_offset(split_dir, 1 - side)
             ghost[o_me : o_me + n_me] = other["send"][o_ot : o_ot + n_me]
-        mf.copy_in(me["ghost"], ghost)
         op = api.AdvectionOperation(mf, VEL, 0.5)
         op.set_kernel(kernel)
-        op.apply(me["dst"], me["src"], 0.0, ghosts=me["ghost"])
+        needed = op.ghost_sides()
+        assert sum(needed) == 1 and needed[2 * split_dir + (0 if VEL[split_dir] > 0 else 1)] == 1
+        for side in range(2):
+            if not needed[2 * split_dir + side]:  # the outflow side is never read: poison it
+                o_me, n_me = mf.halo_offset(split_dir, side), mf.ghost_size(split_dir, side)
+                ghost[o_me : o_me + n_me] = np.nan
+        mf.copy_in(me["ghost"], ghost)
+        if parts:
+            # interior cells first (they must not touch the ghost buffer: poison it meanwhile), then the boundary layer
+            mf.copy_in(me["ghost"], np.full(mf.halo_total, np.nan))
+            op.apply_part(me["dst"], me["src"], 0.0, me["ghost"], api.PART_INTERIOR)
+            mf.copy_in(me["ghost"], ghost)
+            op.apply_part(me["dst"], me["src"], 0.0, me["ghost"], api.PART_BOUNDARY)
+        else:
+            op.apply(me["dst"], me["src"], 0.0, ghosts=me["ghost"])
         assert op.kernel_name == ("generic" if kernel == 1 else "advect_3d3v_k3")
         out = mf.copy_out(me["dst"])
         expect = np.ascontiguousarray(ref_full[me["sl"]]).reshape(-1)
@@ -251,3 +265,42 @@ def test_reference_golden_files_on_gpu(api, ctx, golden_dir, name):
             assert abs(e1 - e2) <= 2e-10 * abs(e2), (name, t1, e1, e2)
         else:
             assert e1 < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_halo_pack_selective_and_direct(api, ctx, dtype):
+    """hd_halo_pack_ex: masked segments stay untouched; a segment can be written straight into another
+    buffer (the peer's ghost segment on a multi-GPU box) instead of the send buffer."""
+    nc = (2, 3, 2, 2)
+    side_kind = [[api.SIDE_GHOST, api.SIDE_GHOST], [api.SIDE_PERIODIC_LOCAL] * 2, [api.SIDE_GHOST, api.SIDE_GHOST], [api.SIDE_PERIODIC_LOCAL] * 2]
+    mf = api.MatrixFree(ctx, 2, 2, 3, nc, (0.0,) * 4, (1.0,) * 4, n_cells_global=(4, 3, 4, 2), cell_offset=(2, 0, 0, 0), side_kind=side_kind, dtype=dtype)
+    src = np.random.default_rng(4).standard_normal(mf.n_dofs).astype(dtype)
+    d_src, d_a, d_b, d_peer = (mf.initialize_dof_vector() for _ in range(4))
+    mf.copy_in(d_src, src)
+    mf.halo_pack(d_src, d_a)
+    full = mf.copy_out(d_a, mf.halo_total)
+    # reference layout: face cells lexicographic, nodal layer 0 / k of direction d
+    u = src.reshape(tuple(reversed(nc)) + (4,) * 4)
+    for d in (0, 2):
+        for side in range(2):
+            sl = [slice(None)] * 8
+            sl[3 - d] = -1 if side else 0
+            sl[4 + 3 - d] = -1 if side else 0
+            o, n = mf.halo_offset(d, side), mf.ghost_size(d, side)
+            assert np.array_equal(full[o : o + n], np.ascontiguousarray(u[tuple(sl)]).reshape(-1))
+    mask = [0] * 12
+    mask[2 * 2 + 1] = 1
+    mask[2 * 0 + 0] = 1
+    peer = [0] * 12
+    itemsize = np.dtype(dtype).itemsize
+    peer[2 * 0 + 0] = d_peer + 64 * itemsize  # direction 0 is the strided (8-byte) gather path
+    mf.copy_in(d_b, np.full(mf.halo_total, 5.0, dtype=dtype))
+    mf.halo_pack(d_src, d_b, send_mask=mask, peer_dst=peer)
+    got = mf.copy_out(d_b, mf.halo_total)
+    o, n = mf.halo_offset(2, 1), mf.ghost_size(2, 1)
+    assert np.array_equal(got[o : o + n], full[o : o + n])
+    untouched = np.ones(mf.halo_total, dtype=bool)
+    untouched[o : o + n] = False
+    assert np.all(got[untouched] == 5.0)
+    o0, n0 = mf.halo_offset(0, 0), mf.ghost_size(0, 0)
+    assert np.array_equal(mf.copy_out(d_peer, 64 + n0)[64:], full[o0 : o0 + n0])
