@@ -174,7 +174,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=CELLS_PER_DIR, help="cells per direction per GPU (default 8 = the BASELINE workload)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fused 3D3V kernel")
+    ap.add_argument("--layout", default="x", choices=["x", "xv"], help="N = 8: cut x_2,x_1,x_0 (bricks of 8^6 cells) or x_2,x_1,v_2 (bricks of 16x8x8x8x8x4 cells)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: direct peer-memory stores over NVLink (default) or NCCL send/recv")
+    ap.add_argument("--overlap", default="kernel", choices=["kernel", "parts"], help="N > 1: one launch that waits for the halo flag in-kernel (default) or interior/boundary launches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -201,7 +203,16 @@ def main():
 
     from hyperdeal_b200.partition import BrickPartition, HaloExchange
 
-    part = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 0))
+    # global lattice of the weak-scaling recipe (x_2, x_1, x_0 doubled in turn); how it is cut into equal bricks is ours
+    recipe = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 0))
+    if args.layout == "x":
+        part = recipe
+    else:
+        # "xv": never cut x_0 (rows of cells are walked along x_0): the third cut goes through v_2 instead
+        cut = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 5))
+        nloc = [g // c for g, c in zip(recipe.n_cells_global, cut.grid)]
+        part = BrickPartition(world, rank, nloc, grid=cut.grid)
+        assert part.n_cells_global == recipe.n_cells_global
     nglob, p = list(part.n_cells_global), list(part.grid)
     ctx = api.Context(local_rank)
     mf = api.MatrixFree(ctx, 3, 3, DEGREE, part.n_cells, (0.0,) * 6, (1.0,) * 6, n_cells_global=part.n_cells_global, cell_offset=part.cell_offset, side_kind=part.side_kind)
@@ -249,21 +260,34 @@ def main():
         if world == 1:
             op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
             return
+        if peer is not None and args.overlap == "kernel":
+            # ONE launch: a warp per CTA stores the boundary layers into the neighbours' ghost buffers over NVLink while the
+            # others do the interior cells; the boundary layer starts when the neighbours' arrival counters are complete
+            g, sends, counters, epoch = peer.begin_fused(ctx)
+            op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
+            peer.consumed(ctx)
+            return
         ev_src.record(main_stream)
         side_stream.wait_event(ev_src)
         ctx.set_stream(side_stream.cuda_stream)
+        m = 0
         with torch.cuda.stream(side_stream):
             if peer is not None:
-                g = peer.start(mf, src.data_ptr())
+                g, m = peer.start(mf, ctx, src.data_ptr())
             else:
                 mf.halo_pack(src.data_ptr(), send.data_ptr(), send_mask=send_mask)
                 HaloExchange.finish(exch.start(send, ghost))
                 g = ghost
-            ev_halo.record(side_stream)
+                ev_halo.record(side_stream)
         ctx.set_stream(main_stream.cuda_stream)
         op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_INTERIOR)
-        main_stream.wait_event(ev_halo)
+        if peer is not None:
+            peer.wait_ready(ctx, m)
+        else:
+            main_stream.wait_event(ev_halo)
         op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
+        if peer is not None:
+            peer.consumed(ctx)
 
     def barrier():
         if world > 1:
@@ -290,6 +314,8 @@ def main():
     ev1.record()
     barrier()
     launches = op.launch_count - launches0
+    if peer is not None and args.overlap == "kernel" and op.overlap_timed_out():
+        raise SystemExit("bench: the in-kernel halo wait timed out on rank %d (halo never signalled)" % rank)
     if world > 1:
         # per-launch kernel time for the roofline entry: one un-split launch on this rank's brick (outside the timed region)
         ctx.timer_start()
@@ -300,7 +326,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    if world > 1:
+    if world > 1 and not (peer is not None and args.overlap == "kernel"):
         launches += args.steps * sum(send_mask)  # pack kernels
     value = n_dofs * world * args.steps / (total_ms * 1e-3) / 1e9
 
@@ -332,7 +358,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D3V k=3 FP64 advection apply, Cartesian periodic, %d^6 cells (%.3g DoFs) per GPU, skew 0.5, ECL" % (args.cells, n_dofs),
-                       "cells_global": nglob, "gpu_grid": p, "halo_bytes_sent_per_gpu_per_step": halo_bytes, "halo": halo_mode, "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
+                       "cells_global": nglob, "cells_per_gpu": list(part.n_cells), "gpu_grid": p, "halo_bytes_sent_per_gpu_per_step": halo_bytes, "halo": halo_mode, "overlap": (args.overlap if peer is not None else "parts") if world > 1 else "none", "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
                        "kernel": name},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": n_dofs * BYTES_PER_DOF, "kernel_ms": k_ms},

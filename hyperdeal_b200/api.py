@@ -26,14 +26,14 @@ FN_ZERO, FN_HYPERRECTANGLE = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhdgpu.so")
+LIB_PATH = os.environ.get("HD_LIBHDGPU", os.path.join(_HERE, "lib", "libhdgpu.so"))  # HD_LIBHDGPU: use another build of the same C ABI
 
 EXPORTS = [
     "hd_last_error", "hd_version", "hd_context_create", "hd_context_destroy", "hd_context_set_stream",
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
@@ -49,6 +49,12 @@ class MeshDesc(ctypes.Structure):
         ("n_cells_global", c_int * HD_MAX_DIM), ("n_cells", c_int * HD_MAX_DIM), ("cell_offset", c_int * HD_MAX_DIM),
         ("side_kind", (c_int * 2) * HD_MAX_DIM),
     ]
+
+
+class HaloSend(ctypes.Structure):
+    """hd_halo_send: boundary layer (dir, side) -> peer-mapped ghost segment + the peer's arrival counter."""
+
+    _fields_ = [("dir", c_int), ("side", c_int), ("dst", c_void_p), ("arrival_counter", c_void_p)]
 
 
 class HdError(RuntimeError):
@@ -94,6 +100,10 @@ def lib():
     L.hd_advection_destroy.argtypes = [c_void_p]
     L.hd_advection_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_apply_part.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int]
+    L.hd_advection_apply_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, POINTER(HaloSend), c_int, c_void_p, c_int]
+    L.hd_advection_overlap_status.argtypes = [c_void_p, POINTER(c_int)]
+    L.hd_stream_write_flag.argtypes = [c_void_p, c_void_p, c_int]
+    L.hd_stream_wait_flag.argtypes = [c_void_p, c_void_p, c_int]
     L.hd_advection_ghost_sides.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p)]
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
@@ -136,6 +146,14 @@ class Context:
 
     def synchronize(self):
         _check(lib().hd_context_synchronize(self._h))
+
+    def write_flag(self, flag_ptr: int, value: int):
+        """enqueue *flag = value on the context's stream (stream memory operation, hd_stream_write_flag)"""
+        _check(lib().hd_stream_write_flag(self._h, c_void_p(flag_ptr), int(value)))
+
+    def wait_flag(self, flag_ptr: int, value: int):
+        """make the context's stream wait until *flag >= value (stream memory operation, hd_stream_wait_flag)"""
+        _check(lib().hd_stream_wait_flag(self._h, c_void_p(flag_ptr), int(value)))
 
     def timer_start(self):
         _check(lib().hd_timer_start(self._h))
@@ -247,6 +265,18 @@ class AdvectionOperation:
     def apply_part(self, dst: int, src: int, time: float, ghosts: int | None, part: int):
         """PART_INTERIOR (no ghost data read) / PART_BOUNDARY / PART_ALL: hd_advection_apply_part."""
         _check(lib().hd_advection_apply_part(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts or 0), float(time), int(part)))
+
+    def apply_overlapped(self, dst: int, src: int, time: float, ghosts: int, sends, counters_ptr: int, epoch: int):
+        """operator + ghost exchange in one kernel (hd_advection_apply_overlapped); sends = [(dir, side, dst_ptr, counter_ptr), ...]"""
+        arr = (HaloSend * max(len(sends), 1))()
+        for i, (d, s, dp, cp) in enumerate(sends):
+            arr[i].dir, arr[i].side, arr[i].dst, arr[i].arrival_counter = int(d), int(s), c_void_p(dp), c_void_p(cp)
+        _check(lib().hd_advection_apply_overlapped(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts), float(time), arr, len(sends), c_void_p(counters_ptr), int(epoch)))
+
+    def overlap_timed_out(self) -> bool:
+        v = c_int()
+        _check(lib().hd_advection_overlap_status(self._h, byref(v)))
+        return bool(v.value)
 
     def ghost_sides(self):
         """needed[2*dir+side]: which ghost sides the operator reads (upwind sides only)."""

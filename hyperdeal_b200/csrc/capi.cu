@@ -50,57 +50,41 @@ namespace
   // (16 bytes whenever the layer is contiguous over at least that much, i.e. for dir >= 1); `out` may be a peer-mapped
   // pointer (the neighbour GPU's ghost segment): the stores then go over NVLink directly.
   template <typename T, int VEC>
-  __global__ void
-  k_halo_pack(const T *__restrict__ src, T *__restrict__ out, LatticeParams lp, int dir, int side, long long count)
+  __global__ void __launch_bounds__(128)
+    k_halo_pack(const T *__restrict__ src, T *__restrict__ out, LatticeParams lp, int dir, int side, int n_face_cells, int nf, int stride_d)
   {
     struct alignas(sizeof(T) * VEC) Chunk
     {
       T v[VEC];
     };
-    const long long nf       = lp.nd / lp.n;
-    long long       stride_d = 1;
-    for (int e = 0; e < dir; ++e)
-      stride_d *= lp.n;
-    const long long gstride = (long long)gridDim.x * blockDim.x;
-    const long long nchunks = count / VEC;
-    constexpr int   UNROLL  = 4; // independent loads in flight per thread (NVLink / strided-HBM latency)
-    for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < nchunks; c0 += UNROLL * gstride)
+    const int layer_off = (side ? lp.n - 1 : 0) * stride_d;
+    const int hi_stride = lp.n * stride_d;
+    for (int fc = blockIdx.x; fc < n_face_cells; fc += gridDim.x)
       {
-        Chunk     v[UNROLL];
-        long long dsti[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
+        // face cell -> cell (uniform over the CTA)
+        long long cell = 0, m = 1;
+        int       r    = fc;
+        for (int e = 0; e < lp.dim; ++e)
           {
-            const long long ci = c0 + u * gstride;
-            dsti[u]            = -1;
-            if (ci >= nchunks)
-              continue;
-            const long long i  = ci * VEC;
-            const long long fc = i / nf, fo = i - fc * nf;
-            // face cell -> cell
-            long long r = fc, cell = 0, m = 1;
-            for (int e = 0; e < lp.dim; ++e)
+            int ce;
+            if (e == dir)
+              ce = side ? lp.ncell[e] - 1 : 0;
+            else
               {
-                int ce;
-                if (e == dir)
-                  ce = side ? lp.ncell[e] - 1 : 0;
-                else
-                  {
-                    ce = int(r % lp.ncell[e]);
-                    r /= lp.ncell[e];
-                  }
-                cell += ce * m;
-                m *= lp.ncell[e];
+                ce = r % lp.ncell[e];
+                r /= lp.ncell[e];
               }
-            const long long lo = fo % stride_d, hi = fo / stride_d;
-            const long long o  = (hi * lp.n + (side ? lp.n - 1 : 0)) * stride_d + lo;
-            v[u]               = *reinterpret_cast<const Chunk *>(src + cell * lp.nd + o);
-            dsti[u]            = i;
+            cell += ce * m;
+            m *= lp.ncell[e];
           }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          if (dsti[u] >= 0)
-            *reinterpret_cast<Chunk *>(out + dsti[u]) = v[u];
+        const T *s = src + cell * lp.nd + layer_off;
+        T *      o = out + (long long)fc * nf;
+#pragma unroll 4
+        for (int i = threadIdx.x * VEC; i < nf; i += 128 * VEC)
+          {
+            const int hi = i / stride_d, lo = i - hi * stride_d;
+            *reinterpret_cast<Chunk *>(o + i) = *reinterpret_cast<const Chunk *>(s + hi * hi_stride + lo);
+          }
       }
   }
 
@@ -787,6 +771,87 @@ hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void
 }
 
 int
+hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const hd_halo_send *sends, int n_sends,
+                              const void *arrival_counters, int epoch)
+{
+  HD_REQUIRE(op && dst && src && ghosts && arrival_counters && epoch > 0, "null argument");
+  HD_REQUIRE(dst != src, "dst and src must not alias (ECL reads neighbours of src)");
+  hd_mesh *m = op->mesh;
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  if (!fast)
+    return hd::fail(HD_ERR_UNSUPPORTED, "hd_advection_apply_overlapped needs the pipelined 3D3V kernel; use hd_advection_apply_part");
+  for (int d = 0; d < m->dim; ++d)
+    for (int s = 0; s < 2; ++s)
+      if (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET)
+        return hd::fail(HD_ERR_UNSUPPORTED, "hd_advection_apply_overlapped: Dirichlet sides are not supported");
+  FusedUpdate fu;
+  return hd::launch_fast6d(op, dst, src, ghosts, time, fu, 3, sends, n_sends, arrival_counters, epoch);
+}
+
+int
+hd_advection_overlap_status(hd_advection *op, int *timed_out)
+{
+  HD_REQUIRE(op && timed_out, "null argument");
+  HD_CUDA(cudaSetDevice(op->mesh->ctx->device));
+  return hd::fast6d_overlap_status(op, timed_out);
+}
+
+namespace
+{
+  // cuStreamWriteValue32 / cuStreamWaitValue32: stream memory operations — no kernel, so they can neither be blocked by
+  // nor block a persistent kernel that fills the SMs
+  typedef int (*StreamValueFn)(void *, unsigned long long, unsigned int, unsigned int);
+  int
+  stream_value_fn(const char *name, StreamValueFn *out)
+  {
+    void *                          f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    HD_CUDA(cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess)
+      return hd::fail(HD_ERR_CUDA, std::string(name) + " is not available in this driver");
+    *out = reinterpret_cast<StreamValueFn>(f);
+    return HD_OK;
+  }
+} // namespace
+
+int
+hd_stream_write_flag(hd_context *ctx, void *flag_device, int value)
+{
+  HD_REQUIRE(ctx && flag_device, "null argument");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  static StreamValueFn fn = nullptr;
+  if (!fn)
+    {
+      const int rc = stream_value_fn("cuStreamWriteValue32", &fn);
+      if (rc != HD_OK)
+        return rc;
+    }
+  const int r = fn(ctx->stream, (unsigned long long)(uintptr_t)flag_device, (unsigned int)value, 0u);
+  if (r != 0)
+    return hd::fail(HD_ERR_CUDA, "cuStreamWriteValue32 failed with code " + std::to_string(r));
+  return HD_OK;
+}
+
+int
+hd_stream_wait_flag(hd_context *ctx, void *flag_device, int value)
+{
+  HD_REQUIRE(ctx && flag_device, "null argument");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  static StreamValueFn fn = nullptr;
+  if (!fn)
+    {
+      const int rc = stream_value_fn("cuStreamWaitValue32", &fn);
+      if (rc != HD_OK)
+        return rc;
+    }
+  const int r = fn(ctx->stream, (unsigned long long)(uintptr_t)flag_device, (unsigned int)value, 0x0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (r != 0)
+    return hd::fail(HD_ERR_CUDA, "cuStreamWaitValue32 failed with code " + std::to_string(r));
+  return HD_OK;
+}
+
+int
 hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time)
 {
   HD_REQUIRE(op && dst_host && src_host, "null argument");
@@ -864,26 +929,37 @@ hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, v
         for (int e = 0; e < d; ++e)
           stride_d *= m->n;
         const int  vec   = int(16 / m->elem_size);
-        const bool wide  = (stride_d % vec == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (m->nd % vec == 0);
-        // one 128-thread CTA per SM (64 registers per thread): small enough to run beside the persistent operator
-        // kernel, so that packing (and the NVLink stores of the direct variant) overlaps with the interior cells
-        constexpr int PT = 128;
-        unsigned      g  = grid_for(m->ctx, ((wide ? cnt / vec : cnt) + 3) / 4, PT);
-        if (g > (unsigned)m->ctx->sm_count)
-          g = (unsigned)m->ctx->sm_count;
+        const bool wide  = (stride_d % vec == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (m->nd % vec == 0) && (m->nf % vec == 0);
+        // 128-thread CTAs, two per SM: small enough to run beside the persistent operator kernel, so that packing
+        // (and the NVLink stores of the direct variant) overlaps with the interior cells
+        const long long nfc = cnt / m->nf;
+        HD_REQUIRE(nfc < (1ll << 31) && m->nf < (1ll << 30), "face too large for the pack kernel");
+        unsigned g = (unsigned)(nfc < 2ll * m->ctx->sm_count ? nfc : 2ll * m->ctx->sm_count);
+        const int nfi = (int)m->nf, sdi = (int)stride_d, nfci = (int)nfc;
+        // An SM only hosts kernels of one shared-memory carve-out at a time: ask for the operator kernel's (maximum shared
+        // memory), otherwise pack CTAs and the persistent operator CTAs exclude each other and nothing overlaps.
+        static bool carveout_set = false;
+        if (!carveout_set)
+          {
+            cudaFuncSetAttribute(k_halo_pack<double, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_halo_pack<double, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_halo_pack<float, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_halo_pack<float, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+          }
         if (m->d.number_type == HD_F64)
           {
             if (wide)
-              k_halo_pack<double, 2><<<g, PT, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, cnt);
+              k_halo_pack<double, 2><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi);
             else
-              k_halo_pack<double, 1><<<g, PT, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, cnt);
+              k_halo_pack<double, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi);
           }
         else
           {
             if (wide)
-              k_halo_pack<float, 4><<<g, PT, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, cnt);
+              k_halo_pack<float, 4><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi);
             else
-              k_halo_pack<float, 1><<<g, PT, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, cnt);
+              k_halo_pack<float, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi);
           }
         HD_CUDA(cudaGetLastError());
       }

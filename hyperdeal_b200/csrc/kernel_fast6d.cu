@@ -39,7 +39,7 @@ namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
   constexpr int STAGES     = 3;
-  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
+  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer, (+ warp 10: halo sender, fused-halo variant only)
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
   constexpr int R1F_OFF    = STAGES * U_BYTES;          // 98304: 2 slots x (direction 1, direction 5)
@@ -78,7 +78,17 @@ namespace
     double *      sol;
     double *      ti_next;
     double        fb, fa;
-    int           pass; // 0 all rows, 1 rows that need no ghost data, 2 rows that need ghost data
+    int           pass; // 0 all cells, 1 cells that need no ghost data, 2 cells that need ghost data, 3 = 1 then 2 in one launch
+    // pass 3 (fused halo): warp 10 of every CTA stores its share of the brick's boundary layers into the neighbours'
+    // ghost segments (peer-mapped pointers) and adds 1 to the neighbours' arrival counters; the boundary phase starts
+    // once halo_flag[i] >= halo_epoch * gridDim.x for all i in halo_mask
+    const int *   halo_flag;
+    int           halo_epoch;
+    unsigned      halo_mask;
+    int           n_sends;
+    int           send_dir[6], send_side[6];
+    double *      send_dst[6];
+    int *         send_flag[6];
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -601,8 +611,89 @@ namespace
       }
   }
 
-  template <bool FUSED>
-  __global__ void __launch_bounds__(THREADS, 1)
+  // ======================================================================= halo sender (fused-halo variant, warp 10)
+  // pack loop of export_to_ghosted_array_start (matrix_free/vector_partitioner.h:1443-1460) fused with the transport:
+  // the nodal face layers go straight into the neighbour GPU's ghost segment over NVLink (peer-mapped pointers), then
+  // the neighbour's arrival counter is bumped.  Kept out of line so that the compute warps' code is laid out and
+  // register-allocated exactly as in the plain variant.
+  __device__ __noinline__ void
+  halo_send(const FastParams &p, const int lane)
+  {
+        if (p.pass == 3 && p.n_sends > 0)
+      {
+        for (int si = 0; si < p.n_sends; ++si)
+          {
+            const int d = p.send_dir[si], side = p.send_side[si];
+            int       nfc = 1;
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+              nfc *= (e == d) ? 1 : p.ncell[e];
+            const int stride_d  = 1 << (2 * d);
+            const int layer_off = (side ? 3 : 0) * stride_d;
+            for (int fc = blockIdx.x; fc < nfc; fc += gridDim.x)
+              {
+                long long cell = 0, m = 1;
+                int       r    = fc;
+#pragma unroll
+                for (int e = 0; e < 6; ++e)
+                  {
+                    int ce;
+                    if (e == d)
+                      ce = side ? p.ncell[e] - 1 : 0;
+                    else
+                      {
+                        ce = r % p.ncell[e];
+                        r /= p.ncell[e];
+                      }
+                    cell += ce * m;
+                    m *= p.ncell[e];
+                  }
+                const double *sp = p.src + cell * CELL + layer_off;
+                double *      op = p.send_dst[si] + (long long)fc * 1024;
+                if (d == 0)
+                  {
+                    // layer of direction 0: single values, 32 bytes apart
+#pragma unroll 1
+                    for (int i0 = lane; i0 < 1024; i0 += 256)
+                      {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                          v[u] = __ldg(sp + 4 * (i0 + 32 * u));
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                          op[i0 + 32 * u] = v[u];
+                      }
+                  }
+                else
+                  {
+                    // 16-byte chunks; the layer is contiguous over 4^d >= 4 values
+#pragma unroll 1
+                    for (int c0 = lane; c0 < 512; c0 += 256)
+                      {
+                        double2 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                          {
+                            const int i = 2 * (c0 + 32 * u), hi = i >> (2 * d), lo = i & (stride_d - 1);
+                            v[u]        = __ldg(reinterpret_cast<const double2 *>(sp + hi * 4 * stride_d + lo));
+                          }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                          *reinterpret_cast<double2 *>(op + 2 * (c0 + 32 * u)) = v[u];
+                      }
+                  }
+              }
+          }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < p.n_sends)
+          asm volatile("red.release.sys.global.add.s32 [%0], 1;" ::"l"(p.send_flag[lane]) : "memory");
+      }
+  }
+
+  template <bool FUSED, bool HALO>
+  __global__ void __launch_bounds__(HALO ? THREADS + 32 : THREADS, 1)
     k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
                      const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ CUtensorMap mapG1,
                      const __grid_constant__ CUtensorMap mapG5, const FastParams p)
@@ -668,13 +759,21 @@ namespace
         // interior pass that needs no ghost data (overlapped with the halo exchange) and a boundary pass, the
         // reference's overlapping levels (matrix_free.templates.h:1516-1566): a row whose directions 1..5 need no
         // ghosts is interior, except for its upwind-most cell if direction 0 is cut.
-        auto fetch_row = [&](int (&cr)[6], int &sb, int &se) -> bool {
+        bool halo_ready = p.pass != 3;
+        auto fetch_row  = [&](int (&cr)[6], int &sb, int &se) -> bool {
           for (;;)
             {
               int row = 0;
               if (lane == 0)
                 row = atomicAdd(p.counters, 1);
-              row = __shfl_sync(0xffffffffu, row, 0);
+              row      = __shfl_sync(0xffffffffu, row, 0);
+              int mode = p.pass;
+              if (p.pass == 3)
+                {
+                  // one launch, two phases over the rows: interior cells, then (once the halo has arrived) the rest
+                  mode = row >= p.nrows ? 2 : 1;
+                  row -= row >= p.nrows ? p.nrows : 0;
+                }
               if (row >= p.nrows)
                 return false;
               int r = row;
@@ -691,21 +790,53 @@ namespace
                 g15 |= needs_ghost(p, cr, d);
               sb = 0;
               se = n0;
-              if (p.pass == 1)
+              if (mode == 1)
                 {
                   if (g15)
                     continue;
                   if (ghost0)
                     sb = 1;
                 }
-              else if (p.pass == 2 && !g15)
+              else if (mode == 2 && !g15)
                 {
                   if (!ghost0)
                     continue;
                   se = 1;
                 }
-              if (sb < se)
-                return true;
+              if (sb >= se)
+                continue;
+              if (mode == 2 && !halo_ready)
+                {
+                  // The ghost faces are written by the neighbour GPUs while this kernel runs; the host enqueues a
+                  // flag write behind them.  Give up after 4 s (error word) rather than hang the GPU.
+                  if (lane == 0)
+                    {
+                      unsigned long long t0, t1;
+                      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                      for (unsigned todo = p.halo_mask; todo;)
+                        {
+                          const int i = __ffs(todo) - 1;
+                          int       v;
+                          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.halo_flag + i) : "memory");
+                          if (v >= p.halo_epoch * int(gridDim.x))
+                            {
+                              todo &= todo - 1;
+                              continue;
+                            }
+                          __nanosleep(500);
+                          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                          if (t1 - t0 > 4000000000ull)
+                            {
+                              atomicExch(p.counters + 2, 1);
+                              break;
+                            }
+                        }
+                      asm volatile("fence.proxy.async;" ::: "memory"); // the TMA (async proxy) reads of the ghosts come after
+                    }
+                  __syncwarp();
+                  halo_ready = true;
+                }
+              return true;
             }
         };
         int c[6], sb = 0, se = 0;
@@ -825,6 +956,8 @@ namespace
                 for (int d = 0; d < 6; ++d)
                   c[d] = info[1 + d];
                 mbar_arrive(bars.emptyU(s)); // the CellInfo is in registers
+                if (p.pass == 3)
+                  asm volatile("fence.proxy.async;" ::: "memory"); // ghost data written by peers, ordered by the producer's acquire
 #pragma unroll
                 for (int j = 2; j >= 0; --j)
                   {
@@ -851,6 +984,8 @@ namespace
               }
           }
       }
+    else if (HALO && warp == 10)
+      halo_send(p, lane);
     else if (warp < 4)
       compute_round<0, FUSED>(p, base, gbase, bars, tid);
     else
@@ -875,7 +1010,7 @@ namespace
     EncodeTiledFn                encode = nullptr;
     std::map<const void *, Maps> cache;
     std::map<const void *, GhostMaps> ghost_cache;
-    bool                         attr_set[2] = {false, false};
+    bool                         attr_set[4] = {false, false, false, false};
     int *                        d_counters  = nullptr;
   };
 
@@ -916,8 +1051,8 @@ namespace
       }
     if (!st->d_counters)
       {
-        HD_CUDA(cudaMalloc(&st->d_counters, 2 * sizeof(int)));
-        HD_CUDA(cudaMemset(st->d_counters, 0, 2 * sizeof(int)));
+        HD_CUDA(cudaMalloc(&st->d_counters, 4 * sizeof(int)));
+        HD_CUDA(cudaMemset(st->d_counters, 0, 4 * sizeof(int)));
       }
     *out = st;
     return HD_OK;
@@ -1023,7 +1158,8 @@ namespace hd
   }
 
   int
-  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu, int part)
+  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu, int part, const hd_halo_send *sends,
+                int n_sends, const void *halo_flag, int halo_epoch)
   {
     hd_mesh *  m = op->mesh;
     FastState *st;
@@ -1071,25 +1207,64 @@ namespace hd
     p.ti_next  = static_cast<double *>(fu.ti_next);
     p.fb       = fu.fb;
     p.fa       = fu.fa;
-    p.pass     = part; // 0 all cells, 1 interior (no ghost data needed), 2 boundary layer
-    const int fidx = fu.enabled ? 1 : 0;
+    p.pass          = part; // 0 all cells, 1 interior (no ghost data needed), 2 boundary layer, 3 both with an in-kernel wait
+    p.halo_flag     = static_cast<const int *>(halo_flag);
+    p.halo_epoch    = halo_epoch;
+    p.n_sends       = 0;
+    for (int i = 0; i < 6; ++i)
+      {
+        p.send_dir[i] = p.send_side[i] = 0;
+        p.send_dst[i]  = nullptr;
+        p.send_flag[i] = nullptr;
+      }
+    if (part == 3)
+      {
+        if (n_sends < 0 || n_sends > 6 || (n_sends > 0 && !sends))
+          return hd::fail(HD_ERR_INVALID, "at most 6 halo sends per operator application");
+        for (int i = 0; i < n_sends; ++i)
+          {
+            const hd_halo_send &h = sends[i];
+            if (h.dir < 0 || h.dir >= 6 || h.side < 0 || h.side > 1 || !h.dst || !h.arrival_counter || (reinterpret_cast<uintptr_t>(h.dst) & 15))
+              return hd::fail(HD_ERR_INVALID, "bad hd_halo_send entry");
+            p.send_dir[i]  = h.dir;
+            p.send_side[i] = h.side;
+            p.send_dst[i]  = static_cast<double *>(h.dst);
+            p.send_flag[i] = static_cast<int *>(h.arrival_counter);
+          }
+        p.n_sends = n_sends;
+      }
+    p.halo_mask     = 0;
+    for (int d = 0; d < 6; ++d)
+      for (int sd = 0; sd < 2; ++sd)
+        if (m->d.side_kind[d][sd] == HD_SIDE_GHOST && ((op->nb_mask[d] >> sd) & 1))
+          p.halo_mask |= 1u << (2 * d + sd);
+    const bool halo = part == 3;
+    const int  fidx = (fu.enabled ? 1 : 0) + (halo ? 2 : 0);
+    auto       kern = fu.enabled ? (halo ? k_advect_3d3v_k3<true, true> : k_advect_3d3v_k3<true, false>) : (halo ? k_advect_3d3v_k3<false, true> : k_advect_3d3v_k3<false, false>);
     if (!st->attr_set[fidx])
       {
-        if (fu.enabled)
-          HD_CUDA(cudaFuncSetAttribute(k_advect_3d3v_k3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        else
-          HD_CUDA(cudaFuncSetAttribute(k_advect_3d3v_k3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         st->attr_set[fidx] = true;
       }
     HD_CUDA(cudaMemcpyToSymbolAsync(cf, &cfh, sizeof(FastCoef), 0, cudaMemcpyHostToDevice, m->ctx->stream));
     long long grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
-    if (fu.enabled)
-      k_advect_3d3v_k3<true><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
-    else
-      k_advect_3d3v_k3<false><<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
+    kern<<<(unsigned)grid, halo ? THREADS + 32 : THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = fu.enabled ? "advect_3d3v_k3_fused_lsrk" : "advect_3d3v_k3";
+    return HD_OK;
+  }
+
+  int
+  fast6d_overlap_status(hd_advection *op, int *timed_out)
+  {
+    FastState *st = static_cast<FastState *>(op->fast_state);
+    *timed_out    = 0;
+    if (st && st->d_counters)
+      {
+        HD_CUDA(cudaMemcpy(timed_out, st->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        HD_CUDA(cudaMemset(st->d_counters + 2, 0, sizeof(int)));
+      }
     return HD_OK;
   }
 

@@ -151,18 +151,26 @@ class HaloExchange:
 
 
 class PeerHaloExchange:
-    """Direct variant for one NVLink/NVSwitch box: the pack kernel (hd_halo_pack_ex) stores every boundary layer
-    straight into the neighbour GPU's ghost segment through peer-mapped pointers — pack and transport are ONE kernel
-    whose stores travel over NVLink — followed by a device-side barrier.  This is the B200 counterpart of the
-    reference's MPI-3 shared-memory window, where ranks of one node read each other's vector directly
-    (matrix_free/vector_partitioner.h:552-640 `sync`, :1387-1460).
+    """Direct variant for one NVLink/NVSwitch box: boundary layers are stored straight into the neighbour GPU's ghost
+    segment through peer-mapped pointers — the B200 counterpart of the reference's MPI-3 shared-memory window, where the
+    ranks of one node read each other's vector directly (matrix_free/vector_partitioner.h:552-640 `sync`, :1387-1460).
 
-    Ghost buffers are symmetric-memory allocations (torch.distributed._symmetric_memory) and double-buffered: step n
-    writes into buffer n % 2, so one barrier per step is enough (a rank can only start writing buffer n % 2 again after
-    its neighbour has passed the barrier of step n + 1, i.e. after that neighbour's boundary pass of step n).
-
-    Requires equal bricks on all ranks (same ghost layout everywhere).
+    Two ways to drive it:
+      * fused (``begin_fused`` + AdvectionOperation.apply_overlapped): one warp per CTA of the operator kernel does the
+        packing and the NVLink stores and bumps the receiver's arrival counter; the kernel's boundary phase waits for its
+        own counters.  One launch per operator application, no extra kernels.  (A separate pack kernel cannot run
+        beside the persistent operator kernel once that one is resident — the SM sub-partitions' register files are
+        full — so "pack on a side stream" only overlaps when it wins the launch race.)
+      * split (``start`` / ``wait_ready``): hd_halo_pack_ex as its own kernel, data-ready flags written and awaited with
+        stream memory operations, operator in two parts (interior, boundary).
+    In both, ghost buffers are double-buffered (step m uses buffer m % 2) and a backward "consumed" flag per message
+    (``consumed``) tells the sender when a buffer may be overwritten: before step m it waits for ack >= m - 2.
+    Buffers, counters and flags are symmetric-memory allocations (torch.distributed._symmetric_memory provides the
+    peer-mapped addresses); all synchronisation is device-side (stream memory operations, no kernels, no host waits).
+    Requires equal bricks on all ranks (same ghost layout and CTA count everywhere).
     """
+
+    COUNT, READY, ACK = 0, 16, 32  # word offsets of the three flag groups (slot = 2*d+side inside each)
 
     def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6):
         import torch
@@ -173,26 +181,64 @@ class PeerHaloExchange:
         group = group if group is not None else dist.group.WORLD
         n = max(int(total), 16)
         self.ghosts = [symm.empty(n, dtype=torch.float64, device=device) for _ in range(2)]
+        self.flags = symm.empty(64, dtype=torch.int32, device=device)
         for g in self.ghosts:
             g.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize()
         self.handles = [symm.rendezvous(g, group) for g in self.ghosts]
-        plan = HaloExchange(part, offsets, sizes, needed)
-        self.mask = plan.send_mask(max_dim)
-        self.bytes_sent = plan.bytes_per_exchange[0] * 8
-        self.peer_dst = []
+        self.flag_handle = symm.rendezvous(self.flags, group)
+        self.plan = HaloExchange(part, offsets, sizes, needed)
+        self.mask = self.plan.send_mask(max_dim)
+        self.bytes_sent = self.plan.bytes_per_exchange[0] * 8
+        self.flag_ptrs = [int(x) for x in self.flag_handle.buffer_ptrs]
+        self.my_flags = self.flag_ptrs[part.rank]
+        self.peer_dst, self.fused_sends = [], []
         for h in self.handles:
-            ptrs = [0] * (2 * max_dim)
-            for s in plan.sends:
+            ptrs, sends = [0] * (2 * max_dim), []
+            for s in self.plan.sends:
                 # my boundary layer (d, side) is the ghost segment (d, 1 - side) of the neighbour behind that side
                 ptrs[2 * s.d + s.side] = int(h.buffer_ptrs[s.peer]) + 8 * offsets[(s.d, 1 - s.side)]
+                sends.append((s.d, s.side, ptrs[2 * s.d + s.side], self.flag_ptrs[s.peer] + 4 * (self.COUNT + 2 * s.d + (1 - s.side))))
             self.peer_dst.append(ptrs)
+            self.fused_sends.append(sends)
         self.step = 0
+        self.fused_steps = 0
+        dist.barrier(group=group)  # every rank has zeroed its flags before anyone signals
 
-    def start(self, mf, src_ptr: int):
-        """Pack-and-store into the neighbours, then signal; call on the stream the pack should run on.
-        Returns the ghost tensor the boundary pass of this step has to read."""
-        b = self.step % 2
+    def _next(self, ctx):
         self.step += 1
-        mf.halo_pack(src_ptr, None, send_mask=self.mask, peer_dst=self.peer_dst[b])
-        self.handles[b].barrier(channel=0)
-        return self.ghosts[b]
+        m = self.step
+        if m > 2:
+            for s in self.plan.sends:
+                ctx.wait_flag(self.my_flags + 4 * (self.ACK + 2 * s.d + s.side), m - 2)
+        return m
+
+    # ---- fused: pack + transport inside the operator kernel
+    def begin_fused(self, ctx):
+        """Enqueue the buffer hand-shake on ctx's stream; returns (ghost tensor, sends, counters_ptr, epoch) for
+        AdvectionOperation.apply_overlapped, to be followed by ``consumed``."""
+        m = self._next(ctx)
+        self.fused_steps += 1
+        return self.ghosts[m % 2], self.fused_sends[m % 2], self.my_flags + 4 * self.COUNT, self.fused_steps
+
+    # ---- split: pack kernel + stream flags + two operator launches
+    def start(self, mf, ctx, src_ptr: int):
+        """Enqueue on ctx's current stream: wait for the buffers to be free, pack-and-store into the neighbours, signal.
+        Returns (ghost tensor, step) for the operator parts of this step."""
+        m = self._next(ctx)
+        mf.halo_pack(src_ptr, None, send_mask=self.mask, peer_dst=self.peer_dst[m % 2])
+        for s in self.plan.sends:
+            ctx.write_flag(self.flag_ptrs[s.peer] + 4 * (self.READY + 2 * s.d + (1 - s.side)), m)
+        return self.ghosts[m % 2], m
+
+    def wait_ready(self, ctx, step: int):
+        """make ctx's current stream wait until this step's ghost faces have arrived"""
+        for r in self.plan.recvs:
+            ctx.wait_flag(self.my_flags + 4 * (self.READY + 2 * r.d + r.side), step)
+
+    def consumed(self, ctx):
+        """enqueue behind the operator: tell the senders that the ghost buffer of this step may be overwritten"""
+        for r in self.plan.recvs:
+            # the sender's layer was its side (1 - r.side)
+            ctx.write_flag(self.flag_ptrs[r.peer] + 4 * (self.ACK + 2 * r.d + (1 - r.side)), self.step)

@@ -162,6 +162,33 @@ enum
   HD_PART_BOUNDARY = 2
 };
 int hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, int part);
+/* Operator + ghost-face exchange in ONE kernel (pipelined 3D3V kernel only; HD_ERR_UNSUPPORTED otherwise: use
+ * hd_halo_pack_ex + the two parts).  One warp of every CTA stores its share of this brick's boundary layers straight
+ * into the neighbour GPUs' ghost segments (sends[i].dst: peer-mapped device pointer of the segment (dir, 1-side) of the
+ * neighbour behind side (dir, side)) and then adds 1 to that neighbour's arrival counter sends[i].arrival_counter
+ * (peer-mapped address of its arrival_counters[2*dir + (1-side)]) — the pack loop and MPI_Isend of
+ * export_to_ghosted_array_start (matrix_free/vector_partitioner.h:1387-1460) over NVLink.  Meanwhile the other warps
+ * work through the interior cells and start on the boundary layer once arrival_counters[2*dir+side] has reached
+ * epoch * (number of CTAs) for every ghost side the operator reads — export_to_ghosted_array_finish (:1482).
+ * Counters are 2*HD_MAX_DIM 32-bit words in this GPU's memory, zero-initialised, never reset; epoch = 1, 2, 3, ... counts
+ * the applications; all GPUs must run equal bricks (equal CTA counts).  Re-use of a ghost buffer is the caller's
+ * business (double-buffer it and hand-shake with hd_stream_write_flag / hd_stream_wait_flag).
+ * The wait gives up after 4 s; hd_advection_overlap_status then reports timed_out = 1 (and the result is invalid). */
+typedef struct hd_halo_send
+{
+  int   dir, side;        /* which boundary layer of this brick                         */
+  void *dst;              /* where it goes: the neighbour's ghost segment (dir, 1-side)  */
+  void *arrival_counter;  /* the neighbour's counter for that ghost side                */
+} hd_halo_send;
+int hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const hd_halo_send *sends, int n_sends,
+                                  const void *arrival_counters, int epoch);
+int hd_advection_overlap_status(hd_advection *op, int *timed_out);
+/* Stream memory operations on the context's stream (no kernel launch): "*flag = value" (the address may be peer-mapped
+ * memory of another GPU) and "wait until *flag >= value".  These carry the halo handshake between GPUs: data-ready
+ * flags forward, buffer-consumed flags backward (the role MPI_Isend/Irecv completion + the shared-memory window
+ * barriers play in matrix_free/vector_partitioner.h:1482-1592). */
+int hd_stream_write_flag(hd_context *ctx, void *flag_device, int value);
+int hd_stream_wait_flag(hd_context *ctx, void *flag_device, int value);
 /* needed[2*dir+side] = 1 if the operator reads ghost side (dir, side): with the upwind flux only the inflow side
  * of a direction is read (beta_f = 0 on the outflow side, advection_operation.h:459-467 for a constant velocity), so
  * the exchange can skip the other one.  needed has 2*HD_MAX_DIM entries. */

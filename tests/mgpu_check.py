@@ -65,12 +65,24 @@ def main():
 
         peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local))
         dst.zero_()
-        for it in range(3):
-            g = peer.start(mf, src.data_ptr())
+        for it in range(4):  # split variant: pack kernel, stream flags, two operator launches (all on one stream)
+            g, m = peer.start(mf, ctx, src.data_ptr())
             op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_INTERIOR)
+            peer.wait_ready(ctx, m)
             op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
+            peer.consumed(ctx)
         torch.cuda.synchronize()
         rel = max(rel, float(np.max(np.abs(dst.cpu().numpy() - expect)) / np.max(np.abs(expect))))
+        if op.kernel_name.startswith("advect_3d3v"):
+            # fused variant: ONE kernel per step packs, sends over NVLink, does the interior, waits, does the boundary
+            dst.zero_()
+            for it in range(5):
+                g, sends, counters, epoch = peer.begin_fused(ctx)
+                op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
+                peer.consumed(ctx)
+            torch.cuda.synchronize()
+            assert not op.overlap_timed_out()
+            rel = max(rel, float(np.max(np.abs(dst.cpu().numpy() - expect)) / np.max(np.abs(expect))))
         t = torch.tensor([rel], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
