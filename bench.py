@@ -263,7 +263,7 @@ def main():
         if peer is not None and args.overlap == "kernel":
             # ONE launch: a warp per CTA stores the boundary layers into the neighbours' ghost buffers over NVLink while the
             # others do the interior cells; the boundary layer starts when the neighbours' arrival counters are complete
-            g, sends, counters, epoch = peer.begin_fused(ctx)
+            g, sends, counters, epoch = peer.begin_fused(ctx, op)
             op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
             peer.consumed(ctx)
             return

@@ -33,7 +33,7 @@ EXPORTS = [
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
@@ -105,7 +105,8 @@ def lib():
     L.hd_stream_write_flag.argtypes = [c_void_p, c_void_p, c_int]
     L.hd_stream_wait_flag.argtypes = [c_void_p, c_void_p, c_int]
     L.hd_advection_ghost_sides.argtypes = [c_void_p, POINTER(c_int)]
-    L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p)]
+    L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p), c_void_p, POINTER(c_int)]
+    L.hd_advection_n_ctas.argtypes = [c_void_p]
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
     L.hd_advection_set_dirichlet_values.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64]
@@ -234,14 +235,17 @@ class MatrixFree:
     def ghost_size(self, d, side):
         return lib().hd_mesh_ghost_size(self._h, d, side)
 
-    def halo_pack(self, src_ptr: int, send_ptr: int, send_mask=None, peer_dst=None):
-        """send_mask / peer_dst: sequences of 2*HD_MAX_DIM entries indexed 2*dir+side (hd_halo_pack_ex)."""
-        if send_mask is None and peer_dst is None:
+    def halo_pack(self, src_ptr: int, send_ptr: int, send_mask=None, peer_dst=None, started_ptr: int | None = None) -> int:
+        """send_mask / peer_dst: sequences of 2*HD_MAX_DIM entries indexed 2*dir+side (hd_halo_pack_ex);
+        started_ptr: device int every pack CTA increments at start.  Returns the number of CTAs launched."""
+        if send_mask is None and peer_dst is None and started_ptr is None:
             _check(lib().hd_halo_pack(self._h, c_void_p(src_ptr), c_void_p(send_ptr)))
-            return
+            return 0
         mask = (c_int * (2 * HD_MAX_DIM))(*[int(x) for x in send_mask]) if send_mask is not None else None
         dst = (c_void_p * (2 * HD_MAX_DIM))(*[c_void_p(x or 0) for x in peer_dst]) if peer_dst is not None else None
-        _check(lib().hd_halo_pack_ex(self._h, c_void_p(src_ptr), c_void_p(send_ptr or 0), mask, dst))
+        n = c_int()
+        _check(lib().hd_halo_pack_ex(self._h, c_void_p(src_ptr), c_void_p(send_ptr or 0), mask, dst, c_void_p(started_ptr or 0), byref(n)))
+        return n.value
 
     def close(self):
         if self._h:
@@ -266,12 +270,16 @@ class AdvectionOperation:
         """PART_INTERIOR (no ghost data read) / PART_BOUNDARY / PART_ALL: hd_advection_apply_part."""
         _check(lib().hd_advection_apply_part(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts or 0), float(time), int(part)))
 
-    def apply_overlapped(self, dst: int, src: int, time: float, ghosts: int, sends, counters_ptr: int, epoch: int):
+    @property
+    def n_ctas(self) -> int:
+        return lib().hd_advection_n_ctas(self._h)
+
+    def apply_overlapped(self, dst: int, src: int, time: float, ghosts: int, sends, counters_ptr: int, target: int):
         """operator + ghost exchange in one kernel (hd_advection_apply_overlapped); sends = [(dir, side, dst_ptr, counter_ptr), ...]"""
         arr = (HaloSend * max(len(sends), 1))()
         for i, (d, s, dp, cp) in enumerate(sends):
             arr[i].dir, arr[i].side, arr[i].dst, arr[i].arrival_counter = int(d), int(s), c_void_p(dp), c_void_p(cp)
-        _check(lib().hd_advection_apply_overlapped(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts), float(time), arr, len(sends), c_void_p(counters_ptr), int(epoch)))
+        _check(lib().hd_advection_apply_overlapped(self._h, c_void_p(dst), c_void_p(src), c_void_p(ghosts), float(time), arr, len(sends), c_void_p(counters_ptr), int(target)))
 
     def overlap_timed_out(self) -> bool:
         v = c_int()

@@ -51,8 +51,12 @@ namespace
   // pointer (the neighbour GPU's ghost segment): the stores then go over NVLink directly.
   template <typename T, int VEC>
   __global__ void __launch_bounds__(128)
-    k_halo_pack(const T *__restrict__ src, T *__restrict__ out, LatticeParams lp, int dir, int side, int n_face_cells, int nf, int stride_d)
+    k_halo_pack(const T *__restrict__ src, T *__restrict__ out, LatticeParams lp, int dir, int side, int n_face_cells, int nf, int stride_d, int *started)
   {
+    // "this CTA is resident": lets the host gate the launch of the persistent operator kernel behind the start of the
+    // pack kernel (a kernel launched after the operator kernel is resident would not get an SM until that one ends)
+    if (started && threadIdx.x == 0)
+      atomicAdd(started, 1);
     struct alignas(sizeof(T) * VEC) Chunk
     {
       T v[VEC];
@@ -772,9 +776,9 @@ hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void
 
 int
 hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const hd_halo_send *sends, int n_sends,
-                              const void *arrival_counters, int epoch)
+                              const void *arrival_counters, int target)
 {
-  HD_REQUIRE(op && dst && src && ghosts && arrival_counters && epoch > 0, "null argument");
+  HD_REQUIRE(op && dst && src && ghosts && arrival_counters && target > 0, "null argument");
   HD_REQUIRE(dst != src, "dst and src must not alias (ECL reads neighbours of src)");
   hd_mesh *m = op->mesh;
   HD_CUDA(cudaSetDevice(m->ctx->device));
@@ -786,7 +790,19 @@ hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, cons
       if (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET)
         return hd::fail(HD_ERR_UNSUPPORTED, "hd_advection_apply_overlapped: Dirichlet sides are not supported");
   FusedUpdate fu;
-  return hd::launch_fast6d(op, dst, src, ghosts, time, fu, 3, sends, n_sends, arrival_counters, epoch);
+  return hd::launch_fast6d(op, dst, src, ghosts, time, fu, 3, sends, n_sends, arrival_counters, target);
+}
+
+int
+hd_advection_n_ctas(const hd_advection *op)
+{
+  if (!op)
+    return 0;
+  const hd_mesh *m = op->mesh;
+  if (!hd::fast6d_supported(op))
+    return 0;
+  long long nrows = m->ncells / m->d.n_cells[0];
+  return (int)(nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count);
 }
 
 int
@@ -905,9 +921,11 @@ hd_advection_set_dirichlet_builtin(hd_advection *op, int fn_id)
 
 // ---- halo -----------------------------------------------------------------------------------
 int
-hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, void *const *peer_dst)
+hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, void *const *peer_dst, void *started_counter, int *ctas_launched)
 {
   HD_REQUIRE(m && src, "null argument");
+  if (ctas_launched)
+    *ctas_launched = 0;
   if (!m->has_ghosts)
     return HD_OK;
   HD_CUDA(cudaSetDevice(m->ctx->device));
@@ -950,18 +968,20 @@ hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, v
         if (m->d.number_type == HD_F64)
           {
             if (wide)
-              k_halo_pack<double, 2><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi);
+              k_halo_pack<double, 2><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi, static_cast<int *>(started_counter));
             else
-              k_halo_pack<double, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi);
+              k_halo_pack<double, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(out), lp, d, s, nfci, nfi, sdi, static_cast<int *>(started_counter));
           }
         else
           {
             if (wide)
-              k_halo_pack<float, 4><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi);
+              k_halo_pack<float, 4><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi, static_cast<int *>(started_counter));
             else
-              k_halo_pack<float, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi);
+              k_halo_pack<float, 1><<<g, 128, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(out), lp, d, s, nfci, nfi, sdi, static_cast<int *>(started_counter));
           }
         HD_CUDA(cudaGetLastError());
+        if (ctas_launched)
+          *ctas_launched += (int)g;
       }
   return HD_OK;
 }
@@ -969,7 +989,7 @@ hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, v
 int
 hd_halo_pack(hd_mesh *m, const void *src, void *send)
 {
-  return hd_halo_pack_ex(m, src, send, nullptr, nullptr);
+  return hd_halo_pack_ex(m, src, send, nullptr, nullptr, nullptr, nullptr);
 }
 
 int

@@ -116,7 +116,7 @@ namespace hd
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);
   int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part,
-                     const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_epoch = 0);
+                     const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_target = 0);
   int  fast6d_overlap_status(hd_advection *op, int *timed_out);
   void fast6d_release(hd_advection *op);
   // dirichlet source term (kernels_generic.cu)

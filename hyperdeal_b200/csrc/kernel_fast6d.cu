@@ -81,9 +81,9 @@ namespace
     int           pass; // 0 all cells, 1 cells that need no ghost data, 2 cells that need ghost data, 3 = 1 then 2 in one launch
     // pass 3 (fused halo): warp 10 of every CTA stores its share of the brick's boundary layers into the neighbours'
     // ghost segments (peer-mapped pointers) and adds 1 to the neighbours' arrival counters; the boundary phase starts
-    // once halo_flag[i] >= halo_epoch * gridDim.x for all i in halo_mask
+    // once halo_flag[i] >= halo_target for all i in halo_mask
     const int *   halo_flag;
-    int           halo_epoch;
+    int           halo_target;
     unsigned      halo_mask;
     int           n_sends;
     int           send_dir[6], send_side[6];
@@ -818,7 +818,7 @@ namespace
                           const int i = __ffs(todo) - 1;
                           int       v;
                           asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.halo_flag + i) : "memory");
-                          if (v >= p.halo_epoch * int(gridDim.x))
+                          if (v >= p.halo_target)
                             {
                               todo &= todo - 1;
                               continue;
@@ -1159,7 +1159,7 @@ namespace hd
 
   int
   launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu, int part, const hd_halo_send *sends,
-                int n_sends, const void *halo_flag, int halo_epoch)
+                int n_sends, const void *halo_flag, int halo_target)
   {
     hd_mesh *  m = op->mesh;
     FastState *st;
@@ -1209,7 +1209,7 @@ namespace hd
     p.fa       = fu.fa;
     p.pass          = part; // 0 all cells, 1 interior (no ghost data needed), 2 boundary layer, 3 both with an in-kernel wait
     p.halo_flag     = static_cast<const int *>(halo_flag);
-    p.halo_epoch    = halo_epoch;
+    p.halo_target   = halo_target;
     p.n_sends       = 0;
     for (int i = 0; i < 6; ++i)
       {
@@ -1238,7 +1238,7 @@ namespace hd
       for (int sd = 0; sd < 2; ++sd)
         if (m->d.side_kind[d][sd] == HD_SIDE_GHOST && ((op->nb_mask[d] >> sd) & 1))
           p.halo_mask |= 1u << (2 * d + sd);
-    const bool halo = part == 3;
+    const bool halo = (part == 3 && n_sends > 0) || getenv("HD_FORCE_HALO_VARIANT") != nullptr; // (env: A/B of the two kernel variants)
     const int  fidx = (fu.enabled ? 1 : 0) + (halo ? 2 : 0);
     auto       kern = fu.enabled ? (halo ? k_advect_3d3v_k3<true, true> : k_advect_3d3v_k3<true, false>) : (halo ? k_advect_3d3v_k3<false, true> : k_advect_3d3v_k3<false, false>);
     if (!st->attr_set[fidx])

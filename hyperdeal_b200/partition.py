@@ -215,12 +215,13 @@ class PeerHaloExchange:
         return m
 
     # ---- fused: pack + transport inside the operator kernel
-    def begin_fused(self, ctx):
-        """Enqueue the buffer hand-shake on ctx's stream; returns (ghost tensor, sends, counters_ptr, epoch) for
-        AdvectionOperation.apply_overlapped, to be followed by ``consumed``."""
+    def begin_fused(self, ctx, op):
+        """Enqueue the buffer hand-shake on ctx's stream; returns (ghost tensor, sends, counters_ptr, target) for
+        AdvectionOperation.apply_overlapped, to be followed by ``consumed``.  Every CTA of a sender adds 1 to my arrival
+        counter per application, hence target = applications * op.n_ctas (equal bricks on all ranks)."""
         m = self._next(ctx)
         self.fused_steps += 1
-        return self.ghosts[m % 2], self.fused_sends[m % 2], self.my_flags + 4 * self.COUNT, self.fused_steps
+        return self.ghosts[m % 2], self.fused_sends[m % 2], self.my_flags + 4 * self.COUNT, self.fused_steps * op.n_ctas
 
     # ---- split: pack kernel + stream flags + two operator launches
     def start(self, mf, ctx, src_ptr: int):

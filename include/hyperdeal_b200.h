@@ -162,17 +162,21 @@ enum
   HD_PART_BOUNDARY = 2
 };
 int hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, int part);
-/* Operator + ghost-face exchange in ONE kernel (pipelined 3D3V kernel only; HD_ERR_UNSUPPORTED otherwise: use
- * hd_halo_pack_ex + the two parts).  One warp of every CTA stores its share of this brick's boundary layers straight
- * into the neighbour GPUs' ghost segments (sends[i].dst: peer-mapped device pointer of the segment (dir, 1-side) of the
- * neighbour behind side (dir, side)) and then adds 1 to that neighbour's arrival counter sends[i].arrival_counter
- * (peer-mapped address of its arrival_counters[2*dir + (1-side)]) — the pack loop and MPI_Isend of
- * export_to_ghosted_array_start (matrix_free/vector_partitioner.h:1387-1460) over NVLink.  Meanwhile the other warps
- * work through the interior cells and start on the boundary layer once arrival_counters[2*dir+side] has reached
- * epoch * (number of CTAs) for every ghost side the operator reads — export_to_ghosted_array_finish (:1482).
- * Counters are 2*HD_MAX_DIM 32-bit words in this GPU's memory, zero-initialised, never reset; epoch = 1, 2, 3, ... counts
- * the applications; all GPUs must run equal bricks (equal CTA counts).  Re-use of a ghost buffer is the caller's
- * business (double-buffer it and hand-shake with hd_stream_write_flag / hd_stream_wait_flag).
+/* Interior cells and boundary layer in ONE launch of the pipelined 3D3V kernel (HD_ERR_UNSUPPORTED for other
+ * configurations: use the two parts): the kernel works through the interior cells and starts on the boundary layer once
+ * arrival_counters[2*dir+side] >= target for every ghost side the operator reads — export_to_ghosted_array_finish
+ * (matrix_free/vector_partitioner.h:1482).  arrival_counters: 2*HD_MAX_DIM 32-bit words in this GPU's memory.
+ *  - n_sends == 0: the ghost data is produced by someone else (hd_halo_pack_ex on another stream, a neighbour GPU) who
+ *    then writes the counters, e.g. with hd_stream_write_flag.  NB: once this persistent kernel is resident no other
+ *    kernel gets an SM until it ends; a pack kernel must therefore have STARTED before this launch (gate the launch
+ *    with hd_stream_wait_flag on hd_halo_pack_ex's started_counter).
+ *  - n_sends > 0 (fused halo): one extra warp per CTA stores its share of this brick's boundary layers straight into
+ *    the neighbour GPUs' ghost segments (sends[i].dst: peer-mapped pointer of the segment (dir, 1-side) of the neighbour
+ *    behind side (dir, side)) and then adds 1 to sends[i].arrival_counter (peer-mapped address of that neighbour's
+ *    arrival_counters[2*dir + (1-side)]) — pack loop + MPI_Isend of export_to_ghosted_array_start (:1387-1460) over
+ *    NVLink inside the operator kernel.  Use target = applications so far * hd_advection_n_ctas (equal bricks on all
+ *    GPUs).
+ * Re-use of a ghost buffer is the caller's business (double-buffer it, hand-shake with hd_stream_write/wait_flag).
  * The wait gives up after 4 s; hd_advection_overlap_status then reports timed_out = 1 (and the result is invalid). */
 typedef struct hd_halo_send
 {
@@ -181,7 +185,9 @@ typedef struct hd_halo_send
   void *arrival_counter;  /* the neighbour's counter for that ghost side                */
 } hd_halo_send;
 int hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const hd_halo_send *sends, int n_sends,
-                                  const void *arrival_counters, int epoch);
+                                  const void *arrival_counters, int target);
+/* CTAs of the pipelined kernel on this mesh (0 if it does not apply). */
+int hd_advection_n_ctas(const hd_advection *op);
 int hd_advection_overlap_status(hd_advection *op, int *timed_out);
 /* Stream memory operations on the context's stream (no kernel launch): "*flag = value" (the address may be peer-mapped
  * memory of another GPU) and "wait until *flag >= value".  These carry the halo handshake between GPUs: data-ready
@@ -222,8 +228,11 @@ int     hd_halo_pack(hd_mesh *mesh, const void *src, void *send_buffer);
 /* Selective / direct variant: send_mask[2*dir+side] (NULL = all) selects the boundary layers to pack;
  * peer_dst[2*dir+side] (NULL or entry NULL = the send buffer segment) is a device pointer the layer is written to
  * instead — e.g. the peer-mapped address of the neighbour GPU's ghost segment (dir, 1-side), in which case the pack
- * kernel's stores travel over NVLink and no separate transport step is needed (the caller synchronises the GPUs). */
-int     hd_halo_pack_ex(hd_mesh *mesh, const void *src, void *send_buffer, const int *send_mask, void *const *peer_dst);
+ * kernel's stores travel over NVLink and no separate transport step is needed (the caller synchronises the GPUs).
+ * started_counter (optional, device int): every CTA adds 1 when it starts; *ctas_launched (optional) returns how many
+ * CTAs this call launched, so that "the pack kernels are resident" can be awaited with hd_stream_wait_flag. */
+int     hd_halo_pack_ex(hd_mesh *mesh, const void *src, void *send_buffer, const int *send_mask, void *const *peer_dst, void *started_counter,
+                        int *ctas_launched);
 int64_t hd_halo_offset(const hd_mesh *mesh, int dir, int side); /* offset (values) of a segment  */
 int64_t hd_halo_total(const hd_mesh *mesh);                     /* total values of all segments  */
 

@@ -77,7 +77,7 @@ def main():
             # fused variant: ONE kernel per step packs, sends over NVLink, does the interior, waits, does the boundary
             dst.zero_()
             for it in range(5):
-                g, sends, counters, epoch = peer.begin_fused(ctx)
+                g, sends, counters, epoch = peer.begin_fused(ctx, op)
                 op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
                 peer.consumed(ctx)
             torch.cuda.synchronize()

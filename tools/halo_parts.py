@@ -58,7 +58,7 @@ def serial():
     op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
     peer.consumed(ctx)
 def fused():
-    g, sends, counters, epoch = peer.begin_fused(ctx)
+    g, sends, counters, epoch = peer.begin_fused(ctx, op)
     op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
     peer.consumed(ctx)
 timeit("fused halo kernel step", fused)
