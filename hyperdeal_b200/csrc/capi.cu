@@ -1,5 +1,6 @@
 // C ABI of libhdgpu.so (see include/hyperdeal_b200.h for the contract and the reference
 // members each entry point replaces).
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -308,6 +309,13 @@ hd_context_create(int device, hd_context **out)
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   HD_CUDA(cudaEventCreate(&ctx->ev0));
   HD_CUDA(cudaEventCreate(&ctx->ev1));
+  if (const char *e = getenv("HD_PERSIST_L2_MB")) // experiment knob: L2 set-aside for evict_last lines (see HD_L2_HINTS)
+    {
+      size_t want = (size_t)atoll(e) << 20;
+      if (want > (size_t)prop.persistingL2CacheMaxSize)
+        want = (size_t)prop.persistingL2CacheMaxSize;
+      HD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    }
   *out = ctx;
   return HD_OK;
 }
@@ -698,6 +706,14 @@ hd_advection_destroy(hd_advection *op)
   cudaFree(op->d_coef);
   cudaFree(op->d_stage_src);
   cudaFree(op->d_stage_dst);
+  if (op->s_h2d)
+    cudaStreamDestroy(op->s_h2d);
+  if (op->s_d2h)
+    cudaStreamDestroy(op->s_d2h);
+  for (cudaEvent_t e : op->ev_in)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : op->ev_done)
+    cudaEventDestroy(e);
   for (int d = 0; d < HD_MAX_DIM; ++d)
     for (int s = 0; s < 2; ++s)
       cudaFree(op->d_g[d][s]);
@@ -712,6 +728,14 @@ hd_advection_set_kernel(hd_advection *op, int which)
   if (which == 2 && !hd::fast6d_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
   op->kernel_choice = which;
+  return HD_OK;
+}
+
+int
+hd_advection_set_l2_hints(hd_advection *op, int mask)
+{
+  HD_REQUIRE(op && mask >= -1 && mask <= 7, "bad argument");
+  op->l2_hints = mask;
   return HD_OK;
 }
 
@@ -880,8 +904,57 @@ hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, 
       HD_CUDA(cudaMalloc(&op->d_stage_src, bytes));
       HD_CUDA(cudaMalloc(&op->d_stage_dst, bytes));
     }
-  HD_CUDA(cudaMemcpyAsync(op->d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, m->ctx->stream));
   FusedUpdate fu;
+  // Pipelined variant (pipelined 3D3V kernel): the lattice is cut into its layers along the slowest direction; layer j
+  // is computed as soon as it and its upwind neighbour layer are on the device, and travels back while the next
+  // layers are still coming in — copy-in, kernel and copy-out run on three streams, PCIe in both directions at once.
+  const int  last = m->dim - 1, nl = m->d.n_cells[last];
+  const bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  if (fast && nl >= 3 && getenv("HD_HOST_SERIAL") == nullptr)
+    {
+      if (!op->s_h2d)
+        {
+          HD_CUDA(cudaStreamCreateWithFlags(&op->s_h2d, cudaStreamNonBlocking));
+          HD_CUDA(cudaStreamCreateWithFlags(&op->s_d2h, cudaStreamNonBlocking));
+        }
+      while ((int)op->ev_in.size() < nl)
+        {
+          cudaEvent_t a, b;
+          HD_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+          HD_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+          op->ev_in.push_back(a);
+          op->ev_done.push_back(b);
+        }
+      const size_t    slab  = bytes / nl;
+      const long long rows  = (m->ncells / m->d.n_cells[0]) / nl;
+      const int       delta = (op->nb_mask[last] & 1) ? -1 : ((op->nb_mask[last] & 2) ? +1 : 0);
+      const char *    hs    = static_cast<const char *>(src_host);
+      char *          hd_   = static_cast<char *>(dst_host);
+      char *          ds = static_cast<char *>(op->d_stage_src), *dd = static_cast<char *>(op->d_stage_dst);
+      // copy-in order: layer 0's upwind neighbour first (the periodic wrap), then ascending
+      for (int i = 0; i < nl; ++i)
+        {
+          const int j = delta < 0 ? (i + nl - 1) % nl : i;
+          HD_CUDA(cudaMemcpyAsync(ds + j * slab, hs + j * slab, slab, cudaMemcpyHostToDevice, op->s_h2d));
+          HD_CUDA(cudaEventRecord(op->ev_in[j], op->s_h2d));
+        }
+      for (int j = 0; j < nl; ++j)
+        {
+          HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[j], 0));
+          if (delta != 0)
+            HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[(j + delta + nl) % nl], 0));
+          int rc = hd::launch_fast6d(op, dd, ds, nullptr, time, fu, HD_PART_ALL, nullptr, 0, nullptr, 0, j * rows, (j + 1) * rows);
+          if (rc != HD_OK)
+            return rc;
+          HD_CUDA(cudaEventRecord(op->ev_done[j], m->ctx->stream));
+          HD_CUDA(cudaStreamWaitEvent(op->s_d2h, op->ev_done[j], 0));
+          HD_CUDA(cudaMemcpyAsync(hd_ + j * slab, dd + j * slab, slab, cudaMemcpyDeviceToHost, op->s_d2h));
+        }
+      HD_CUDA(cudaStreamSynchronize(op->s_d2h));
+      HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+      return HD_OK;
+    }
+  HD_CUDA(cudaMemcpyAsync(op->d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, m->ctx->stream));
   int         rc = apply_impl(op, op->d_stage_dst, op->d_stage_src, nullptr, time, fu);
   if (rc != HD_OK)
     return rc;

@@ -89,8 +89,12 @@ struct hd_advection
   int64_t g_count[HD_MAX_DIM][2];
   // staging for apply_host
   void *  d_stage_src = nullptr, *d_stage_dst = nullptr;
+  // apply_host pipeline: copy-in / copy-out streams and per-slab events (slabs = layers of the slowest direction)
+  cudaStream_t             s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
+  int   l2_hints   = -1; // pipelined kernel: L2 residency hints (bit mask), -1 = default (env HD_L2_HINTS or all)
 };
 
 struct hd_lsrk
@@ -116,7 +120,8 @@ namespace hd
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);
   int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part,
-                     const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_target = 0);
+                     const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_target = 0, long long row_begin = 0,
+                     long long row_end = -1);
   int  fast6d_overlap_status(hd_advection *op, int *timed_out);
   void fast6d_release(hd_advection *op);
   // dirichlet source term (kernels_generic.cu)

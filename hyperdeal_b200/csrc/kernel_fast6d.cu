@@ -60,9 +60,8 @@ namespace
     RoleCoef r[2]; // round 1: directions (0,1 | 5), round 2: (2,3 | 4)
   };
 
-  // (k+1)x(k+1) matrices of the current launch; DFMA reads them through the constant bank.
-  // Uploaded stream-ordered before every launch (launches of one device serialise on the context stream).
-  __constant__ FastCoef cf;
+  // The (k+1)x(k+1) matrices of a launch travel as a __grid_constant__ kernel parameter: DFMA reads them straight
+  // from the parameter constant bank (uniform operands), no upload, launches stay independent of each other.
 
   struct FastParams
   {
@@ -74,6 +73,7 @@ namespace
     int           up_kind[6];   // HD_SIDE_* of the brick side the upwind neighbour may lie behind
     long long     ghost_off[6]; // ghost segment of that side
     int           nrows;
+    int           row_begin, row_end; // rows [row_begin, row_end) of the lattice are processed (default: all)
     int *         counters; // [0] next row, [1] finished CTAs (self-resetting)
     double *      sol;
     double *      ti_next;
@@ -89,6 +89,10 @@ namespace
     int           send_dir[6], send_side[6];
     double *      send_dst[6];
     int *         send_flag[6];
+    // L2 residency hints (bit mask, HD_L2_HINTS): 1 = the direction-4 outflow layer of every cell is loaded evict_last
+    // (its downwind neighbour reads it ncell[1..3] rows later), 2 = the direction-4/5 face loads (last use resp.
+    // streaming miss) are evict_first, 4 = streaming (.cs) stores/loads of dst, sol, Ti'
+    int           hints;
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -138,6 +142,34 @@ namespace
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                  "l"(map), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
+  }
+  __device__ __forceinline__ void
+  tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint64_t policy)
+  {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+                 : "memory");
+  }
+  __device__ __forceinline__ void
+  tma_load_3d_hint(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar, uint64_t policy)
+  {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+                 : "memory");
+  }
+  __device__ __forceinline__ uint64_t
+  policy_evict_last()
+  {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+  }
+  __device__ __forceinline__ uint64_t
+  policy_evict_first()
+  {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
   }
   __device__ __forceinline__ void
   tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
@@ -269,11 +301,12 @@ namespace
   // unrolled form, 2 x 25 KiB, lost 30-45 % of its issue slots to instruction fetch: profiles/r01b).
   template <int ROLE, bool FUSED>
   __device__ __forceinline__ void
-  compute_round(const FastParams &p, const uint32_t base, unsigned char *gbase, const Bars bars, const int tid_in_role)
+  compute_round(const FastParams &p, const FastCoef &cf, const uint32_t base, unsigned char *gbase, const Bars bars, const int tid_in_role)
   {
     const bool      act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
     const bool      r1faces = act1 || act5;
     const bool      descend = p.up_delta[0] > 0;
+    const bool      stream  = (p.hints & 4) != 0;
     constexpr int   role    = ROLE;
     const RoleCoef &rc      = cf.r[ROLE];
     const int       lane    = tid_in_role & 31;
@@ -585,14 +618,23 @@ namespace
                     double sv[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                      sv[q] = solr[(q + 16 * cl) * 16];
+                      sv[q] = stream ? __ldcs(solr + (q + 16 * cl) * 16) : solr[(q + 16 * cl) * 16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
                       {
-                        const double kv          = acc[cl][q >> 2][q & 3];
-                        solw[(q + 16 * cl) * 16] = fma(p.fb, kv, sv[q]);
-                        if (p.fa != 0.0)
-                          tiw[(q + 16 * cl) * 16] = fma(p.fa, kv, sv[q]);
+                        const double kv = acc[cl][q >> 2][q & 3];
+                        if (stream)
+                          {
+                            __stcs(solw + (q + 16 * cl) * 16, fma(p.fb, kv, sv[q]));
+                            if (p.fa != 0.0)
+                              __stcs(tiw + (q + 16 * cl) * 16, fma(p.fa, kv, sv[q]));
+                          }
+                        else
+                          {
+                            solw[(q + 16 * cl) * 16] = fma(p.fb, kv, sv[q]);
+                            if (p.fa != 0.0)
+                              tiw[(q + 16 * cl) * 16] = fma(p.fa, kv, sv[q]);
+                          }
                       }
                   }
               }
@@ -605,7 +647,12 @@ namespace
                   for (int b = 0; b < 4; ++b)
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
-                      out[(a + 4 * b + 16 * cl) * 16] = acc[cl][b][a];
+                      {
+                        if (stream)
+                          __stcs(out + (a + 4 * b + 16 * cl) * 16, acc[cl][b][a]);
+                        else
+                          out[(a + 4 * b + 16 * cl) * 16] = acc[cl][b][a];
+                      }
               }
           }
       }
@@ -696,7 +743,8 @@ namespace
   __global__ void __launch_bounds__(HALO ? THREADS + 32 : THREADS, 1)
     k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
                      const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ CUtensorMap mapG1,
-                     const __grid_constant__ CUtensorMap mapG5, const FastParams p)
+                     const __grid_constant__ CUtensorMap mapG5, const __grid_constant__ CUtensorMap mapU16, const __grid_constant__ FastParams p,
+                     const __grid_constant__ FastCoef cf)
   {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw  = smem_u32(smem_raw);
@@ -749,8 +797,13 @@ namespace
           {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU16));
           }
         const uint32_t f_bytes  = (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
+        const bool     keep4    = (p.hints & 1) != 0 && p.up_delta[4] != 0;
+        const int      keep_row = p.up_delta[4] < 0 ? 48 : 0; // rows (i2,i3,i4) of a piece with i4 = 3 resp. 0
+        const bool     first5   = (p.hints & 2) != 0;
+        const uint64_t pol_last = policy_evict_last(), pol_first = policy_evict_first();
         const bool     ghost0   = act0 && p.up_kind[0] == HD_SIDE_GHOST;
         int            k        = 0; // cell sequence number of this CTA
         int            nrow_seq = 0; // row sequence number of this CTA
@@ -774,7 +827,8 @@ namespace
                   mode = row >= p.nrows ? 2 : 1;
                   row -= row >= p.nrows ? p.nrows : 0;
                 }
-              if (row >= p.nrows)
+              row += p.row_begin;
+              if (row >= p.row_end)
                 return false;
               int r = row;
 #pragma unroll
@@ -882,9 +936,29 @@ namespace
                     mbar_arrive(bars.infoFull(s)); // (release: the face producer may start on this cell's faces now)
                     const uint32_t dstU = base + s * U_BYTES;
                     mbar_expect_tx(bars.fullU(s), U_BYTES);
+                    if (keep4)
+                      {
+                        // the direction-4 outflow layer (16 of the 64 rows of every i5 piece) stays in L2 for the downwind
+                        // neighbour, which comes ncell[1]*ncell[2]*ncell[3] rows later; everything else is normal
 #pragma unroll
-                    for (int piece = 0; piece < 4; ++piece)
-                      tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), bars.fullU(s));
+                        for (int piece = 0; piece < 4; ++piece)
+                          {
+                            const int r0 = int(cell * 256 + piece * 64);
+                            tma_load_2d_hint(dstU + piece * 8192 + keep_row * 128, &mapU16, 0, r0 + keep_row, bars.fullU(s), pol_last);
+#pragma unroll
+                            for (int g = 0; g < 3; ++g)
+                              {
+                                const int rr = (keep_row == 0 ? 16 : 0) + 16 * g;
+                                tma_load_2d(dstU + piece * 8192 + rr * 128, &mapU16, 0, r0 + rr, bars.fullU(s));
+                              }
+                          }
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int piece = 0; piece < 4; ++piece)
+                          tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), bars.fullU(s));
+                      }
                   }
                 if (r1faces)
                   {
@@ -906,7 +980,13 @@ namespace
                             if (needs_ghost(p, c, 5)) // ghost segment viewed as rows of 16 doubles (128 B swizzle)
                               tma_load_2d(dstF + F_BYTES, &mapG5, 0, int((p.ghost_off[5] + face_cell(p, c, 5) * 1024) >> 4), bars.r1fFull(f));
                             else
-                              tma_load_2d(dstF + F_BYTES, &mapU, 0, int(upwind_cell(p, c, 5) * 256 + (p.up_delta[5] < 0 ? 192 : 0)), bars.r1fFull(f));
+                              {
+                                const int r5 = int(upwind_cell(p, c, 5) * 256 + (p.up_delta[5] < 0 ? 192 : 0));
+                                if (first5)
+                                  tma_load_2d_hint(dstF + F_BYTES, &mapU, 0, r5, bars.r1fFull(f), pol_first);
+                                else
+                                  tma_load_2d(dstF + F_BYTES, &mapU, 0, r5, bars.r1fFull(f));
+                              }
                           }
                       }
                   }
@@ -943,6 +1023,8 @@ namespace
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
+            const bool     first4    = (p.hints & 2) != 0;
+            const uint64_t pol_first = policy_evict_first();
             for (int k = 0;; ++k)
               {
                 const int s = k % STAGES;
@@ -977,6 +1059,8 @@ namespace
                           tma_load_3d(dstF, &mapT2, 0, layer, int(nb * 64), bars.r2fFull(f, j));
                         else if (d == 3)
                           tma_load_3d(dstF, &mapT3, 0, layer, int(nb * 16), bars.r2fFull(f, j));
+                        else if (first4)
+                          tma_load_3d_hint(dstF, &mapT4, 0, layer, int(nb * 4), bars.r2fFull(f, j), pol_first);
                         else
                           tma_load_3d(dstF, &mapT4, 0, layer, int(nb * 4), bars.r2fFull(f, j));
                       }
@@ -987,9 +1071,9 @@ namespace
     else if (HALO && warp == 10)
       halo_send(p, lane);
     else if (warp < 4)
-      compute_round<0, FUSED>(p, base, gbase, bars, tid);
+      compute_round<0, FUSED>(p, cf, base, gbase, bars, tid);
     else
-      compute_round<1, FUSED>(p, base, gbase, bars, tid - 128);
+      compute_round<1, FUSED>(p, cf, base, gbase, bars, tid - 128);
   }
 
   // ------------------------------------------------------------------------------- host side
@@ -998,7 +1082,7 @@ namespace
 
   struct Maps
   {
-    CUtensorMap u, t1, t2, t3, t4;
+    CUtensorMap u, u16, t1, t2, t3, t4;
   };
   struct GhostMaps
   {
@@ -1079,6 +1163,12 @@ namespace
                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (r != CUDA_SUCCESS)
             return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(u) failed with code " + std::to_string((int)r));
+          // the same view in boxes of 16 rows (one i4 layer of an i5 piece), for loads with per-layer L2 hints
+          box[1] = 16;
+          r      = st->encode(&m.u16, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS)
+            return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(u16) failed with code " + std::to_string((int)r));
         }
         int rc;
         if ((rc = encode_face_map(st, &m.t1, src, ncells, 1)) != HD_OK)
@@ -1159,7 +1249,7 @@ namespace hd
 
   int
   launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu, int part, const hd_halo_send *sends,
-                int n_sends, const void *halo_flag, int halo_target)
+                int n_sends, const void *halo_flag, int halo_target, long long row_begin, long long row_end)
   {
     hd_mesh *  m = op->mesh;
     FastState *st;
@@ -1202,6 +1292,13 @@ namespace hd
           Ld[i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
       }
     p.nrows    = (int)nrows;
+    if (row_end < 0)
+      row_end = nrows;
+    if (row_begin < 0 || row_begin > row_end || row_end > nrows || (part == 3 && (row_begin != 0 || row_end != nrows)))
+      return hd::fail(HD_ERR_INVALID, "bad row range");
+    p.row_begin = (int)row_begin;
+    p.row_end   = (int)row_end;
+    nrows       = row_end - row_begin; // (grid size)
     p.counters = st->d_counters;
     p.sol      = static_cast<double *>(fu.sol);
     p.ti_next  = static_cast<double *>(fu.ti_next);
@@ -1233,6 +1330,13 @@ namespace hd
           }
         p.n_sends = n_sends;
       }
+    {
+      static const int env_hints = [] {
+        const char *e = getenv("HD_L2_HINTS");
+        return e ? atoi(e) : 0; // measured on 8^6 cells: no gain from any combination (profiles/r01e_l2_hints.txt)
+      }();
+      p.hints = op->l2_hints >= 0 ? op->l2_hints : env_hints;
+    }
     p.halo_mask     = 0;
     for (int d = 0; d < 6; ++d)
       for (int sd = 0; sd < 2; ++sd)
@@ -1246,9 +1350,8 @@ namespace hd
         HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         st->attr_set[fidx] = true;
       }
-    HD_CUDA(cudaMemcpyToSymbolAsync(cf, &cfh, sizeof(FastCoef), 0, cudaMemcpyHostToDevice, m->ctx->stream));
     long long grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
-    kern<<<(unsigned)grid, halo ? THREADS + 32 : THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, p);
+    kern<<<(unsigned)grid, halo ? THREADS + 32 : THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, maps->u16, p, cfh);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = fu.enabled ? "advect_3d3v_k3_fused_lsrk" : "advect_3d3v_k3";

@@ -204,6 +204,10 @@ int hd_advection_ghost_sides(const hd_advection *op, int *needed);
 int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time);
 /* Select the kernel: 0 = automatic (fastest available), 1 = generic kernel, 2 = fused 3D3V k=3 kernel. */
 int hd_advection_set_kernel(hd_advection *op, int which);
+/* Pipelined 3D3V kernel: L2 residency hints, a bit mask (1: keep the direction-4 outflow layers in L2 for the downwind
+ * neighbour, 2: evict-first on the far face loads, 4: streaming stores; -1 = default = environment HD_L2_HINTS, else 0).
+ * A tuning knob, results do not depend on it. */
+int hd_advection_set_l2_hints(hd_advection *op, int mask);
 /* Name of the kernel the last apply launched (for logs and tests). */
 const char *hd_advection_kernel_name(const hd_advection *op);
 /* number of kernel launches issued by this operator so far */
