@@ -908,16 +908,20 @@ hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, 
   // Pipelined variant (pipelined 3D3V kernel): the lattice is cut into its layers along the slowest direction; layer j
   // is computed as soon as it and its upwind neighbour layer are on the device, and travels back while the next
   // layers are still coming in — copy-in, kernel and copy-out run on three streams, PCIe in both directions at once.
-  const int  last = m->dim - 1, nl = m->d.n_cells[last];
+  const int  last = m->dim - 1, n5 = m->d.n_cells[last];
   const bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
-  if (fast && nl >= 3 && getenv("HD_HOST_SERIAL") == nullptr)
+  if (fast && n5 >= 3 && getenv("HD_HOST_SERIAL") == nullptr)
     {
+      // units of the pipeline: layers of the slowest direction, cut again along the second slowest one if it is long
+      // enough (shorter start-up and drain: a unit waits for itself and its two upwind neighbour units only)
+      const int n4 = m->d.n_cells[last - 1] >= 3 ? m->d.n_cells[last - 1] : 1;
+      const int nu = n4 * n5;
       if (!op->s_h2d)
         {
           HD_CUDA(cudaStreamCreateWithFlags(&op->s_h2d, cudaStreamNonBlocking));
           HD_CUDA(cudaStreamCreateWithFlags(&op->s_d2h, cudaStreamNonBlocking));
         }
-      while ((int)op->ev_in.size() < nl)
+      while ((int)op->ev_in.size() < nu)
         {
           cudaEvent_t a, b;
           HD_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -925,31 +929,38 @@ hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, 
           op->ev_in.push_back(a);
           op->ev_done.push_back(b);
         }
-      const size_t    slab  = bytes / nl;
-      const long long rows  = (m->ncells / m->d.n_cells[0]) / nl;
-      const int       delta = (op->nb_mask[last] & 1) ? -1 : ((op->nb_mask[last] & 2) ? +1 : 0);
-      const char *    hs    = static_cast<const char *>(src_host);
-      char *          hd_   = static_cast<char *>(dst_host);
+      const size_t    unit = bytes / nu;
+      const long long rows = (m->ncells / m->d.n_cells[0]) / nu;
+      auto            upwind = [&](int d) { return (op->nb_mask[d] & 1) ? -1 : ((op->nb_mask[d] & 2) ? +1 : 0); };
+      const int       d5 = upwind(last), d4 = n4 > 1 ? upwind(last - 1) : 0;
+      const char *    hs = static_cast<const char *>(src_host);
+      char *          hd_ = static_cast<char *>(dst_host);
       char *          ds = static_cast<char *>(op->d_stage_src), *dd = static_cast<char *>(op->d_stage_dst);
-      // copy-in order: layer 0's upwind neighbour first (the periodic wrap), then ascending
-      for (int i = 0; i < nl; ++i)
-        {
-          const int j = delta < 0 ? (i + nl - 1) % nl : i;
-          HD_CUDA(cudaMemcpyAsync(ds + j * slab, hs + j * slab, slab, cudaMemcpyHostToDevice, op->s_h2d));
-          HD_CUDA(cudaEventRecord(op->ev_in[j], op->s_h2d));
-        }
-      for (int j = 0; j < nl; ++j)
-        {
-          HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[j], 0));
-          if (delta != 0)
-            HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[(j + delta + nl) % nl], 0));
-          int rc = hd::launch_fast6d(op, dd, ds, nullptr, time, fu, HD_PART_ALL, nullptr, 0, nullptr, 0, j * rows, (j + 1) * rows);
-          if (rc != HD_OK)
-            return rc;
-          HD_CUDA(cudaEventRecord(op->ev_done[j], m->ctx->stream));
-          HD_CUDA(cudaStreamWaitEvent(op->s_d2h, op->ev_done[j], 0));
-          HD_CUDA(cudaMemcpyAsync(hd_ + j * slab, dd + j * slab, slab, cudaMemcpyDeviceToHost, op->s_d2h));
-        }
+      // copy-in order: along each of the two directions the upwind neighbour of index 0 (the periodic wrap) goes first
+      for (int jj = 0; jj < n5; ++jj)
+        for (int ii = 0; ii < n4; ++ii)
+          {
+            const int    j = d5 < 0 ? (jj + n5 - 1) % n5 : jj, i = d4 < 0 ? (ii + n4 - 1) % n4 : ii;
+            const size_t u = (size_t)j * n4 + i;
+            HD_CUDA(cudaMemcpyAsync(ds + u * unit, hs + u * unit, unit, cudaMemcpyHostToDevice, op->s_h2d));
+            HD_CUDA(cudaEventRecord(op->ev_in[u], op->s_h2d));
+          }
+      for (int j = 0; j < n5; ++j)
+        for (int i = 0; i < n4; ++i)
+          {
+            const size_t u = (size_t)j * n4 + i;
+            HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[u], 0));
+            if (d4 != 0)
+              HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[(size_t)j * n4 + (i + d4 + n4) % n4], 0));
+            if (d5 != 0)
+              HD_CUDA(cudaStreamWaitEvent(m->ctx->stream, op->ev_in[(size_t)((j + d5 + n5) % n5) * n4 + i], 0));
+            int rc = hd::launch_fast6d(op, dd, ds, nullptr, time, fu, HD_PART_ALL, nullptr, 0, nullptr, 0, (long long)u * rows, (long long)(u + 1) * rows);
+            if (rc != HD_OK)
+              return rc;
+            HD_CUDA(cudaEventRecord(op->ev_done[u], m->ctx->stream));
+            HD_CUDA(cudaStreamWaitEvent(op->s_d2h, op->ev_done[u], 0));
+            HD_CUDA(cudaMemcpyAsync(hd_ + u * unit, dd + u * unit, unit, cudaMemcpyDeviceToHost, op->s_d2h));
+          }
       HD_CUDA(cudaStreamSynchronize(op->s_d2h));
       HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
       return HD_OK;

@@ -190,15 +190,15 @@ def test_apply_host_matches_device_path(api, ctx):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("a5", [0.5, -0.5, 0.0])
-@pytest.mark.parametrize("n5", [3, 5, 2])
-def test_apply_host_pipelined_3d3v(api, ctx, a5, n5):
+@pytest.mark.parametrize("a4,a5", [(-0.15, 0.5), (0.15, -0.5), (0.0, 0.0), (0.15, 0.5)])
+@pytest.mark.parametrize("n4,n5", [(2, 3), (3, 5), (4, 3), (2, 2)])
+def test_apply_host_pipelined_3d3v(api, ctx, a4, a5, n4, n5):
     """hd_advection_apply_host with the pipelined kernel: layers of the slowest direction are copied in, computed and
-    copied out on three streams (n5 >= 3; n5 = 2 takes the serial path).  Bit-identical to the device-resident apply,
+    copied out on three streams (n5 >= 3, cut again along direction 4 if n4 >= 3; n5 = 2 takes the serial path).  Bit-identical to the device-resident apply,
     for both upwind orientations of the slowest direction and for a_5 = 0."""
-    nc = (3, 2, 2, 2, 2, n5)
+    nc = (3, 2, 2, 2, n4, n5)
     mf = api.MatrixFree(ctx, 3, 3, 3, nc, (0.0,) * 6, (1.0,) * 6)
-    vel = tuple(VEL[:5]) + (a5,)
+    vel = tuple(VEL[:4]) + (a4, a5)
     op = api.AdvectionOperation(mf, vel, 0.5)
     src = np.random.default_rng(5).standard_normal(mf.n_dofs)
     d_src, d_dst = mf.initialize_dof_vector(), mf.initialize_dof_vector()
