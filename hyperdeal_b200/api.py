@@ -33,7 +33,7 @@ EXPORTS = [
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
@@ -110,6 +110,7 @@ def lib():
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
     L.hd_advection_set_l2_hints.argtypes = [c_void_p, c_int]
+    L.hd_advection_set_row_tile.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_advection_set_dirichlet_values.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64]
     L.hd_advection_set_dirichlet_builtin.argtypes = [c_void_p, c_int]
     L.hd_halo_pack.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -305,6 +306,10 @@ class AdvectionOperation:
 
     def set_l2_hints(self, mask: int):
         _check(lib().hd_advection_set_l2_hints(self._h, mask))
+
+    def set_row_tile(self, tile):
+        """rows per tile along directions 1..5 of the pipelined kernel's cell traversal (hd_advection_set_row_tile)"""
+        _check(lib().hd_advection_set_row_tile(self._h, (c_int * 5)(*[int(x) for x in tile])))
 
     @property
     def kernel_name(self) -> str:

@@ -1,0 +1,792 @@
+// hyperdeal_b200.hpp — header-only C++ host layer over the C ABI of libhdgpu.so
+// (include/hyperdeal_b200.h).
+//
+// It re-creates, for the advection hot path, the class and method names a hyper.deal driver
+// uses, so that examples/advection and performance/operators_advection_* read
+// the same after switching the include.  Every class cites the reference declaration it mirrors
+// (paths relative to the hyper.deal source tree).  Nothing is computed on the host: each method
+// forwards to one C-ABI call; failures of the library surface as hyperdeal::ExcMessage
+// (the reference's AssertThrow -> exception convention, drivers catch in main and return 1).
+//
+// What cannot be mirrored: user-supplied cell/face lambdas (MatrixFree::cell_loop / loop with
+// FEEvaluation objects) cannot run on the device; those members exist and throw
+// ExcNotImplemented, like the reference does for unsupported options
+// (matrix_free/matrix_free.templates.h:870-875).
+#ifndef HYPERDEAL_B200_HPP
+#define HYPERDEAL_B200_HPP
+
+#include <hyperdeal_b200.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+namespace hyperdeal
+{
+  // ---- errors -------------------------------------------------------------------------------
+  struct ExcMessage : std::runtime_error
+  {
+    explicit ExcMessage(const std::string &m)
+      : std::runtime_error(m)
+    {}
+  };
+  struct ExcNotImplemented : ExcMessage
+  {
+    explicit ExcNotImplemented(const std::string &what = "")
+      : ExcMessage("ExcNotImplemented: " + what)
+    {}
+  };
+
+  namespace internal
+  {
+    inline void
+    check(const int rc, const char *call)
+    {
+      if (rc < 0)
+        throw ExcMessage(std::string(call) + ": " + hd_last_error() + " (code " + std::to_string(rc) + ")");
+    }
+    template <typename Number>
+    constexpr int
+    number_type()
+    {
+      static_assert(std::is_same<Number, double>::value || std::is_same<Number, float>::value, "Number must be double or float");
+      return std::is_same<Number, double>::value ? HD_F64 : HD_F32;
+    }
+  } // namespace internal
+#define HD_CALL(expr) ::hyperdeal::internal::check((expr), #expr)
+
+  // ---- the few deal.II vocabulary types the signatures mention --------------------------------
+  namespace dealii_compat
+  {
+    namespace types
+    {
+      using boundary_id = unsigned int;
+    }
+
+    template <int rank, int dim, typename Number = double>
+    class Tensor;
+    template <int dim, typename Number>
+    class Tensor<1, dim, Number>
+    {
+    public:
+      Tensor() { v.fill(Number(0)); }
+      Number &operator[](const unsigned int i) { return v[i]; }
+      const Number &operator[](const unsigned int i) const { return v[i]; }
+
+    protected:
+      std::array<Number, dim> v;
+    };
+
+    template <int dim, typename Number = double>
+    class Point : public Tensor<1, dim, Number>
+    {
+    public:
+      Point() = default;
+      explicit Point(const Number x) { this->v[0] = x; }
+      Point(const Number x, const Number y)
+      {
+        this->v[0] = x;
+        this->v[1] = y;
+      }
+      Point(const Number x, const Number y, const Number z)
+      {
+        this->v[0] = x;
+        this->v[1] = y;
+        this->v[2] = z;
+      }
+    };
+
+    // dealii::Function: value(p) + the time the drivers set before evaluating it.
+    template <int dim, typename Number = double>
+    class Function
+    {
+    public:
+      virtual ~Function() = default;
+      virtual Number value(const Point<dim, Number> &, const unsigned int = 0) const { return Number(0); }
+      void   set_time(const Number t) { time = t; }
+      Number get_time() const { return time; }
+      // id of the device-side implementation of this field (HD_FN_*), or -1 if it only exists on the host
+      virtual int device_function_id() const { return -1; }
+
+    private:
+      Number time = Number(0);
+    };
+    namespace Functions
+    {
+      template <int dim, typename Number = double>
+      class ZeroFunction : public Function<dim, Number>
+      {
+      public:
+        int device_function_id() const override { return HD_FN_ZERO; }
+      };
+    } // namespace Functions
+  }   // namespace dealii_compat
+
+  // ---- communicator stand-in: one process = one GPU ---------------------------------------------
+  // Takes the place of the (comm, comm_sm) pair of hyperdeal::MatrixFree's constructor (matrix_free/matrix_free.h:108).
+  class DeviceCommunicator
+  {
+  public:
+    explicit DeviceCommunicator(const int device = 0)
+    {
+      HD_CALL(hd_context_create(device, &ctx));
+    }
+    ~DeviceCommunicator()
+    {
+      if (ctx)
+        hd_context_destroy(ctx);
+    }
+    DeviceCommunicator(const DeviceCommunicator &) = delete;
+    DeviceCommunicator &operator=(const DeviceCommunicator &) = delete;
+    hd_context *context() const { return ctx; }
+    void        set_stream(void *cuda_stream) const { HD_CALL(hd_context_set_stream(ctx, cuda_stream)); }
+    void        synchronize() const { HD_CALL(hd_context_synchronize(ctx)); }
+
+  private:
+    hd_context *ctx = nullptr;
+  };
+
+  // ---- low-dimensional lattice: what the two dealii::MatrixFree arguments describe on this path ----
+  // (subdivided_hyper_rectangle, grid/grid_generator.cc:235, with FE_DGQ(degree) and QGauss(n_points) or the
+  // collocation quadrature, tests/tests_mf.h:162-202)
+  template <int dim>
+  struct CartesianLattice
+  {
+    std::array<double, dim>       left{}, right{};
+    std::array<unsigned int, dim> n_cells{};
+    bool                          periodic    = true;
+    unsigned int                  degree      = 3;
+    unsigned int                  n_points    = 4;
+    bool                          collocation = false;
+  };
+
+  template <typename Number>
+  class DeviceVector;
+
+  // ---- hyperdeal::MatrixFree (matrix_free/matrix_free.h:39) ------------------------------------------
+  template <int dim_x, int dim_v, typename Number = double>
+  class MatrixFree
+  {
+  public:
+    static const int dim = dim_x + dim_v;
+
+    struct AdditionalData // matrix_free.h:63-102
+    {
+      AdditionalData()
+        : do_ghost_faces(true)
+        , do_buffering(false)
+        , use_ecl(true)
+        , overlapping_level(0)
+      {}
+      bool         do_ghost_faces;
+      bool         do_buffering;
+      bool         use_ecl;
+      unsigned int overlapping_level;
+    };
+
+    MatrixFree(const DeviceCommunicator &comm, const CartesianLattice<dim_x> &matrix_free_x, const CartesianLattice<dim_v> &matrix_free_v)
+      : comm(comm)
+      , lattice_x(matrix_free_x)
+      , lattice_v(matrix_free_v)
+    {}
+    ~MatrixFree()
+    {
+      if (mesh)
+        hd_mesh_destroy(mesh);
+    }
+    MatrixFree(const MatrixFree &) = delete;
+    MatrixFree &operator=(const MatrixFree &) = delete;
+
+    // matrix_free.templates.h:862: builds the device-side lattice description.  FCL (use_ecl = false) and buffering give
+    // the same results as ECL and are served by the same kernels; ghost cells are refused as in the reference (:870).
+    void
+    reinit(const AdditionalData &ad = AdditionalData())
+    {
+      if (!ad.do_ghost_faces)
+        throw ExcNotImplemented("ghost cells (do_ghost_faces = false)");
+      if (lattice_x.degree != lattice_v.degree || lattice_x.n_points != lattice_v.n_points || lattice_x.collocation != lattice_v.collocation)
+        throw ExcNotImplemented("different degree / quadrature in x and v");
+      additional_data = ad;
+      hd_mesh_desc d{};
+      d.dim_x       = dim_x;
+      d.dim_v       = dim_v;
+      d.degree      = lattice_x.degree;
+      d.n_points    = lattice_x.n_points;
+      d.collocation = lattice_x.collocation;
+      d.number_type = internal::number_type<Number>();
+      for (int i = 0; i < HD_MAX_DIM; ++i)
+        {
+          d.left[i]           = 0.0;
+          d.right[i]          = 1.0;
+          d.n_cells_global[i] = d.n_cells[i] = 1;
+          d.cell_offset[i]                   = 0;
+          d.side_kind[i][0] = d.side_kind[i][1] = HD_SIDE_PERIODIC_LOCAL;
+        }
+      for (int i = 0; i < dim; ++i)
+        {
+          const bool in_x     = i < dim_x;
+          const int  j        = in_x ? i : i - dim_x;
+          d.left[i]           = in_x ? lattice_x.left[j] : lattice_v.left[j];
+          d.right[i]          = in_x ? lattice_x.right[j] : lattice_v.right[j];
+          d.n_cells_global[i] = d.n_cells[i] = in_x ? lattice_x.n_cells[j] : lattice_v.n_cells[j];
+          const bool periodic                = in_x ? lattice_x.periodic : lattice_v.periodic;
+          d.side_kind[i][0] = d.side_kind[i][1] = periodic ? HD_SIDE_PERIODIC_LOCAL : HD_SIDE_DIRICHLET;
+        }
+      if (mesh)
+        hd_mesh_destroy(mesh);
+      mesh = nullptr;
+      HD_CALL(hd_mesh_create(comm.context(), &d, &mesh));
+      desc = d;
+    }
+
+    // matrix_free.templates.h:1369
+    void
+    initialize_dof_vector(DeviceVector<Number> &vec, const unsigned int dof_handler_index = 0, const bool do_ghosts = true, const bool zero_out = true) const
+    {
+      if (dof_handler_index != 0)
+        throw ExcNotImplemented("dof_handler_index != 0");
+      vec.reinit(mesh, do_ghosts);
+      (void)zero_out; // vectors are always zero-initialised (hd_vector_alloc)
+    }
+
+    // user-supplied host lambdas cannot run on the device (see the header comment)
+    template <typename OutVector, typename InVector, typename Fn>
+    void
+    cell_loop(const Fn &, OutVector &, const InVector &) const
+    {
+      throw ExcNotImplemented("MatrixFree::cell_loop with a host lambda; use advection::AdvectionOperation / VectorTools");
+    }
+    template <typename OutVector, typename InVector, typename Fn>
+    void
+    loop_cell_centric(const Fn &, OutVector &, const InVector &) const
+    {
+      throw ExcNotImplemented("MatrixFree::loop_cell_centric with a host lambda");
+    }
+
+    const DeviceCommunicator &get_communicator() const { return comm; }
+    bool                      is_ecl_supported() const { return true; }
+    bool                      are_ghost_faces_supported() const { return true; }
+    const CartesianLattice<dim_x> &get_matrix_free_x() const { return lattice_x; }
+    const CartesianLattice<dim_v> &get_matrix_free_v() const { return lattice_v; }
+    const AdditionalData &         get_additional_data() const { return additional_data; }
+    hd_mesh *                      get_mesh() const { return mesh; }
+    const hd_mesh_desc &           get_mesh_desc() const { return desc; }
+    std::int64_t                   n_dofs() const { return hd_mesh_n_dofs(mesh); }
+    std::int64_t                   n_cells() const { return hd_mesh_n_cells(mesh); }
+    // boundary id of side (direction, side) as subdivided_hyper_rectangle leaves it (grid/grid_generator.cc:235, no
+    // colorize): 0 everywhere, except that a 1-D triangulation numbers its two end points 0 and 1 — the reason for the
+    // "hack for 1D" in examples/advection/cases/hyperrectangle.h:190-199
+    dealii_compat::types::boundary_id
+    get_boundary_id(const unsigned int direction, const unsigned int side) const
+    {
+      const bool one_d = direction < (unsigned int)dim_x ? dim_x == 1 : dim_v == 1;
+      return one_d ? side : 0;
+    }
+    std::size_t
+    memory_consumption() const
+    {
+      return sizeof(*this);
+    }
+
+  private:
+    const DeviceCommunicator &comm;
+    CartesianLattice<dim_x>   lattice_x;
+    CartesianLattice<dim_v>   lattice_v;
+    AdditionalData            additional_data;
+    hd_mesh *                 mesh = nullptr;
+    hd_mesh_desc              desc{};
+  };
+
+  // ---- VectorType: dealii::LinearAlgebra::distributed::Vector<Number> on the device ------------------------
+  // Members the drivers use: begin(), operator=(0), zero_out_ghost_values, has_ghost_elements, size,
+  // memory_consumption; plus explicit host transfers.
+  template <typename Number>
+  class DeviceVector
+  {
+  public:
+    using value_type = Number;
+    DeviceVector()   = default;
+    ~DeviceVector() { clear(); }
+    DeviceVector(const DeviceVector &) = delete;
+    DeviceVector &operator=(const DeviceVector &) = delete;
+
+    void
+    reinit(hd_mesh *m, const bool do_ghosts)
+    {
+      clear();
+      mesh    = m;
+      ghosted = do_ghosts;
+      HD_CALL(hd_vector_alloc(mesh, do_ghosts ? 1 : 0, &ptr));
+      n = hd_mesh_n_dofs(mesh);
+    }
+    void
+    clear()
+    {
+      if (ptr)
+        hd_vector_free(mesh, ptr);
+      ptr = nullptr;
+    }
+    Number *      begin() { return static_cast<Number *>(ptr); }
+    const Number *begin() const { return static_cast<const Number *>(ptr); }
+    std::int64_t  size() const { return n; }
+    std::int64_t  locally_owned_size() const { return n; }
+    bool          has_ghost_elements() const { return ghosted; }
+    void          zero_out_ghost_values() const {}
+    std::size_t   memory_consumption() const { return std::size_t(n) * sizeof(Number); }
+    hd_mesh *     get_mesh() const { return mesh; }
+    DeviceVector &
+    operator=(const Number s)
+    {
+      if (s != Number(0))
+        throw ExcNotImplemented("vector = s with s != 0");
+      HD_CALL(hd_vector_zero(mesh, ptr));
+      return *this;
+    }
+    void
+    copy_locally_owned_data_from(const DeviceVector &src)
+    {
+      HD_CALL(hd_vector_copy(mesh, ptr, src.ptr));
+    }
+    void
+    copy_from_host(const std::vector<Number> &h)
+    {
+      HD_CALL(hd_vector_copy_in(mesh, ptr, h.data(), std::int64_t(h.size())));
+    }
+    void
+    copy_to_host(std::vector<Number> &h) const
+    {
+      h.resize(n);
+      HD_CALL(hd_vector_copy_out(mesh, ptr, h.data(), n));
+    }
+
+  private:
+    hd_mesh *    mesh    = nullptr;
+    void *       ptr     = nullptr;
+    std::int64_t n       = 0;
+    bool         ghosted = false;
+  };
+
+  // ---- timers (base/timers.h:36): device-event timing of a section on the context's stream -------------------
+  class Timers
+  {
+  public:
+    explicit Timers(const bool = false) {}
+    struct Timer
+    {
+      double       accumulated_us = 0;
+      unsigned int counter        = 0;
+      double       get_accumulated_time() const { return accumulated_us; }
+      unsigned int get_counter() const { return counter; }
+    };
+    Timer &operator[](const std::string &label) { return timers[label]; }
+    void   reset() { timers.clear(); }
+
+  private:
+    std::map<std::string, Timer> timers;
+  };
+  class DynamicConvergenceTable // base/dynamic_convergence_table.h: label -> value rows
+  {
+  public:
+    void set(const std::string &label, const double v) { values[label] = v; }
+    void
+    print() const
+    {
+      for (const auto &kv : values)
+        std::printf("%-40s %.10g\n", kv.first.c_str(), kv.second);
+    }
+    std::map<std::string, double> values;
+  };
+
+  namespace advection
+  {
+    // operators/advection/advection_operation_parameters.h:29-41 (sic: "Paramters")
+    struct AdvectionOperationParamters
+    {
+      double factor_skew = 0.0;
+    };
+
+    enum class BoundaryType // boundary_descriptor.h:31-37
+    {
+      Undefined,
+      DirichletInhomogenous,
+      DirichletHomogenous,
+    };
+
+    // boundary_descriptor.h:42-107
+    template <int dim, typename Number>
+    struct BoundaryDescriptor
+    {
+      std::map<dealii_compat::types::boundary_id, std::shared_ptr<dealii_compat::Function<dim, Number>>> dirichlet_bc;
+      std::set<dealii_compat::types::boundary_id>                                                        homogeneous_dirichlet_bc;
+
+      std::pair<BoundaryType, std::shared_ptr<dealii_compat::Function<dim, Number>>>
+      get_boundary(const dealii_compat::types::boundary_id &boundary_id) const
+      {
+        const auto it = dirichlet_bc.find(boundary_id);
+        if (it != dirichlet_bc.end())
+          return {BoundaryType::DirichletInhomogenous, it->second};
+        if (homogeneous_dirichlet_bc.count(boundary_id))
+          return {BoundaryType::DirichletHomogenous, std::make_shared<dealii_compat::Functions::ZeroFunction<dim, Number>>()};
+        throw ExcMessage("Boundary type of face is invalid or not implemented.");
+      }
+      void
+      set_time(const Number time)
+      {
+        for (auto &bc : dirichlet_bc)
+          bc.second->set_time(time);
+      }
+    };
+
+    // operators/advection/velocity_field_view.h:69-166
+    template <int dim, typename Number>
+    class ConstantVelocityFieldView
+    {
+    public:
+      explicit ConstantVelocityFieldView(const dealii_compat::Tensor<1, dim, Number> &transport_direction)
+        : transport_direction(transport_direction)
+      {}
+      const dealii_compat::Tensor<1, dim, Number> &get_transport_direction() const { return transport_direction; }
+
+    private:
+      dealii_compat::Tensor<1, dim, Number> transport_direction;
+    };
+
+    enum class AdvectionOperationEvaluationLevel // advection_operation.h:44-50; only `all` has a device path
+    {
+      cell,
+      all_without_neighbor_load,
+      all
+    };
+
+    // operators/advection/advection_operation.h:56
+    template <int dim_x, int dim_v, int degree, int n_points, typename Number, typename VectorType, typename VelocityField>
+    class AdvectionOperation
+    {
+    public:
+      static const int dim = dim_x + dim_v;
+
+      AdvectionOperation(const MatrixFree<dim_x, dim_v, Number> &data, DynamicConvergenceTable &table)
+        : data(data)
+        , table(table)
+      {}
+      ~AdvectionOperation()
+      {
+        if (op)
+          hd_advection_destroy(op);
+      }
+      AdvectionOperation(const AdvectionOperation &) = delete;
+      AdvectionOperation &operator=(const AdvectionOperation &) = delete;
+
+      // advection_operation.h:98
+      void
+      reinit(std::shared_ptr<BoundaryDescriptor<dim, Number>> boundary_descriptor, std::shared_ptr<VelocityField> velocity_field, const AdvectionOperationParamters additional_data)
+      {
+        const auto &d = data.get_mesh_desc();
+        if (d.degree != degree || d.n_points != n_points)
+          throw ExcMessage("Degrees " + std::to_string(d.degree) + " and " + std::to_string(degree) + " do not match!");
+        this->boundary_descriptor = boundary_descriptor;
+        this->velocity_field      = velocity_field;
+        double a[HD_MAX_DIM]      = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < dim; ++i)
+          a[i] = velocity_field->get_transport_direction()[i];
+        if (op)
+          hd_advection_destroy(op);
+        op = nullptr;
+        HD_CALL(hd_advection_create(data.get_mesh(), additional_data.factor_skew, a, &op));
+        // Dirichlet sides: u+ = -u- + 2 g; g comes from the descriptor (advection_operation.h:484-520)
+        host_sampled_bc = false;
+        for (int dir = 0; dir < dim; ++dir)
+          for (int side = 0; side < 2; ++side)
+            if (d.side_kind[dir][side] == HD_SIDE_DIRICHLET)
+              {
+                const auto bc = boundary_descriptor->get_boundary(data.get_boundary_id(dir, side));
+                const int  id = bc.second->device_function_id();
+                if (id >= 0)
+                  HD_CALL(hd_advection_set_dirichlet_builtin(op, id));
+                else
+                  host_sampled_bc = true;
+              }
+      }
+
+      // advection_operation.h:137: dst = M^-1 A(src, time)
+      template <AdvectionOperationEvaluationLevel eval_level = AdvectionOperationEvaluationLevel::all>
+      void
+      apply(VectorType &dst, const VectorType &src, const Number time, Timers * = nullptr)
+      {
+        if (eval_level != AdvectionOperationEvaluationLevel::all)
+          throw ExcNotImplemented("partial evaluation levels (profiling variants of the CPU kernel)");
+        if (host_sampled_bc)
+          upload_dirichlet_values(time);
+        HD_CALL(hd_advection_apply(op, dst.begin(), src.begin(), nullptr, double(time)));
+      }
+
+      hd_advection *handle() const { return op; }
+      const char *  kernel_name() const { return hd_advection_kernel_name(op); }
+      const MatrixFree<dim_x, dim_v, Number> &get_matrix_free() const { return data; }
+
+    private:
+      // boundary data that only exists as a host dealii::Function: sample g at the face quadrature points of every
+      // boundary face for the stage time (MatrixFreeTools::evaluate_scalar_function, matrix_free/tools.h:31) and upload
+      void
+      upload_dirichlet_values(const Number time)
+      {
+        const auto &        d  = data.get_mesh_desc();
+        const int           nq = d.n_points;
+        std::vector<double> xq(nq);
+        hd_mesh_basis(data.get_mesh(), 1, xq.data());
+        boundary_descriptor->set_time(time);
+        for (int dir = 0; dir < dim; ++dir)
+          for (int side = 0; side < 2; ++side)
+            {
+              if (d.side_kind[dir][side] != HD_SIDE_DIRICHLET)
+                continue;
+              const auto bc = boundary_descriptor->get_boundary(data.get_boundary_id(dir, side));
+              if (bc.second->device_function_id() >= 0)
+                continue;
+              std::int64_t n_face_cells = 1, n_face_q = 1;
+              for (int e = 0; e < dim; ++e)
+                if (e != dir)
+                  {
+                    n_face_cells *= d.n_cells[e];
+                    n_face_q *= nq;
+                  }
+              std::vector<double>                g(n_face_cells * n_face_q);
+              dealii_compat::Point<dim, Number> p;
+              for (std::int64_t fc = 0; fc < n_face_cells; ++fc)
+                for (std::int64_t q = 0; q < n_face_q; ++q)
+                  {
+                    std::int64_t c = fc, qq = q;
+                    for (int e = 0; e < dim; ++e)
+                      {
+                        const double h = (d.right[e] - d.left[e]) / d.n_cells_global[e];
+                        if (e == dir)
+                          {
+                            p[e] = side == 0 ? d.left[e] : d.right[e];
+                            continue;
+                          }
+                        const int ce = c % d.n_cells[e];
+                        c /= d.n_cells[e];
+                        const int qe = qq % nq;
+                        qq /= nq;
+                        p[e] = d.left[e] + (d.cell_offset[e] + ce + xq[qe]) * h;
+                      }
+                    g[fc * n_face_q + q] = bc.second->value(p);
+                  }
+              HD_CALL(hd_advection_set_dirichlet_values(op, dir, side, g.data(), std::int64_t(g.size())));
+            }
+      }
+
+      const MatrixFree<dim_x, dim_v, Number> &         data;
+      DynamicConvergenceTable &                        table;
+      std::shared_ptr<BoundaryDescriptor<dim, Number>> boundary_descriptor;
+      std::shared_ptr<VelocityField>                   velocity_field;
+      hd_advection *                                   op              = nullptr;
+      bool                                             host_sampled_bc = false;
+    };
+
+    // operators/advection/cfl.h:58-124 on a Cartesian lattice: the inverse Jacobian is diag(1/h_d), so the critical
+    // step of one space is 1 / max_d |u_d / h_d|, and the phase-space value is the minimum over x and v.
+    template <int dim_x, int dim_v, typename Number>
+    Number
+    compute_critical_time_step(const MatrixFree<dim_x, dim_v, Number> &matrix_free, const dealii_compat::Tensor<1, dim_x + dim_v, Number> &u)
+    {
+      const auto &d        = matrix_free.get_mesh_desc();
+      Number      crit[2]  = {std::numeric_limits<Number>::infinity(), std::numeric_limits<Number>::infinity()};
+      Number      v_max[2] = {0, 0};
+      for (int i = 0; i < dim_x + dim_v; ++i)
+        {
+          const Number h = (d.right[i] - d.left[i]) / d.n_cells_global[i];
+          v_max[i < dim_x ? 0 : 1] = std::max(v_max[i < dim_x ? 0 : 1], std::abs(u[i] / h));
+        }
+      for (int s = 0; s < 2; ++s)
+        crit[s] = Number(1.0) / v_max[s];
+      return std::min(crit[0], crit[1]);
+    }
+  } // namespace advection
+
+  // ---- base/time_integrators.h:48 ---------------------------------------------------------------------------
+  template <typename Number, typename VectorType>
+  class LowStorageRungeKuttaIntegrator
+  {
+  public:
+    LowStorageRungeKuttaIntegrator(VectorType &vec_Ki, VectorType &vec_Ti, const std::string type, const bool only_Ti_is_ghosted = true)
+      : vec_Ki(vec_Ki)
+      , vec_Ti(vec_Ti)
+      , only_Ti_is_ghosted(only_Ti_is_ghosted)
+    {
+      HD_CALL(hd_lsrk_create(vec_Ti.get_mesh(), type.c_str(), &rk));
+      const int s = hd_lsrk_n_stages(rk);
+      bi.resize(s);
+      ai.resize(std::max(s - 1, 1));
+      hd_lsrk_coefficients(rk, 0, bi.data());
+      hd_lsrk_coefficients(rk, 1, ai.data());
+      ai.resize(s - 1);
+    }
+    ~LowStorageRungeKuttaIntegrator()
+    {
+      if (rk)
+        hd_lsrk_destroy(rk);
+    }
+
+    // the reference signature (time_integrators.h:66-72; note the (src, dst) order of `op`): unfused — `op` is any
+    // callable that fills dst on the device, the stage update is one streaming kernel (hd_lsrk_stage_update)
+    void
+    perform_time_step(VectorType &solution, const Number &current_time, const Number &time_step, const std::function<void(const VectorType &, VectorType &, const Number)> &op)
+    {
+      vec_Ti.copy_locally_owned_data_from(solution); // time_integrators.templates.h:146-163 (only_Ti_is_ghosted branch)
+      double sum_previous_bi = 0.0;
+      for (unsigned int stage = 0; stage < bi.size(); ++stage)
+        {
+          double c_i = 0.0;
+          if (stage > 0)
+            {
+              c_i = sum_previous_bi + ai[stage - 1];
+              sum_previous_bi += bi[stage - 1];
+            }
+          op(vec_Ti, vec_Ki, Number(current_time + c_i * time_step));
+          const double fa = stage + 1 == bi.size() ? 0.0 : ai[stage] * time_step;
+          HD_CALL(hd_lsrk_stage_update(vec_Ti.get_mesh(), solution.begin(), vec_Ti.begin(), vec_Ki.begin(), bi[stage] * time_step, fa));
+        }
+    }
+
+    // fused device path: the operator applies the stage update in its epilogue (32 instead of 48 B/DoF per stage)
+    template <int dim_x, int dim_v, int degree, int n_points, typename VelocityField>
+    void
+    perform_time_step(VectorType &solution, const Number &current_time, const Number &time_step,
+                      advection::AdvectionOperation<dim_x, dim_v, degree, n_points, Number, VectorType, VelocityField> &op)
+    {
+      HD_CALL(hd_lsrk_step(rk, op.handle(), solution.begin(), vec_Ki.begin(), vec_Ti.begin(), double(current_time), double(time_step)));
+    }
+
+    unsigned int n_stages() const { return bi.size(); }
+
+  private:
+    VectorType &        vec_Ki;
+    VectorType &        vec_Ti;
+    const bool          only_Ti_is_ghosted;
+    std::vector<double> ai, bi;
+    hd_lsrk *           rk = nullptr;
+  };
+
+  // ---- base/time_loop_parameters.h:27-49, base/time_loop.h:30-80 ------------------------------------------------
+  template <typename Number>
+  struct TimeLoopParamters
+  {
+    Number       time_step            = 0.1;
+    Number       start_time           = 0.0;
+    Number       final_time           = 20.0;
+    unsigned int max_time_step_number = 100000000;
+  };
+
+  template <typename Number, typename VectorType>
+  class TimeLoop
+  {
+  public:
+    void
+    reinit(const TimeLoopParamters<Number> &p)
+    {
+      time_step            = p.time_step;
+      start_time           = p.start_time;
+      final_time           = p.final_time;
+      max_time_step_number = p.max_time_step_number;
+    }
+    // source/base/time_loop.cc:35-67
+    int
+    loop(VectorType &                                                                                                                                         solution,
+         const std::function<void(VectorType &, const Number, const Number, const std::function<void(const VectorType &, VectorType &, const Number)> &)> &time_integrator,
+         const std::function<void(const VectorType &, VectorType &, const Number)> &                                                                      runnable,
+         const std::function<void(const Number)> &                                                                                                        diagnostics)
+    {
+      unsigned int time_step_number = 1;
+      diagnostics(start_time);
+      for (Number time = start_time + time_step; time <= final_time * (1.0000000000001) && time_step_number <= max_time_step_number; time += time_step, ++time_step_number)
+        {
+          time_integrator(solution, time - time_step, time_step, runnable);
+          diagnostics(time);
+        }
+      return time_step_number - 1;
+    }
+    Number       time_step            = 0.1;
+    Number       start_time           = 0.0;
+    Number       final_time           = 20.0;
+    unsigned int max_time_step_number = 100000000;
+  };
+
+  // ---- numerics/vector_tools.h:88, :151 --------------------------------------------------------------------------
+  namespace VectorTools
+  {
+    // nodal interpolation at the Gauss-Lobatto points.  A function with a device implementation is evaluated on the
+    // GPU; any other dealii::Function is sampled by the host at the nodes and uploaded (input preparation only).
+    template <int degree, int n_points, int dim_x, int dim_v, typename Number, typename VectorType>
+    void
+    interpolate(const std::shared_ptr<dealii_compat::Function<dim_x + dim_v, Number>> analytical_solution, const MatrixFree<dim_x, dim_v, Number> &matrix_free, VectorType &dst,
+                const unsigned int = 0, const unsigned int = 0, const unsigned int = 2, const unsigned int = 2)
+    {
+      const int id = analytical_solution->device_function_id();
+      if (id >= 0)
+        {
+          HD_CALL(hd_interpolate_builtin(matrix_free.get_mesh(), dst.begin(), id, double(analytical_solution->get_time())));
+          return;
+        }
+      constexpr int       dim = dim_x + dim_v;
+      const auto &        d   = matrix_free.get_mesh_desc();
+      const int           n   = d.degree + 1;
+      std::vector<double> nodes(n);
+      hd_mesh_basis(matrix_free.get_mesh(), 0, nodes.data());
+      std::vector<Number>               h(matrix_free.n_dofs());
+      dealii_compat::Point<dim, Number> p;
+      std::int64_t                      idx = 0;
+      const std::int64_t                n_cells = matrix_free.n_cells();
+      std::int64_t                      dofs_per_cell = 1;
+      for (int e = 0; e < dim; ++e)
+        dofs_per_cell *= n;
+      for (std::int64_t c = 0; c < n_cells; ++c)
+        for (std::int64_t i = 0; i < dofs_per_cell; ++i, ++idx)
+          {
+            std::int64_t cc = c, ii = i;
+            for (int e = 0; e < dim; ++e)
+              {
+                const double he = (d.right[e] - d.left[e]) / d.n_cells_global[e];
+                const int    ce = cc % d.n_cells[e];
+                cc /= d.n_cells[e];
+                const int ie = ii % n;
+                ii /= n;
+                p[e] = d.left[e] + (d.cell_offset[e] + ce + nodes[ie]) * he;
+              }
+            h[idx] = analytical_solution->value(p);
+          }
+      dst.copy_from_host(h);
+    }
+
+    // {L2 norm of u_h, L2 norm of u_h - f} at the quadrature points; device reduction, device-side f only
+    template <int degree, int n_points, int dim_x, int dim_v, typename Number, typename VectorType>
+    std::array<Number, 2>
+    norm_and_error(const std::shared_ptr<dealii_compat::Function<dim_x + dim_v, Number>> analytical_solution, const MatrixFree<dim_x, dim_v, Number> &matrix_free, const VectorType &src,
+                   const unsigned int = 0, const unsigned int = 0, const unsigned int = 0, const unsigned int = 0)
+    {
+      const int id = analytical_solution->device_function_id();
+      if (id < 0)
+        throw ExcNotImplemented("norm_and_error against a host-only Function");
+      double out[2];
+      HD_CALL(hd_norm_and_error_builtin(matrix_free.get_mesh(), src.begin(), id, double(analytical_solution->get_time()), out));
+      return {{Number(std::sqrt(out[0])), Number(std::sqrt(out[1]))}};
+    }
+  } // namespace VectorTools
+} // namespace hyperdeal
+
+#ifndef HYPERDEAL_B200_NO_DEALII_ALIAS
+namespace dealii = hyperdeal::dealii_compat;
+#endif
+
+#endif

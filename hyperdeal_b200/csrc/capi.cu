@@ -739,6 +739,18 @@ hd_advection_set_l2_hints(hd_advection *op, int mask)
   return HD_OK;
 }
 
+int
+hd_advection_set_row_tile(hd_advection *op, const int *tile)
+{
+  HD_REQUIRE(op && tile, "null argument");
+  for (int i = 0; i < 5; ++i)
+    {
+      HD_REQUIRE(tile[i] >= -1, "bad tile extent");
+      op->row_tile[i] = tile[i];
+    }
+  return HD_OK;
+}
+
 const char *
 hd_advection_kernel_name(const hd_advection *op)
 {

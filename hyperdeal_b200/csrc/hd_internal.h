@@ -94,6 +94,7 @@ struct hd_advection
   std::vector<cudaEvent_t> ev_in, ev_done;
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
+  int   row_tile[5] = {-1, -1, -1, -1, -1}; // pipelined kernel: row tile per direction 1..5 (-1 = default, 0 = full extent)
   int   l2_hints   = -1; // pipelined kernel: L2 residency hints (bit mask), -1 = default (env HD_L2_HINTS or all)
 };
 

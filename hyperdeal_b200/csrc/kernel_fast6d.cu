@@ -29,6 +29,8 @@
 // Algorithmic traffic 16 B/DoF (fused: 32 B/DoF); see DESIGN.md §4 for the roofline budget.
 #include <cuda.h>
 
+#include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -38,6 +40,7 @@
 namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
+#define HD_DEFAULT_ROW_TILE 0, 0, 0, 0, 0 // tuned on 8^6 cells, see profiles/r01f_row_tile_sweep.txt
   constexpr int STAGES     = 3;
   constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer, (+ warp 10: halo sender, fused-halo variant only)
   constexpr int U_BYTES    = 32768;
@@ -93,6 +96,11 @@ namespace
     // (its downwind neighbour reads it ncell[1..3] rows later), 2 = the direction-4/5 face loads (last use resp.
     // streaming miss) are evict_first, 4 = streaming (.cs) stores/loads of dst, sol, Ti'
     int           hints;
+    // Row order: rows are handed out tile by tile (tile[d] rows along direction d = 1..5, lexicographic inside a tile
+    // and over the tiles) so that the upwind face layers of ALL five row directions are re-used from L2 within a tile:
+    // inside a tile the re-use distance of direction d is tile[1]*..*tile[d-1] rows of 2 x 256 KiB traffic.
+    // tile[d] == ncell[d] for every d is the plain lattice order.
+    int           tile[6];
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -834,8 +842,15 @@ namespace
 #pragma unroll
               for (int d = 1; d < 6; ++d)
                 {
-                  cr[d] = r % p.ncell[d];
-                  r /= p.ncell[d];
+                  cr[d] = r % p.tile[d];
+                  r /= p.tile[d];
+                }
+#pragma unroll
+              for (int d = 1; d < 6; ++d)
+                {
+                  const int nt = p.ncell[d] / p.tile[d];
+                  cr[d] += (r % nt) * p.tile[d];
+                  r /= nt;
                 }
               cr[0]    = 0;
               bool g15 = false;
@@ -1336,6 +1351,32 @@ namespace hd
         return e ? atoi(e) : 0; // measured on 8^6 cells: no gain from any combination (profiles/r01e_l2_hints.txt)
       }();
       p.hints = op->l2_hints >= 0 ? op->l2_hints : env_hints;
+    }
+    {
+      // row tiles (see FastParams::tile); HD_ROW_TILE="t1,t2,t3,t4,t5" overrides the default, 0 = full extent.
+      // Launches on a row range (the pipelined host path walks slabs of the slowest directions) keep the lattice order.
+      static const std::array<int, 5> env_tile = [] {
+        std::array<int, 5> t = {{HD_DEFAULT_ROW_TILE}};
+        if (const char *e = getenv("HD_ROW_TILE"))
+          {
+            int v[5] = {0, 0, 0, 0, 0};
+            sscanf(e, "%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4);
+            for (int i = 0; i < 5; ++i)
+              t[i] = v[i];
+          }
+        return t;
+      }();
+      const bool full = p.row_begin == 0 && p.row_end == p.nrows;
+      p.tile[0]       = 1;
+      for (int d = 1; d < 6; ++d)
+        {
+          int want = op->row_tile[d - 1] >= 0 ? op->row_tile[d - 1] : env_tile[d - 1];
+          int t    = p.ncell[d];
+          if (full && want > 0 && want < t)
+            for (t = want; p.ncell[d] % t != 0; --t) // largest divisor of ncell[d] not above the request
+              ;
+          p.tile[d] = t;
+        }
     }
     p.halo_mask     = 0;
     for (int d = 0; d < 6; ++d)

@@ -208,6 +208,11 @@ int hd_advection_set_kernel(hd_advection *op, int which);
  * neighbour, 2: evict-first on the far face loads, 4: streaming stores; -1 = default = environment HD_L2_HINTS, else 0).
  * A tuning knob, results do not depend on it. */
 int hd_advection_set_l2_hints(hd_advection *op, int mask);
+/* Pipelined 3D3V kernel: order in which the rows of cells (cells along x_0) are visited — the device counterpart of the
+ * cell order of MatrixFree::loop_cell_centric (matrix_free.templates.h:1497-1581: v outer, x inner).  Rows are handed out
+ * tile by tile, tile[i] rows along direction i+1 (i = 0..4; -1 = library default, 0 = the full extent, i.e. lattice
+ * order), so that upwind face layers are re-read from L2 instead of HBM.  A tuning knob, results do not depend on it. */
+int hd_advection_set_row_tile(hd_advection *op, const int *tile);
 /* Name of the kernel the last apply launched (for logs and tests). */
 const char *hd_advection_kernel_name(const hd_advection *op);
 /* number of kernel launches issued by this operator so far */

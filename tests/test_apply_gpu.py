@@ -273,3 +273,25 @@ def test_fast_kernel_many_rows(api, ctx):
     """4^6 cells: every CTA walks several rows, all ring/parity phases wrap many times."""
     rel, name = _run(api, ctx, 3, 3, (4, 4, 4, 4, 4, 4), 3, skew=0.5, kernel=2)
     assert name == "advect_3d3v_k3" and rel <= TOL64
+
+
+@pytest.mark.parametrize("tile", [(2, 2, 2, 2, 0), (4, 2, 3, 1, 2), (3, 0, 2, 2, 4), (1, 1, 1, 1, 1), (5, 7, 5, 5, 3)])
+def test_fast_kernel_row_tiles_are_order_only(api, ctx, tile):
+    """hd_advection_set_row_tile changes the order in which rows of cells are visited (L2 blocking), never the result:
+    bit-identical to the lattice order, also for extents the tile does not divide"""
+    nc = (3, 4, 2, 6, 3, 4)
+    mf = api.MatrixFree(ctx, 3, 3, 3, nc, (0.0,) * 6, (1.0,) * 6)
+    op = api.AdvectionOperation(mf, (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5)
+    op.set_kernel(2)
+    src = np.random.default_rng(7).standard_normal(mf.n_dofs)
+    d_src, d_a, d_b = (mf.initialize_dof_vector() for _ in range(3))
+    mf.copy_in(d_src, src)
+    op.set_row_tile((0, 0, 0, 0, 0))
+    op.apply(d_a, d_src, 0.0)
+    op.set_row_tile(tile)
+    op.apply(d_b, d_src, 0.0)
+    a, b = mf.copy_out(d_a), mf.copy_out(d_b)
+    assert np.array_equal(a, b)
+    assert np.abs(a).max() > 0
+    for p in (d_src, d_a, d_b):
+        mf.free_vector(p)
