@@ -218,7 +218,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=CELLS_PER_DIR, help="cells per direction per GPU (default 8 = the BASELINE workload)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fused 3D3V kernel")
-    ap.add_argument("--layout", default="x", choices=["x", "xv"], help="N = 8: cut x_2,x_1,x_0 (bricks of 8^6 cells) or x_2,x_1,v_2 (bricks of 16x8x8x8x8x4 cells)")
+    ap.add_argument("--layout", default="x24", choices=["x", "xv", "x24"],
+                    help="how the N = 8 lattice (16,16,16,8,8,8) is cut: x = x_2,x_1,x_0 in two (bricks of 8^6 cells); xv = x_2,x_1,v_2 in two (16x8x8x8x8x4); "
+                         "x24 (default) = x_2 in four, x_1 in two (16x8x4x8x8x8): two cut directions instead of three, rows of cells (along x_0) stay whole")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: direct peer-memory stores over NVLink (default) or NCCL send/recv")
     ap.add_argument("--overlap", default="kernel", choices=["kernel", "parts"], help="N > 1: one launch that waits for the halo flag in-kernel (default) or interior/boundary launches")
     ap.add_argument("--no-e2e", action="store_true")
@@ -249,11 +251,11 @@ def main():
 
     # global lattice of the weak-scaling recipe (x_2, x_1, x_0 doubled in turn); how it is cut into equal bricks is ours
     recipe = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 0))
-    if args.layout == "x":
+    if args.layout == "x" or world < 8:
         part = recipe
     else:
-        # "xv": never cut x_0 (rows of cells are walked along x_0): the third cut goes through v_2 instead
-        cut = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 5))
+        # never cut x_0 (rows of cells are walked along x_0): the third cut goes through v_2 ("xv") or through x_2 again ("x24")
+        cut = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 5) if args.layout == "xv" else (2, 1, 2))
         nloc = [g // c for g, c in zip(recipe.n_cells_global, cut.grid)]
         part = BrickPartition(world, rank, nloc, grid=cut.grid)
         assert part.n_cells_global == recipe.n_cells_global

@@ -33,7 +33,7 @@ EXPORTS = [
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
+    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
@@ -107,6 +107,8 @@ def lib():
     L.hd_advection_ghost_sides.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p), c_void_p, POINTER(c_int)]
     L.hd_advection_n_ctas.argtypes = [c_void_p]
+    L.hd_advection_n_halo_senders.argtypes = [c_void_p]
+    L.hd_advection_set_halo_senders.argtypes = [c_void_p, c_int]
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
     L.hd_advection_set_l2_hints.argtypes = [c_void_p, c_int]
@@ -275,6 +277,14 @@ class AdvectionOperation:
     @property
     def n_ctas(self) -> int:
         return lib().hd_advection_n_ctas(self._h)
+
+    @property
+    def n_halo_senders(self) -> int:
+        """CTAs that send the halo in apply_overlapped = increments per arrival counter per application"""
+        return lib().hd_advection_n_halo_senders(self._h)
+
+    def set_halo_senders(self, n: int):
+        _check(lib().hd_advection_set_halo_senders(self._h, int(n)))
 
     def apply_overlapped(self, dst: int, src: int, time: float, ghosts: int, sends, counters_ptr: int, target: int):
         """operator + ghost exchange in one kernel (hd_advection_apply_overlapped); sends = [(dir, side, dst_ptr, counter_ptr), ...]"""

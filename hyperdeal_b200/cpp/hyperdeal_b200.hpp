@@ -532,6 +532,7 @@ namespace hyperdeal
       }
 
       hd_advection *handle() const { return op; }
+      bool          needs_host_boundary_data() const { return host_sampled_bc; }
       const char *  kernel_name() const { return hd_advection_kernel_name(op); }
       const MatrixFree<dim_x, dim_v, Number> &get_matrix_free() const { return data; }
 
@@ -666,6 +667,12 @@ namespace hyperdeal
     perform_time_step(VectorType &solution, const Number &current_time, const Number &time_step,
                       advection::AdvectionOperation<dim_x, dim_v, degree, n_points, Number, VectorType, VelocityField> &op)
     {
+      if (op.needs_host_boundary_data())
+        {
+          // boundary data that lives in a host dealii::Function must be re-sampled at every stage time: stage by stage
+          perform_time_step(solution, current_time, time_step, [&op](const VectorType &src, VectorType &dst, const Number t) { op.apply(dst, src, t); });
+          return;
+        }
       HD_CALL(hd_lsrk_step(rk, op.handle(), solution.begin(), vec_Ki.begin(), vec_Ti.begin(), double(current_time), double(time_step)));
     }
 

@@ -842,6 +842,22 @@ hd_advection_n_ctas(const hd_advection *op)
 }
 
 int
+hd_advection_n_halo_senders(const hd_advection *op)
+{
+  if (!op || !hd::fast6d_supported(op))
+    return 0;
+  return hd::fast6d_halo_senders(op);
+}
+
+int
+hd_advection_set_halo_senders(hd_advection *op, int n)
+{
+  HD_REQUIRE(op && n >= 0, "bad argument");
+  op->halo_senders = n;
+  return HD_OK;
+}
+
+int
 hd_advection_overlap_status(hd_advection *op, int *timed_out)
 {
   HD_REQUIRE(op && timed_out, "null argument");

@@ -95,6 +95,7 @@ struct hd_advection
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
   int   row_tile[5] = {-1, -1, -1, -1, -1}; // pipelined kernel: row tile per direction 1..5 (-1 = default, 0 = full extent)
+  int   halo_senders = 0; // fused-halo kernel: CTAs that pack and send (0 = default, env HD_HALO_SENDERS or 32)
   int   l2_hints   = -1; // pipelined kernel: L2 residency hints (bit mask), -1 = default (env HD_L2_HINTS or all)
 };
 
@@ -120,6 +121,7 @@ namespace hd
   int launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);
+  int  fast6d_halo_senders(const hd_advection *op);
   int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part,
                      const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_target = 0, long long row_begin = 0,
                      long long row_end = -1);

@@ -40,9 +40,9 @@
 namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
-#define HD_DEFAULT_ROW_TILE 0, 0, 0, 0, 0 // tuned on 8^6 cells, see profiles/r01f_row_tile_sweep.txt
+#define HD_DEFAULT_ROW_TILE 0, 2, 2, 2, 0 // measured on 8^6 cells: DRAM reads 12.9 instead of 14.0 GB per apply, profiles/r01f_row_tile_sweep.txt
   constexpr int STAGES     = 3;
-  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer, (+ warp 10: halo sender, fused-halo variant only)
+  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
   constexpr int R1F_OFF    = STAGES * U_BYTES;          // 98304: 2 slots x (direction 1, direction 5)
@@ -77,6 +77,12 @@ namespace
     long long     ghost_off[6]; // ghost segment of that side
     int           nrows;
     int           row_begin, row_end; // rows [row_begin, row_end) of the lattice are processed (default: all)
+    // interior / boundary work lists (passes 1-3), enumerated directly: a row direction d (1..5) whose upwind side is a
+    // GHOST side has its ghost-reading layer at coordinate cutg[d] (-1: direction not cut).  Interior rows = no cut
+    // direction at its ghost layer (n_int of them); boundary rows = union over the cut directions k of
+    // {c_k at the ghost layer, cut directions below k not} with bsize[k] rows each (n_bnd in total).
+    int           cutg[6], bsize[6];
+    int           n_int, n_bnd, n_items;
     int *         counters; // [0] next row, [1] finished CTAs (self-resetting)
     double *      sol;
     double *      ti_next;
@@ -89,6 +95,7 @@ namespace
     int           halo_target;
     unsigned      halo_mask;
     int           n_sends;
+    int           n_sender_ctas;
     int           send_dir[6], send_side[6];
     double *      send_dst[6];
     int *         send_flag[6];
@@ -666,89 +673,87 @@ namespace
       }
   }
 
-  // ======================================================================= halo sender (fused-halo variant, warp 10)
+  // ======================================================================= halo senders (fused-halo variant)
   // pack loop of export_to_ghosted_array_start (matrix_free/vector_partitioner.h:1443-1460) fused with the transport:
   // the nodal face layers go straight into the neighbour GPU's ghost segment over NVLink (peer-mapped pointers), then
-  // the neighbour's arrival counter is bumped.  Kept out of line so that the compute warps' code is laid out and
-  // register-allocated exactly as in the plain variant.
+  // the neighbour's arrival counter is bumped.  The first n_sender_ctas CTAs do this with ALL their warps before they
+  // take their first row of cells (rows are handed out dynamically, so the late start balances itself): a warp moves
+  // one face cell (8 KiB) per iteration with 16 x 16 B loads in flight per lane, i.e. 80 KiB in flight per sender CTA.
+  // Kept out of line so that the compute warps' code is laid out and register-allocated exactly as in the plain variant.
   __device__ __noinline__ void
-  halo_send(const FastParams &p, const int lane)
+  halo_send_cta(const FastParams &p)
   {
-        if (p.pass == 3 && p.n_sends > 0)
+    const int lane = threadIdx.x & 31;
+    const int gw   = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); // this warp among all sender warps
+    const int nw   = p.n_sender_ctas * (THREADS / 32);
+    for (int si = 0; si < p.n_sends; ++si)
       {
-        for (int si = 0; si < p.n_sends; ++si)
+        const int d = p.send_dir[si], side = p.send_side[si];
+        int       nfc = 1;
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          nfc *= (e == d) ? 1 : p.ncell[e];
+        const int stride_d  = 1 << (2 * d);
+        const int layer_off = (side ? 3 : 0) * stride_d;
+        for (int fc = gw; fc < nfc; fc += nw)
           {
-            const int d = p.send_dir[si], side = p.send_side[si];
-            int       nfc = 1;
+            long long cell = 0, m = 1;
+            int       r    = fc;
 #pragma unroll
             for (int e = 0; e < 6; ++e)
-              nfc *= (e == d) ? 1 : p.ncell[e];
-            const int stride_d  = 1 << (2 * d);
-            const int layer_off = (side ? 3 : 0) * stride_d;
-            for (int fc = blockIdx.x; fc < nfc; fc += gridDim.x)
               {
-                long long cell = 0, m = 1;
-                int       r    = fc;
-#pragma unroll
-                for (int e = 0; e < 6; ++e)
-                  {
-                    int ce;
-                    if (e == d)
-                      ce = side ? p.ncell[e] - 1 : 0;
-                    else
-                      {
-                        ce = r % p.ncell[e];
-                        r /= p.ncell[e];
-                      }
-                    cell += ce * m;
-                    m *= p.ncell[e];
-                  }
-                const double *sp = p.src + cell * CELL + layer_off;
-                double *      op = p.send_dst[si] + (long long)fc * 1024;
-                if (d == 0)
-                  {
-                    // layer of direction 0: single values, 32 bytes apart
-#pragma unroll 1
-                    for (int i0 = lane; i0 < 1024; i0 += 256)
-                      {
-                        double v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                          v[u] = __ldg(sp + 4 * (i0 + 32 * u));
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                          op[i0 + 32 * u] = v[u];
-                      }
-                  }
+                int ce;
+                if (e == d)
+                  ce = side ? p.ncell[e] - 1 : 0;
                 else
                   {
-                    // 16-byte chunks; the layer is contiguous over 4^d >= 4 values
-#pragma unroll 1
-                    for (int c0 = lane; c0 < 512; c0 += 256)
-                      {
-                        double2 v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                          {
-                            const int i = 2 * (c0 + 32 * u), hi = i >> (2 * d), lo = i & (stride_d - 1);
-                            v[u]        = __ldg(reinterpret_cast<const double2 *>(sp + hi * 4 * stride_d + lo));
-                          }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                          *reinterpret_cast<double2 *>(op + 2 * (c0 + 32 * u)) = v[u];
-                      }
+                    ce = r % p.ncell[e];
+                    r /= p.ncell[e];
                   }
+                cell += ce * m;
+                m *= p.ncell[e];
+              }
+            const double *sp = p.src + cell * CELL + layer_off;
+            double *      op = p.send_dst[si] + (long long)fc * 1024;
+            if (d == 0)
+              {
+                // layer of direction 0: single values, 32 bytes apart; lane takes values 2*lane, 2*lane+1 of 64-value groups
+                double2 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  {
+                    const int i = 2 * (lane + 32 * u);
+                    v[u].x      = __ldg(sp + 4 * i);
+                    v[u].y      = __ldg(sp + 4 * i + 4);
+                  }
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  *reinterpret_cast<double2 *>(op + 2 * (lane + 32 * u)) = v[u];
+              }
+            else
+              {
+                // 16-byte chunks; the layer is contiguous over 4^d >= 4 values
+                double2 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  {
+                    const int i = 2 * (lane + 32 * u), hi = i >> (2 * d), lo = i & (stride_d - 1);
+                    v[u]        = __ldg(reinterpret_cast<const double2 *>(sp + hi * 4 * stride_d + lo));
+                  }
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  *reinterpret_cast<double2 *>(op + 2 * (lane + 32 * u)) = v[u];
               }
           }
-        __threadfence_system();
-        __syncwarp();
-        if (lane < p.n_sends)
-          asm volatile("red.release.sys.global.add.s32 [%0], 1;" ::"l"(p.send_flag[lane]) : "memory");
       }
+    __threadfence_system();
+    __syncthreads();
+    if (int(threadIdx.x) < p.n_sends)
+      asm volatile("red.release.sys.global.add.s32 [%0], 1;" ::"l"(p.send_flag[threadIdx.x]) : "memory");
   }
 
   template <bool FUSED, bool HALO>
-  __global__ void __launch_bounds__(HALO ? THREADS + 32 : THREADS, 1)
+  __global__ void __launch_bounds__(THREADS, 1)
     k_advect_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
                      const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ CUtensorMap mapG1,
                      const __grid_constant__ CUtensorMap mapG5, const __grid_constant__ CUtensorMap mapU16, const __grid_constant__ FastParams p,
@@ -791,6 +796,12 @@ namespace
       }
     __syncthreads();
 
+    if (HALO)
+      {
+        if (p.pass == 3 && p.n_sends > 0 && int(blockIdx.x) < p.n_sender_ctas) // (CTA-uniform)
+          halo_send_cta(p);
+      }
+
     const int  n0      = p.ncell[0];
     const bool act0    = p.up_delta[0] != 0;
     const bool act1    = p.up_delta[1] != 0;
@@ -821,55 +832,103 @@ namespace
         // reference's overlapping levels (matrix_free.templates.h:1516-1566): a row whose directions 1..5 need no
         // ghosts is interior, except for its upwind-most cell if direction 0 is cut.
         bool halo_ready = p.pass != 3;
+        // interior rows: mixed-radix decode that leaves out the ghost layer of every cut direction
+        auto decode_interior = [&](int i, int (&cr)[6]) {
+#pragma unroll
+          for (int d = 1; d < 6; ++d)
+            {
+              const bool cut = p.cutg[d] >= 0;
+              const int  r   = p.ncell[d] - (cut ? 1 : 0);
+              const int  q   = i % r;
+              i /= r;
+              cr[d] = (cut && p.cutg[d] == 0) ? q + 1 : q;
+            }
+        };
+        auto decode_boundary = [&](int i, int (&cr)[6]) {
+          int dk = 0; // the cut direction whose ghost layer this row lies in (lower cut directions are not at theirs)
+#pragma unroll
+          for (int d = 1; d < 6; ++d)
+            if (dk == 0)
+              {
+                if (i < p.bsize[d])
+                  dk = d;
+                else
+                  i -= p.bsize[d];
+              }
+#pragma unroll
+          for (int d = 1; d < 6; ++d)
+            {
+              const bool cut = p.cutg[d] >= 0;
+              if (d == dk)
+                cr[d] = p.cutg[d];
+              else
+                {
+                  const bool skip = cut && d < dk;
+                  const int  r    = p.ncell[d] - (skip ? 1 : 0);
+                  const int  q    = i % r;
+                  i /= r;
+                  cr[d] = (skip && p.cutg[d] == 0) ? q + 1 : q;
+                }
+            }
+        };
+        // The work items come from a global counter; the next one is requested while the current one is being loaded,
+        // so that the atomic's round trip (microseconds on a busy memory system) never stalls the ring.
+        int  next_item  = 0;
+        if (lane == 0)
+          next_item = atomicAdd(p.counters, 1);
         auto fetch_row  = [&](int (&cr)[6], int &sb, int &se) -> bool {
           for (;;)
             {
-              int row = 0;
+              int item = 0;
               if (lane == 0)
-                row = atomicAdd(p.counters, 1);
-              row      = __shfl_sync(0xffffffffu, row, 0);
-              int mode = p.pass;
+                {
+                  item = next_item;
+                  if (item < p.n_items)
+                    next_item = atomicAdd(p.counters, 1);
+                }
+              item = __shfl_sync(0xffffffffu, item, 0);
+              if (item >= p.n_items)
+                return false;
+              cr[0] = 0;
+              sb    = 0;
+              se    = n0;
+              int mode = p.pass; // 0: all cells of a lattice row, 1: interior list, 2: boundary list
               if (p.pass == 3)
                 {
-                  // one launch, two phases over the rows: interior cells, then (once the halo has arrived) the rest
-                  mode = row >= p.nrows ? 2 : 1;
-                  row -= row >= p.nrows ? p.nrows : 0;
+                  // one launch, two phases: interior cells, then (once the halo has arrived) the rest
+                  mode = item >= p.n_int ? 2 : 1;
+                  item -= item >= p.n_int ? p.n_int : 0;
                 }
-              row += p.row_begin;
-              if (row >= p.row_end)
-                return false;
-              int r = row;
-#pragma unroll
-              for (int d = 1; d < 6; ++d)
+              if (mode == 0)
                 {
-                  cr[d] = r % p.tile[d];
-                  r /= p.tile[d];
+                  int r = item + p.row_begin;
+#pragma unroll
+                  for (int d = 1; d < 6; ++d)
+                    {
+                      cr[d] = r % p.tile[d];
+                      r /= p.tile[d];
+                    }
+#pragma unroll
+                  for (int d = 1; d < 6; ++d)
+                    {
+                      const int nt = p.ncell[d] / p.tile[d];
+                      cr[d] += (r % nt) * p.tile[d];
+                      r /= nt;
+                    }
                 }
-#pragma unroll
-              for (int d = 1; d < 6; ++d)
+              else if (mode == 1)
                 {
-                  const int nt = p.ncell[d] / p.tile[d];
-                  cr[d] += (r % nt) * p.tile[d];
-                  r /= nt;
-                }
-              cr[0]    = 0;
-              bool g15 = false;
-#pragma unroll
-              for (int d = 1; d < 6; ++d)
-                g15 |= needs_ghost(p, cr, d);
-              sb = 0;
-              se = n0;
-              if (mode == 1)
-                {
-                  if (g15)
-                    continue;
+                  // a row whose directions 1..5 need no ghosts; its upwind-most cell is left out if direction 0 is cut
+                  decode_interior(item, cr);
                   if (ghost0)
                     sb = 1;
                 }
-              else if (mode == 2 && !g15)
+              else if (item < p.n_bnd)
+                decode_boundary(item, cr);
+              else
                 {
-                  if (!ghost0)
-                    continue;
+                  // the upwind-most cells of the interior rows (direction 0 cut)
+                  decode_interior(item - p.n_bnd, cr);
                   se = 1;
                 }
               if (sb >= se)
@@ -1083,8 +1142,6 @@ namespace
               }
           }
       }
-    else if (HALO && warp == 10)
-      halo_send(p, lane);
     else if (warp < 4)
       compute_round<0, FUSED>(p, cf, base, gbase, bars, tid);
     else
@@ -1244,6 +1301,23 @@ namespace
 
 namespace hd
 {
+  // CTAs that pack and send the halo in the fused-halo variant (and signal the neighbours' arrival counters)
+  int
+  fast6d_halo_senders(const hd_advection *op)
+  {
+    static const int env = [] {
+      const char *e = getenv("HD_HALO_SENDERS");
+      return e ? atoi(e) : 32;
+    }();
+    const hd_mesh *m     = op->mesh;
+    long long      nrows = m->ncells / m->d.n_cells[0];
+    long long      grid  = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
+    int            want  = op->halo_senders > 0 ? op->halo_senders : env;
+    if (want < 1)
+      want = 1;
+    return (int)(want < grid ? want : grid);
+  }
+
   bool
   fast6d_supported(const hd_advection *op)
   {
@@ -1309,11 +1383,41 @@ namespace hd
     p.nrows    = (int)nrows;
     if (row_end < 0)
       row_end = nrows;
-    if (row_begin < 0 || row_begin > row_end || row_end > nrows || (part == 3 && (row_begin != 0 || row_end != nrows)))
+    if (row_begin < 0 || row_begin > row_end || row_end > nrows || (part != 0 && (row_begin != 0 || row_end != nrows)))
       return hd::fail(HD_ERR_INVALID, "bad row range");
     p.row_begin = (int)row_begin;
     p.row_end   = (int)row_end;
-    nrows       = row_end - row_begin; // (grid size)
+    {
+      // interior / boundary work lists (see FastParams)
+      long long n_int = 1, n_bnd = 0;
+      for (int d = 1; d < 6; ++d)
+        {
+          const bool cut = p.up_delta[d] != 0 && p.up_kind[d] == HD_SIDE_GHOST;
+          p.cutg[d]      = cut ? (p.up_delta[d] < 0 ? 0 : p.ncell[d] - 1) : -1;
+          n_int *= p.ncell[d] - (cut ? 1 : 0);
+        }
+      p.cutg[0] = p.bsize[0] = 0;
+      for (int k = 1; k < 6; ++k)
+        {
+          long long sz = 0;
+          if (p.cutg[k] >= 0)
+            {
+              sz = 1;
+              for (int d = 1; d < 6; ++d)
+                if (d != k)
+                  sz *= p.ncell[d] - ((p.cutg[d] >= 0 && d < k) ? 1 : 0);
+            }
+          p.bsize[k] = (int)sz;
+          n_bnd += sz;
+        }
+      const bool ghost0 = p.up_delta[0] != 0 && p.up_kind[0] == HD_SIDE_GHOST;
+      p.n_int           = (int)n_int;
+      p.n_bnd           = (int)n_bnd;
+      const long long n_b_items = n_bnd + (ghost0 ? n_int : 0);
+      const long long items     = part == 0 ? row_end - row_begin : (part == 1 ? n_int : (part == 2 ? n_b_items : n_int + n_b_items));
+      p.n_items = (int)items;
+      nrows     = items > 0 ? items : 1; // (grid size)
+    }
     p.counters = st->d_counters;
     p.sol      = static_cast<double *>(fu.sol);
     p.ti_next  = static_cast<double *>(fu.ti_next);
@@ -1391,8 +1495,9 @@ namespace hd
         HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         st->attr_set[fidx] = true;
       }
-    long long grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
-    kern<<<(unsigned)grid, halo ? THREADS + 32 : THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, maps->u16, p, cfh);
+    long long grid  = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
+    p.n_sender_ctas = hd::fast6d_halo_senders(op);
+    kern<<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, maps->u16, p, cfh);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = fu.enabled ? "advect_3d3v_k3_fused_lsrk" : "advect_3d3v_k3";

@@ -156,9 +156,9 @@ class PeerHaloExchange:
     ranks of one node read each other's vector directly (matrix_free/vector_partitioner.h:552-640 `sync`, :1387-1460).
 
     Two ways to drive it:
-      * fused (``begin_fused`` + AdvectionOperation.apply_overlapped): one warp per CTA of the operator kernel does the
-        packing and the NVLink stores and bumps the receiver's arrival counter; the kernel's boundary phase waits for its
-        own counters.  One launch per operator application, no extra kernels.  (A separate pack kernel cannot run
+      * fused (``begin_fused`` + AdvectionOperation.apply_overlapped): the first ``op.n_halo_senders`` CTAs of the operator
+        kernel start with the packing and the NVLink stores and bump the receiver's arrival counter, then join the others
+        on the cells; the kernel's boundary phase waits for its own counters.  One launch per operator application, no extra kernels.  (A separate pack kernel cannot run
         beside the persistent operator kernel once that one is resident — the SM sub-partitions' register files are
         full — so "pack on a side stream" only overlaps when it wins the launch race.)
       * split (``start`` / ``wait_ready``): hd_halo_pack_ex as its own kernel, data-ready flags written and awaited with
@@ -217,11 +217,11 @@ class PeerHaloExchange:
     # ---- fused: pack + transport inside the operator kernel
     def begin_fused(self, ctx, op):
         """Enqueue the buffer hand-shake on ctx's stream; returns (ghost tensor, sends, counters_ptr, target) for
-        AdvectionOperation.apply_overlapped, to be followed by ``consumed``.  Every CTA of a sender adds 1 to my arrival
-        counter per application, hence target = applications * op.n_ctas (equal bricks on all ranks)."""
+        AdvectionOperation.apply_overlapped, to be followed by ``consumed``.  Every sender CTA of a neighbour adds 1 to my arrival
+        counter per application, hence target = applications * op.n_halo_senders (equal bricks on all ranks)."""
         m = self._next(ctx)
         self.fused_steps += 1
-        return self.ghosts[m % 2], self.fused_sends[m % 2], self.my_flags + 4 * self.COUNT, self.fused_steps * op.n_ctas
+        return self.ghosts[m % 2], self.fused_sends[m % 2], self.my_flags + 4 * self.COUNT, self.fused_steps * op.n_halo_senders
 
     # ---- split: pack kernel + stream flags + two operator launches
     def start(self, mf, ctx, src_ptr: int):

@@ -170,12 +170,12 @@ int hd_advection_apply_part(hd_advection *op, void *dst, const void *src, const 
  *    then writes the counters, e.g. with hd_stream_write_flag.  NB: once this persistent kernel is resident no other
  *    kernel gets an SM until it ends; a pack kernel must therefore have STARTED before this launch (gate the launch
  *    with hd_stream_wait_flag on hd_halo_pack_ex's started_counter).
- *  - n_sends > 0 (fused halo): one extra warp per CTA stores its share of this brick's boundary layers straight into
- *    the neighbour GPUs' ghost segments (sends[i].dst: peer-mapped pointer of the segment (dir, 1-side) of the neighbour
- *    behind side (dir, side)) and then adds 1 to sends[i].arrival_counter (peer-mapped address of that neighbour's
- *    arrival_counters[2*dir + (1-side)]) — pack loop + MPI_Isend of export_to_ghosted_array_start (:1387-1460) over
- *    NVLink inside the operator kernel.  Use target = applications so far * hd_advection_n_ctas (equal bricks on all
- *    GPUs).
+ *  - n_sends > 0 (fused halo): the first hd_advection_n_halo_senders CTAs of the kernel begin by storing this brick's
+ *    boundary layers straight into the neighbour GPUs' ghost segments (sends[i].dst: peer-mapped pointer of the segment
+ *    (dir, 1-side) of the neighbour behind side (dir, side)), each adds 1 to sends[i].arrival_counter (peer-mapped
+ *    address of that neighbour's arrival_counters[2*dir + (1-side)]) when its share is out, and then joins the others
+ *    on the cells — pack loop + MPI_Isend of export_to_ghosted_array_start (:1387-1460) over NVLink inside the operator
+ *    kernel.  Use target = applications so far * hd_advection_n_halo_senders (equal bricks on all GPUs).
  * Re-use of a ghost buffer is the caller's business (double-buffer it, hand-shake with hd_stream_write/wait_flag).
  * The wait gives up after 4 s; hd_advection_overlap_status then reports timed_out = 1 (and the result is invalid). */
 typedef struct hd_halo_send
@@ -188,6 +188,10 @@ int hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, 
                                   const void *arrival_counters, int target);
 /* CTAs of the pipelined kernel on this mesh (0 if it does not apply). */
 int hd_advection_n_ctas(const hd_advection *op);
+/* How many of them send the halo in the fused variant, i.e. the increments an arrival counter receives per application
+ * (0 if the kernel does not apply); set_halo_senders(n) overrides the default (0 = default: env HD_HALO_SENDERS, else 32). */
+int hd_advection_n_halo_senders(const hd_advection *op);
+int hd_advection_set_halo_senders(hd_advection *op, int n);
 int hd_advection_overlap_status(hd_advection *op, int *timed_out);
 /* Stream memory operations on the context's stream (no kernel launch): "*flag = value" (the address may be peer-mapped
  * memory of another GPU) and "wait until *flag >= value".  These carry the halo handshake between GPUs: data-ready

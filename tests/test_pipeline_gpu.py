@@ -336,7 +336,7 @@ def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel):
     assert len(sends) == len(dirs)
     for epoch in (1, 2, 3):
         ghost.fill_(float("nan"))
-        op.apply_overlapped(dst.data_ptr(), d_src, 0.0, ghost.data_ptr(), sends, counters.data_ptr(), epoch * op.n_ctas)
+        op.apply_overlapped(dst.data_ptr(), d_src, 0.0, ghost.data_ptr(), sends, counters.data_ptr(), epoch * op.n_halo_senders)
         torch.cuda.synchronize()
         assert not op.overlap_timed_out()
         assert op.kernel_name == "advect_3d3v_k3"

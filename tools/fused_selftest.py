@@ -26,10 +26,10 @@ def timeit(name, fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     print("%-36s %.3f ms" % (name, e0.elapsed_time(e1) / reps), flush=True)
-epoch = [0]
+arrived = [0]  # what every arrival counter holds after the applications so far
 def fused():
-    epoch[0] += 1
-    op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, ghost.data_ptr(), sends, counters.data_ptr(), epoch[0] * op.n_ctas)
+    arrived[0] += op.n_halo_senders
+    op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, ghost.data_ptr(), sends, counters.data_ptr(), arrived[0])
 mask = [0] * 12
 for (d, s, _, _) in sends: mask[2 * d + s] = 1
 send = torch.zeros(mf.halo_total, dtype=torch.float64, device="cuda")
@@ -38,5 +38,7 @@ timeit("apply all (ghosts in place)", lambda: op.apply(dst.data_ptr(), src.data_
 timeit("interior", lambda: op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, ghost.data_ptr(), api.PART_INTERIOR))
 timeit("boundary", lambda: op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, ghost.data_ptr(), api.PART_BOUNDARY))
 timeit("pack kernel", lambda: mf.halo_pack(src.data_ptr(), send.data_ptr(), send_mask=mask))
-timeit("fused (pack+interior+wait+boundary)", fused)
+for ns in [int(x) for x in os.environ.get("SENDERS", "16,32,64,148").split(",")]:
+    op.set_halo_senders(ns)
+    timeit("fused (pack+interior+wait+boundary), %3d sender CTAs" % op.n_halo_senders, fused)
 assert not op.overlap_timed_out()

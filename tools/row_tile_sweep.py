@@ -35,6 +35,8 @@ for shp in shapes:
             op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print("tile %-16s %.3f ms  %.1f GDoF/s  identical=%s" % (shp, ms, n / ms / 1e6, same), flush=True)
+        import pynvml
+        pynvml.nvmlInit(); hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+        print("tile %-16s %.3f ms  %.1f GDoF/s  identical=%s  sm_clock_after=%d MHz power=%.0f W" % (shp, ms, n / ms / 1e6, same, pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hnd) / 1e3), flush=True)
     else:
         print("tile %-16s identical=%s" % (shp, same), flush=True)
