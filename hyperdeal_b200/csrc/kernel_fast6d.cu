@@ -34,15 +34,39 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <type_traits>
 
 #include "hd_internal.h"
+
+// Register budget.  An SM sub-partition holds 16384 registers = 512 per lane and hosts one warp of every warpgroup.
+// The kernel is launched with 168 registers per thread (3 x 168 = 504 <= 512); the producer warpgroup then hands
+// registers back (setmaxnreg.dec) and the two compute warpgroups take them (setmaxnreg.inc).  The pool is what the
+// launch allocated, so 2 x HD_REGS_COMPUTE + HD_REGS_PRODUCER <= 504 — an inc beyond that waits forever.
+#ifndef HD_REGS_COMPUTE
+#define HD_REGS_COMPUTE 216
+#endif
+#ifndef HD_REGS_PRODUCER
+#define HD_REGS_PRODUCER 72
+#endif
+static_assert(2 * HD_REGS_COMPUTE + HD_REGS_PRODUCER <= 504 && HD_REGS_COMPUTE % 8 == 0 && HD_REGS_PRODUCER % 8 == 0, "register split exceeds the launch allocation");
+#define HD_STR2(x) #x
+#define HD_STR(x) HD_STR2(x)
+#ifndef HD_PEEL
+#define HD_PEEL 0 // 1: own planes as two straight-line bodies (static accumulator indices).  Measured: 173 vs 222 GDoF/s, the +11 KB of code overflow the 32 KB instruction cache (profiles/r01g_variants.txt)
+#endif
+#ifndef HD_HINTS
+#define HD_HINTS 0 // 1: compile the L2-hint code paths (hd_advection_set_l2_hints) in.  Off: no hint combination ever gained anything, and the 4.7 KB of code they add cost 3-5 % (instruction cache, profiles/r01g_variants.txt)
+#endif
+#ifndef HD_PAIR
+#define HD_PAIR 1 // 1: rolled loop over two plane pairs, 0: rolled loop over four planes (v5)
+#endif
 
 namespace
 {
   constexpr int CELL       = 4096; // doubles per cell
 #define HD_DEFAULT_ROW_TILE 0, 2, 2, 2, 0 // measured on 8^6 cells: DRAM reads 12.9 instead of 14.0 GB per apply, profiles/r01f_row_tile_sweep.txt
   constexpr int STAGES     = 3;
-  constexpr int THREADS    = 320; // warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer
+  constexpr int THREADS    = 384; // three warpgroups: warps 0-3 round 1, 4-7 round 2, 8 cell producer, 9 face producer (10, 11 idle)
   constexpr int U_BYTES    = 32768;
   constexpr int F_BYTES    = 8192;
   constexpr int R1F_OFF    = STAGES * U_BYTES;          // 98304: 2 slots x (direction 1, direction 5)
@@ -321,7 +345,7 @@ namespace
     const bool      act0 = p.up_delta[0] != 0, act1 = p.up_delta[1] != 0, act5 = p.up_delta[5] != 0;
     const bool      r1faces = act1 || act5;
     const bool      descend = p.up_delta[0] > 0;
-    const bool      stream  = (p.hints & 4) != 0;
+    const bool      stream  = HD_HINTS && (p.hints & 4) != 0;
     constexpr int   role    = ROLE;
     const RoleCoef &rc      = cf.r[ROLE];
     const int       lane    = tid_in_role & 31;
@@ -365,6 +389,7 @@ namespace
           break;
 
         double acc[2][4][4]; // [c - 2h][b][a]
+#if !HD_PEEL
 #pragma unroll
         for (int x = 0; x < 2; ++x)
 #pragma unroll
@@ -372,6 +397,7 @@ namespace
 #pragma unroll
             for (int z = 0; z < 4; ++z)
               acc[x][y][z] = 0.0;
+#endif
         // ---- prologue
         const bool     from_t0 = (role == 0) && inf.w != 0;
         uint32_t       t0b = 0, fbuf = 0;
@@ -422,6 +448,241 @@ namespace
                   Q[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
             }
         };
+#if HD_PEEL
+        // Own planes (it = 0, 1) as two straight-line bodies with static accumulator indices: the in-plane chains start
+        // from the cross-plane term and end in the accumulator (no separate multiply / add), the first body initialises
+        // the accumulators (no zeroing); each body also takes the cross-plane sweep of one of the two other planes.
+        auto own_plane = [&](auto IT) {
+          constexpr int it = decltype(IT)::value;
+          const int     sp = 2 * h + it;         // own output plane c = 2h + it is source plane sp
+          const int     so = (sp + 2) & 3;       // the other plane swept in this body
+          double        P[4][4], Q[4][4];        // [b][a]
+          load_plane(P, sp);
+          load_plane(Q, so);
+          const double cown = rc.C[sp * 4 + sp], coth = rc.C[(2 * h + 1 - it) * 4 + sp];
+          double       fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
+          if (role == 0)
+            {
+              if (actA)
+                {
+                  if (from_t0)
+                    {
+                      const double2 v0 = lds128(t0b + sp * 2048), v1 = lds128(t0b + sp * 2048 + 16);
+                      fa[0] = v0.x;
+                      fa[1] = v0.y;
+                      fa[2] = v1.x;
+                      fa[3] = v1.y;
+                    }
+                  else
+                    {
+#pragma unroll
+                      for (int b = 0; b < 4; ++b)
+                        fa[b] = tr[it][b];
+                    }
+                  // this cell's end layer is the next cell's trace
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+                    tr[it][b] = descend ? P[b][0] : P[b][3];
+                }
+              if (actB)
+                {
+                  const uint32_t r32 = uint32_t(t) + 64u * uint32_t(sp);
+                  const uint32_t fl  = (r32 >> 2) & 1u;
+                  const uint32_t tb  = fbuf + r32 * 32u;
+                  const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
+                  fb[0] = v0.x;
+                  fb[1] = v0.y;
+                  fb[2] = v1.x;
+                  fb[3] = v1.y;
+                }
+            }
+          else
+            {
+              if (actA)
+                {
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+                    fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(sp));
+                }
+              if (actB)
+                {
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(sp));
+                }
+            }
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              {
+                double v = it == 0 ? cown * P[b][a] : fma(cown, P[b][a], acc[it][b][a]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  v = fma(rc.A[a * 4 + j], P[b][j], v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  v = fma(rc.B[b * 4 + j], P[j][a], v);
+                v               = fma(rc.LA[a], fa[b], v);
+                v               = fma(rc.LB[b], fb[a], v);
+                acc[it][b][a]     = v;
+                acc[1 - it][b][a] = it == 0 ? coth * P[b][a] : fma(coth, P[b][a], acc[1 - it][b][a]);
+              }
+          const double q0 = rc.C[(2 * h) * 4 + so], q1 = rc.C[(2 * h + 1) * 4 + so];
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              {
+                acc[0][b][a] = fma(q0, Q[b][a], acc[0][b][a]);
+                acc[1][b][a] = fma(q1, Q[b][a], acc[1][b][a]);
+              }
+        };
+        own_plane(std::integral_constant<int, 0>{});
+        own_plane(std::integral_constant<int, 1>{});
+        if (role != 0)
+          {
+            // in-plane faces of directions 2 and 3 are done: let the face producer refill this slot
+            if (actA)
+              release(bars.r2fEmpty(f, 0));
+            if (actB)
+              release(bars.r2fEmpty(f, 1));
+          }
+#elif HD_PAIR
+        // Two plane pairs (own plane it, other plane it + 2) per rolled iteration: both planes are requested from shared
+        // memory at once (two exposed load latencies per cell instead of four), and the in-plane chains start from the
+        // cross-plane term of the own plane instead of a separate multiply.
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it)
+          {
+            const int sp = 2 * h + it, so = (sp + 2) & 3;
+            double    P[4][4], Q[4][4]; // [b][a]
+            load_plane(P, sp);
+            load_plane(Q, so);
+            const double q0 = rc.C[(2 * h) * 4 + so], q1 = rc.C[(2 * h + 1) * 4 + so];
+            const double cown = rc.C[sp * 4 + sp], coth = rc.C[(2 * h + 1 - it) * 4 + sp];
+            double       fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
+            if (role == 0)
+              {
+                if (actA)
+                  {
+                    if (from_t0)
+                      {
+                        const double2 v0 = lds128(t0b + sp * 2048), v1 = lds128(t0b + sp * 2048 + 16);
+                        fa[0] = v0.x;
+                        fa[1] = v0.y;
+                        fa[2] = v1.x;
+                        fa[3] = v1.y;
+                      }
+                    else if (it == 0)
+                      {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          fa[b] = tr[0][b];
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          fa[b] = tr[1][b];
+                      }
+                    if (it == 0)
+                      {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          tr[0][b] = descend ? P[b][0] : P[b][3];
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                          tr[1][b] = descend ? P[b][0] : P[b][3];
+                      }
+                  }
+                if (actB)
+                  {
+                    const uint32_t r32 = uint32_t(t) + 64u * uint32_t(sp);
+                    const uint32_t fl  = (r32 >> 2) & 1u;
+                    const uint32_t tb  = fbuf + r32 * 32u;
+                    const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
+                    fb[0] = v0.x;
+                    fb[1] = v0.y;
+                    fb[2] = v1.x;
+                    fb[3] = v1.y;
+                  }
+              }
+            else
+              {
+                if (actA)
+                  {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                      fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(sp));
+                  }
+                if (actB)
+                  {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(sp));
+                  }
+              }
+            // cross-plane sweep of the other plane into both output planes
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                {
+                  acc[0][b][a] = fma(q0, Q[b][a], acc[0][b][a]);
+                  acc[1][b][a] = fma(q1, Q[b][a], acc[1][b][a]);
+                }
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              {
+                double q[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  {
+                    double v = cown * P[b][a];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      v = fma(rc.A[a * 4 + j], P[b][j], v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      v = fma(rc.B[b * 4 + j], P[j][a], v);
+                    v    = fma(rc.LA[a], fa[b], v);
+                    v    = fma(rc.LB[b], fb[a], v);
+                    q[a] = v;
+                  }
+                // one uniform branch per row keeps the register indices static
+                if (it == 1)
+                  {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      {
+                        acc[1][b][a] += q[a];
+                        acc[0][b][a] = fma(coth, P[b][a], acc[0][b][a]);
+                      }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      {
+                        acc[0][b][a] += q[a];
+                        acc[1][b][a] = fma(coth, P[b][a], acc[1][b][a]);
+                      }
+                  }
+              }
+          }
+        if (role != 0)
+          {
+            // in-plane faces of directions 2 and 3 are done: let the face producer refill this slot
+            if (actA)
+              release(bars.r2fEmpty(f, 0));
+            if (actB)
+              release(bars.r2fEmpty(f, 1));
+          }
+#else
 #pragma unroll 1
         for (int it = 0; it < 4; ++it)
           {
@@ -549,6 +810,8 @@ namespace
                   release(bars.r2fEmpty(f, 1));
               }
           }
+
+#endif
 
         // ---- the cell stage is free (both rounds read it at the same time), then the face of direction C
         release(bars.emptyU(s));
@@ -809,6 +1072,17 @@ namespace
     const bool r1faces = act1 || act5;
     const bool descend = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
 
+    if (warp < 8)
+      {
+        // compute warpgroups: take the registers the producer warpgroup hands back
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HD_STR(HD_REGS_COMPUTE) ";");
+        if (warp < 4)
+          compute_round<0, FUSED>(p, cf, base, gbase, bars, tid);
+        else
+          compute_round<1, FUSED>(p, cf, base, gbase, bars, tid - 128);
+        return;
+      }
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " HD_STR(HD_REGS_PRODUCER) ";");
     if (warp == 8)
       {
         // ======================================================================= cell producer
@@ -819,9 +1093,9 @@ namespace
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU16));
           }
         const uint32_t f_bytes  = (act1 ? F_BYTES : 0) + (act5 ? F_BYTES : 0);
-        const bool     keep4    = (p.hints & 1) != 0 && p.up_delta[4] != 0;
+        const bool     keep4    = HD_HINTS && (p.hints & 1) != 0 && p.up_delta[4] != 0;
         const int      keep_row = p.up_delta[4] < 0 ? 48 : 0; // rows (i2,i3,i4) of a piece with i4 = 3 resp. 0
-        const bool     first5   = (p.hints & 2) != 0;
+        const bool     first5   = HD_HINTS && (p.hints & 2) != 0;
         const uint64_t pol_last = policy_evict_last(), pol_first = policy_evict_first();
         const bool     ghost0   = act0 && p.up_kind[0] == HD_SIDE_GHOST;
         int            k        = 0; // cell sequence number of this CTA
@@ -1097,7 +1371,7 @@ namespace
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
-            const bool     first4    = (p.hints & 2) != 0;
+            const bool     first4    = HD_HINTS && (p.hints & 2) != 0;
             const uint64_t pol_first = policy_evict_first();
             for (int k = 0;; ++k)
               {
@@ -1142,10 +1416,6 @@ namespace
               }
           }
       }
-    else if (warp < 4)
-      compute_round<0, FUSED>(p, cf, base, gbase, bars, tid);
-    else
-      compute_round<1, FUSED>(p, cf, base, gbase, bars, tid - 128);
   }
 
   // ------------------------------------------------------------------------------- host side

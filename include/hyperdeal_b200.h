@@ -210,7 +210,8 @@ int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_ho
 int hd_advection_set_kernel(hd_advection *op, int which);
 /* Pipelined 3D3V kernel: L2 residency hints, a bit mask (1: keep the direction-4 outflow layers in L2 for the downwind
  * neighbour, 2: evict-first on the far face loads, 4: streaming stores; -1 = default = environment HD_L2_HINTS, else 0).
- * A tuning knob, results do not depend on it. */
+ * A tuning knob, results do not depend on it; only effective in builds with -DHD_HINTS=1 (off by default: measured
+ * no gain, and the extra code costs instruction-cache space). */
 int hd_advection_set_l2_hints(hd_advection *op, int mask);
 /* Pipelined 3D3V kernel: order in which the rows of cells (cells along x_0) are visited — the device counterpart of the
  * cell order of MatrixFree::loop_cell_centric (matrix_free.templates.h:1497-1581: v outer, x inner).  Rows are handed out
