@@ -4,28 +4,29 @@
 //   dst_cell = sum_{d=0..5} (I x .. C_d .. x I) u_cell + L_d(i_d) * trace_d(upwind neighbour)
 // i.e. advection_operation.h:221-566 for Cartesian cells and a constant velocity, 30 DFMA per DoF.
 //
-// How it is mapped onto one SM (one persistent CTA per SM, 6 warps, mbarrier-only pipeline):
-//   warp 4      cell producer: takes rows of cells (along x_0) from a global atomic counter — so the
-//               148 CTAs sweep the lattice as one compact window and neighbour faces are still in L2
-//               — and TMA-loads (cp.async.bulk.tensor, 128B swizzle) each cell (32 KiB) into a 3-deep
-//               ring, the upwind face layers of directions 1 and 5 into a 2-deep ring, and gathers the
-//               direction-0 trace of the first cell of a row with cp.async.
-//   warp 5      face producer for round 2: TMA-loads the upwind face layers of directions 2,3,4
-//               (8 KiB each, from src or from the ghost buffer) into a 3-slot ring.
-//   warps 0,1   round 1: thread (i2,i3,i4) owns the 4x4x4 sub-tensor over (i0,i1,i5); 64 FP64
-//               accumulators in registers, u streamed plane by plane from shared memory; directions
-//               0,1,5.  The direction-0 neighbour trace never touches memory inside a row: cells are
-//               walked in upwind order and the thread keeps the previous cell's end layer in 16
-//               registers.  Result -> shared "partial" buffer (2-deep).
-//   warps 2,3   round 2, one cell behind: thread (i0,i1,i5) owns the sub-tensor over (i2,i3,i4);
-//               accumulators start from round 1's partial sums, directions 2,3,4, then coalesced
-//               128 B-per-half-warp stores to dst — or the fused LSRK update (sol += b dt K,
+// How it is mapped onto one SM (one persistent CTA per SM, three warpgroups of 128 threads, mbarrier-only pipeline):
+//   warp 8      cell producer: takes rows of cells (along x_0) from a global atomic counter (the next item is requested
+//               one item ahead) — so the 148 CTAs sweep the lattice as one compact window and neighbour faces are still
+//               in L2 — and TMA-loads (cp.async.bulk.tensor, 128B swizzle) each cell (32 KiB) into a 3-deep ring, the
+//               upwind face layers of directions 1 and 5 into a 2-deep ring, and gathers the direction-0 trace of the
+//               first cell of a row with cp.async.  Rows are visited tile by tile (FastParams::tile) for L2 re-use.
+//   warp 9      face producer for round 2: TMA-loads the upwind face layers of directions 2,3,4 (8 KiB each, from src
+//               or from the ghost buffer) into a 2-slot ring.   (warps 10, 11 only donate their registers)
+//   warps 0-3   round 1, directions (0,1 | 5): thread (i2,i3,i4; half h) owns two of the four output planes of a 4x4x4
+//               sub-tensor over (i0,i1,i5): 32 FP64 accumulators, u streamed plane pair by plane pair from shared
+//               memory.  The direction-0 neighbour trace never touches memory inside a row: cells are walked in upwind
+//               order and the thread keeps the previous cell's end layer in 8 registers.  Result -> shared buffer.
+//   warps 4-7   round 2, directions (2,3 | 4) on the same cell at the same time; adds round 1's sums in its epilogue,
+//               then coalesced 128 B-per-half-warp stores to dst — or the fused LSRK update (sol += b dt K,
 //               Ti' = sol_old + a dt K, time_integrators.templates.h:117-132) so K is never written.
-// All (k+1)x(k+1) matrices sit in the kernel-parameter constant bank (uniform-register DFMA operands).
+// Registers: launched with 168 per thread; the producer warpgroup drops to 72 and the compute warpgroups rise to 216
+// (setmaxnreg).  All (k+1)x(k+1) matrices sit in the kernel-parameter constant bank (uniform-register DFMA operands).
+// The hot loops of both compute roles plus the producers must fit the 32 KB instruction cache: every variant that
+// grew them lost 3-25 % (profiles/r01g_variants.txt), hence the rolled plane-pair loop.
 //
-// Shared memory: 3x32 (cells) + 2x16 (faces 1,5) + 2x32 (partials) + 3x8 (faces 2,3,4) + 8 (trace) KiB.
-// The shallow shared-memory ring is fed from L2: the producer prefetches (cp.async.bulk.prefetch.L2) the
-// cell PREFETCH_DIST cells ahead and its direction-4/5 face layers, so TMA loads see L2 latency, not DRAM's.
+// Shared memory: 3x32 (cells) + 2x16 (faces 1,5) + 32 (partial sums) + 2x24 (faces 2,3,4) + 8 (trace) KiB.
+// Multi-GPU (pass 3, fused halo): the first n_sender_ctas CTAs begin by storing the brick's boundary layers into the
+// neighbour GPUs' ghost buffers over NVLink, interior cells run meanwhile, boundary cells after the arrival counters.
 // Algorithmic traffic 16 B/DoF (fused: 32 B/DoF); see DESIGN.md §4 for the roofline budget.
 #include <cuda.h>
 
@@ -51,14 +52,8 @@
 static_assert(2 * HD_REGS_COMPUTE + HD_REGS_PRODUCER <= 504 && HD_REGS_COMPUTE % 8 == 0 && HD_REGS_PRODUCER % 8 == 0, "register split exceeds the launch allocation");
 #define HD_STR2(x) #x
 #define HD_STR(x) HD_STR2(x)
-#ifndef HD_PEEL
-#define HD_PEEL 0 // 1: own planes as two straight-line bodies (static accumulator indices).  Measured: 173 vs 222 GDoF/s, the +11 KB of code overflow the 32 KB instruction cache (profiles/r01g_variants.txt)
-#endif
 #ifndef HD_HINTS
 #define HD_HINTS 0 // 1: compile the L2-hint code paths (hd_advection_set_l2_hints) in.  Off: no hint combination ever gained anything, and the 4.7 KB of code they add cost 3-5 % (instruction cache, profiles/r01g_variants.txt)
-#endif
-#ifndef HD_PAIR
-#define HD_PAIR 1 // 1: rolled loop over two plane pairs, 0: rolled loop over four planes (v5)
 #endif
 
 namespace
@@ -389,7 +384,6 @@ namespace
           break;
 
         double acc[2][4][4]; // [c - 2h][b][a]
-#if !HD_PEEL
 #pragma unroll
         for (int x = 0; x < 2; ++x)
 #pragma unroll
@@ -397,7 +391,6 @@ namespace
 #pragma unroll
             for (int z = 0; z < 4; ++z)
               acc[x][y][z] = 0.0;
-#endif
         // ---- prologue
         const bool     from_t0 = (role == 0) && inf.w != 0;
         uint32_t       t0b = 0, fbuf = 0;
@@ -448,107 +441,6 @@ namespace
                   Q[b][a] = lds64(up + uint32_t(a + 4 * b) * 128u + (col ^ (uint32_t((a + 4 * b) & 7) << 4)));
             }
         };
-#if HD_PEEL
-        // Own planes (it = 0, 1) as two straight-line bodies with static accumulator indices: the in-plane chains start
-        // from the cross-plane term and end in the accumulator (no separate multiply / add), the first body initialises
-        // the accumulators (no zeroing); each body also takes the cross-plane sweep of one of the two other planes.
-        auto own_plane = [&](auto IT) {
-          constexpr int it = decltype(IT)::value;
-          const int     sp = 2 * h + it;         // own output plane c = 2h + it is source plane sp
-          const int     so = (sp + 2) & 3;       // the other plane swept in this body
-          double        P[4][4], Q[4][4];        // [b][a]
-          load_plane(P, sp);
-          load_plane(Q, so);
-          const double cown = rc.C[sp * 4 + sp], coth = rc.C[(2 * h + 1 - it) * 4 + sp];
-          double       fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
-          if (role == 0)
-            {
-              if (actA)
-                {
-                  if (from_t0)
-                    {
-                      const double2 v0 = lds128(t0b + sp * 2048), v1 = lds128(t0b + sp * 2048 + 16);
-                      fa[0] = v0.x;
-                      fa[1] = v0.y;
-                      fa[2] = v1.x;
-                      fa[3] = v1.y;
-                    }
-                  else
-                    {
-#pragma unroll
-                      for (int b = 0; b < 4; ++b)
-                        fa[b] = tr[it][b];
-                    }
-                  // this cell's end layer is the next cell's trace
-#pragma unroll
-                  for (int b = 0; b < 4; ++b)
-                    tr[it][b] = descend ? P[b][0] : P[b][3];
-                }
-              if (actB)
-                {
-                  const uint32_t r32 = uint32_t(t) + 64u * uint32_t(sp);
-                  const uint32_t fl  = (r32 >> 2) & 1u;
-                  const uint32_t tb  = fbuf + r32 * 32u;
-                  const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
-                  fb[0] = v0.x;
-                  fb[1] = v0.y;
-                  fb[2] = v1.x;
-                  fb[3] = v1.y;
-                }
-            }
-          else
-            {
-              if (actA)
-                {
-#pragma unroll
-                  for (int b = 0; b < 4; ++b)
-                    fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(sp));
-                }
-              if (actB)
-                {
-#pragma unroll
-                  for (int a = 0; a < 4; ++a)
-                    fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(sp));
-                }
-            }
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-              {
-                double v = it == 0 ? cown * P[b][a] : fma(cown, P[b][a], acc[it][b][a]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  v = fma(rc.A[a * 4 + j], P[b][j], v);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  v = fma(rc.B[b * 4 + j], P[j][a], v);
-                v               = fma(rc.LA[a], fa[b], v);
-                v               = fma(rc.LB[b], fb[a], v);
-                acc[it][b][a]     = v;
-                acc[1 - it][b][a] = it == 0 ? coth * P[b][a] : fma(coth, P[b][a], acc[1 - it][b][a]);
-              }
-          const double q0 = rc.C[(2 * h) * 4 + so], q1 = rc.C[(2 * h + 1) * 4 + so];
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-              {
-                acc[0][b][a] = fma(q0, Q[b][a], acc[0][b][a]);
-                acc[1][b][a] = fma(q1, Q[b][a], acc[1][b][a]);
-              }
-        };
-        own_plane(std::integral_constant<int, 0>{});
-        own_plane(std::integral_constant<int, 1>{});
-        if (role != 0)
-          {
-            // in-plane faces of directions 2 and 3 are done: let the face producer refill this slot
-            if (actA)
-              release(bars.r2fEmpty(f, 0));
-            if (actB)
-              release(bars.r2fEmpty(f, 1));
-          }
-#elif HD_PAIR
         // Two plane pairs (own plane it, other plane it + 2) per rolled iteration: both planes are requested from shared
         // memory at once (two exposed load latencies per cell instead of four), and the in-plane chains start from the
         // cross-plane term of the own plane instead of a separate multiply.
@@ -635,43 +527,54 @@ namespace
                   acc[0][b][a] = fma(q0, Q[b][a], acc[0][b][a]);
                   acc[1][b][a] = fma(q1, Q[b][a], acc[1][b][a]);
                 }
+            // all 16 in-plane chains of the plane are independent instruction streams (the 216-register budget pays
+            // for the 16 temporaries); one uniform branch per plane keeps the accumulator indices static
+            double q[4][4];
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-              {
-                double q[4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                q[b][a] = cown * P[b][a];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
-                  {
-                    double v = cown * P[b][a];
+                  q[b][a] = fma(rc.A[a * 4 + j], P[b][j], q[b][a]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      v = fma(rc.A[a * 4 + j], P[b][j], v);
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      v = fma(rc.B[b * 4 + j], P[j][a], v);
-                    v    = fma(rc.LA[a], fa[b], v);
-                    v    = fma(rc.LB[b], fb[a], v);
-                    q[a] = v;
-                  }
-                // one uniform branch per row keeps the register indices static
-                if (it == 1)
-                  {
+              for (int b = 0; b < 4; ++b)
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                      {
-                        acc[1][b][a] += q[a];
-                        acc[0][b][a] = fma(coth, P[b][a], acc[0][b][a]);
-                      }
-                  }
-                else
-                  {
+                for (int a = 0; a < 4; ++a)
+                  q[b][a] = fma(rc.B[b * 4 + j], P[j][a], q[b][a]);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                      {
-                        acc[0][b][a] += q[a];
-                        acc[1][b][a] = fma(coth, P[b][a], acc[1][b][a]);
-                      }
-                  }
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                q[b][a] = fma(rc.LB[b], fb[a], fma(rc.LA[a], fa[b], q[b][a]));
+            if (it == 1)
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      acc[1][b][a] += q[b][a];
+                      acc[0][b][a] = fma(coth, P[b][a], acc[0][b][a]);
+                    }
+              }
+            else
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      acc[0][b][a] += q[b][a];
+                      acc[1][b][a] = fma(coth, P[b][a], acc[1][b][a]);
+                    }
               }
           }
         if (role != 0)
@@ -682,136 +585,6 @@ namespace
             if (actB)
               release(bars.r2fEmpty(f, 1));
           }
-#else
-#pragma unroll 1
-        for (int it = 0; it < 4; ++it)
-          {
-            const int sp = (it + 2 * h) & 3;
-            double    P[4][4]; // [b][a]
-            load_plane(P, sp);
-            // cross-plane sweep into the two own output planes
-            const double c0 = rc.C[(2 * h) * 4 + sp], c1 = rc.C[(2 * h + 1) * 4 + sp];
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-                {
-                  acc[0][b][a] = fma(c0, P[b][a], acc[0][b][a]);
-                  acc[1][b][a] = fma(c1, P[b][a], acc[1][b][a]);
-                }
-            // in-plane sweeps: only for the planes this thread owns (it = 0, 1)
-            if (it < 2)
-              {
-                double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0};
-                if (role == 0)
-                  {
-                    if (actA)
-                      {
-                        if (from_t0)
-                          {
-                            const double2 v0 = lds128(t0b + sp * 2048), v1 = lds128(t0b + sp * 2048 + 16);
-                            fa[0] = v0.x;
-                            fa[1] = v0.y;
-                            fa[2] = v1.x;
-                            fa[3] = v1.y;
-                          }
-                        else if (it == 0)
-                          {
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                              fa[b] = tr[0][b];
-                          }
-                        else
-                          {
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                              fa[b] = tr[1][b];
-                          }
-                        // this cell's end layer is the next cell's trace (uniform branches keep the indices static)
-                        if (it == 0)
-                          {
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                              tr[0][b] = descend ? P[b][0] : P[b][3];
-                          }
-                        else
-                          {
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                              tr[1][b] = descend ? P[b][0] : P[b][3];
-                          }
-                      }
-                    if (actB)
-                      {
-                        const uint32_t r32 = uint32_t(t) + 64u * uint32_t(sp);
-                        const uint32_t fl  = (r32 >> 2) & 1u;
-                        const uint32_t tb  = fbuf + r32 * 32u;
-                        const double2  v0 = lds128(tb + ((0u ^ fl) << 4)), v1 = lds128(tb + ((1u ^ fl) << 4));
-                        fb[0] = v0.x;
-                        fb[1] = v0.y;
-                        fb[2] = v1.x;
-                        fb[3] = v1.y;
-                      }
-                  }
-                else
-                  {
-                    if (actA)
-                      {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                          fa[b] = lds64(fcol + 128u * uint32_t(b) + 512u * uint32_t(sp));
-                      }
-                    if (actB)
-                      {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                          fb[a] = lds64(fcol + F_BYTES + 128u * uint32_t(a) + 512u * uint32_t(sp));
-                      }
-                  }
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                  {
-                    double q[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                      {
-                        double v = rc.A[a * 4 + 0] * P[b][0];
-#pragma unroll
-                        for (int j = 1; j < 4; ++j)
-                          v = fma(rc.A[a * 4 + j], P[b][j], v);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                          v = fma(rc.B[b * 4 + j], P[j][a], v);
-                        v    = fma(rc.LA[a], fa[b], v);
-                        v    = fma(rc.LB[b], fb[a], v);
-                        q[a] = v;
-                      }
-                    // one uniform branch per row keeps the register indices static
-                    if (it == 1)
-                      {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                          acc[1][b][a] += q[a];
-                      }
-                    else
-                      {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                          acc[0][b][a] += q[a];
-                      }
-                  }
-              }
-            if (it == 1 && role != 0)
-              {
-                // in-plane faces of directions 2 and 3 are done: let the face producer refill this slot
-                if (actA)
-                  release(bars.r2fEmpty(f, 0));
-                if (actB)
-                  release(bars.r2fEmpty(f, 1));
-              }
-          }
-
-#endif
 
         // ---- the cell stage is free (both rounds read it at the same time), then the face of direction C
         release(bars.emptyU(s));
