@@ -724,9 +724,11 @@ hd_advection_destroy(hd_advection *op)
 int
 hd_advection_set_kernel(hd_advection *op, int which)
 {
-  HD_REQUIRE(op && which >= 0 && which <= 2, "bad argument");
+  HD_REQUIRE(op && which >= 0 && which <= 3, "bad argument");
   if (which == 2 && !hd::fast6d_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
+  if (which == 3 && !hd::tile_supported(op))
+    return hd::fail(HD_ERR_UNSUPPORTED, "the tile kernel covers degree 3 in 1D1V / 2D2V without Dirichlet sides");
   op->kernel_choice = which;
   return HD_OK;
 }
@@ -778,10 +780,11 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
     rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu, part);
   else
     {
-      // the generic kernel has no interior/boundary split: everything runs in the boundary part
+      // the generic and tile kernels have no interior/boundary split: everything runs in the boundary part
       if (part == HD_PART_INTERIOR)
         return HD_OK;
-      rc = hd::launch_generic(op, dst, src, ghosts, time, fu);
+      const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_supported(op));
+      rc              = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);
     }
   if (rc != HD_OK)
     return rc;

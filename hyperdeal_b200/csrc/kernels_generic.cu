@@ -437,6 +437,275 @@ namespace
     return hd::fail(HD_ERR_UNSUPPORTED, "dim_x + dim_v must be in 2..6");
   }
 
+  // --------------------------------------------------------------------------------------
+  // Tile kernel: degree 3, dim_x + dim_v = 2 or 4 (1D1V, 2D2V — BASELINE.json configs[0]), periodic and ghost sides.
+  //
+  // The generic kernel above re-reads every value of a cell 13 times from shared memory (one line of outputs per thread,
+  // all directions) and is shared-memory bound at ~20 % of the HBM roofline.  Here the directions are taken two at a
+  // time ("rounds", like the pipelined 3D3V kernel): in round r a thread owns the 4x4 tile over directions (2r, 2r+1) of
+  // one cell in registers — 16 loads for 16 x (4 + 4) FMAs — and hands its partial sums to the next round through a
+  // second shared-memory buffer; the last round writes dst (or the fused LSRK update) coalesced.  A CTA of 256 threads
+  // works on 256 / 4^(dim-2) consecutive cells (contiguous in memory, staged with 16-byte loads); tiles are padded by 16
+  // bytes so that the 128-bit tile loads of round 0 are conflict-free.  The (k+1)x(k+1) matrices are a __grid_constant__
+  // kernel parameter (FMA operands straight from the constant bank).  Neighbour traces: the direction-0 trace comes from
+  // shared memory when the neighbour cell is in the same CTA (its values are 32 B apart in global memory), all others
+  // are contiguous in global memory and read through L1/L2.
+  template <typename T>
+  struct TileCoef
+  {
+    T C[4][16]; // [direction][out * 4 + in]
+    T L0[4][4]; // lifting of the lower neighbour's trace
+    T L1[4][4]; // ... upper neighbour's
+  };
+
+  template <typename T, int DIM>
+  __global__ void __launch_bounds__(256) k_apply_tile(const __grid_constant__ GenParams<T, DIM> p, const __grid_constant__ TileCoef<T> cf)
+  {
+    constexpr int N   = 4;
+    constexpr int ND  = IPow<N, DIM>::value;
+    constexpr int NT  = ND / 16;          // tiles per cell and round
+    constexpr int CPB = 256 / NT;         // cells per CTA
+    constexpr int PAD = 16 / sizeof(T);   // padding per tile (values)
+    constexpr int TS  = 16 + PAD;         // padded tile size
+    constexpr int NDP = NT * TS;          // padded cell size
+    constexpr int V4  = 16 * sizeof(T) / 16, TS4 = TS * sizeof(T) / 16; // 16-byte words per tile, plain and padded
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *             u     = reinterpret_cast<T *>(smem_raw);
+    T *             part  = u + (size_t)CPB * NDP;
+    const long long cell0 = (long long)blockIdx.x * CPB;
+    long long       n_valid = p.ncells - cell0;
+    if (n_valid > CPB)
+      n_valid = CPB;
+    {
+      const int4 *g4 = reinterpret_cast<const int4 *>(p.src + cell0 * ND);
+      int4 *      s4 = reinterpret_cast<int4 *>(u);
+      const int   n4 = int(n_valid * ND * sizeof(T) / 16);
+      for (int i = threadIdx.x; i < n4; i += 256)
+        s4[(i / V4) * TS4 + (i % V4)] = __ldg(g4 + i);
+    }
+    __syncthreads();
+
+    const int       lc     = threadIdx.x / NT, tt = threadIdx.x % NT;
+    const long long cell   = cell0 + lc;
+    const bool      active = lc < n_valid;
+    int             c[DIM];
+    long long       cstr[DIM];
+    {
+      long long r = active ? cell : 0, m = 1;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        {
+          c[d]    = int(r % p.ncell[d]);
+          r /= p.ncell[d];
+          cstr[d] = m;
+          m *= p.ncell[d];
+        }
+    }
+    auto padded = [](int i) { return i + PAD * (i >> 4); };
+    const T *uc = u + (size_t)lc * NDP;
+    T *      pc = part + (size_t)lc * NDP;
+
+#pragma unroll
+    for (int r = 0; r < DIM / 2; ++r)
+      {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int dA = 2 * r, dB = 2 * r + 1;
+        const int sA = 1 << (2 * dA), sB = 1 << (2 * dB);
+        const int base = (tt % sA) + (tt / sA) * (sA * 16); // dof index of the tile's (a, b) = (0, 0) entry
+        if (active)
+          {
+            T U[4][4], out[4][4]; // [b][a]
+            if (r == 0)
+              {
+                // the tile is contiguous: 128-bit loads
+                const int4 *q = reinterpret_cast<const int4 *>(uc + tt * TS);
+                int4        w[V4];
+#pragma unroll
+                for (int i = 0; i < V4; ++i)
+                  w[i] = q[i];
+                const T *wv = reinterpret_cast<const T *>(w);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      U[b][a]   = wv[4 * b + a];
+                      out[b][a] = T(0);
+                    }
+              }
+            else
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      const int i = padded(base + a * sA + b * sB);
+                      U[b][a]     = uc[i];
+                      out[b][a]   = pc[i];
+                    }
+              }
+            // the two in-tile sweeps
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                {
+                  T v = out[b][a];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    v += cf.C[dA][a * 4 + j] * U[b][j];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    v += cf.C[dB][b * 4 + j] * U[j][a];
+                  out[b][a] = v;
+                }
+            // neighbour traces of the two directions
+#pragma unroll
+            for (int which = 0; which < 2; ++which)
+              {
+                const int d = which ? dB : dA, sd = which ? sB : sA, so = which ? sA : sB; // so: stride of the tile's other direction
+#pragma unroll
+                for (int side = 0; side < 2; ++side)
+                  {
+                    if (!((p.nb_mask[d] >> side) & 1))
+                      continue;
+                    const bool at_edge = side ? (c[d] == p.ncell[d] - 1) : (c[d] == 0);
+                    const int  layer   = side ? 0 : N - 1; // neighbour's layer touching the shared face
+                    T          tv[4];
+                    if (at_edge && p.side_kind[d][side] == HD_SIDE_GHOST)
+                      {
+                        long long fc = 0, m = 1;
+#pragma unroll
+                        for (int e = 0; e < DIM; ++e)
+                          if (e != d)
+                            {
+                              fc += c[e] * m;
+                              m *= p.ncell[e];
+                            }
+                        const T *g = p.ghost + p.ghost_off[d][side] + fc * (ND / N);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                          {
+                            const int o = base + x * so; // dof index with digit d = 0
+                            tv[x]       = __ldg(g + (o % sd) + (o / (sd * N)) * sd);
+                          }
+                      }
+                    else
+                      {
+                        long long nb = cell + (side ? cstr[d] : -cstr[d]);
+                        if (at_edge) // periodic inside the brick
+                          nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
+                        const int o = base + layer * sd;
+                        if (d == 0 && nb >= cell0 && nb < cell0 + n_valid)
+                          {
+                            const T *un = u + (size_t)(nb - cell0) * NDP;
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                              tv[x] = un[padded(o + x * so)];
+                          }
+                        else
+                          {
+                            const T *g = p.src + nb * ND + o;
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                              tv[x] = __ldg(g + x * so);
+                          }
+                      }
+                    const T *L = side ? cf.L1[d] : cf.L0[d];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        out[b][a] += which ? L[b] * tv[a] : L[a] * tv[b];
+                  }
+              }
+            if (r == DIM / 2 - 1)
+              {
+                const long long g = cell * ND + base;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      const long long i = g + a * sA + b * sB;
+                      if (p.fused)
+                        {
+                          const T s = p.sol[i];
+                          p.sol[i]  = s + p.fb * out[b][a];
+                          if (p.fa != T(0))
+                            p.ti_next[i] = s + p.fa * out[b][a];
+                        }
+                      else
+                        p.dst[i] = out[b][a];
+                    }
+              }
+            else
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    pc[padded(base + a * sA + b * sB)] = out[b][a];
+              }
+          }
+        if (r < DIM / 2 - 1)
+          __syncthreads();
+      }
+  }
+
+  template <typename T, int DIM>
+  int
+  launch_tile_t(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu)
+  {
+    hd_mesh *         m   = op->mesh;
+    constexpr int     ND  = IPow<4, DIM>::value;
+    constexpr int     CPB = 256 / (ND / 16);
+    constexpr int     NDP = (ND / 16) * (16 + 16 / (int)sizeof(T));
+    GenParams<T, DIM> p;
+    TileCoef<T>       cf;
+    p.src   = static_cast<const T *>(src);
+    p.dst   = static_cast<T *>(dst);
+    p.ghost = static_cast<const T *>(ghosts);
+    p.coef  = nullptr;
+    for (int d = 0; d < 4; ++d)
+      for (int i = 0; i < 16; ++i)
+        {
+          cf.C[d][i] = d < DIM ? T(op->hC[d][0][i]) : T(0);
+          if (i < 4)
+            {
+              cf.L0[d][i] = d < DIM ? T(op->hL0[d][i]) : T(0);
+              cf.L1[d][i] = d < DIM ? T(op->hL1[d][i]) : T(0);
+            }
+        }
+    for (int d = 0; d < DIM; ++d)
+      {
+        p.ncell[d]        = m->d.n_cells[d];
+        p.side_kind[d][0] = m->d.side_kind[d][0];
+        p.side_kind[d][1] = m->d.side_kind[d][1];
+        p.nb_mask[d]      = op->nb_mask[d];
+        p.ghost_off[d][0] = m->ghost_off[d][0];
+        p.ghost_off[d][1] = m->ghost_off[d][1];
+      }
+    p.ncells  = m->ncells;
+    p.sol     = static_cast<T *>(fu.sol);
+    p.ti_next = static_cast<T *>(fu.ti_next);
+    p.fb      = T(fu.fb);
+    p.fa      = T(fu.fa);
+    p.fused   = fu.enabled;
+    const size_t smem = (size_t)(DIM > 2 ? 2 : 1) * CPB * NDP * sizeof(T);
+    auto         kern = k_apply_tile<T, DIM>;
+    if (smem > 48 * 1024)
+      HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (m->ncells + CPB - 1) / CPB;
+    kern<<<(unsigned)grid, 256, smem, m->ctx->stream>>>(p, cf);
+    HD_CUDA(cudaGetLastError());
+    op->launches++;
+    op->last_kernel = "tile";
+    return HD_OK;
+  }
+
   template <typename T>
   int
   launch_n(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu)
@@ -460,6 +729,30 @@ namespace
 
 namespace hd
 {
+  // the tile kernel covers degree 3 in 1D1V and 2D2V without Dirichlet sides (those keep the generic kernel, whose
+  // matrices come in four boundary variants)
+  bool
+  tile_supported(const hd_advection *op)
+  {
+    const hd_mesh *m = op->mesh;
+    if (m->n != 4 || (m->dim != 2 && m->dim != 4))
+      return false;
+    for (int d = 0; d < m->dim; ++d)
+      for (int s = 0; s < 2; ++s)
+        if (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET || m->d.side_kind[d][s] == HD_SIDE_DIRICHLET_HOM)
+          return false;
+    return true;
+  }
+
+  int
+  launch_tile(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
+  {
+    const bool f64 = op->mesh->d.number_type == HD_F64;
+    if (op->mesh->dim == 2)
+      return f64 ? launch_tile_t<double, 2>(op, dst, src, ghosts, fu) : launch_tile_t<float, 2>(op, dst, src, ghosts, fu);
+    return f64 ? launch_tile_t<double, 4>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4>(op, dst, src, ghosts, fu);
+  }
+
   int
   launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
   {
