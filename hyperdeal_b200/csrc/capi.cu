@@ -93,18 +93,17 @@ namespace
       }
   }
 
+  // The built-in fields are products of 1-D factors: value(x) = prod_d builtin_factor(d, x_d), multiplied in the order
+  // d = 0, 1, ... (examples/advection/cases/hyperrectangle.h:46-57: sin in direction 0, cos in the others).  The kernels below evaluate the factors once per cell and direction.
   __device__ double
-  builtin_value(int fn_id, int dim, const double *x, double t)
+  builtin_factor(int fn_id, int d, double x, double t)
   {
     if (fn_id == HD_FN_HYPERRECTANGLE)
       {
-        // examples/advection/cases/hyperrectangle.h:46-57
         const double adv[6] = {1.0, 0.15, -0.05, 0.0, 0.0, 0.0};
         const double PI     = 3.14159265358979323846;
-        double       r      = sin(2.0 * (x[0] - t * adv[0]) * PI);
-        for (int d = 1; d < dim; ++d)
-          r *= cos(2.0 * (x[d] - t * adv[d]) * PI);
-        return r;
+        const double arg    = 2.0 * (x - t * adv[d]) * PI;
+        return d == 0 ? sin(arg) : cos(arg);
       }
     return 0.0;
   }
@@ -112,23 +111,41 @@ namespace
   // VectorTools::interpolate, numerics/vector_tools.h:88-137
   template <typename T>
   __global__ void
-  k_interpolate(T *__restrict__ vec, LatticeParams lp, const double *__restrict__ nodes, int fn_id, double time)
+  k_interpolate(T *__restrict__ vec, LatticeParams lp, const double *__restrict__ nodes, int fn_id, double time, int cells_per_cta)
   {
-    const long long total   = lp.nd * lp.ncells;
-    const long long gstride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride)
+    // a CTA takes cells_per_cta consecutive cells: 1-D factor tables [cell][direction][node] in shared memory, then one
+    // product of dim table entries per nodal value (coalesced stores)
+    extern __shared__ double tab[];
+    const int       dim = lp.dim, n = lp.n;
+    const long long cell0 = (long long)blockIdx.x * cells_per_cta;
+    long long       nloc  = lp.ncells - cell0;
+    if (nloc > cells_per_cta)
+      nloc = cells_per_cta;
+    for (int e = threadIdx.x; e < nloc * dim * n; e += blockDim.x)
       {
-        long long cell = i / lp.nd, o = i - cell * lp.nd;
-        double    x[HD_MAX_DIM];
-        for (int d = 0; d < lp.dim; ++d)
+        const int lc = e / (dim * n), d = (e / n) % dim, id = e % n;
+        long long r  = cell0 + lc;
+        for (int k = 0; k < d; ++k)
+          r /= lp.ncell[k];
+        const int    c = int(r % lp.ncell[d]);
+        const double x = lp.left[d] + lp.h[d] * ((c + lp.cell_offset[d]) + nodes[id]);
+        tab[e]         = builtin_factor(fn_id, d, x, time);
+      }
+    __syncthreads();
+    const long long total = nloc * lp.nd;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x)
+      {
+        const int     lc = int(i / lp.nd);
+        long long     o  = i - lc * lp.nd;
+        const double *t  = tab + lc * dim * n;
+        double        r  = t[o % n];
+        o /= n;
+        for (int d = 1; d < dim; ++d)
           {
-            const int c = int(cell % lp.ncell[d]);
-            cell /= lp.ncell[d];
-            const int id = int(o % lp.n);
-            o /= lp.n;
-            x[d] = lp.left[d] + lp.h[d] * ((c + lp.cell_offset[d]) + nodes[id]);
+            r *= t[d * n + o % n];
+            o /= n;
           }
-        vec[i] = T(builtin_value(fn_id, lp.dim, x, time));
+        vec[cell0 * lp.nd + i] = T(r);
       }
   }
 
@@ -183,20 +200,27 @@ namespace
         c[d] = int(r % lp.ncell[d]);
         r /= lp.ncell[d];
       }
+    // 1-D factors of the analytic field at the quadrature points of this cell (the sweeps are done: outb is free)
+    double *ftab = outb;
+    for (int e = threadIdx.x; e < dim * nq; e += blockDim.x)
+      {
+        const int d = e / nq, q = e % nq;
+        ftab[e]     = builtin_factor(fn_id, d, lp.left[d] + lp.h[d] * ((c[d] + lp.cell_offset[d]) + xq[q]), time);
+      }
+    __syncthreads();
     double s_norm = 0, s_err = 0;
     for (long long i = threadIdx.x; i < nqd; i += blockDim.x)
       {
         long long rr = i;
-        double    x[HD_MAX_DIM], jxw = 1;
+        double    jxw = 1, f = 1;
         for (int d = 0; d < dim; ++d)
           {
             const int q = int(rr % nq);
             rr /= nq;
-            x[d] = lp.left[d] + lp.h[d] * ((c[d] + lp.cell_offset[d]) + xq[q]);
+            f   = d == 0 ? ftab[q] : f * ftab[d * nq + q];
             jxw *= lp.h[d] * w[q];
           }
         const double u = in[i];
-        const double f = builtin_value(fn_id, dim, x, time);
         s_norm += u * u * jxw;
         s_err += (u - f) * (u - f) * jxw;
       }
@@ -783,7 +807,7 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
       // the generic and tile kernels have no interior/boundary split: everything runs in the boundary part
       if (part == HD_PART_INTERIOR)
         return HD_OK;
-      const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_supported(op));
+      const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_preferred(op));
       rc              = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);
     }
   if (rc != HD_OK)
@@ -1247,12 +1271,14 @@ hd_interpolate_builtin(hd_mesh *m, void *vec, int fn_id, double time)
 {
   HD_REQUIRE(m && vec, "null argument");
   HD_CUDA(cudaSetDevice(m->ctx->device));
-  const LatticeParams lp = lattice(m);
-  const unsigned      g  = grid_for(m->ctx, m->ndofs, 256);
+  const LatticeParams lp  = lattice(m);
+  const int           cpb = m->nd >= 1024 ? 1 : int(1024 / m->nd); // >= 1024 nodal values per CTA
+  const size_t        smem = (size_t)cpb * m->dim * m->n * sizeof(double);
+  const long long     g    = (m->ncells + cpb - 1) / cpb;
   if (m->d.number_type == HD_F64)
-    k_interpolate<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<double *>(vec), lp, m->d_basis, fn_id, time);
+    k_interpolate<double><<<(unsigned)g, 256, smem, m->ctx->stream>>>(static_cast<double *>(vec), lp, m->d_basis, fn_id, time, cpb);
   else
-    k_interpolate<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<float *>(vec), lp, m->d_basis, fn_id, time);
+    k_interpolate<float><<<(unsigned)g, 256, smem, m->ctx->stream>>>(static_cast<float *>(vec), lp, m->d_basis, fn_id, time, cpb);
   HD_CUDA(cudaGetLastError());
   return HD_OK;
 }

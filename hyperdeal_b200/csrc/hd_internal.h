@@ -120,6 +120,7 @@ namespace hd
   // kernels_generic.cu
   int launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   bool tile_supported(const hd_advection *op);
+  bool tile_preferred(const hd_advection *op);
   int  launch_tile(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);

@@ -9,6 +9,8 @@
 // either from `src` itself or from the ghost-face buffer for bricks owned by another GPU.
 // This kernel is the correctness workhorse and the fallback for every configuration; the
 // 3D3V k=3 double case has its own pipelined kernel (kernel_fast6d.cu).
+#include <cstdlib>
+
 #include "hd_internal.h"
 
 namespace
@@ -458,13 +460,13 @@ namespace
     T L1[4][4]; // ... upper neighbour's
   };
 
-  template <typename T, int DIM>
-  __global__ void __launch_bounds__(256) k_apply_tile(const __grid_constant__ GenParams<T, DIM> p, const __grid_constant__ TileCoef<T> cf)
+  template <typename T, int DIM, int THREADS>
+  __global__ void __launch_bounds__(THREADS) k_apply_tile(const __grid_constant__ GenParams<T, DIM> p, const __grid_constant__ TileCoef<T> cf)
   {
     constexpr int N   = 4;
     constexpr int ND  = IPow<N, DIM>::value;
     constexpr int NT  = ND / 16;          // tiles per cell and round
-    constexpr int CPB = 256 / NT;         // cells per CTA
+    constexpr int CPB = THREADS / NT;     // cells per CTA
     constexpr int PAD = 16 / sizeof(T);   // padding per tile (values)
     constexpr int TS  = 16 + PAD;         // padded tile size
     constexpr int NDP = NT * TS;          // padded cell size
@@ -480,7 +482,7 @@ namespace
       const int4 *g4 = reinterpret_cast<const int4 *>(p.src + cell0 * ND);
       int4 *      s4 = reinterpret_cast<int4 *>(u);
       const int   n4 = int(n_valid * ND * sizeof(T) / 16);
-      for (int i = threadIdx.x; i < n4; i += 256)
+      for (int i = threadIdx.x; i < n4; i += THREADS)
         s4[(i / V4) * TS4 + (i % V4)] = __ldg(g4 + i);
     }
     __syncthreads();
@@ -655,13 +657,13 @@ namespace
       }
   }
 
-  template <typename T, int DIM>
+  template <typename T, int DIM, int THREADS>
   int
   launch_tile_t(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu)
   {
     hd_mesh *         m   = op->mesh;
     constexpr int     ND  = IPow<4, DIM>::value;
-    constexpr int     CPB = 256 / (ND / 16);
+    constexpr int     CPB = THREADS / (ND / 16);
     constexpr int     NDP = (ND / 16) * (16 + 16 / (int)sizeof(T));
     GenParams<T, DIM> p;
     TileCoef<T>       cf;
@@ -695,11 +697,11 @@ namespace
     p.fa      = T(fu.fa);
     p.fused   = fu.enabled;
     const size_t smem = (size_t)(DIM > 2 ? 2 : 1) * CPB * NDP * sizeof(T);
-    auto         kern = k_apply_tile<T, DIM>;
+    auto         kern = k_apply_tile<T, DIM, THREADS>;
     if (smem > 48 * 1024)
       HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (m->ncells + CPB - 1) / CPB;
-    kern<<<(unsigned)grid, 256, smem, m->ctx->stream>>>(p, cf);
+    kern<<<(unsigned)grid, THREADS, smem, m->ctx->stream>>>(p, cf);
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = "tile";
@@ -732,6 +734,13 @@ namespace hd
   // the tile kernel covers degree 3 in 1D1V and 2D2V without Dirichlet sides (those keep the generic kernel, whose
   // matrices come in four boundary variants)
   bool
+  tile_preferred(const hd_advection *op)
+  {
+    // automatic choice: 2D2V only — in 1D1V (16 values per cell) the generic kernel is the faster one (170 vs 158 GDoF/s)
+    return tile_supported(op) && op->mesh->dim == 4;
+  }
+
+  bool
   tile_supported(const hd_advection *op)
   {
     const hd_mesh *m = op->mesh;
@@ -749,8 +758,20 @@ namespace hd
   {
     const bool f64 = op->mesh->d.number_type == HD_F64;
     if (op->mesh->dim == 2)
-      return f64 ? launch_tile_t<double, 2>(op, dst, src, ghosts, fu) : launch_tile_t<float, 2>(op, dst, src, ghosts, fu);
-    return f64 ? launch_tile_t<double, 4>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4>(op, dst, src, ghosts, fu);
+      return f64 ? launch_tile_t<double, 2, 256>(op, dst, src, ghosts, fu) : launch_tile_t<float, 2, 256>(op, dst, src, ghosts, fu);
+    // CTA size (cells per CTA = threads / 16): 128 threads = 8 cells, 36 KiB of shared memory, 6 CTAs per SM measured best
+    // (228 vs 211 GDoF/s with 256, 149 with 512); HD_TILE_THREADS = 64 | 128 | 256 | 512 for experiments
+    static const int threads = [] {
+      const char *e = getenv("HD_TILE_THREADS");
+      return e ? atoi(e) : 128;
+    }();
+    if (threads == 64)
+      return f64 ? launch_tile_t<double, 4, 64>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4, 64>(op, dst, src, ghosts, fu);
+    if (threads == 128)
+      return f64 ? launch_tile_t<double, 4, 128>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4, 128>(op, dst, src, ghosts, fu);
+    if (threads == 512)
+      return f64 ? launch_tile_t<double, 4, 512>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4, 512>(op, dst, src, ghosts, fu);
+    return f64 ? launch_tile_t<double, 4, 256>(op, dst, src, ghosts, fu) : launch_tile_t<float, 4, 256>(op, dst, src, ghosts, fu);
   }
 
   int
