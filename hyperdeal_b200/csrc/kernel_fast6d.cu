@@ -249,6 +249,14 @@ namespace
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
   }
+  // global load that stays where it is written (asm volatile is not moved across the other volatile asm around it)
+  __device__ __forceinline__ double
+  ldg_f64_here(const double *p)
+  {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+  }
   __device__ __forceinline__ void
   sts128(uint32_t addr, double a, double b)
   {
@@ -382,6 +390,16 @@ namespace
         const int  cellid = *reinterpret_cast<const volatile int *>(gbase + INFO_OFF + 32 * s);
         if (cellid < 0)
           break;
+        // fused LSRK update: the 32 values of `sol` this thread updates in the epilogue are requested now (first half)
+        // and after the plane loop (second half), so that their HBM latency is hidden behind the cell's arithmetic
+        double          svA[16], svB[16];
+        const long long gfu = (long long)cellid * CELL + cc + 1024 * i5 + 512 * h;
+        if (FUSED && role == 1)
+          {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              svA[q] = ldg_f64_here(p.sol + gfu + q * 16);
+          }
 
         double acc[2][4][4]; // [c - 2h][b][a]
 #pragma unroll
@@ -586,6 +604,12 @@ namespace
               release(bars.r2fEmpty(f, 1));
           }
 
+        if (FUSED && role == 1)
+          {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              svB[q] = ldg_f64_here(p.sol + gfu + (q + 16) * 16);
+          }
         // ---- the cell stage is free (both rounds read it at the same time), then the face of direction C
         release(bars.emptyU(s));
         if (role == 0)
@@ -660,31 +684,27 @@ namespace
             const long long g = (long long)cellid * CELL + cc + 1024 * i5 + 512 * h;
             if (FUSED)
               {
-                const double *solr = p.sol + g;
                 double *      solw = p.sol + g;
                 double *      tiw  = p.ti_next + g;
 #pragma unroll
                 for (int cl = 0; cl < 2; ++cl)
                   {
-                    double sv[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                      sv[q] = stream ? __ldcs(solr + (q + 16 * cl) * 16) : solr[(q + 16 * cl) * 16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
                       {
                         const double kv = acc[cl][q >> 2][q & 3];
+                        const double sv = cl == 0 ? svA[q] : svB[q];
                         if (stream)
                           {
-                            __stcs(solw + (q + 16 * cl) * 16, fma(p.fb, kv, sv[q]));
+                            __stcs(solw + (q + 16 * cl) * 16, fma(p.fb, kv, sv));
                             if (p.fa != 0.0)
-                              __stcs(tiw + (q + 16 * cl) * 16, fma(p.fa, kv, sv[q]));
+                              __stcs(tiw + (q + 16 * cl) * 16, fma(p.fa, kv, sv));
                           }
                         else
                           {
-                            solw[(q + 16 * cl) * 16] = fma(p.fb, kv, sv[q]);
+                            solw[(q + 16 * cl) * 16] = fma(p.fb, kv, sv);
                             if (p.fa != 0.0)
-                              tiw[(q + 16 * cl) * 16] = fma(p.fa, kv, sv[q]);
+                              tiw[(q + 16 * cl) * 16] = fma(p.fa, kv, sv);
                           }
                       }
                   }
