@@ -452,6 +452,14 @@ namespace
   // kernel parameter (FMA operands straight from the constant bank).  Neighbour traces: the direction-0 trace comes from
   // shared memory when the neighbour cell is in the same CTA (its values are 32 B apart in global memory), all others
   // are contiguous in global memory and read through L1/L2.
+  // minimum CTAs per SM the register allocation of the tile kernel is held to: FP64 5 x 128 threads at 96 registers
+  // (measured 270 GDoF/s; 132 registers / 3 CTAs: 207, 80 registers with spills / 6 CTAs: 169), FP32 8
+  constexpr int
+  tile_min_ctas(int elem_size, int threads)
+  {
+    const int want = (elem_size == 8 ? 640 : 1024) / threads; // resident threads per SM the registers must allow
+    return want < 1 ? 1 : want;
+  }
   template <typename T>
   struct TileCoef
   {
@@ -461,7 +469,7 @@ namespace
   };
 
   template <typename T, int DIM, int THREADS>
-  __global__ void __launch_bounds__(THREADS) k_apply_tile(const __grid_constant__ GenParams<T, DIM> p, const __grid_constant__ TileCoef<T> cf)
+  __global__ void __launch_bounds__(THREADS, tile_min_ctas(sizeof(T), THREADS)) k_apply_tile(const __grid_constant__ GenParams<T, DIM> p, const __grid_constant__ TileCoef<T> cf)
   {
     constexpr int N   = 4;
     constexpr int ND  = IPow<N, DIM>::value;
@@ -478,15 +486,7 @@ namespace
     long long       n_valid = p.ncells - cell0;
     if (n_valid > CPB)
       n_valid = CPB;
-    {
-      const int4 *g4 = reinterpret_cast<const int4 *>(p.src + cell0 * ND);
-      int4 *      s4 = reinterpret_cast<int4 *>(u);
-      const int   n4 = int(n_valid * ND * sizeof(T) / 16);
-      for (int i = threadIdx.x; i < n4; i += THREADS)
-        s4[(i / V4) * TS4 + (i % V4)] = __ldg(g4 + i);
-    }
-    __syncthreads();
-
+    // cell coordinates first: the neighbour-trace loads below do not depend on the staged data
     const int       lc     = threadIdx.x / NT, tt = threadIdx.x % NT;
     const long long cell   = cell0 + lc;
     const bool      active = lc < n_valid;
@@ -507,14 +507,106 @@ namespace
     const T *uc = u + (size_t)lc * NDP;
     T *      pc = part + (size_t)lc * NDP;
 
+    // Neighbour traces of the two directions of round r: tv[which][side][x] (which: 0 = direction 2r, 1 = 2r+1; x runs
+    // along the tile's other direction).  Global / ghost sources are requested here; a direction-0 neighbour inside this
+    // CTA's batch is taken from shared memory later (from_smem), once the batch has landed.
+    auto request_traces = [&](const int r, T(&tv)[2][2][4], const T *(&from_smem)[2]) {
+      const int dA = 2 * r, dB = 2 * r + 1;
+      const int sA = 1 << (2 * dA), sB = 1 << (2 * dB);
+      const int base = (tt % sA) + (tt / sA) * (sA * 16);
+#pragma unroll
+      for (int which = 0; which < 2; ++which)
+        {
+          const int d = which ? dB : dA, sd = which ? sB : sA, so = which ? sA : sB;
+#pragma unroll
+          for (int side = 0; side < 2; ++side)
+            {
+#pragma unroll
+              for (int x = 0; x < 4; ++x)
+                tv[which][side][x] = T(0);
+              if (which == 0)
+                from_smem[side] = nullptr;
+              if (!active || !((p.nb_mask[d] >> side) & 1))
+                continue;
+              const bool at_edge = side ? (c[d] == p.ncell[d] - 1) : (c[d] == 0);
+              const int  layer   = side ? 0 : N - 1; // neighbour's layer touching the shared face
+              if (at_edge && p.side_kind[d][side] == HD_SIDE_GHOST)
+                {
+                  long long fc = 0, m = 1;
+#pragma unroll
+                  for (int e = 0; e < DIM; ++e)
+                    if (e != d)
+                      {
+                        fc += c[e] * m;
+                        m *= p.ncell[e];
+                      }
+                  const T *g = p.ghost + p.ghost_off[d][side] + fc * (ND / N);
+#pragma unroll
+                  for (int x = 0; x < 4; ++x)
+                    {
+                      const int o        = base + x * so; // dof index with digit d = 0
+                      tv[which][side][x] = __ldg(g + (o % sd) + (o / (sd * N)) * sd);
+                    }
+                }
+              else
+                {
+                  long long nb = cell + (side ? cstr[d] : -cstr[d]);
+                  if (at_edge) // periodic inside the brick
+                    nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
+                  const int o = base + layer * sd;
+                  if (d == 0 && nb >= cell0 && nb < cell0 + n_valid)
+                    from_smem[side] = u + (size_t)(nb - cell0) * NDP; // (which == 0 here)
+                  else
+                    {
+                      const T *g = p.src + nb * ND + o;
+#pragma unroll
+                      for (int x = 0; x < 4; ++x)
+                        tv[which][side][x] = __ldg(g + x * so);
+                    }
+                }
+            }
+        }
+    };
+
+    T        tv[2][2][4];
+    const T *from_smem[2];
+    request_traces(0, tv, from_smem);
+
+    // stage the batch (16-byte loads, all of a thread's loads in flight before the first store)
+    {
+      const int4 *  g4  = reinterpret_cast<const int4 *>(p.src + cell0 * ND);
+      int4 *        s4  = reinterpret_cast<int4 *>(u);
+      constexpr int PER = CPB * ND * (int)sizeof(T) / 16 / THREADS;
+      if (n_valid == CPB)
+        {
+          int4 w[PER];
+#pragma unroll
+          for (int k = 0; k < PER; ++k)
+            w[k] = __ldg(g4 + threadIdx.x + k * THREADS);
+#pragma unroll
+          for (int k = 0; k < PER; ++k)
+            {
+              const int i                        = threadIdx.x + k * THREADS;
+              s4[(i / V4) * TS4 + (i % V4)] = w[k];
+            }
+        }
+      else
+        {
+          const int n4 = int(n_valid * ND * sizeof(T) / 16);
+          for (int i = threadIdx.x; i < n4; i += THREADS)
+            s4[(i / V4) * TS4 + (i % V4)] = __ldg(g4 + i);
+        }
+    }
+    __syncthreads();
+
 #pragma unroll
     for (int r = 0; r < DIM / 2; ++r)
       {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int dA = 2 * r, dB = 2 * r + 1;
         const int sA = 1 << (2 * dA), sB = 1 << (2 * dB);
         const int base = (tt % sA) + (tt / sA) * (sA * 16); // dof index of the tile's (a, b) = (0, 0) entry
+        if (r > 0)
+          request_traces(r, tv, from_smem);
         if (active)
           {
             T U[4][4], out[4][4]; // [b][a]
@@ -534,6 +626,16 @@ namespace
                     {
                       U[b][a]   = wv[4 * b + a];
                       out[b][a] = T(0);
+                    }
+                // direction-0 neighbours inside the batch
+#pragma unroll
+                for (int side = 0; side < 2; ++side)
+                  if (from_smem[side])
+                    {
+                      const int o = base + (side ? 0 : N - 1) * sA;
+#pragma unroll
+                      for (int x = 0; x < 4; ++x)
+                        tv[0][side][x] = from_smem[side][padded(o + x * sB)];
                     }
               }
             else
@@ -563,65 +665,17 @@ namespace
                     v += cf.C[dB][b * 4 + j] * U[j][a];
                   out[b][a] = v;
                 }
-            // neighbour traces of the two directions
+            // neighbour traces (zero where there is none)
 #pragma unroll
-            for (int which = 0; which < 2; ++which)
+            for (int side = 0; side < 2; ++side)
               {
-                const int d = which ? dB : dA, sd = which ? sB : sA, so = which ? sA : sB; // so: stride of the tile's other direction
+                const T *LA = side ? cf.L1[dA] : cf.L0[dA];
+                const T *LB = side ? cf.L1[dB] : cf.L0[dB];
 #pragma unroll
-                for (int side = 0; side < 2; ++side)
-                  {
-                    if (!((p.nb_mask[d] >> side) & 1))
-                      continue;
-                    const bool at_edge = side ? (c[d] == p.ncell[d] - 1) : (c[d] == 0);
-                    const int  layer   = side ? 0 : N - 1; // neighbour's layer touching the shared face
-                    T          tv[4];
-                    if (at_edge && p.side_kind[d][side] == HD_SIDE_GHOST)
-                      {
-                        long long fc = 0, m = 1;
+                for (int b = 0; b < 4; ++b)
 #pragma unroll
-                        for (int e = 0; e < DIM; ++e)
-                          if (e != d)
-                            {
-                              fc += c[e] * m;
-                              m *= p.ncell[e];
-                            }
-                        const T *g = p.ghost + p.ghost_off[d][side] + fc * (ND / N);
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-                          {
-                            const int o = base + x * so; // dof index with digit d = 0
-                            tv[x]       = __ldg(g + (o % sd) + (o / (sd * N)) * sd);
-                          }
-                      }
-                    else
-                      {
-                        long long nb = cell + (side ? cstr[d] : -cstr[d]);
-                        if (at_edge) // periodic inside the brick
-                          nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
-                        const int o = base + layer * sd;
-                        if (d == 0 && nb >= cell0 && nb < cell0 + n_valid)
-                          {
-                            const T *un = u + (size_t)(nb - cell0) * NDP;
-#pragma unroll
-                            for (int x = 0; x < 4; ++x)
-                              tv[x] = un[padded(o + x * so)];
-                          }
-                        else
-                          {
-                            const T *g = p.src + nb * ND + o;
-#pragma unroll
-                            for (int x = 0; x < 4; ++x)
-                              tv[x] = __ldg(g + x * so);
-                          }
-                      }
-                    const T *L = side ? cf.L1[d] : cf.L0[d];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-#pragma unroll
-                      for (int a = 0; a < 4; ++a)
-                        out[b][a] += which ? L[b] * tv[a] : L[a] * tv[b];
-                  }
+                  for (int a = 0; a < 4; ++a)
+                    out[b][a] += LA[a] * tv[0][side][b] + LB[b] * tv[1][side][a];
               }
             if (r == DIM / 2 - 1)
               {
