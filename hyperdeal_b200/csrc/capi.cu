@@ -752,7 +752,7 @@ hd_advection_set_kernel(hd_advection *op, int which)
   if (which == 2 && !hd::fast6d_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
   if (which == 3 && !hd::tile_supported(op))
-    return hd::fail(HD_ERR_UNSUPPORTED, "the tile kernel covers degree 3 in 1D1V / 2D2V without Dirichlet sides");
+    return hd::fail(HD_ERR_UNSUPPORTED, "the tile kernel covers degree 3 in 1D1V / 2D2V / 3D3V without Dirichlet sides");
   op->kernel_choice = which;
   return HD_OK;
 }

@@ -440,7 +440,7 @@ namespace
   }
 
   // --------------------------------------------------------------------------------------
-  // Tile kernel: degree 3, dim_x + dim_v = 2 or 4 (1D1V, 2D2V — BASELINE.json configs[0]), periodic and ghost sides.
+  // Tile kernel: degree 3, dim_x + dim_v = 2, 4 or 6 (1D1V, 2D2V — BASELINE.json configs[0] —, 3D3V), periodic and ghost sides.
   //
   // The generic kernel above re-reads every value of a cell 13 times from shared memory (one line of outputs per thread,
   // all directions) and is shared-memory bound at ~20 % of the HBM roofline.  Here the directions are taken two at a
@@ -463,9 +463,9 @@ namespace
   template <typename T>
   struct TileCoef
   {
-    T C[4][16]; // [direction][out * 4 + in]
-    T L0[4][4]; // lifting of the lower neighbour's trace
-    T L1[4][4]; // ... upper neighbour's
+    T C[6][16]; // [direction][out * 4 + in]
+    T L0[6][4]; // lifting of the lower neighbour's trace
+    T L1[6][4]; // ... upper neighbour's
   };
 
   template <typename T, int DIM, int THREADS>
@@ -725,7 +725,7 @@ namespace
     p.dst   = static_cast<T *>(dst);
     p.ghost = static_cast<const T *>(ghosts);
     p.coef  = nullptr;
-    for (int d = 0; d < 4; ++d)
+    for (int d = 0; d < 6; ++d)
       for (int i = 0; i < 16; ++i)
         {
           cf.C[d][i] = d < DIM ? T(op->hC[d][0][i]) : T(0);
@@ -785,20 +785,21 @@ namespace
 
 namespace hd
 {
-  // the tile kernel covers degree 3 in 1D1V and 2D2V without Dirichlet sides (those keep the generic kernel, whose
+  // the tile kernel covers degree 3 in 1D1V, 2D2V and 3D3V without Dirichlet sides (those keep the generic kernel, whose
   // matrices come in four boundary variants)
   bool
   tile_preferred(const hd_advection *op)
   {
-    // automatic choice: 2D2V only — in 1D1V (16 values per cell) the generic kernel is the faster one (170 vs 158 GDoF/s)
-    return tile_supported(op) && op->mesh->dim == 4;
+    // automatic choice: 2D2V, and the 3D3V cases the pipelined kernel does not take (FP32) — in 1D1V (16 values per cell)
+    // the generic kernel is the faster one (170 vs 158 GDoF/s)
+    return tile_supported(op) && op->mesh->dim >= 4;
   }
 
   bool
   tile_supported(const hd_advection *op)
   {
     const hd_mesh *m = op->mesh;
-    if (m->n != 4 || (m->dim != 2 && m->dim != 4))
+    if (m->n != 4 || (m->dim != 2 && m->dim != 4 && m->dim != 6))
       return false;
     for (int d = 0; d < m->dim; ++d)
       for (int s = 0; s < 2; ++s)
@@ -813,6 +814,8 @@ namespace hd
     const bool f64 = op->mesh->d.number_type == HD_F64;
     if (op->mesh->dim == 2)
       return f64 ? launch_tile_t<double, 2, 256>(op, dst, src, ghosts, fu) : launch_tile_t<float, 2, 256>(op, dst, src, ghosts, fu);
+    if (op->mesh->dim == 6) // one cell (256 tiles per round) per CTA, three rounds
+      return f64 ? launch_tile_t<double, 6, 256>(op, dst, src, ghosts, fu) : launch_tile_t<float, 6, 256>(op, dst, src, ghosts, fu);
     // CTA size (cells per CTA = threads / 16): 128 threads = 8 cells, 36 KiB of shared memory, 6 CTAs per SM measured best
     // (228 vs 211 GDoF/s with 256, 149 with 512); HD_TILE_THREADS = 64 | 128 | 256 | 512 for experiments
     static const int threads = [] {

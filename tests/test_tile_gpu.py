@@ -67,6 +67,10 @@ CASES = [
     (2, 2, (1, 1, 1, 1), None, False, 1.0, None),
     (2, 2, (17, 2, 1, 3), None, False, 0.5, (-1.0, -0.15, 0.05, -0.1)),  # all signs flipped
     (2, 2, (4, 4, 2, 2), None, False, 0.5, (0.0, 0.3, 0.0, -0.2)),       # zero components: no traces in those directions
+    (3, 3, (2, 2, 2, 2, 2, 2), None, False, 0.5, None),     # three rounds, one cell per CTA
+    (3, 3, (3, 2, 1, 2, 2, 3), None, False, 0.0, None),     # ragged, a direction with one cell
+    (3, 3, (4, 1, 2, 3, 1, 2), None, False, 0.5, (-1.0, -0.15, 0.05, -0.1, 0.15, -0.5)),
+    (3, 3, (2, 3, 2, 1, 2, 2), None, False, 0.5, (0.0, 0.3, 0.0, 0.0, -0.2, 0.0)),
 ]
 
 
@@ -77,10 +81,18 @@ def test_tile_kernel_matches_oracle_f64(api, ctx, dx, dv, nc, nq, colloc, skew, 
     assert rel <= 1e-12, rel
 
 
-@pytest.mark.parametrize("dx,dv,nc", [(1, 1, (9, 5)), (2, 2, (3, 2, 2, 3))])
+@pytest.mark.parametrize("dx,dv,nc", [(1, 1, (9, 5)), (2, 2, (3, 2, 2, 3)), (3, 3, (2, 2, 1, 2, 3, 2))])
 def test_tile_kernel_float(api, ctx, dx, dv, nc):
     rel, name = _run(api, ctx, dx, dv, nc, skew=0.5, dtype=np.float32)
     assert name == "tile" and rel <= 1e-5, rel
+
+
+def test_auto_selects_tile_kernel_for_3d3v_float(api, ctx):
+    """FP64 3D3V goes to the pipelined kernel, FP32 3D3V to the tile kernel"""
+    rel, name = _run(api, ctx, 3, 3, (2, 2, 2, 2, 2, 2), skew=0.5, kernel=0)
+    assert name == "advect_3d3v_k3" and rel <= 1e-12
+    rel, name = _run(api, ctx, 3, 3, (2, 2, 2, 2, 2, 2), skew=0.5, kernel=0, dtype=np.float32)
+    assert name == "tile" and rel <= 1e-5
 
 
 def test_auto_selects_tile_kernel_and_agrees_with_generic(api, ctx):
@@ -91,8 +103,8 @@ def test_auto_selects_tile_kernel_and_agrees_with_generic(api, ctx):
 
 
 def test_tile_kernel_refuses_what_it_does_not_cover(api, ctx):
-    mf = api.MatrixFree(ctx, 3, 3, 3, (2,) * 6, (0.0,) * 6, (1.0,) * 6)
-    op = api.AdvectionOperation(mf, VEL, 0.5)
+    mf = api.MatrixFree(ctx, 2, 1, 3, (2,) * 3, (0.0,) * 3, (1.0,) * 3)  # odd number of directions
+    op = api.AdvectionOperation(mf, VEL[:3], 0.5)
     with pytest.raises(api.HdError):
         op.set_kernel(3)
     mf2 = api.MatrixFree(ctx, 2, 2, 3, (2,) * 4, (0.0,) * 4, (1.0,) * 4, periodic=False)
@@ -105,13 +117,13 @@ def test_tile_kernel_refuses_what_it_does_not_cover(api, ctx):
         op3.set_kernel(3)
 
 
-@pytest.mark.parametrize("dx,dv,split_dir", [(2, 2, 0), (2, 2, 1), (2, 2, 2), (2, 2, 3), (1, 1, 0), (1, 1, 1)])
+@pytest.mark.parametrize("dx,dv,split_dir", [(2, 2, 0), (2, 2, 1), (2, 2, 2), (2, 2, 3), (1, 1, 0), (1, 1, 1), (3, 3, 0), (3, 3, 3), (3, 3, 5)])
 @pytest.mark.parametrize("vel_sign", [1.0, -1.0])
 def test_tile_kernel_two_bricks_with_ghost_faces(api, ctx, dx, dv, split_dir, vel_sign):
     """two bricks along one direction, faces exchanged by hand through hd_halo_pack: the ghost path of the tile kernel"""
     dim, k = dx + dv, 3
     vel = vel_sign * VEL[:dim]
-    nc = [3, 2, 2, 3][:dim]
+    nc = [3, 2, 2, 3, 2, 2][:dim]
     nc[split_dir] = 4
     left, right = (-1.0,) * dim, (1.0,) * dim
     om = O.Mesh(dx, dv, tuple(nc), left, right, (True,) * dim)

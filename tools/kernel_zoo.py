@@ -45,6 +45,8 @@ if sel in ("all", "apply"):
     torch.cuda.empty_cache()
     apply_case("apply 3D3V k=3 f64, 8^6 cells, generic kernel", 3, 3, 3, [8] * 6, np.float64, kernel=1)
     torch.cuda.empty_cache()
+    apply_case("apply 3D3V k=3 f64, 8^6 cells, tile kernel", 3, 3, 3, [8] * 6, np.float64, kernel=3)
+    torch.cuda.empty_cache()
     apply_case("apply 2D2V k=3 f64, 64x64x32x32 cells (configs[0])", 2, 2, 3, [64, 64, 32, 32], np.float64)
     torch.cuda.empty_cache()
     apply_case("apply 2D2V k=3 f64, 64x64x32x32 cells, generic kernel", 2, 2, 3, [64, 64, 32, 32], np.float64, kernel=1)
@@ -54,6 +56,8 @@ if sel in ("all", "apply"):
     apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2])", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32)
     torch.cuda.empty_cache()
     apply_case("apply 3D3V k=3 f32, 8^6 cells", 3, 3, 3, [8] * 6, np.float32)
+    torch.cuda.empty_cache()
+    apply_case("apply 3D3V k=3 f32, 8^6 cells, generic kernel", 3, 3, 3, [8] * 6, np.float32, kernel=1)
     torch.cuda.empty_cache()
     apply_case("apply 1D1V k=3 f64, 8192x8192 cells", 1, 1, 3, [8192, 8192], np.float64)
     torch.cuda.empty_cache()
