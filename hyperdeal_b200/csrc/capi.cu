@@ -748,7 +748,9 @@ hd_advection_destroy(hd_advection *op)
 int
 hd_advection_set_kernel(hd_advection *op, int which)
 {
-  HD_REQUIRE(op && which >= 0 && which <= 3, "bad argument");
+  HD_REQUIRE(op && which >= 0 && which <= 4, "bad argument");
+  if (which == 4 && !hd::tile_row_supported(op))
+    return hd::fail(HD_ERR_UNSUPPORTED, "the row-persistent tile kernel covers degree 3 in 3D3V without Dirichlet sides");
   if (which == 2 && !hd::fast6d_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
   if (which == 3 && !hd::tile_supported(op))
@@ -808,7 +810,10 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
       if (part == HD_PART_INTERIOR)
         return HD_OK;
       const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_preferred(op));
-      rc              = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);
+      if (op->kernel_choice == 4)
+        rc = hd::launch_tile_row(op, dst, src, ghosts, time, fu);
+      else
+        rc = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);
     }
   if (rc != HD_OK)
     return rc;

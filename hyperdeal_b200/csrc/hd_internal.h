@@ -121,6 +121,8 @@ namespace hd
   int launch_generic(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   bool tile_supported(const hd_advection *op);
   bool tile_preferred(const hd_advection *op);
+  bool tile_row_supported(const hd_advection *op);
+  int  launch_tile_row(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   int  launch_tile(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);

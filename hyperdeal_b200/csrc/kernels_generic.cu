@@ -711,6 +711,280 @@ namespace
       }
   }
 
+  // --------------------------------------------------------------------------------------
+  // Row-persistent tile kernel (3D3V, degree 3): the tile kernel's three rounds, but a CTA walks a whole row of cells
+  // along x_0 in upwind order.  The previous cell stays in shared memory, so the direction-0 neighbour traces (values
+  // 32 B apart in global memory — a full extra cell of sector traffic for the plain tile kernel) never leave the SM, and
+  // the next cell is staged with cp.async while rounds 1 and 2 of the current one run.  One code path for all threads,
+  // __syncthreads only.  Shared memory: 2 cell buffers + partial sums = 3 x 36 KiB (FP64), two CTAs per SM.
+  __device__ __forceinline__ void
+  cp_async_16(void *smem_dst, const void *gmem_src)
+  {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_wait_all()
+  {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+
+  template <typename T>
+  __global__ void __launch_bounds__(256, 2) k_apply_tile_row(const __grid_constant__ GenParams<T, 6> p, const __grid_constant__ TileCoef<T> cf)
+  {
+    constexpr int N = 4, DIM = 6, ND = 4096, NT = 256, THREADS = 256;
+    constexpr int PAD = 16 / sizeof(T), TS = 16 + PAD, NDP = NT * TS;
+    constexpr int V4 = 16 * sizeof(T) / 16, TS4 = TS * sizeof(T) / 16, PER = ND * (int)sizeof(T) / 16 / THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *       ub0  = reinterpret_cast<T *>(smem_raw);
+    T *       ub1  = ub0 + NDP;
+    T *       part = ub1 + NDP;
+    const int tt   = threadIdx.x;
+    const int n0   = p.ncell[0];
+    const long long nrows = p.ncells / n0;
+    const bool descend = (p.nb_mask[0] & 2) != 0; // upwind neighbour is the upper cell: walk downwards
+    auto padded = [](int i) { return i + PAD * (i >> 4); };
+    auto stage = [&](T *dst, long long cell) {
+      const int4 *g4 = reinterpret_cast<const int4 *>(p.src + cell * ND);
+      int4 *      s4 = reinterpret_cast<int4 *>(dst);
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        {
+          const int i = tt + k * THREADS;
+          cp_async_16(s4 + (i / V4) * TS4 + (i % V4), g4 + i);
+        }
+    };
+
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x)
+      {
+        int       c[DIM];
+        long long cstr[DIM];
+        {
+          long long r = row, m = n0;
+          cstr[0]     = 1;
+#pragma unroll
+          for (int d = 1; d < DIM; ++d)
+            {
+              c[d]    = int(r % p.ncell[d]);
+              r /= p.ncell[d];
+              cstr[d] = m;
+              m *= p.ncell[d];
+            }
+        }
+        const long long row_cell0 = row * n0;
+        stage(ub0, row_cell0 + (descend ? n0 - 1 : 0));
+        cp_async_wait_all();
+        __syncthreads();
+
+        for (int step = 0; step < n0; ++step)
+          {
+            c[0]                 = descend ? n0 - 1 - step : step;
+            const long long cell = row_cell0 + c[0];
+            const T *       uc   = (step & 1) ? ub1 : ub0; // this cell
+            T *             un   = (step & 1) ? ub0 : ub1; // the previous cell of the walk = upwind neighbour; then the next cell
+#pragma unroll
+            for (int r = 0; r < DIM / 2; ++r)
+              {
+                const int dA = 2 * r, dB = 2 * r + 1;
+                const int sA = 1 << (2 * dA), sB = 1 << (2 * dB);
+                const int base = (tt % sA) + (tt / sA) * (sA * 16);
+                // ---- neighbour traces tv[which][side][x]
+                T tv[2][2][4];
+#pragma unroll
+                for (int which = 0; which < 2; ++which)
+                  {
+                    const int d = which ? dB : dA, sd = which ? sB : sA, so = which ? sA : sB;
+#pragma unroll
+                    for (int side = 0; side < 2; ++side)
+                      {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                          tv[which][side][x] = T(0);
+                        if (!((p.nb_mask[d] >> side) & 1))
+                          continue;
+                        const bool at_edge = side ? (c[d] == p.ncell[d] - 1) : (c[d] == 0);
+                        const int  layer   = side ? 0 : N - 1;
+                        if (d == 0 && step > 0)
+                          {
+                            // the previous cell of the walk is still in shared memory
+                            const int o = base + layer * sd;
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                              tv[which][side][x] = un[padded(o + x * so)];
+                          }
+                        else if (at_edge && p.side_kind[d][side] == HD_SIDE_GHOST)
+                          {
+                            long long fc = 0, m = 1;
+#pragma unroll
+                            for (int e = 0; e < DIM; ++e)
+                              if (e != d)
+                                {
+                                  fc += c[e] * m;
+                                  m *= p.ncell[e];
+                                }
+                            const T *g = p.ghost + p.ghost_off[d][side] + fc * (ND / N);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                              {
+                                const int o        = base + x * so;
+                                tv[which][side][x] = __ldg(g + (o % sd) + (o / (sd * N)) * sd);
+                              }
+                          }
+                        else
+                          {
+                            long long nb = cell + (side ? cstr[d] : -cstr[d]);
+                            if (at_edge)
+                              nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
+                            const T *g = p.src + nb * ND + base + layer * sd;
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                              tv[which][side][x] = __ldg(g + x * so);
+                          }
+                      }
+                  }
+                // ---- the tile and the partial sums of the previous round
+                T U[4][4], out[4][4];
+                if (r == 0)
+                  {
+                    const int4 *q = reinterpret_cast<const int4 *>(uc + tt * TS);
+                    int4        w[V4];
+#pragma unroll
+                    for (int i = 0; i < V4; ++i)
+                      w[i] = q[i];
+                    const T *wv = reinterpret_cast<const T *>(w);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        {
+                          U[b][a]   = wv[4 * b + a];
+                          out[b][a] = T(0);
+                        }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        {
+                          const int i = padded(base + a * sA + b * sB);
+                          U[b][a]     = uc[i];
+                          out[b][a]   = part[i];
+                        }
+                  }
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                  for (int a = 0; a < 4; ++a)
+                    {
+                      T v = out[b][a];
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v += cf.C[dA][a * 4 + j] * U[b][j];
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        v += cf.C[dB][b * 4 + j] * U[j][a];
+                      out[b][a] = v;
+                    }
+#pragma unroll
+                for (int side = 0; side < 2; ++side)
+                  {
+                    const T *LA = side ? cf.L1[dA] : cf.L0[dA];
+                    const T *LB = side ? cf.L1[dB] : cf.L0[dB];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        out[b][a] += LA[a] * tv[0][side][b] + LB[b] * tv[1][side][a];
+                  }
+                if (r == DIM / 2 - 1)
+                  {
+                    const long long g = cell * ND + base;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        {
+                          const long long i = g + a * sA + b * sB;
+                          if (p.fused)
+                            {
+                              const T s = p.sol[i];
+                              p.sol[i]  = s + p.fb * out[b][a];
+                              if (p.fa != T(0))
+                                p.ti_next[i] = s + p.fa * out[b][a];
+                            }
+                          else
+                            p.dst[i] = out[b][a];
+                        }
+                    // the next cell has landed, `part` and the old cell buffer are free again
+                    cp_async_wait_all();
+                    __syncthreads();
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                      for (int a = 0; a < 4; ++a)
+                        part[padded(base + a * sA + b * sB)] = out[b][a];
+                    __syncthreads();
+                    // round 0 was the last reader of the previous cell: its buffer takes the next cell of the walk
+                    if (r == 0 && step + 1 < n0)
+                      stage(un, row_cell0 + (descend ? n0 - 2 - step : step + 1));
+                  }
+              }
+          }
+      }
+  }
+
+  template <typename T>
+  int
+  launch_tile_row_t(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu)
+  {
+    hd_mesh *       m   = op->mesh;
+    constexpr int   NDP = 256 * (16 + 16 / (int)sizeof(T));
+    GenParams<T, 6> p;
+    TileCoef<T>     cf;
+    p.src   = static_cast<const T *>(src);
+    p.dst   = static_cast<T *>(dst);
+    p.ghost = static_cast<const T *>(ghosts);
+    p.coef  = nullptr;
+    for (int d = 0; d < 6; ++d)
+      {
+        for (int i = 0; i < 16; ++i)
+          cf.C[d][i] = T(op->hC[d][0][i]);
+        for (int i = 0; i < 4; ++i)
+          {
+            cf.L0[d][i] = T(op->hL0[d][i]);
+            cf.L1[d][i] = T(op->hL1[d][i]);
+          }
+        p.ncell[d]        = m->d.n_cells[d];
+        p.side_kind[d][0] = m->d.side_kind[d][0];
+        p.side_kind[d][1] = m->d.side_kind[d][1];
+        p.nb_mask[d]      = op->nb_mask[d];
+        p.ghost_off[d][0] = m->ghost_off[d][0];
+        p.ghost_off[d][1] = m->ghost_off[d][1];
+      }
+    p.ncells  = m->ncells;
+    p.sol     = static_cast<T *>(fu.sol);
+    p.ti_next = static_cast<T *>(fu.ti_next);
+    p.fb      = T(fu.fb);
+    p.fa      = T(fu.fa);
+    p.fused   = fu.enabled;
+    const size_t smem = (size_t)3 * NDP * sizeof(T);
+    auto         kern = k_apply_tile_row<T>;
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nrows = m->ncells / m->d.n_cells[0];
+    const long long slots = 2ll * m->ctx->sm_count;
+    const long long grid  = nrows < slots ? nrows : slots;
+    kern<<<(unsigned)grid, 256, smem, m->ctx->stream>>>(p, cf);
+    HD_CUDA(cudaGetLastError());
+    op->launches++;
+    op->last_kernel = "tile_row";
+    return HD_OK;
+  }
+
   template <typename T, int DIM, int THREADS>
   int
   launch_tile_t(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu)
@@ -806,6 +1080,20 @@ namespace hd
         if (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET || m->d.side_kind[d][s] == HD_SIDE_DIRICHLET_HOM)
           return false;
     return true;
+  }
+
+  // the row-persistent variant: 3D3V, and the upwind neighbour along x_0 must be on one side only (it always is for the
+  // upwind flux; a zero x_0 velocity needs no neighbour at all)
+  bool
+  tile_row_supported(const hd_advection *op)
+  {
+    return tile_supported(op) && op->mesh->dim == 6 && op->nb_mask[0] != 3;
+  }
+
+  int
+  launch_tile_row(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
+  {
+    return op->mesh->d.number_type == HD_F64 ? launch_tile_row_t<double>(op, dst, src, ghosts, fu) : launch_tile_row_t<float>(op, dst, src, ghosts, fu);
   }
 
   int

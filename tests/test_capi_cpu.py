@@ -52,3 +52,13 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".hpp", ".cc", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "hd_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: the header must compile as C99 without any C++ or CUDA type in it"""
+    import subprocess
+
+    src = tmp_path / "t.c"
+    src.write_text('#include "hyperdeal_b200.h"\nint main(void) { hd_mesh_desc d; hd_halo_send s; (void)d; (void)s; return hd_version() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

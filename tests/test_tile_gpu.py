@@ -195,3 +195,114 @@ def test_tile_kernel_fused_lsrk(api, ctx, rk):
         integ.perform_time_step(sol, s * dt, dt, op)
     assert op.kernel_name == "tile"
     assert _rel(mf.copy_out(sol), ref) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# the row-persistent 3D3V variant (k_apply_tile_row, hd_advection_set_kernel(4))
+ROW_CASES = [
+    # cells                 velocity                                   skew
+    ((2, 2, 2, 2, 2, 2), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5),
+    ((3, 2, 1, 2, 2, 3), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.0),     # ragged, odd row length
+    ((4, 1, 2, 3, 1, 2), (-1.0, -0.15, 0.05, -0.1, 0.15, -0.5), 0.5),   # descending walk
+    ((2, 3, 2, 1, 2, 2), (0.0, 0.3, 0.0, 0.0, -0.2, 0.0), 0.5),         # no direction-0 neighbour at all
+    ((1, 2, 2, 2, 1, 2), (0.4, -0.3, 0.2, -0.1, 0.6, 0.7), 1.0),        # rows of one cell: the neighbour is the cell itself
+    ((7, 2, 2, 1, 2, 1), (-0.4, 0.3, 0.2, 0.1, 0.6, -0.7), 0.5),
+    ((8, 4, 4, 2, 2, 2), (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5),     # 512 rows: every CTA walks several rows
+]
+
+
+@pytest.mark.parametrize("nc,vel,skew", ROW_CASES)
+def test_tile_row_kernel_matches_oracle(api, ctx, nc, vel, skew):
+    rel, name = _run(api, ctx, 3, 3, nc, skew=skew, vel=vel, kernel=4)
+    assert name == "tile_row"
+    assert rel <= 1e-12, rel
+
+
+def test_tile_row_kernel_float(api, ctx):
+    rel, name = _run(api, ctx, 3, 3, (3, 2, 1, 2, 3, 2), skew=0.5, dtype=np.float32, kernel=4)
+    assert name == "tile_row" and rel <= 1e-5, rel
+
+
+def test_tile_row_kernel_refuses_other_dimensions(api, ctx):
+    mf = api.MatrixFree(ctx, 2, 2, 3, (2,) * 4, (0.0,) * 4, (1.0,) * 4)
+    op = api.AdvectionOperation(mf, VEL[:4], 0.5)
+    with pytest.raises(api.HdError):
+        op.set_kernel(4)
+
+
+@pytest.mark.parametrize("split_dir", [0, 2, 5])
+@pytest.mark.parametrize("vel_sign", [1.0, -1.0])
+def test_tile_row_kernel_two_bricks_with_ghost_faces(api, ctx, split_dir, vel_sign):
+    dx, dv, dim, k = 3, 3, 6, 3
+    vel = vel_sign * VEL
+    nc = [3, 2, 2, 3, 2, 2]
+    nc[split_dir] = 4
+    left, right = (-1.0,) * dim, (1.0,) * dim
+    om = O.Mesh(dx, dv, tuple(nc), left, right, (True,) * dim)
+    orc = O.Oracle(om, k, skew=0.5, velocity=vel, nthreads=8)
+    src = np.random.default_rng(9).standard_normal(orc.ndofs)
+    ref = orc.apply(src)
+    nd = 4**dim
+    full = src.reshape(tuple(reversed(nc)) + (nd,))
+    ref_full = ref.reshape(tuple(reversed(nc)) + (nd,))
+    axis = dim - 1 - split_dir
+    bricks = []
+    for b in range(2):
+        loc = list(nc)
+        loc[split_dir] = 2
+        off = [0] * dim
+        off[split_dir] = 2 * b
+        side_kind = [[api.SIDE_PERIODIC_LOCAL] * 2 for _ in range(dim)]
+        side_kind[split_dir] = [api.SIDE_GHOST, api.SIDE_GHOST]
+        mf = api.MatrixFree(ctx, dx, dv, k, loc, left, right, n_cells_global=nc, cell_offset=off, side_kind=side_kind)
+        sl = [slice(None)] * (dim + 1)
+        sl[axis] = slice(2 * b, 2 * b + 2)
+        u = np.ascontiguousarray(full[tuple(sl)]).reshape(-1)
+        d_src, d_dst = mf.initialize_dof_vector(), mf.initialize_dof_vector()
+        mf.copy_in(d_src, u)
+        d_send, d_ghost = mf.initialize_dof_vector(), mf.initialize_dof_vector()
+        mf.halo_pack(d_src, d_send)
+        send = mf.copy_out(d_send, mf.halo_total)
+        bricks.append(dict(mf=mf, src=d_src, dst=d_dst, send=send, ghost=d_ghost, sl=tuple(sl)))
+    for b in range(2):
+        me, other = bricks[b], bricks[1 - b]
+        mf = me["mf"]
+        ghost = np.zeros(mf.halo_total)
+        for side in range(2):
+            o_me, n_me = mf.halo_offset(split_dir, side), mf.ghost_size(split_dir, side)
+            o_ot = other["mf"].halo_offset(split_dir, 1 - side)
+            ghost[o_me : o_me + n_me] = other["send"][o_ot : o_ot + n_me]
+        op = api.AdvectionOperation(mf, vel, 0.5)
+        op.set_kernel(4)
+        needed = op.ghost_sides()
+        for side in range(2):
+            if not needed[2 * split_dir + side]:
+                o_me, n_me = mf.halo_offset(split_dir, side), mf.ghost_size(split_dir, side)
+                ghost[o_me : o_me + n_me] = np.nan
+        mf.copy_in(me["ghost"], ghost)
+        op.apply(me["dst"], me["src"], 0.0, ghosts=me["ghost"])
+        assert op.kernel_name == "tile_row"
+        out = mf.copy_out(me["dst"])
+        expect = np.ascontiguousarray(ref_full[me["sl"]]).reshape(-1)
+        assert _rel(out, expect) <= 1e-12
+
+
+def test_tile_row_kernel_fused_lsrk(api, ctx):
+    dx, dv, nc, k = 3, 3, (3, 2, 2, 1, 2, 2), 3
+    left, right = (-1.0,) * 6, (1.0,) * 6
+    om = O.Mesh(dx, dv, nc, left, right, (True,) * 6)
+    orc = O.Oracle(om, k, skew=0.5, velocity=VEL, nthreads=4)
+    mf = api.MatrixFree(ctx, dx, dv, k, nc, left, right)
+    op = api.AdvectionOperation(mf, VEL, 0.5)
+    op.set_kernel(4)
+    sol0 = np.random.default_rng(1).standard_normal(mf.n_dofs)
+    dt, ref = 0.004, sol0
+    for s in range(2):
+        ref = O.lsrk_step(lambda v, tt: orc.apply(v, tt), ref, s * dt, dt, "rk45")
+    sol, Ki, Ti = (mf.initialize_dof_vector() for _ in range(3))
+    mf.copy_in(sol, sol0)
+    integ = api.LowStorageRungeKuttaIntegrator(mf, Ki, Ti, "rk45")
+    for s in range(2):
+        integ.perform_time_step(sol, s * dt, dt, op)
+    assert op.kernel_name == "tile_row"
+    assert _rel(mf.copy_out(sol), ref) <= 1e-12

@@ -65,6 +65,13 @@ if sel in ("all", "apply"):
     torch.cuda.empty_cache()
     apply_case("apply 2D2V k=3 n_q=5 f64, 32^4 cells (over-integration)", 2, 2, 3, [32] * 4, np.float64, nq=5)
     torch.cuda.empty_cache()
+if sel in ("all", "row"):
+    apply_case("apply 3D3V k=3 f64, 8^6 cells, row-persistent tile kernel", 3, 3, 3, [8] * 6, np.float64, kernel=4)
+    torch.cuda.empty_cache()
+    apply_case("apply 3D3V k=3 f32, 8^6 cells, row-persistent tile kernel", 3, 3, 3, [8] * 6, np.float32, kernel=4)
+    torch.cuda.empty_cache()
+    apply_case("apply 3D3V k=3 f64, 8^6 cells", 3, 3, 3, [8] * 6, np.float64)
+    torch.cuda.empty_cache()
 if sel in ("all", "lsrk"):
     mf, op, src, dst = apply_case("apply 3D3V k=3 f64, 8^6 cells (again)", 3, 3, 3, [8] * 6, np.float64)
     Ki = torch.empty_like(src)
