@@ -112,3 +112,29 @@ def test_cpp_operators_advection_driver(drivers, golden_dir):
     rows = dict(line.rsplit(None, 1) for line in r.stdout.splitlines() if line.startswith(("info", "throughput")))
     assert float(rows["info->size [DoFs]"]) == 2 * 4 * 2 * 2 * 2 * 4 * 4096
     assert float(rows["throughput [GDoFs/s]"]) > 0
+
+
+def test_json_parameter_reader(tmp_path, golden_dir):
+    """the ParameterHandler-style JSON reader of the drivers: nested sections, quoted and bare values, booleans"""
+    src = tmp_path / "j.cc"
+    src.write_text(
+        '#include "json_parameters.hpp"\n#include <cstdio>\n'
+        "int main(int argc, char **argv) {\n"
+        "  hyperdeal::JsonParameters a(argv[1]), b(argv[2]);\n"
+        '  std::printf("%ld %g %d %s %ld|", a.get_int("General/DimX", 0), a.get_double("TemporalDiscretization/CFLNumber", 0), (int)a.get_bool("Case/PeriodicX", true),\n'
+        '              a.get("TemporalDiscretization/RKType", "?").c_str(), a.get_int("Case/NSubdivisionsV/Y", 0));\n'
+        '  std::printf("%ld %g %d %ld %d\\n", b.get_int("General/Dim", 0), b.get_double("AdvectionOperation/SkewFactor", 0), (int)b.get_bool("MatrixFree/UseECL", false),\n'
+        '              b.get_int("Case/NSubdivisionsX/Y", 0), (int)b.has("Nope/Key"));\n'
+        "  try { hyperdeal::JsonParameters c(argv[3]); } catch (const std::exception &e) { std::printf(\"error: %s\\n\", e.what()); }\n"
+        "  return 0;\n}\n")
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"A": {"B": 1, }')
+    exe = tmp_path / "j"
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "hyperdeal_b200", "cpp"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), os.path.join(golden_dir, "adv_2D_2D_k3.hyperrectangle_03.json"), os.path.join(golden_dir, "operators_advection_small.json"), str(bad)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "2 0.3 0 rk45 4|6 0.5 1 2 0"
+    assert lines[1].startswith("error: parameter file:")

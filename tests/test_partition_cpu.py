@@ -136,3 +136,30 @@ def test_ghost_layout_matches_header_contract():
     assert sizes[(0, 0)] == 3 * 4 * 16 and sizes[(2, 1)] == 2 * 3 * 16 and sizes[(1, 0)] == 0
     assert offsets[(0, 1)] == sizes[(0, 0)] and offsets[(2, 0)] == 2 * sizes[(0, 0)]
     assert total == 2 * sizes[(0, 0)] + 2 * sizes[(2, 0)]
+
+
+def test_x24_layout_of_the_8_gpu_bench():
+    """bench.py --layout x24: the 8-GPU lattice (16,16,16,8,8,8) cut as x_2 in four and x_1 in two; bricks of
+    16x8x4x8x8x8 cells, neighbours in a direction cut in four are different ranks on the two sides"""
+    recipe = BrickPartition(8, 0, (8,) * 6, split_order=(2, 1, 0))
+    for rank in range(8):
+        cut = BrickPartition(8, rank, (8,) * 6, split_order=(2, 1, 2))
+        assert cut.grid == (1, 2, 4, 1, 1, 1)
+        nloc = [g // c for g, c in zip(recipe.n_cells_global, cut.grid)]
+        part = BrickPartition(8, rank, nloc, grid=cut.grid)
+        assert part.n_cells == (16, 8, 4, 8, 8, 8) and part.n_cells_global == recipe.n_cells_global
+        lo, hi = part.neighbour(2, 0), part.neighbour(2, 1)
+        assert lo != hi and lo != rank
+        # neighbour relations are mutual
+        assert BrickPartition(8, lo, nloc, grid=cut.grid).neighbour(2, 1) == rank
+        assert BrickPartition(8, hi, nloc, grid=cut.grid).neighbour(2, 0) == rank
+        assert part.neighbour(1, 0) == part.neighbour(1, 1)  # cut in two: the same rank on both sides
+        assert part.side_kind[0] == [0, 0] and part.side_kind[1] == [1, 1] and part.side_kind[2] == [1, 1]
+
+
+@pytest.mark.timeout(240)
+def test_eight_ranks_x24_exchange():
+    """the halo exchange plan on the x24 grid (1,2,4): every rank receives exactly its neighbours' boundary layers"""
+    res = _run(8, (2, 2, 1, 1, 1, 1), split_order=(2, 1, 2))
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == (1, 2, 4, 1, 1, 1)
