@@ -37,7 +37,7 @@ EXPORTS = [
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
-    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_timer_start", "hd_timer_stop",
+    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_timer_start", "hd_timer_stop",
 ]
 
 
@@ -75,7 +75,7 @@ def lib():
     L.hd_last_error.restype = c_char_p
     L.hd_advection_kernel_name.restype = c_char_p
     L.hd_advection_kernel_name.argtypes = [c_void_p]
-    for name in ("hd_mesh_n_dofs", "hd_mesh_n_cells", "hd_halo_total", "hd_advection_launch_count"):
+    for name in ("hd_mesh_n_dofs", "hd_mesh_n_dofs_x", "hd_mesh_n_cells", "hd_halo_total", "hd_advection_launch_count"):
         getattr(L, name).restype = c_int64
         getattr(L, name).argtypes = [c_void_p]
     for name in ("hd_mesh_ghost_size", "hd_halo_offset"):
@@ -123,6 +123,8 @@ def lib():
     L.hd_lsrk_stage_update.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
     L.hd_lsrk_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
     L.hd_interpolate_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double]
+    L.hd_vector_alloc_x.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.hd_velocity_space_integration.argtypes = [c_void_p, c_void_p, c_void_p]
     L.hd_norm_and_error_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double, POINTER(c_double)]
     L.hd_timer_start.argtypes = [c_void_p]
     L.hd_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
@@ -208,11 +210,18 @@ class MatrixFree:
         self.n_cells_total = lib().hd_mesh_n_cells(self._h)
         self.dofs_per_cell = lib().hd_mesh_dofs_per_cell(self._h)
         self.halo_total = lib().hd_halo_total(self._h)
+        self.n_dofs_x = lib().hd_mesh_n_dofs_x(self._h)
 
     # -- initialize_dof_vector (matrix_free.templates.h:1369)
     def initialize_dof_vector(self, do_ghosts=False) -> int:
         p = c_void_p()
         _check(lib().hd_vector_alloc(self._h, int(do_ghosts), byref(p)))
+        return p.value
+
+    def initialize_dof_vector_x(self) -> int:
+        """x-space vector (matrix_free_x.initialize_dof_vector of examples/vlasov_poisson/include/application.h)"""
+        p = c_void_p()
+        _check(lib().hd_vector_alloc_x(self._h, byref(p)))
         return p.value
 
     def free_vector(self, ptr: int):
@@ -389,6 +398,11 @@ class VectorTools:
     @staticmethod
     def interpolate(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):
         _check(lib().hd_interpolate_builtin(matrix_free._h, c_void_p(vec), fn_id, float(time)))
+
+    @staticmethod
+    def velocity_space_integration(matrix_free: MatrixFree, dst_x: int, src: int):
+        """particle density at the x-space nodes (numerics/vector_tools.h:238-315, quad_no_v = 2)"""
+        _check(lib().hd_velocity_space_integration(matrix_free._h, c_void_p(dst_x), c_void_p(src)))
 
     @staticmethod
     def norm_and_error_sums(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):

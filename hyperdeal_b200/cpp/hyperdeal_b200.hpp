@@ -330,6 +330,16 @@ namespace hyperdeal
       HD_CALL(hd_vector_alloc(mesh, do_ghosts ? 1 : 0, &ptr));
       n = hd_mesh_n_dofs(mesh);
     }
+    // x-space vector (dealii::MatrixFree<dim_x>::initialize_dof_vector in examples/vlasov_poisson/include/application.h)
+    void
+    reinit_x(hd_mesh *m)
+    {
+      clear();
+      mesh    = m;
+      ghosted = false;
+      HD_CALL(hd_vector_alloc_x(mesh, &ptr));
+      n = hd_mesh_n_dofs_x(mesh);
+    }
     void
     clear()
     {
@@ -774,6 +784,18 @@ namespace hyperdeal
             h[idx] = analytical_solution->value(p);
           }
       dst.copy_from_host(h);
+    }
+
+    // numerics/vector_tools.h:238-315: particle density at the x-space nodes, rho = int f dv with the Gauss-Lobatto rule
+    // (quad_no_v = 2, the only rule the drivers use); dst is an x-space vector (DeviceVector::reinit_x)
+    template <int degree, int n_points, int dim_x, int dim_v, typename Number, typename Vector_Out, typename Vector_In>
+    void
+    velocity_space_integration(const MatrixFree<dim_x, dim_v, Number> &data, Vector_Out &dst, const Vector_In &src, const unsigned int = 0, const unsigned int = 0,
+                               const unsigned int quad_no_v = 2)
+    {
+      if (quad_no_v != 2)
+        throw ExcNotImplemented("velocity_space_integration with a quadrature other than Gauss-Lobatto (quad_no_v = 2)");
+      HD_CALL(hd_velocity_space_integration(data.get_mesh(), dst.begin(), src.begin()));
     }
 
     // {L2 norm of u_h, L2 norm of u_h - f} at the quadrature points; device reduction, device-side f only

@@ -215,6 +215,7 @@ namespace hd
     int             n = 0, nq = 0;
     bool            collocation = false;
     std::vector<LD> nodes, xq, w;
+    std::vector<LD> w_nodes; // Gauss-Lobatto weights at the nodes (the reference's quadrature index 2)
     std::vector<LD> S;    // nq x n
     std::vector<LD> D;    // nq x nq
     std::vector<LD> Sinv; // n x nq
@@ -230,8 +231,7 @@ namespace hd
       collocation = colloc;
       if (colloc && nq != n)
         throw std::runtime_error("collocation requires n_points == degree + 1");
-      std::vector<LD> wn;
-      gauss_lobatto(n, nodes, wn);
+      gauss_lobatto(n, nodes, w_nodes);
       if (colloc)
         gauss_lobatto(nq, xq, w);
       else

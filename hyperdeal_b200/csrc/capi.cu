@@ -256,6 +256,32 @@ namespace
       }
   }
 
+  // VectorTools::velocity_space_integration, numerics/vector_tools.h:238-315 with quad_no_v = 2 (Gauss-Lobatto = the nodes):
+  // rho[x-cell][x-node] = sum over v-cells and v-nodes of f * JxW_v.  Thread = one x-space value (coalesced over the x-nodes
+  // of a cell), blockIdx.y = a range of v-cells; partial sums are accumulated in double and added atomically.
+  template <typename T>
+  __global__ void __launch_bounds__(256)
+    k_velocity_space_integration(const T *__restrict__ f, T *__restrict__ rho, const double *__restrict__ wv, long long n_x_dofs, long long ncx, long long ncv, int ndx, int ndv)
+  {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_x_dofs)
+      return;
+    const long long xc = i / ndx;
+    const int       xn = int(i - xc * ndx);
+    const long long per = (ncv + gridDim.y - 1) / gridDim.y;
+    const long long v0 = blockIdx.y * per, v1 = v0 + per < ncv ? v0 + per : ncv;
+    double          acc = 0.0;
+    for (long long vc = v0; vc < v1; ++vc)
+      {
+        const T *p = f + ((vc * ncx + xc) * ndv) * ndx + xn;
+#pragma unroll 4
+        for (int vn = 0; vn < ndv; ++vn)
+          acc += double(p[(long long)vn * ndx]) * wv[vn];
+      }
+    if (v1 > v0)
+      atomicAdd(rho + i, T(acc));
+  }
+
   LatticeParams
   lattice(const hd_mesh *m)
   {
@@ -477,6 +503,20 @@ hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
   HD_CUDA(cudaMalloc(&m->d_basis, hb.size() * sizeof(double)));
   HD_CUDA(cudaMemcpy(m->d_basis, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
   HD_CUDA(cudaMalloc(&m->d_reduce, 2 * sizeof(double)));
+  {
+    // Gauss-Lobatto JxW at the nodes of one v-cell, lowest v-direction fastest (velocity_space_integration)
+    std::vector<double> wv(1, 1.0);
+    for (int d = desc->dim_x; d < m->dim; ++d)
+      {
+        std::vector<double> nxt;
+        for (int i = 0; i < m->n; ++i)
+          for (double x : wv)
+            nxt.push_back(x * (double)m->basis.w_nodes[i] * m->h[d]);
+        wv.swap(nxt);
+      }
+    HD_CUDA(cudaMalloc(&m->d_wv, wv.size() * sizeof(double)));
+    HD_CUDA(cudaMemcpy(m->d_wv, wv.data(), wv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   *out = m;
   return HD_OK;
 }
@@ -488,6 +528,7 @@ hd_mesh_destroy(hd_mesh *m)
     return HD_OK;
   cudaFree(m->d_basis);
   cudaFree(m->d_reduce);
+  cudaFree(m->d_wv);
   delete m;
   return HD_OK;
 }
@@ -1271,6 +1312,66 @@ hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *
 }
 
 // ---- VectorTools ------------------------------------------------------------------------------
+int64_t
+hd_mesh_n_dofs_x(const hd_mesh *m)
+{
+  if (!m)
+    return 0;
+  int64_t n = 1;
+  for (int d = 0; d < m->d.dim_x; ++d)
+    n *= (int64_t)m->d.n_cells[d] * m->n;
+  return n;
+}
+
+int
+hd_vector_alloc_x(hd_mesh *m, void **ptr)
+{
+  HD_REQUIRE(m && ptr, "null argument");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t bytes = (size_t)hd_mesh_n_dofs_x(m) * m->elem_size;
+  HD_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+  HD_CUDA(cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_velocity_space_integration(hd_mesh *m, void *dst_x, const void *src)
+{
+  HD_REQUIRE(m && dst_x && src, "null argument");
+  HD_REQUIRE(m->d.dim_v >= 1, "no velocity space");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const long long nx = hd_mesh_n_dofs_x(m);
+  long long       ncx = 1, ncv = 1;
+  int             ndx = 1, ndv = 1;
+  for (int d = 0; d < m->dim; ++d)
+    {
+      if (d < m->d.dim_x)
+        {
+          ncx *= m->d.n_cells[d];
+          ndx *= m->n;
+        }
+      else
+        {
+          ncv *= m->d.n_cells[d];
+          ndv *= m->n;
+        }
+    }
+  HD_CUDA(cudaMemsetAsync(dst_x, 0, (size_t)nx * m->elem_size, m->ctx->stream));
+  const unsigned gx   = (unsigned)((nx + 255) / 256);
+  long long      want = (8ll * m->ctx->sm_count + gx - 1) / gx; // about 8 CTAs per SM in total
+  if (want > ncv)
+    want = ncv;
+  if (want < 1)
+    want = 1;
+  const dim3 grid(gx, (unsigned)want);
+  if (m->d.number_type == HD_F64)
+    k_velocity_space_integration<double><<<grid, 256, 0, m->ctx->stream>>>(static_cast<const double *>(src), static_cast<double *>(dst_x), m->d_wv, nx, ncx, ncv, ndx, ndv);
+  else
+    k_velocity_space_integration<float><<<grid, 256, 0, m->ctx->stream>>>(static_cast<const float *>(src), static_cast<float *>(dst_x), m->d_wv, nx, ncx, ncv, ndx, ndv);
+  HD_CUDA(cudaGetLastError());
+  return HD_OK;
+}
+
 int
 hd_interpolate_builtin(hd_mesh *m, void *vec, int fn_id, double time)
 {

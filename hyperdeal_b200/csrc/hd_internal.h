@@ -59,6 +59,7 @@ struct hd_mesh
   // device copies (double) of nodes[n], xq[nq], w[nq], S[nq*n]
   double *d_basis = nullptr;
   double *d_reduce = nullptr; // 2 doubles for norm reductions
+  double *d_wv     = nullptr; // n^dim_v doubles: Gauss-Lobatto JxW of one v-cell (velocity_space_integration)
 };
 
 // per-direction collapsed matrices as uploaded to the device (T = Number)

@@ -276,6 +276,16 @@ int hd_interpolate_builtin(hd_mesh *mesh, void *vec, int fn_id, double time);
  * all-reduces over GPUs and takes the square roots, vector_tools.h:212-219). */
 int hd_norm_and_error_builtin(hd_mesh *mesh, const void *vec, int fn_id, double time, double out[2]);
 
+/* VectorTools::velocity_space_integration (numerics/vector_tools.h:238-315) with quad_no_v = 2, the call of the
+ * Vlasov-Poisson driver (examples/vlasov_poisson/include/application.h:520-527): the particle density at the x-space nodes,
+ *   rho[x-cell][x-node] = sum over the OWNED v-cells and their Gauss-Lobatto nodes of f * JxW_v .
+ * dst_x: device pointer to hd_mesh_n_dofs_x values of the mesh's number type (x-cells lexicographic with x_0 fastest,
+ * (k+1)^dim_x nodal values per cell — the layout of the x-space DoF vector, hd_vector_alloc_x); it is overwritten.
+ * With a partition of v-space the caller sums dst_x over the GPUs that share the x-brick (vector_tools.h:308-314). */
+int64_t hd_mesh_n_dofs_x(const hd_mesh *mesh);
+int     hd_vector_alloc_x(hd_mesh *mesh, void **device_ptr);
+int     hd_velocity_space_integration(hd_mesh *mesh, void *dst_x, const void *src);
+
 /* ---- timing ----------------------------------------------------------------------------- */
 /* CUDA-event timing on the context's stream (the device-side counterpart of hyperdeal::Timers,
  * base/timers.h:36): returns milliseconds between the two calls. */
