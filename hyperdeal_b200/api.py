@@ -33,7 +33,7 @@ EXPORTS = [
     "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
-    "hd_advection_destroy", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
+    "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
@@ -98,6 +98,7 @@ def lib():
     L.hd_vector_copy.argtypes = [c_void_p, c_void_p, c_void_p]
     L.hd_advection_create.argtypes = [c_void_p, c_double, POINTER(c_double), POINTER(c_void_p)]
     L.hd_advection_destroy.argtypes = [c_void_p]
+    L.hd_advection_set_phase_space_velocity.argtypes = [c_void_p, c_void_p]
     L.hd_advection_apply.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_apply_part.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int]
     L.hd_advection_apply_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, POINTER(HaloSend), c_int, c_void_p, c_int]
@@ -274,6 +275,10 @@ class AdvectionOperation:
         v = (c_double * HD_MAX_DIM)(*([float(x) for x in velocity] + [0.0] * (HD_MAX_DIM - len(velocity))))
         self._h = c_void_p()
         _check(lib().hd_advection_create(matrix_free._h, float(skew_factor), v, byref(self._h)))
+
+    def set_phase_space_velocity(self, a_v_ptr: int | None):
+        """a_x = v(q_v), a_v = device table [x-cell][q_x][dim_v] (hd_advection_set_phase_space_velocity); None: constant velocity"""
+        _check(lib().hd_advection_set_phase_space_velocity(self._h, c_void_p(a_v_ptr or 0)))
 
     def apply(self, dst: int, src: int, time: float = 0.0, ghosts: int | None = None):
         """dst = M^-1 A(src, time); dst/src are device pointers (advection_operation.h:137)."""

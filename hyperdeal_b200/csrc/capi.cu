@@ -769,6 +769,7 @@ hd_advection_destroy(hd_advection *op)
     return HD_OK;
   hd::fast6d_release(op);
   cudaFree(op->d_coef);
+  cudaFree(op->d_vp_coef);
   cudaFree(op->d_stage_src);
   cudaFree(op->d_stage_dst);
   if (op->s_h2d)
@@ -783,6 +784,25 @@ hd_advection_destroy(hd_advection *op)
     for (int s = 0; s < 2; ++s)
       cudaFree(op->d_g[d][s]);
   delete op;
+  return HD_OK;
+}
+
+int
+hd_advection_set_phase_space_velocity(hd_advection *op, const double *a_v_device)
+{
+  HD_REQUIRE(op, "null argument");
+  if (!a_v_device)
+    {
+      op->d_av = nullptr;
+      return HD_OK;
+    }
+  std::string why;
+  if (!hd::vp_supported(op, &why))
+    return hd::fail(HD_ERR_UNSUPPORTED, why);
+  int rc = hd::vp_upload_coefficients(op);
+  if (rc != HD_OK)
+    return rc;
+  op->d_av = a_v_device;
   return HD_OK;
 }
 
@@ -842,6 +862,13 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
   HD_REQUIRE(!m->has_ghosts || ghosts, "mesh has HD_SIDE_GHOST sides but no ghost buffer was passed");
   HD_CUDA(cudaSetDevice(m->ctx->device));
   int  rc;
+  if (op->d_av)
+    {
+      // phase-space velocity field: the general-velocity kernel, no interior/boundary split
+      if (part == HD_PART_INTERIOR)
+        return HD_OK;
+      return hd::launch_vp(op, dst, src, time, fu);
+    }
   bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (fast)
     rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu, part);

@@ -93,6 +93,10 @@ struct hd_advection
   // apply_host pipeline: copy-in / copy-out streams and per-slab events (slabs = layers of the slowest direction)
   cudaStream_t             s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  // phase-space velocity field (kernel_vp.cu): caller-owned a_v table on the device (nullptr = constant velocity) and the
+  // speed-independent coefficient block
+  const void *d_av      = nullptr;
+  void *      d_vp_coef = nullptr;
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
   int   row_tile[5] = {-1, -1, -1, -1, -1}; // pipelined kernel: row tile per direction 1..5 (-1 = default, 0 = full extent)
@@ -133,6 +137,10 @@ namespace hd
                      long long row_end = -1);
   int  fast6d_overlap_status(hd_advection *op, int *timed_out);
   void fast6d_release(hd_advection *op);
+  // kernel_vp.cu
+  bool vp_supported(const hd_advection *op, std::string *why);
+  int  vp_upload_coefficients(hd_advection *op);
+  int  launch_vp(hd_advection *op, void *dst, const void *src, double time, const FusedUpdate &fu);
   // dirichlet source term (kernels_generic.cu)
   int launch_dirichlet_source(hd_advection *op, void *dst, double time, const FusedUpdate &fu);
 } // namespace hd

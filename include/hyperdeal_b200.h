@@ -142,6 +142,14 @@ int hd_vector_copy(hd_mesh *mesh, void *dst, const void *src);
 int hd_advection_create(hd_mesh *mesh, double skew_factor, const double *velocity, hd_advection **out);
 int hd_advection_destroy(hd_advection *op);
 
+/* PhaseSpaceVelocityFieldView of the Vlasov-Poisson driver (examples/vlasov_poisson/include/velocity_field_view.h:111-175)
+ * instead of the constant transport direction: a_x = v at the v-space quadrature points (taken from the mesh), a_v = the
+ * table a_v_device[x-cell][x-quadrature point][dim_v] (doubles on the device; x-cells and quadrature points lexicographic with
+ * x_0 fastest — DerivativeContainer's layout, derivative_container.h:157-190; typically grad(phi)).  The table is read at
+ * every apply and stays caller-owned; NULL returns to the constant velocity.  Needs dim_x == dim_v and a periodic single-GPU
+ * lattice (HD_ERR_UNSUPPORTED otherwise).  EXPERIMENTAL: the kernel behind it has not been validated on a GPU yet. */
+int hd_advection_set_phase_space_velocity(hd_advection *op, const double *a_v_device);
+
 /* AdvectionOperation::apply(dst, src, time) (advection_operation.h:137): dst = M^-1 A(src, time)
  * for the owned cells; dst is overwritten (ECL semantics, advection_operation.h:562).
  * src/dst: device pointers with the vector layout above; they must not alias.
