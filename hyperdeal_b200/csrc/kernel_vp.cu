@@ -16,9 +16,9 @@
 // Correctness-first mapping, the counterpart of the generic kernel: one CTA per cell, everything in shared memory in
 // double, block-wide barriers between the sweeps.  Periodic single-GPU lattices only.
 //
-// The per-cell body is written against (tid, nthreads) and a barrier macro, so that tests/test_vp_kernel_emulation.py can
-// compile THIS file with g++ (-DHD_VP_HOST_EMULATION: one "thread", barriers are no-ops) and check the index logic and the
-// coefficients against the oracle without a GPU.  That build exists only inside the tests; the product has no CPU path.
+// The per-cell body is written against (tid, nthreads) and a barrier macro, so that tests/vp_emulation_harness.cpp can
+// include THIS file under g++ (-DHD_VP_HOST_EMULATION: one "thread", barriers are no-ops) and check the index logic and the
+// coefficients against the oracle without a GPU.  The harness and its entry point live in tests/; the product has no CPU path.
 #ifdef HD_VP_HOST_EMULATION
 #  include <cmath>
 #  include <cstddef>
@@ -278,71 +278,7 @@ namespace
 #endif
 } // namespace
 
-#ifdef HD_VP_HOST_EMULATION
-// test harness entry point (tests only): every cell of a periodic lattice, one sequential "thread" per cell
-extern "C" int
-hd_vp_emulate(const double *src, double *dst, const double *a_v, int dim_x, int dim_v, int degree, int n_points, const int *ncell, const double *left,
-              const double *right, double skew)
-{
-  try
-    {
-      hd::Basis1D b;
-      b.init(degree, n_points, false);
-      const int dim = dim_x + dim_v, n = b.n, nq = b.nq;
-      VpParams  p;
-      double    h[HD_MAX_DIM];
-      long long ncells = 1, nd = 1, cap = 1;
-      for (int d = 0; d < HD_MAX_DIM; ++d)
-        {
-          p.ncell[d]       = d < dim ? ncell[d] : 1;
-          p.cell_offset[d] = 0;
-          p.left[d]        = d < dim ? left[d] : 0.0;
-          h[d] = p.h[d] = d < dim ? (right[d] - left[d]) / ncell[d] : 1.0;
-          if (d < dim)
-            {
-              ncells *= ncell[d];
-              nd *= n;
-              cap *= n > nq ? n : nq;
-            }
-        }
-      std::vector<double> coef, basis;
-      vp_coefficients(b, dim, h, skew, coef);
-      for (auto v : b.nodes)
-        basis.push_back((double)v);
-      for (auto v : b.xq)
-        basis.push_back((double)v);
-      for (auto v : b.w)
-        basis.push_back((double)v);
-      for (auto v : b.S)
-        basis.push_back((double)v);
-      for (auto v : b.Sinv)
-        basis.push_back((double)v);
-      p.src = src;
-      p.dst = dst;
-      p.coef = coef.data();
-      p.basis = basis.data();
-      p.a_v = a_v;
-      p.dim_x = dim_x;
-      p.dim_v = dim_v;
-      p.n = n;
-      p.nq = nq;
-      p.nd = nd;
-      p.ncells = ncells;
-      p.cap = (int)cap;
-      p.sol = p.ti_next = nullptr;
-      p.fb = p.fa = 0.0;
-      p.fused = 0;
-      std::vector<double> sm(6 * (size_t)cap + 2 * (size_t)n * n);
-      for (long long cell = 0; cell < ncells; ++cell)
-        vp_cell<double>(p, sm.data(), cell, 0, 1);
-      return 0;
-    }
-  catch (const std::exception &)
-    {
-      return -1;
-    }
-}
-#else
+#ifndef HD_VP_HOST_EMULATION
 
 namespace hd
 {

@@ -1,6 +1,6 @@
 """CPU check of the general-velocity kernel's source (hyperdeal_b200/csrc/kernel_vp.cu): the per-cell body is written against
 (tid, nthreads) and a barrier macro, so the very same code compiles with g++ as one sequential "thread" per cell
-(-DHD_VP_HOST_EMULATION).  A barrier-synchronised kernel computes the same thing in that mode, so its index logic, sweeps and
+(tests/vp_emulation_harness.cpp includes it with -DHD_VP_HOST_EMULATION).  A barrier-synchronised kernel computes the same thing in that mode, so its index logic, sweeps and
 coefficients (basis.hpp, the product's own) can be compared with the oracle's literal kernel without a GPU.  This harness
 exists only here; the product library has no CPU path.  What it cannot show: races, launch configuration, shared-memory
 limits — those need the GPU run of tests/test_vp_kernel_gpu.py."""
@@ -20,7 +20,7 @@ from oracle import oracle_vp as V
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("vpemu") / "libvpemu.so")
     csrc = os.path.join(ROOT, "hyperdeal_b200", "csrc")
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-DHD_VP_HOST_EMULATION", "-I", csrc, os.path.join(csrc, "kernel_vp.cu"), "-o", so]
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", csrc, os.path.join(ROOT, "tests", "vp_emulation_harness.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lib = ctypes.CDLL(so)

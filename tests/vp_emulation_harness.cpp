@@ -1,0 +1,69 @@
+// TEST HARNESS (tests/test_vp_kernel_emulation.py) — not product code, never linked into libhdgpu.so.
+// Includes the source of the general-velocity kernel with the host-emulation switch: the per-cell body then runs as ONE
+// sequential "thread" per cell with barriers as no-ops, which computes what the barrier-synchronised CUDA kernel computes.
+#define HD_VP_HOST_EMULATION
+#include "../hyperdeal_b200/csrc/kernel_vp.cu"
+
+// test harness entry point (tests only): every cell of a periodic lattice, one sequential "thread" per cell
+extern "C" int
+hd_vp_emulate(const double *src, double *dst, const double *a_v, int dim_x, int dim_v, int degree, int n_points, const int *ncell, const double *left,
+              const double *right, double skew)
+{
+  try
+    {
+      hd::Basis1D b;
+      b.init(degree, n_points, false);
+      const int dim = dim_x + dim_v, n = b.n, nq = b.nq;
+      VpParams  p;
+      double    h[HD_MAX_DIM];
+      long long ncells = 1, nd = 1, cap = 1;
+      for (int d = 0; d < HD_MAX_DIM; ++d)
+        {
+          p.ncell[d]       = d < dim ? ncell[d] : 1;
+          p.cell_offset[d] = 0;
+          p.left[d]        = d < dim ? left[d] : 0.0;
+          h[d] = p.h[d] = d < dim ? (right[d] - left[d]) / ncell[d] : 1.0;
+          if (d < dim)
+            {
+              ncells *= ncell[d];
+              nd *= n;
+              cap *= n > nq ? n : nq;
+            }
+        }
+      std::vector<double> coef, basis;
+      vp_coefficients(b, dim, h, skew, coef);
+      for (auto v : b.nodes)
+        basis.push_back((double)v);
+      for (auto v : b.xq)
+        basis.push_back((double)v);
+      for (auto v : b.w)
+        basis.push_back((double)v);
+      for (auto v : b.S)
+        basis.push_back((double)v);
+      for (auto v : b.Sinv)
+        basis.push_back((double)v);
+      p.src = src;
+      p.dst = dst;
+      p.coef = coef.data();
+      p.basis = basis.data();
+      p.a_v = a_v;
+      p.dim_x = dim_x;
+      p.dim_v = dim_v;
+      p.n = n;
+      p.nq = nq;
+      p.nd = nd;
+      p.ncells = ncells;
+      p.cap = (int)cap;
+      p.sol = p.ti_next = nullptr;
+      p.fb = p.fa = 0.0;
+      p.fused = 0;
+      std::vector<double> sm(6 * (size_t)cap + 2 * (size_t)n * n);
+      for (long long cell = 0; cell < ncells; ++cell)
+        vp_cell<double>(p, sm.data(), cell, 0, 1);
+      return 0;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}
