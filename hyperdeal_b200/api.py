@@ -37,7 +37,7 @@ EXPORTS = [
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
-    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_timer_start", "hd_timer_stop",
+    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_potential", "hd_timer_start", "hd_timer_stop",
 ]
 
 
@@ -125,6 +125,11 @@ def lib():
     L.hd_lsrk_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
     L.hd_interpolate_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double]
     L.hd_vector_alloc_x.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.hd_poisson_create.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.hd_poisson_destroy.argtypes = [c_void_p]
+    L.hd_poisson_solve.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_int, POINTER(c_int)]
+    L.hd_poisson_potential.argtypes = [c_void_p]
+    L.hd_poisson_potential.restype = c_void_p
     L.hd_velocity_space_integration.argtypes = [c_void_p, c_void_p, c_void_p]
     L.hd_norm_and_error_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double, POINTER(c_double)]
     L.hd_timer_start.argtypes = [c_void_p]
@@ -396,6 +401,30 @@ class LowStorageRungeKuttaIntegrator:
     def close(self):
         if self._h:
             lib().hd_lsrk_destroy(self._h)
+            self._h = c_void_p()
+
+
+class PoissonSolver:
+    """x-space field solve of the Vlasov-Poisson right-hand side (hd_poisson_*; examples/vlasov_poisson/include/poisson.h,
+    application.h:529-583): density -> potential -> grad(phi) table for AdvectionOperation.set_phase_space_velocity."""
+
+    def __init__(self, matrix_free: MatrixFree):
+        self.mf = matrix_free
+        self._h = c_void_p()
+        _check(lib().hd_poisson_create(matrix_free._h, byref(self._h)))
+
+    def solve(self, rho_x: int, a_v: int, rel_tol: float = 1e-10, max_iterations: int = 10000) -> int:
+        it = c_int()
+        _check(lib().hd_poisson_solve(self._h, c_void_p(rho_x), c_void_p(a_v), float(rel_tol), int(max_iterations), byref(it)))
+        return it.value
+
+    @property
+    def potential(self) -> int:
+        return lib().hd_poisson_potential(self._h)
+
+    def close(self):
+        if self._h:
+            lib().hd_poisson_destroy(self._h)
             self._h = c_void_p()
 
 

@@ -73,6 +73,7 @@ typedef struct hd_context   hd_context;
 typedef struct hd_mesh      hd_mesh;
 typedef struct hd_advection hd_advection;
 typedef struct hd_lsrk      hd_lsrk;
+typedef struct hd_poisson   hd_poisson;
 
 /* Description of the Cartesian phase-space lattice owned by this process.
  * Replaces the two dealii::Triangulation/dealii::MatrixFree objects handed to
@@ -293,6 +294,20 @@ int hd_norm_and_error_builtin(hd_mesh *mesh, const void *vec, int fn_id, double 
 int64_t hd_mesh_n_dofs_x(const hd_mesh *mesh);
 int     hd_vector_alloc_x(hd_mesh *mesh, void **device_ptr);
 int     hd_velocity_space_integration(hd_mesh *mesh, void *dst_x, const void *src);
+
+/* ---- x-space field solve of the Vlasov-Poisson right-hand side (EXPERIMENTAL: not validated on a GPU yet) ---------------
+ * Steps 2-4 of examples/vlasov_poisson/include/application.h:529-583 on a periodic Cartesian x-lattice:
+ *   rhs = -M (rho - mean), mean removed again;  K phi = rhs with the symmetric-interior-penalty DG Laplacian of
+ *   examples/vlasov_poisson/include/poisson.h:166-250, solved by conjugate gradients on the device from the previous potential
+ *   (the reference: preconditioned CG to a relative residual of 1e-7, poisson.h:593-603);  a_v = grad(phi) at the quadrature
+ *   points of every x-cell (DerivativeContainer::update, derivative_container.h:157-190) in the layout
+ *   hd_advection_set_phase_space_velocity reads: a_v_device[x-cell][x-quadrature point][dim_x] doubles.
+ * rho_x: the density of hd_velocity_space_integration (mesh number type).  *iterations (optional) returns the CG steps taken. */
+int hd_poisson_create(hd_mesh *mesh, hd_poisson **out);
+int hd_poisson_destroy(hd_poisson *ps);
+int hd_poisson_solve(hd_poisson *ps, const void *rho_x, double *a_v_device, double rel_tol, int max_iterations, int *iterations);
+/* potential of the last solve: device pointer to hd_mesh_n_dofs_x doubles (x-space layout), owned by the solver */
+const double *hd_poisson_potential(const hd_poisson *ps);
 
 /* ---- timing ----------------------------------------------------------------------------- */
 /* CUDA-event timing on the context's stream (the device-side counterpart of hyperdeal::Timers,

@@ -67,3 +67,74 @@ hd_vp_emulate(const double *src, double *dst, const double *a_v, int dim_x, int 
       return -1;
     }
 }
+
+// ---- x-space field solve (poisson_x.cu): operator, mass matrix and gradient bodies, one sequential "thread" per cell
+#include "../hyperdeal_b200/csrc/poisson_x.cu"
+
+namespace
+{
+  struct XsHost
+  {
+    hd::Basis1D         b;
+    std::vector<double> coef, basis, sm;
+    XsParams            p;
+    XsHost(int dim_x, int degree, int n_points, const int *ncell, const double *h)
+    {
+      b.init(degree, n_points, false);
+      xs_coefficients(b, dim_x, h, coef);
+      for (auto v : b.nodes)
+        basis.push_back((double)v);
+      for (auto v : b.xq)
+        basis.push_back((double)v);
+      for (auto v : b.w)
+        basis.push_back((double)v);
+      for (auto v : b.S)
+        basis.push_back((double)v);
+      for (auto v : b.Sinv)
+        basis.push_back((double)v);
+      p.coef   = coef.data();
+      p.basis  = basis.data();
+      p.dim_x  = dim_x;
+      p.n      = b.n;
+      p.nq     = b.nq;
+      p.nd     = 1;
+      p.ncells = 1;
+      long long cap = 1;
+      for (int d = 0; d < 3; ++d)
+        {
+          p.ncell[d] = d < dim_x ? ncell[d] : 1;
+          if (d < dim_x)
+            {
+              p.nd *= b.n;
+              p.ncells *= ncell[d];
+              cap *= b.n > b.nq ? b.n : b.nq;
+            }
+        }
+      sm.resize(3 * (size_t)cap);
+    }
+  };
+} // namespace
+
+// which: 0 = K src, 1 = scale * M src, 2 = gradient table of src (dst: [cell][q][d])
+extern "C" int
+hd_xs_emulate(int which, const double *src, double *dst, int dim_x, int degree, int n_points, const int *ncell, const double *h, double scale)
+{
+  try
+    {
+      XsHost x(dim_x, degree, n_points, ncell, h);
+      for (long long cell = 0; cell < x.p.ncells; ++cell)
+        {
+          if (which == 0)
+            xs_laplace_cell(x.p, x.sm.data(), src, dst, cell, 0, 1);
+          else if (which == 1)
+            xs_mass_cell(x.p, x.sm.data(), src, dst, scale, cell, 0, 1);
+          else
+            xs_gradient_cell(x.p, x.sm.data(), src, dst, cell, 0, 1);
+        }
+      return 0;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}
