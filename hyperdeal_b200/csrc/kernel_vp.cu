@@ -2,9 +2,9 @@
 //   a_x = v at the v-space quadrature points, a_v = a table per (x-cell, x-quadrature point), typically grad(phi)
 // (examples/vlasov_poisson/include/velocity_field_view.h:111-175 — PhaseSpaceVelocityFieldView).
 //
-// STATUS: written after the GPU budget of round 1 was spent — the algebra is verified on the CPU against the literal
-// kernel (tests/test_collapsed_general_velocity.py), this device code has NOT run on a GPU yet.  It is only reachable
-// through hd_advection_set_phase_space_velocity; its tests (tests/test_vp_kernel_gpu.py) run in a separate process.
+// STATUS: parity with the literal oracle at round-off on B200 (tests/test_vp_kernel_gpu.py, profiles/r01n_vp_kernel_gpu.txt:
+// 1D1V, 2D2V incl. over-integration, 3D3V, FP32); not optimised and not yet timed.  Reachable only through
+// hd_advection_set_phase_space_velocity.
 //
 // Collapsed form: with C = a C_a + |a| C_abs and L_f = a L_a,f + |a| L_abs,f the speed-independent parts of
 // the constant-velocity matrices (basis.hpp), direction d contributes

@@ -148,7 +148,7 @@ int hd_advection_destroy(hd_advection *op);
  * table a_v_device[x-cell][x-quadrature point][dim_v] (doubles on the device; x-cells and quadrature points lexicographic with
  * x_0 fastest — DerivativeContainer's layout, derivative_container.h:157-190; typically grad(phi)).  The table is read at
  * every apply and stays caller-owned; NULL returns to the constant velocity.  Needs dim_x == dim_v and a periodic single-GPU
- * lattice (HD_ERR_UNSUPPORTED otherwise).  EXPERIMENTAL: the kernel behind it has not been validated on a GPU yet. */
+ * lattice (HD_ERR_UNSUPPORTED otherwise).  Served by a correctness-first kernel (one CTA per cell), parity-checked, not yet tuned. */
 int hd_advection_set_phase_space_velocity(hd_advection *op, const double *a_v_device);
 
 /* AdvectionOperation::apply(dst, src, time) (advection_operation.h:137): dst = M^-1 A(src, time)
