@@ -37,7 +37,7 @@ EXPORTS = [
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
-    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_potential", "hd_timer_start", "hd_timer_stop",
+    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_potential", "hd_phase_space_diagnostics", "hd_field_energy", "hd_timer_start", "hd_timer_stop",
 ]
 
 
@@ -130,6 +130,8 @@ def lib():
     L.hd_poisson_solve.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_int, POINTER(c_int)]
     L.hd_poisson_potential.argtypes = [c_void_p]
     L.hd_poisson_potential.restype = c_void_p
+    L.hd_phase_space_diagnostics.argtypes = [c_void_p, c_void_p, POINTER(c_double)]
+    L.hd_field_energy.argtypes = [c_void_p, c_void_p, POINTER(c_double)]
     L.hd_velocity_space_integration.argtypes = [c_void_p, c_void_p, c_void_p]
     L.hd_norm_and_error_builtin.argtypes = [c_void_p, c_void_p, c_int, c_double, POINTER(c_double)]
     L.hd_timer_start.argtypes = [c_void_p]
@@ -437,6 +439,22 @@ class VectorTools:
     def velocity_space_integration(matrix_free: MatrixFree, dst_x: int, src: int):
         """particle density at the x-space nodes (numerics/vector_tools.h:238-315, quad_no_v = 2)"""
         _check(lib().hd_velocity_space_integration(matrix_free._h, c_void_p(dst_x), c_void_p(src)))
+
+    @staticmethod
+    def phase_space_diagnostics(matrix_free: MatrixFree, vec: int):
+        """[mass, L2 norm, kinetic energy, momentum...] (examples/vlasov_poisson/include/diagnostics.h:34-86)"""
+        out = (c_double * 6)()
+        _check(lib().hd_phase_space_diagnostics(matrix_free._h, c_void_p(vec), out))
+        r = list(out)
+        r[1] = math.sqrt(r[1])
+        return r
+
+    @staticmethod
+    def field_energy(matrix_free: MatrixFree, a_v: int):
+        """sum_q (d_d phi)^2 JxW per x-direction (diagnostics.h:88-143) from the gradient table of PoissonSolver.solve"""
+        out = (c_double * 3)()
+        _check(lib().hd_field_energy(matrix_free._h, c_void_p(a_v), out))
+        return list(out)[: matrix_free.dim_x]
 
     @staticmethod
     def norm_and_error_sums(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):

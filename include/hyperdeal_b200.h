@@ -309,6 +309,14 @@ int hd_poisson_solve(hd_poisson *ps, const void *rho_x, double *a_v_device, doub
 /* potential of the last solve: device pointer to hd_mesh_n_dofs_x doubles (x-space layout), owned by the solver */
 const double *hd_poisson_potential(const hd_poisson *ps);
 
+/* Diagnostics of the Vlasov-Poisson driver (examples/vlasov_poisson/include/diagnostics.h; EXPERIMENTAL like the field solve):
+ * phase_space_diagnostics (:34-86) at the Gauss points of the OWNED cells: out = {sum f JxW (mass), sum f^2 JxW (the caller
+ * all-reduces and takes the square root: L2 norm), sum |v|^2 f JxW (kinetic energy), sum v_d f JxW for d < dim_v (momentum), 0..};
+ * compute_electric_energy (:88-143): out[d] = sum_q (a_v[.][q][d])^2 JxW over the x-lattice, d < dim_x, from the gradient
+ * table of hd_poisson_solve. */
+int hd_phase_space_diagnostics(hd_mesh *mesh, const void *vec, double out[6]);
+int hd_field_energy(hd_mesh *mesh, const double *a_v_device, double *out);
+
 /* ---- timing ----------------------------------------------------------------------------- */
 /* CUDA-event timing on the context's stream (the device-side counterpart of hyperdeal::Timers,
  * base/timers.h:36): returns milliseconds between the two calls. */

@@ -138,3 +138,77 @@ hd_xs_emulate(int which, const double *src, double *dst, int dim_x, int degree, 
       return -1;
     }
 }
+
+// ---- diagnostics (vp_diagnostics.cu)
+#include "../hyperdeal_b200/csrc/vp_diagnostics.cu"
+
+extern "C" int
+hd_diag_emulate(const double *f, const double *a_v, double *out6, double *energy3, int dim_x, int dim_v, int degree, int n_points, const int *ncell, const double *left,
+                const double *right)
+{
+  try
+    {
+      hd::Basis1D b;
+      b.init(degree, n_points, false);
+      std::vector<double> basis;
+      for (auto v : b.nodes)
+        basis.push_back((double)v);
+      for (auto v : b.xq)
+        basis.push_back((double)v);
+      for (auto v : b.w)
+        basis.push_back((double)v);
+      for (auto v : b.S)
+        basis.push_back((double)v);
+      for (auto v : b.Sinv)
+        basis.push_back((double)v);
+      const int  dim = dim_x + dim_v;
+      DiagParams p;
+      p.basis = basis.data();
+      p.dim_x = dim_x;
+      p.dim_v = dim_v;
+      p.n     = b.n;
+      p.nq    = b.nq;
+      p.nd = p.ncells = 1;
+      long long cap = 1, ncx = 1;
+      for (int d = 0; d < HD_MAX_DIM; ++d)
+        {
+          p.ncell[d]       = d < dim ? ncell[d] : 1;
+          p.cell_offset[d] = 0;
+          p.left[d]        = d < dim ? left[d] : 0.0;
+          p.h[d]           = d < dim ? (right[d] - left[d]) / ncell[d] : 1.0;
+          if (d < dim)
+            {
+              p.nd *= b.n;
+              p.ncells *= ncell[d];
+              cap *= b.n > b.nq ? b.n : b.nq;
+            }
+          if (d < dim_x)
+            ncx *= ncell[d];
+        }
+      p.cap = (int)cap;
+      std::vector<double> sm(2 * (size_t)cap + 6);
+      for (int k = 0; k < 6; ++k)
+        out6[k] = 0.0;
+      for (long long cell = 0; cell < p.ncells; ++cell)
+        {
+          double partial[6];
+          diag_cell<double>(p, sm.data(), f, partial, cell, 0, 1);
+          for (int k = 0; k < 6; ++k)
+            out6[k] += partial[k];
+        }
+      for (int d = 0; d < 3; ++d)
+        energy3[d] = 0.0;
+      for (long long cell = 0; cell < ncx; ++cell)
+        {
+          double partial[3] = {0, 0, 0};
+          field_energy_cell(p, a_v, partial, cell);
+          for (int d = 0; d < dim_x; ++d)
+            energy3[d] += partial[d];
+        }
+      return 0;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}

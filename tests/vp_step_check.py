@@ -73,6 +73,12 @@ def main():
             jxw = np.kron(vp.b.w * vp.h[1], vp.b.w * vp.h[0])
             en = [float(np.sum(g[:, :, d] ** 2 * jxw[None, :])) for d in range(2)]
             out_rows.append([t] + en + vp.phase_space_diagnostics(f))
+            # the same numbers from the device diagnostics
+            dev = api.VectorTools.field_energy(mf, a_v.data_ptr()) + api.VectorTools.phase_space_diagnostics(mf, sol)
+            ref_row = out_rows[-1][1:]
+            okd = all(abs(a - b) <= 1e-11 * max(abs(b), 1.0) for a, b in zip(dev, ref_row))
+            bad += not okd
+            print("VPD %s device diagnostics at t=%.3f" % ("OK" if okd else "FAIL", t), flush=True)
     for r, g in zip(out_rows, gold[1:]):
         ok = abs(r[1] - g[1]) <= 1e-7 * g[1] and abs(r[3] - g[3]) <= 1e-12 * g[3] and abs(r[4] - g[4]) <= 1e-10 * g[4] and abs(r[5] - g[5]) <= 1e-10 * g[5]
         bad += not ok
