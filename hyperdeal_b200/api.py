@@ -30,7 +30,7 @@ LIB_PATH = os.environ.get("HD_LIBHDGPU", os.path.join(_HERE, "lib", "libhdgpu.so
 
 EXPORTS = [
     "hd_last_error", "hd_version", "hd_context_create", "hd_context_destroy", "hd_context_set_stream",
-    "hd_context_synchronize", "hd_device_count", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
+    "hd_context_synchronize", "hd_device_count", "hd_device_malloc", "hd_device_free", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
     "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",

@@ -15,7 +15,7 @@ CPP = os.path.join(HERE, "cpp")
 BIN = os.path.join(HERE, "bin")
 INCLUDE = os.path.join(HERE, "..", "include")
 LIBDIR = os.path.join(HERE, "lib")
-DRIVERS = ["advection", "operators_advection"]
+DRIVERS = ["advection", "operators_advection", "vlasov_poisson"]
 HEADERS = ["hyperdeal_b200.hpp", "json_parameters.hpp"]
 
 

@@ -260,6 +260,13 @@ namespace hyperdeal
       (void)zero_out; // vectors are always zero-initialised (hd_vector_alloc)
     }
 
+    // x-space vector (dealii::MatrixFree<dim_x>::initialize_dof_vector of the Vlasov-Poisson driver)
+    void
+    initialize_dof_vector_x(DeviceVector<Number> &vec) const
+    {
+      vec.reinit_x(mesh);
+    }
+
     // user-supplied host lambdas cannot run on the device (see the header comment)
     template <typename OutVector, typename InVector, typename Fn>
     void
@@ -467,6 +474,7 @@ namespace hyperdeal
         : transport_direction(transport_direction)
       {}
       const dealii_compat::Tensor<1, dim, Number> &get_transport_direction() const { return transport_direction; }
+      const double *                               phase_space_table() const { return nullptr; }
 
     private:
       dealii_compat::Tensor<1, dim, Number> transport_direction;
@@ -514,6 +522,9 @@ namespace hyperdeal
           hd_advection_destroy(op);
         op = nullptr;
         HD_CALL(hd_advection_create(data.get_mesh(), additional_data.factor_skew, a, &op));
+        // a PhaseSpaceVelocityFieldView hands over its gradient table: a_x = v, a_v = table (velocity_field_view.h:111-175)
+        if (velocity_field->phase_space_table() != nullptr)
+          HD_CALL(hd_advection_set_phase_space_velocity(op, velocity_field->phase_space_table()));
         // Dirichlet sides: u+ = -u- + 2 g; g comes from the descriptor (advection_operation.h:484-520)
         host_sampled_bc = false;
         for (int dir = 0; dir < dim; ++dir)
@@ -624,6 +635,104 @@ namespace hyperdeal
         crit[s] = Number(1.0) / v_max[s];
       return std::min(crit[0], crit[1]);
     }
+  } // namespace advection
+
+  // ---- Vlasov-Poisson pieces (examples/vlasov_poisson/include) ---------------------------------------------------------------
+  namespace vp
+  {
+    // DerivativeContainer (derivative_container.h:30-257): grad(phi) at the quadrature points of every x-cell, on the device
+    template <int dim_x, int dim_v, typename Number>
+    class DerivativeContainer
+    {
+    public:
+      explicit DerivativeContainer(const MatrixFree<dim_x, dim_v, Number> &mf)
+        : mf(mf)
+      {
+        const auto & d = mf.get_mesh_desc();
+        std::int64_t n = dim_x;
+        for (int e = 0; e < dim_x; ++e)
+          n *= std::int64_t(d.n_cells[e]) * d.n_points;
+        HD_CALL(hd_device_malloc(mf.get_communicator().context(), std::size_t(n) * sizeof(double), &table));
+      }
+      ~DerivativeContainer()
+      {
+        if (table)
+          hd_device_free(mf.get_communicator().context(), table);
+      }
+      DerivativeContainer(const DerivativeContainer &) = delete;
+      DerivativeContainer &operator=(const DerivativeContainer &) = delete;
+      double *device_table() const { return static_cast<double *>(table); }
+
+    private:
+      const MatrixFree<dim_x, dim_v, Number> &mf;
+      void *                                  table = nullptr;
+    };
+
+    // LaplaceOperator + PoissonSolver (poisson.h:57-610) and the right-hand side of application.h:529-565 in one object:
+    // solve(negative_electric_field, particle_density) fills the gradient table
+    template <int dim_x, int dim_v, typename Number>
+    class PoissonSolver
+    {
+    public:
+      explicit PoissonSolver(const MatrixFree<dim_x, dim_v, Number> &mf) { HD_CALL(hd_poisson_create(mf.get_mesh(), &ps)); }
+      ~PoissonSolver()
+      {
+        if (ps)
+          hd_poisson_destroy(ps);
+      }
+      PoissonSolver(const PoissonSolver &) = delete;
+      PoissonSolver &operator=(const PoissonSolver &) = delete;
+      unsigned int
+      solve(DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field, const DeviceVector<Number> &particle_density, const double rel_tol = 1e-10)
+      {
+        int it = 0;
+        HD_CALL(hd_poisson_solve(ps, particle_density.begin(), negative_electric_field.device_table(), rel_tol, 10000, &it));
+        return it;
+      }
+
+    private:
+      hd_poisson *ps = nullptr;
+    };
+
+    // diagnostics.h:34-143
+    template <int dim_x, int dim_v, typename Number>
+    std::array<Number, 6>
+    phase_space_diagnostics(const MatrixFree<dim_x, dim_v, Number> &matrix_free, const DeviceVector<Number> &src)
+    {
+      double out[6];
+      HD_CALL(hd_phase_space_diagnostics(matrix_free.get_mesh(), src.begin(), out));
+      out[1] = std::sqrt(out[1]);
+      return {{Number(out[0]), Number(out[1]), Number(out[2]), Number(out[3]), Number(out[4]), Number(out[5])}};
+    }
+    template <int dim_x, int dim_v, typename Number>
+    std::array<Number, dim_x>
+    compute_electric_energy(const MatrixFree<dim_x, dim_v, Number> &matrix_free, const DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field)
+    {
+      double out[3] = {0, 0, 0};
+      HD_CALL(hd_field_energy(matrix_free.get_mesh(), negative_electric_field.device_table(), out));
+      std::array<Number, dim_x> r;
+      for (int d = 0; d < dim_x; ++d)
+        r[d] = Number(out[d]);
+      return r;
+    }
+  } // namespace vp
+
+  namespace advection
+  {
+    // examples/vlasov_poisson/include/velocity_field_view.h:34-213: a_x = v, a_v = negative electric field
+    template <int dim_x, int dim_v, typename Number>
+    class PhaseSpaceVelocityFieldView
+    {
+    public:
+      PhaseSpaceVelocityFieldView(const MatrixFree<dim_x, dim_v, Number> &, const vp::DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field)
+        : negative_electric_field(negative_electric_field)
+      {}
+      dealii_compat::Tensor<1, dim_x + dim_v, Number> get_transport_direction() const { return dealii_compat::Tensor<1, dim_x + dim_v, Number>(); }
+      const double *                                  phase_space_table() const { return negative_electric_field.device_table(); }
+
+    private:
+      const vp::DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field;
+    };
   } // namespace advection
 
   // ---- base/time_integrators.h:48 ---------------------------------------------------------------------------

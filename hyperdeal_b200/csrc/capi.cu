@@ -329,6 +329,26 @@ hd_version(void)
   return 100;
 }
 
+// plain device buffers for host layers that do not link the CUDA runtime themselves (e.g. the gradient table of hd_poisson_solve)
+int
+hd_device_malloc(hd_context *ctx, size_t bytes, void **ptr)
+{
+  HD_REQUIRE(ctx && ptr, "null argument");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  HD_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+  HD_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_device_free(hd_context *ctx, void *ptr)
+{
+  HD_REQUIRE(ctx, "null argument");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  HD_CUDA(cudaFree(ptr));
+  return HD_OK;
+}
+
 int
 hd_device_count(int *count)
 {

@@ -107,6 +107,10 @@ int hd_context_destroy(hd_context *ctx);
 int hd_context_set_stream(hd_context *ctx, void *stream);
 int hd_context_synchronize(hd_context *ctx);
 int hd_device_count(int *count);
+/* plain zero-initialised device buffers for host layers that do not link the CUDA runtime themselves (e.g. the gradient
+ * table hd_poisson_solve fills and hd_advection_set_phase_space_velocity reads) */
+int hd_device_malloc(hd_context *ctx, size_t bytes, void **device_ptr);
+int hd_device_free(hd_context *ctx, void *device_ptr);
 
 /* ---- mesh / matrix-free data -------------------------------------------------------- */
 /* hyperdeal::MatrixFree::reinit (matrix_free.templates.h:862). */
