@@ -1323,6 +1323,7 @@ hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *
   hd_mesh *m = rk->mesh;
   HD_REQUIRE(m == op->mesh, "integrator and operator belong to different meshes");
   HD_REQUIRE(!m->has_ghosts, "hd_lsrk_step is for single-GPU meshes; drive stages with hd_lsrk_stage_update otherwise");
+  HD_REQUIRE(!op->d_av, "hd_lsrk_step with a phase-space velocity field: the field changes at every stage; drive the stages with hd_lsrk_stage_update");
   HD_CUDA(cudaSetDevice(m->ctx->device));
   const size_t bytes = (size_t)m->ndofs * m->elem_size;
   // Fused path: the operator's epilogue does the stage update, so K is never stored and each
