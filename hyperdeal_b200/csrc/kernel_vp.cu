@@ -2,7 +2,7 @@
 //   a_x = v at the v-space quadrature points, a_v = a table per (x-cell, x-quadrature point), typically grad(phi)
 // (examples/vlasov_poisson/include/velocity_field_view.h:111-175 — PhaseSpaceVelocityFieldView).
 //
-// STATUS: parity with the literal oracle at round-off on B200 (tests/test_vp_kernel_gpu.py, profiles/r01n_vp_kernel_gpu.txt:
+// STATUS: parity with the literal oracle at round-off on B200 (tests/test_vp_gpu.py, profiles/r01n_vp_kernel_gpu.txt:
 // 1D1V, 2D2V incl. over-integration, 3D3V, FP32); not optimised and not yet timed.  Reachable only through
 // hd_advection_set_phase_space_velocity.
 //

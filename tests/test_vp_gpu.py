@@ -1,7 +1,14 @@
-"""First device piece of the Vlasov-Poisson rows: hd_velocity_space_integration against the oracle's
-restatement of VectorTools::velocity_space_integration (numerics/vector_tools.h:238-315, quad_no_v = 2)."""
+"""Validated device pieces of the Vlasov-Poisson rows: hd_velocity_space_integration against the oracle's
+restatement of VectorTools::velocity_space_integration (numerics/vector_tools.h:238-315, quad_no_v = 2), and the general-velocity
+advection kernel (kernel_vp.cu, hd_advection_set_phase_space_velocity) against the literal oracle with the same velocity tables."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
+
+from conftest import ROOT
 
 from oracle import oracle_vp as V
 
@@ -58,3 +65,12 @@ def test_density_of_the_landau_initial_condition(api, ctx):
     api.VectorTools.velocity_space_integration(mf, d_rho, d_f)
     rho = mf.copy_out(d_rho, mf.n_dofs_x)
     assert np.max(np.abs(rho - vp.velocity_space_integration(f0))) <= 1e-13 * np.max(np.abs(rho))
+
+
+def test_general_velocity_kernel_matches_oracle():
+    """six cases (1D1V, 2D2V incl. over-integration, 3D3V, FP32) in a child process (tests/vp_kernel_check.py); first GPU run:
+    profiles/r01n_vp_kernel_gpu.txt"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "vp_kernel_check.py")], capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("VPK OK") == 6 and "VPK FAIL" not in r.stdout

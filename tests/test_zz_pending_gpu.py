@@ -1,0 +1,50 @@
+"""Device code written after round 1's GPU budget was spent: the x-space field solve (poisson_x.cu), the
+Vlasov-Poisson diagnostics (vp_diagnostics.cu) and the drivers on top of them.  Their source is verified on the CPU
+(tests/test_poisson_emulation.py, tests/test_vp_diagnostics_emulation.py); the device run is pending, hence the non-strict xfail.
+Everything here runs in child processes, and this file sorts last, so a fault of unvalidated device code cannot touch the CUDA
+context of the validated tests."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+PENDING = "poisson_x.cu / vp_diagnostics.cu have not run on a GPU yet (written after the round-1 GPU budget was spent)"
+
+
+@pytest.fixture(scope="module")
+def drivers():
+    from hyperdeal_b200 import build, build_cpp
+
+    build.build()
+    return {os.path.basename(p): p for p in build_cpp.build()}
+
+
+@pytest.mark.xfail(strict=False, reason=PENDING)
+def test_vlasov_poisson_right_hand_side_and_golden_run_on_device():
+    """density integration -> field solve -> general-velocity operator, one right-hand side against the oracle and then the
+    reference's 2D2V Landau-damping golden (examples/vlasov_poisson/tests/vp_2D_2D_k3.hyperrectangle_01.out)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "vp_step_check.py")], capture_output=True, text=True, timeout=180)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("VPS OK") == 6 and "VPS FAIL" not in r.stdout and "VPD FAIL" not in r.stdout
+
+
+@pytest.mark.xfail(strict=False, reason=PENDING)
+def test_cpp_vlasov_poisson_driver_reproduces_golden(drivers, golden_dir, tmp_path):
+    """examples/vlasov_poisson re-hosted (hyperdeal_b200/cpp/vlasov_poisson.cc) on the reference's 2D2V Landau-damping case:
+    time_history_diagnostic.out against examples/vlasov_poisson/tests/vp_2D_2D_k3.hyperrectangle_01.out"""
+    from oracle import oracle_vp as V
+
+    r = subprocess.run([drivers["vlasov_poisson"], os.path.join(golden_dir, "vp_2D_2D_k3.hyperrectangle_01.json")], capture_output=True, text=True, timeout=180, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    rows = V.parse_vp_golden(str(tmp_path / "time_history_diagnostic.out"))
+    gold = V.parse_vp_golden(os.path.join(golden_dir, "vp_2D_2D_k3.hyperrectangle_01.out"))
+    assert len(rows) == len(gold) == 6
+    for a, g in zip(rows, gold):
+        assert abs(a[0] - g[0]) < 6e-4
+        assert abs(a[1] - g[1]) <= 1e-7 * max(g[1], 1e-30) or g[1] == 0.0 == a[1]
+        assert abs(a[3] - g[3]) <= 1e-12 * g[3] and abs(a[4] - g[4]) <= 1e-10 * g[4] and abs(a[5] - g[5]) <= 1e-10 * g[5]
