@@ -402,9 +402,16 @@ def main():
         need = 2 * n_dofs * 8 * world
         ok = torch.tensor([1 if psutil.virtual_memory().available > 2 * need else 0], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        h_src = h_dst = None
         if ok.item() == 1:
-            h_src = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
-            h_dst = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
+            try:  # the pinned allocation itself may still fail on one rank: agree on the outcome before anyone enters a barrier
+                h_src = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
+                h_dst = torch.empty(n_dofs, dtype=torch.float64, pin_memory=True)
+            except RuntimeError:
+                h_src = h_dst = None
+            ok = torch.tensor([1 if h_dst is not None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 1:
             h_src.copy_(src)
 
             def e2e_step():
