@@ -34,3 +34,14 @@ def test_product_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0
     assert "CUDA" in (r.stderr + r.stdout)
+
+
+def test_tools_and_entry_points_compile():
+    """every script under tools/, bench.py and __graft_entry__.py at least byte-compiles (they only run on a GPU box)"""
+    import glob
+    import py_compile
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py"),
+                                                                          os.path.join(ROOT, "tests", "mgpu_check.py"), os.path.join(ROOT, "tests", "vp_kernel_check.py"),
+                                                                          os.path.join(ROOT, "tests", "vp_step_check.py")]:
+        py_compile.compile(path, doraise=True)
