@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhdgpu.so")
-SOURCES = ["capi.cu", "kernels_generic.cu", "kernel_fast6d.cu", "kernel_vp.cu", "poisson_x.cu", "vp_diagnostics.cu"]
+SOURCES = ["capi.cu", "kernels_generic.cu", "kernel_fast6d.cu", "kernel_vp.cu", "poisson_x.cu", "vp_diagnostics.cu", "kernel_tile_global.cu"]
 HEADERS = ["hd_internal.h", "basis.hpp", os.path.join("..", "..", "include", "hyperdeal_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -829,7 +829,9 @@ hd_advection_set_phase_space_velocity(hd_advection *op, const double *a_v_device
 int
 hd_advection_set_kernel(hd_advection *op, int which)
 {
-  HD_REQUIRE(op && which >= 0 && which <= 4, "bad argument");
+  HD_REQUIRE(op && which >= 0 && which <= 5, "bad argument");
+  if (which == 5 && !hd::tile_global_supported(op))
+    return hd::fail(HD_ERR_UNSUPPORTED, "the global-memory tile kernel covers degree 3 and 5 with an even number of directions, without Dirichlet sides");
   if (which == 4 && !hd::tile_row_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the row-persistent tile kernel covers degree 3 in 3D3V without Dirichlet sides");
   if (which == 2 && !hd::fast6d_supported(op))
@@ -900,6 +902,8 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
       const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_preferred(op));
       if (op->kernel_choice == 4)
         rc = hd::launch_tile_row(op, dst, src, ghosts, time, fu);
+      else if (op->kernel_choice == 5)
+        rc = hd::launch_tile_global(op, dst, src, ghosts, time, fu);
       else
         rc = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);
     }

@@ -137,6 +137,9 @@ namespace hd
                      long long row_end = -1);
   int  fast6d_overlap_status(hd_advection *op, int *timed_out);
   void fast6d_release(hd_advection *op);
+  // kernel_tile_global.cu
+  bool tile_global_supported(const hd_advection *op);
+  int  launch_tile_global(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_vp.cu
   bool vp_supported(const hd_advection *op, std::string *why);
   int  vp_upload_coefficients(hd_advection *op);

@@ -1,0 +1,282 @@
+// Tile kernel for cells that do not fit into shared memory twice — first of all 3D3V degree 5 in FP32 (BASELINE.json
+// configs[2]: 6^6 = 46 656 values = 182 KiB per cell), which today runs on the generic kernel at 10 % of the HBM roofline.
+//
+// Same rounds as the shared-memory tile kernel (kernels_generic.cu: two directions per round, an N x N tile per thread in
+// registers), but nothing is staged: a CTA owns one cell, reads its tiles straight from global memory (the cell is re-read in
+// every round and stays in L1/L2) and keeps the partial sums of the rounds in `dst` itself (written in round 0, read-modified-
+// written in the later rounds; a block-wide barrier separates the rounds).  HBM traffic stays at read src + write dst; the
+// extra passes are L2 traffic on a per-SM working set of two cells (148 x 364 KiB = 54 MB, inside the 126 MB L2).
+// The fused LSRK update is applied in the last round.  Periodic and ghost sides (no Dirichlet), even dim_x + dim_v.
+//
+// STATUS: written after the GPU budget of round 1 was spent; the body is checked on the CPU against the oracle through
+// tests/vp_emulation_harness.cpp (tests/test_tile_global_emulation.py); not yet run on a GPU, never selected automatically
+// (hd_advection_set_kernel(op, 5)).
+#ifdef HD_VP_HOST_EMULATION
+#  ifndef HD_MAX_DIM
+#    include <cmath>
+#    include <cstddef>
+#    include <vector>
+#    define HD_MAX_DIM 6
+#  endif
+#  ifndef HD_SIDE_GHOST_DEFINED
+#    define HD_SIDE_GHOST_DEFINED
+enum
+{
+  HD_SIDE_PERIODIC_LOCAL = 0,
+  HD_SIDE_GHOST          = 1
+};
+#  endif
+#  define HD_TG_FN inline
+#  define HD_TG_SYNC() ((void)0)
+#  define HD_TG_LDG(p) (*(p))
+#  define HD_TG_UNROLL
+#else
+#  include "hd_internal.h"
+#  define HD_TG_FN __device__
+#  define HD_TG_SYNC() __syncthreads()
+#  define HD_TG_LDG(p) __ldg(p)
+#  define HD_TG_UNROLL _Pragma("unroll")
+#endif
+
+namespace
+{
+  template <typename T, int N>
+  struct TgCoef
+  {
+    T C[HD_MAX_DIM][N * N]; // [direction][out * N + in]
+    T L0[HD_MAX_DIM][N];    // lifting of the lower neighbour's trace
+    T L1[HD_MAX_DIM][N];    // ... upper neighbour's
+  };
+
+  template <typename T>
+  struct TgParams
+  {
+    const T * src;
+    T *       dst;
+    const T * ghost;
+    int       dim;
+    int       ncell[HD_MAX_DIM];
+    int       side_kind[HD_MAX_DIM][2];
+    int       nb_mask[HD_MAX_DIM];
+    long long ghost_off[HD_MAX_DIM][2];
+    long long ncells;
+    T *       sol;
+    T *       ti_next;
+    T         fb, fa;
+    int       fused;
+  };
+
+  template <typename T, int N>
+  HD_TG_FN void
+  tg_cell(const TgParams<T> &p, const TgCoef<T, N> &cf, const long long cell, const int tid, const int nthr)
+  {
+    const int dim = p.dim;
+    long long nd = 1;
+    for (int d = 0; d < dim; ++d)
+      nd *= N;
+    const long long nt = nd / (N * N); // tiles per round
+    int             c[HD_MAX_DIM];
+    long long       cstr[HD_MAX_DIM];
+    {
+      long long r = cell, m = 1;
+      for (int d = 0; d < dim; ++d)
+        {
+          c[d]    = int(r % p.ncell[d]);
+          r /= p.ncell[d];
+          cstr[d] = m;
+          m *= p.ncell[d];
+        }
+    }
+    const T *uc = p.src + cell * nd;
+    T *      oc = p.dst + cell * nd;
+    for (int r = 0; r < dim / 2; ++r)
+      {
+        const int dA = 2 * r, dB = 2 * r + 1;
+        long long sA = 1;
+        for (int k = 0; k < dA; ++k)
+          sA *= N;
+        const long long sB   = sA * N;
+        const bool      last = r == dim / 2 - 1;
+        for (long long tt = tid; tt < nt; tt += nthr)
+          {
+            const long long base = (tt % sA) + (tt / sA) * (sA * N * N); // dof index of the tile's (a, b) = (0, 0) entry
+            T               U[N][N], out[N][N];
+            HD_TG_UNROLL
+            for (int b = 0; b < N; ++b)
+              HD_TG_UNROLL
+              for (int a = 0; a < N; ++a)
+                {
+                  U[b][a]   = HD_TG_LDG(uc + base + a * sA + b * sB);
+                  out[b][a] = r == 0 ? T(0) : oc[base + a * sA + b * sB];
+                }
+            HD_TG_UNROLL
+            for (int b = 0; b < N; ++b)
+              HD_TG_UNROLL
+              for (int a = 0; a < N; ++a)
+                {
+                  T v = out[b][a];
+                  HD_TG_UNROLL
+                  for (int j = 0; j < N; ++j)
+                    v += cf.C[dA][a * N + j] * U[b][j];
+                  HD_TG_UNROLL
+                  for (int j = 0; j < N; ++j)
+                    v += cf.C[dB][b * N + j] * U[j][a];
+                  out[b][a] = v;
+                }
+            for (int which = 0; which < 2; ++which)
+              {
+                const int       d  = which ? dB : dA;
+                const long long sd = which ? sB : sA, so = which ? sA : sB;
+                for (int side = 0; side < 2; ++side)
+                  {
+                    if (!((p.nb_mask[d] >> side) & 1))
+                      continue;
+                    const bool at_edge = side ? (c[d] == p.ncell[d] - 1) : (c[d] == 0);
+                    const int  layer   = side ? 0 : N - 1; // neighbour's layer touching the shared face
+                    T          tv[N];
+                    if (at_edge && p.side_kind[d][side] == HD_SIDE_GHOST)
+                      {
+                        long long fc = 0, m = 1;
+                        for (int e = 0; e < dim; ++e)
+                          if (e != d)
+                            {
+                              fc += c[e] * m;
+                              m *= p.ncell[e];
+                            }
+                        const T *g = p.ghost + p.ghost_off[d][side] + fc * (nd / N);
+                        HD_TG_UNROLL
+                        for (int x = 0; x < N; ++x)
+                          {
+                            const long long o = base + x * so; // dof index with digit d = 0
+                            tv[x]             = HD_TG_LDG(g + (o % sd) + (o / (sd * N)) * sd);
+                          }
+                      }
+                    else
+                      {
+                        long long nb = cell + (side ? cstr[d] : -cstr[d]);
+                        if (at_edge) // periodic inside the brick
+                          nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
+                        const T *g = p.src + nb * nd + base + layer * sd;
+                        HD_TG_UNROLL
+                        for (int x = 0; x < N; ++x)
+                          tv[x] = HD_TG_LDG(g + x * so);
+                      }
+                    const T *L = side ? cf.L1[d] : cf.L0[d];
+                    HD_TG_UNROLL
+                    for (int b = 0; b < N; ++b)
+                      HD_TG_UNROLL
+                      for (int a = 0; a < N; ++a)
+                        out[b][a] += which ? L[b] * tv[a] : L[a] * tv[b];
+                  }
+              }
+            HD_TG_UNROLL
+            for (int b = 0; b < N; ++b)
+              HD_TG_UNROLL
+              for (int a = 0; a < N; ++a)
+                {
+                  const long long i = base + a * sA + b * sB;
+                  if (last && p.fused)
+                    {
+                      const long long g = cell * nd + i;
+                      const T         s = p.sol[g];
+                      p.sol[g]          = s + p.fb * out[b][a];
+                      if (p.fa != T(0))
+                        p.ti_next[g] = s + p.fa * out[b][a];
+                    }
+                  else
+                    oc[i] = out[b][a];
+                }
+          }
+        HD_TG_SYNC(); // the next round reads the partial sums other threads of this CTA have written
+      }
+  }
+} // namespace
+
+#ifndef HD_VP_HOST_EMULATION
+namespace
+{
+  template <typename T, int N>
+  __global__ void __launch_bounds__(256) k_apply_tile_global(const __grid_constant__ TgParams<T> p, const __grid_constant__ TgCoef<T, N> cf)
+  {
+    tg_cell<T, N>(p, cf, blockIdx.x, threadIdx.x, blockDim.x);
+  }
+
+  template <typename T, int N>
+  int
+  launch_tg(hd_advection *op, void *dst, const void *src, const void *ghosts, const FusedUpdate &fu, void *scratch)
+  {
+    hd_mesh *    m = op->mesh;
+    TgParams<T>  p;
+    TgCoef<T, N> cf;
+    p.src   = static_cast<const T *>(src);
+    p.dst   = static_cast<T *>(fu.enabled ? scratch : dst); // fused update: the partial sums need a buffer of their own
+    p.ghost = static_cast<const T *>(ghosts);
+    p.dim   = m->dim;
+    for (int d = 0; d < HD_MAX_DIM; ++d)
+      {
+        for (int i = 0; i < N * N; ++i)
+          cf.C[d][i] = d < m->dim ? T(op->hC[d][0][i]) : T(0);
+        for (int i = 0; i < N; ++i)
+          {
+            cf.L0[d][i] = d < m->dim ? T(op->hL0[d][i]) : T(0);
+            cf.L1[d][i] = d < m->dim ? T(op->hL1[d][i]) : T(0);
+          }
+        p.ncell[d]        = d < m->dim ? m->d.n_cells[d] : 1;
+        p.side_kind[d][0] = m->d.side_kind[d][0];
+        p.side_kind[d][1] = m->d.side_kind[d][1];
+        p.nb_mask[d]      = op->nb_mask[d];
+        p.ghost_off[d][0] = m->ghost_off[d][0];
+        p.ghost_off[d][1] = m->ghost_off[d][1];
+      }
+    p.ncells  = m->ncells;
+    p.sol     = static_cast<T *>(fu.sol);
+    p.ti_next = static_cast<T *>(fu.ti_next);
+    p.fb      = T(fu.fb);
+    p.fa      = T(fu.fa);
+    p.fused   = fu.enabled;
+    k_apply_tile_global<T, N><<<(unsigned)m->ncells, 256, 0, m->ctx->stream>>>(p, cf);
+    HD_CUDA(cudaGetLastError());
+    op->launches++;
+    op->last_kernel = "tile_global";
+    return HD_OK;
+  }
+} // namespace
+
+namespace hd
+{
+  bool
+  tile_global_supported(const hd_advection *op)
+  {
+    const hd_mesh *m = op->mesh;
+    if ((m->n != 6 && m->n != 4) || m->dim % 2 != 0 || m->dim < 2)
+      return false;
+    for (int d = 0; d < m->dim; ++d)
+      for (int s = 0; s < 2; ++s)
+        if (m->d.side_kind[d][s] == HD_SIDE_DIRICHLET || m->d.side_kind[d][s] == HD_SIDE_DIRICHLET_HOM)
+          return false;
+    return true;
+  }
+
+  int
+  launch_tile_global(hd_advection *op, void *dst, const void *src, const void *ghosts, double, const FusedUpdate &fu)
+  {
+    hd_mesh *m       = op->mesh;
+    void *   scratch = nullptr;
+    if (fu.enabled)
+      {
+        // rounds before the last one park their partial sums in the operator's staging vector
+        const size_t bytes = (size_t)m->ndofs * m->elem_size;
+        if (!op->d_stage_dst)
+          {
+            HD_CUDA(cudaMalloc(&op->d_stage_src, bytes));
+            HD_CUDA(cudaMalloc(&op->d_stage_dst, bytes));
+          }
+        scratch = op->d_stage_dst;
+      }
+    const bool f64 = m->d.number_type == HD_F64;
+    if (m->n == 6)
+      return f64 ? launch_tg<double, 6>(op, dst, src, ghosts, fu, scratch) : launch_tg<float, 6>(op, dst, src, ghosts, fu, scratch);
+    return f64 ? launch_tg<double, 4>(op, dst, src, ghosts, fu, scratch) : launch_tg<float, 4>(op, dst, src, ghosts, fu, scratch);
+  }
+} // namespace hd
+#endif

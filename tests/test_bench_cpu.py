@@ -43,5 +43,5 @@ def test_tools_and_entry_points_compile():
 
     for path in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py"),
                                                                           os.path.join(ROOT, "tests", "mgpu_check.py"), os.path.join(ROOT, "tests", "vp_kernel_check.py"),
-                                                                          os.path.join(ROOT, "tests", "vp_step_check.py")]:
+                                                                          os.path.join(ROOT, "tests", "vp_step_check.py"), os.path.join(ROOT, "tests", "tile_global_check.py")]:
         py_compile.compile(path, doraise=True)

@@ -12,7 +12,7 @@ import pytest
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
-PENDING = "poisson_x.cu / vp_diagnostics.cu have not run on a GPU yet (written after the round-1 GPU budget was spent)"
+PENDING = "poisson_x.cu / vp_diagnostics.cu / kernel_tile_global.cu have not run on a GPU yet (written after the round-1 GPU budget was spent)"
 
 
 @pytest.fixture(scope="module")
@@ -48,3 +48,12 @@ def test_cpp_vlasov_poisson_driver_reproduces_golden(drivers, golden_dir, tmp_pa
         assert abs(a[0] - g[0]) < 6e-4
         assert abs(a[1] - g[1]) <= 1e-7 * max(g[1], 1e-30) or g[1] == 0.0 == a[1]
         assert abs(a[3] - g[3]) <= 1e-12 * g[3] and abs(a[4] - g[4]) <= 1e-10 * g[4] and abs(a[5] - g[5]) <= 1e-10 * g[5]
+
+
+@pytest.mark.xfail(strict=False, reason=PENDING)
+def test_global_memory_tile_kernel_matches_oracle():
+    """kernel_tile_global.cu (hd_advection_set_kernel 5): degree 5 and 3, FP32/FP64, plain apply and fused LSRK step"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tile_global_check.py")], capture_output=True, text=True, timeout=180)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("TG OK") == 6 and "TG FAIL" not in r.stdout

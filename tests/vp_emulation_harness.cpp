@@ -212,3 +212,75 @@ hd_diag_emulate(const double *f, const double *a_v, double *out6, double *energy
       return -1;
     }
 }
+
+// ---- tile kernel with the partial sums in global memory (kernel_tile_global.cu), periodic lattices
+#include "../hyperdeal_b200/csrc/kernel_tile_global.cu"
+
+namespace
+{
+  template <int N>
+  int
+  tg_emulate_n(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew)
+  {
+    hd::Basis1D b;
+    b.init(degree, degree + 1, false);
+    b.set_skew((hd::LD)skew);
+    TgParams<double>  p;
+    TgCoef<double, N> cf;
+    p.src = src;
+    p.dst = dst;
+    p.ghost = nullptr;
+    p.dim = dim;
+    p.ncells = 1;
+    for (int d = 0; d < HD_MAX_DIM; ++d)
+      {
+        p.ncell[d] = d < dim ? ncell[d] : 1;
+        p.side_kind[d][0] = p.side_kind[d][1] = HD_SIDE_PERIODIC_LOCAL;
+        p.ghost_off[d][0] = p.ghost_off[d][1] = 0;
+        p.nb_mask[d] = 0;
+        for (int i = 0; i < N * N; ++i)
+          cf.C[d][i] = 0.0;
+        for (int i = 0; i < N; ++i)
+          cf.L0[d][i] = cf.L1[d][i] = 0.0;
+        if (d >= dim)
+          continue;
+        p.ncells *= ncell[d];
+        std::vector<hd::LD> C[4], L0, L1;
+        b.direction_matrices((hd::LD)velocity[d], (hd::LD)((right[d] - left[d]) / ncell[d]), (hd::LD)skew, C, L0, L1);
+        bool any0 = false, any1 = false;
+        for (int i = 0; i < N * N; ++i)
+          cf.C[d][i] = (double)C[0][i];
+        for (int i = 0; i < N; ++i)
+          {
+            cf.L0[d][i] = (double)L0[i];
+            cf.L1[d][i] = (double)L1[i];
+            any0 |= L0[i] != 0;
+            any1 |= L1[i] != 0;
+          }
+        p.nb_mask[d] = (any0 ? 1 : 0) | (any1 ? 2 : 0);
+      }
+    p.sol = p.ti_next = nullptr;
+    p.fb = p.fa = 0.0;
+    p.fused = 0;
+    for (long long cell = 0; cell < p.ncells; ++cell)
+      tg_cell<double, N>(p, cf, cell, 0, 1);
+    return 0;
+  }
+} // namespace
+
+extern "C" int
+hd_tg_emulate(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew)
+{
+  try
+    {
+      if (degree == 5)
+        return tg_emulate_n<6>(src, dst, dim, degree, ncell, left, right, velocity, skew);
+      if (degree == 3)
+        return tg_emulate_n<4>(src, dst, dim, degree, ncell, left, right, velocity, skew);
+      return -2;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}

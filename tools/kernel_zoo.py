@@ -72,6 +72,11 @@ if sel in ("all", "row"):
     torch.cuda.empty_cache()
     apply_case("apply 3D3V k=3 f64, 8^6 cells", 3, 3, 3, [8] * 6, np.float64)
     torch.cuda.empty_cache()
+if sel in ("tg",):  # the not yet validated global-memory tile kernel on BASELINE.json configs[2]
+    apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), global-memory tile kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=5)
+    torch.cuda.empty_cache()
+    apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), generic kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=1)
+    torch.cuda.empty_cache()
 if sel in ("all", "lsrk"):
     mf, op, src, dst = apply_case("apply 3D3V k=3 f64, 8^6 cells (again)", 3, 3, 3, [8] * 6, np.float64)
     Ki = torch.empty_like(src)
