@@ -829,12 +829,12 @@ hd_advection_set_phase_space_velocity(hd_advection *op, const double *a_v_device
 int
 hd_advection_set_kernel(hd_advection *op, int which)
 {
-  HD_REQUIRE(op && which >= 0 && which <= 5, "bad argument");
+  HD_REQUIRE(op && which >= 0 && which <= 6, "bad argument");
   if (which == 5 && !hd::tile_global_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the global-memory tile kernel covers degree 3 and 5 with an even number of directions, without Dirichlet sides");
   if (which == 4 && !hd::tile_row_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the row-persistent tile kernel covers degree 3 in 3D3V without Dirichlet sides");
-  if (which == 2 && !hd::fast6d_supported(op))
+  if ((which == 2 || which == 6) && !hd::fast6d_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the fused 3D3V k=3 kernel does not cover this configuration");
   if (which == 3 && !hd::tile_supported(op))
     return hd::fail(HD_ERR_UNSUPPORTED, "the tile kernel covers degree 3 in 1D1V / 2D2V / 3D3V without Dirichlet sides");
@@ -891,7 +891,7 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
         return HD_OK;
       return hd::launch_vp(op, dst, src, time, fu);
     }
-  bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  bool fast = op->kernel_choice == 2 || op->kernel_choice == 6 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (fast)
     rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu, part);
   else
@@ -942,7 +942,7 @@ hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, cons
   HD_REQUIRE(dst != src, "dst and src must not alias (ECL reads neighbours of src)");
   hd_mesh *m = op->mesh;
   HD_CUDA(cudaSetDevice(m->ctx->device));
-  const bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  const bool fast = op->kernel_choice == 2 || op->kernel_choice == 6 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (!fast)
     return hd::fail(HD_ERR_UNSUPPORTED, "hd_advection_apply_overlapped needs the pipelined 3D3V kernel; use hd_advection_apply_part");
   for (int d = 0; d < m->dim; ++d)
@@ -1061,7 +1061,7 @@ hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, 
   // is computed as soon as it and its upwind neighbour layer are on the device, and travels back while the next
   // layers are still coming in — copy-in, kernel and copy-out run on three streams, PCIe in both directions at once.
   const int  last = m->dim - 1, n5 = m->d.n_cells[last];
-  const bool fast = op->kernel_choice == 2 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  const bool fast = op->kernel_choice == 2 || op->kernel_choice == 6 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (fast && n5 >= 3 && getenv("HD_HOST_SERIAL") == nullptr)
     {
       // units of the pipeline: layers of the slowest direction, cut again along the second slowest one if it is long

@@ -131,6 +131,7 @@ namespace hd
   int  launch_tile(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu);
   // kernel_fast6d.cu
   bool fast6d_supported(const hd_advection *op);
+  bool fast6d_use_rounds(const hd_advection *op);
   int  fast6d_halo_senders(const hd_advection *op);
   int  launch_fast6d(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part,
                      const hd_halo_send *sends = nullptr, int n_sends = 0, const void *halo_flag = nullptr, int halo_target = 0, long long row_begin = 0,

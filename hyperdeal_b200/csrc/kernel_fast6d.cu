@@ -38,6 +38,7 @@
 #include <type_traits>
 
 #include "hd_internal.h"
+#include "rounds6d_tasks.cuh"
 
 // Register budget.  An SM sub-partition holds 16384 registers = 512 per lane and hosts one warp of every warpgroup.
 // The kernel is launched with 168 registers per thread (3 x 168 = 504 <= 512); the producer warpgroup then hands
@@ -127,6 +128,9 @@ namespace
     // inside a tile the re-use distance of direction d is tile[1]*..*tile[d-1] rows of 2 x 256 KiB traffic.
     // tile[d] == ncell[d] for every d is the plain lattice order.
     int           tile[6];
+    // three-round kernel: bit d (1..5) = the producer asks for the upwind face layer of direction d of every cell to be in
+    // L2 before the compute warps read it; bit 6 = same for the cell's `sol` values (fused LSRK)
+    int           r6_prefetch;
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -736,12 +740,13 @@ namespace
   // take their first row of cells (rows are handed out dynamically, so the late start balances itself): a warp moves
   // one face cell (8 KiB) per iteration with 16 x 16 B loads in flight per lane, i.e. 80 KiB in flight per sender CTA.
   // Kept out of line so that the compute warps' code is laid out and register-allocated exactly as in the plain variant.
+  template <int NT>
   __device__ __noinline__ void
   halo_send_cta(const FastParams &p)
   {
     const int lane = threadIdx.x & 31;
-    const int gw   = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); // this warp among all sender warps
-    const int nw   = p.n_sender_ctas * (THREADS / 32);
+    const int gw   = blockIdx.x * (NT / 32) + (threadIdx.x >> 5); // this warp among all sender warps
+    const int nw   = p.n_sender_ctas * (NT / 32);
     for (int si = 0; si < p.n_sends; ++si)
       {
         const int d = p.send_dir[si], side = p.send_side[si];
@@ -855,7 +860,7 @@ namespace
     if (HALO)
       {
         if (p.pass == 3 && p.n_sends > 0 && int(blockIdx.x) < p.n_sender_ctas) // (CTA-uniform)
-          halo_send_cta(p);
+          halo_send_cta<THREADS>(p);
       }
 
     const int  n0      = p.ncell[0];
@@ -1211,6 +1216,8 @@ namespace
       }
   }
 
+#include "kernel_rounds6d.cuh"
+
   // ------------------------------------------------------------------------------- host side
   typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1229,7 +1236,7 @@ namespace
     EncodeTiledFn                encode = nullptr;
     std::map<const void *, Maps> cache;
     std::map<const void *, GhostMaps> ghost_cache;
-    bool                         attr_set[4] = {false, false, false, false};
+    bool                         attr_set[8] = {false, false, false, false, false, false, false, false};
     int *                        d_counters  = nullptr;
   };
 
@@ -1381,6 +1388,22 @@ namespace hd
     return (int)(want < grid ? want : grid);
   }
 
+  // which of the two 3D3V degree-3 FP64 kernels runs: hd_advection_set_kernel(op, 2) = the two-role pipelined kernel,
+  // 6 = the three-round kernel; automatic choice: HD_FAST_VARIANT=pipe|rounds, default rounds
+  bool
+  fast6d_use_rounds(const hd_advection *op)
+  {
+    static const int env = [] {
+      const char *e = getenv("HD_FAST_VARIANT");
+      return (e && std::strcmp(e, "pipe") == 0) ? 0 : 1;
+    }();
+    if (op->kernel_choice == 6)
+      return true;
+    if (op->kernel_choice == 2)
+      return false;
+    return env != 0;
+  }
+
   bool
   fast6d_supported(const hd_advection *op)
   {
@@ -1518,6 +1541,7 @@ namespace hd
         return e ? atoi(e) : 0; // measured on 8^6 cells: no gain from any combination (profiles/r01e_l2_hints.txt)
       }();
       p.hints = op->l2_hints >= 0 ? op->l2_hints : env_hints;
+      p.r6_prefetch = 0;
     }
     {
       // row tiles (see FastParams::tile); HD_ROW_TILE="t1,t2,t3,t4,t5" overrides the default, 0 = full extent.
@@ -1551,6 +1575,41 @@ namespace hd
         if (m->d.side_kind[d][sd] == HD_SIDE_GHOST && ((op->nb_mask[d] >> sd) & 1))
           p.halo_mask |= 1u << (2 * d + sd);
     const bool halo = (part == 3 && n_sends > 0) || getenv("HD_FORCE_HALO_VARIANT") != nullptr; // (env: A/B of the two kernel variants)
+    long long  grid = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
+    p.n_sender_ctas = hd::fast6d_halo_senders(op);
+    if (hd::fast6d_use_rounds(op))
+      {
+        // three-round kernel (kernel_rounds6d.cuh)
+        static const int env_pf = [] {
+          const char *e = getenv("HD_R6_PREFETCH");
+          return e ? atoi(e) : 0x7e;
+        }();
+        p.r6_prefetch = env_pf;
+        r6::Coef rc6;
+        for (int d = 0; d < 6; ++d)
+          {
+            double *   Cd = (d & 1) ? rc6.B[d / 2] : rc6.A[d / 2];
+            double *   Ld = (d & 1) ? rc6.LB[d / 2] : rc6.LA[d / 2];
+            const bool lo = (op->nb_mask[d] & 1) != 0, hi = (op->nb_mask[d] & 2) != 0;
+            for (int i = 0; i < 16; ++i)
+              Cd[i] = op->hC[d][0][i];
+            for (int i = 0; i < 4; ++i)
+              Ld[i] = lo ? op->hL0[d][i] : (hi ? op->hL1[d][i] : 0.0);
+          }
+        const int ridx = 4 + (fu.enabled ? 1 : 0) + (halo ? 2 : 0);
+        auto      rk   = fu.enabled ? (halo ? k_rounds_3d3v_k3<true, true> : k_rounds_3d3v_k3<true, false>) :
+                                      (halo ? k_rounds_3d3v_k3<false, true> : k_rounds_3d3v_k3<false, false>);
+        if (!st->attr_set[ridx])
+          {
+            HD_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, R6_SMEM_BYTES));
+            st->attr_set[ridx] = true;
+          }
+        rk<<<(unsigned)grid, R6_THREADS, R6_SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p, rc6);
+        HD_CUDA(cudaGetLastError());
+        op->launches++;
+        op->last_kernel = fu.enabled ? "rounds_3d3v_k3_fused_lsrk" : "rounds_3d3v_k3";
+        return HD_OK;
+      }
     const int  fidx = (fu.enabled ? 1 : 0) + (halo ? 2 : 0);
     auto       kern = fu.enabled ? (halo ? k_advect_3d3v_k3<true, true> : k_advect_3d3v_k3<true, false>) : (halo ? k_advect_3d3v_k3<false, true> : k_advect_3d3v_k3<false, false>);
     if (!st->attr_set[fidx])
@@ -1558,8 +1617,6 @@ namespace hd
         HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         st->attr_set[fidx] = true;
       }
-    long long grid  = nrows < m->ctx->sm_count ? nrows : m->ctx->sm_count;
-    p.n_sender_ctas = hd::fast6d_halo_senders(op);
     kern<<<(unsigned)grid, THREADS, SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, gmaps->g5, maps->u16, p, cfh);
     HD_CUDA(cudaGetLastError());
     op->launches++;

@@ -1,0 +1,613 @@
+// Three-round 3D3V, degree-3, FP64 advection kernel (k_rounds_3d3v_k3) — included by kernel_fast6d.cu inside its
+// anonymous namespace (it shares FastParams, the PTX wrappers, the row scheduler conventions and the halo senders).
+//
+// Why a second kernel: the two-role kernel above keeps two heavy compute warps per SM sub-partition (32 accumulators,
+// ~1150 instructions per warp and cell, half of them not FP64); its time is the serial length of that instruction
+// stream (profiles/r01h: FP64 pipe 42 %, issue 46 %, nothing saturated).  Here every sub-partition hosts THREE light
+// compute warps that run one 160-DFMA task at a time (rounds6d_tasks.cuh), ~1300 instructions per sub-partition and
+// cell instead of ~2300, and the face layers never pass through shared memory.
+//
+// One persistent CTA per SM, 512 threads = four warpgroups, mbarrier-only pipeline:
+//   warpgroup r = 0,1,2   round r (directions 2r, 2r+1) of the cells this CTA works on, pipelined over consecutive cells:
+//                         while round 2 finishes cell c, round 1 works on c+1 and round 0 on c+2.  The partial sums
+//                         travel through three shared-memory buffers P (round 0 writes, round 1 updates in place, round
+//                         2 reads and writes dst — or the fused LSRK update, time_integrators.templates.h:117-132).
+//                         The upwind trace values come from global memory (L2) one task ahead of their use; the
+//                         direction-0 trace inside a row walk is the thread's own end layer of the previous cell and
+//                         stays in registers.
+//   warp 12               producer: takes rows of cells from the global counter (same work lists, row tiles and
+//                         interior/boundary phases as the two-role kernel), computes the trace base offsets of every
+//                         cell (lanes 0-5, one direction each), TMA-loads the cell (128 B swizzle) into a 4-stage ring
+//                         and asks L2 for the face layers the compute warps will read (cp.async.bulk.prefetch).
+//   warps 13-15           only donate their registers (setmaxnreg: compute 152, producer warpgroup 56; 3*152+56 = 512).
+// Shared memory: 4 x 32 KiB (cells) + 3 x 32 KiB (partial sums) + 256 B (cell info) + barriers = 225.5 KiB.
+// Per cell and SM: FP64 pipe 960 warp-DFMA per sub-partition (1920 cycles), shared memory 256 KiB of wavefronts (2048
+// cycles), HBM 64 KiB algorithmic.
+
+#ifndef HD_R6_REGS_COMPUTE
+#define HD_R6_REGS_COMPUTE 152
+#endif
+#ifndef HD_R6_REGS_PRODUCER
+#define HD_R6_REGS_PRODUCER 56
+#endif
+#ifndef HD_R6_UNROLL_TASKS
+#define HD_R6_UNROLL_TASKS 0 // 1: both tasks of a cell as straight-line code (no register moves for the trace double buffer, twice the code)
+#endif
+static_assert(3 * HD_R6_REGS_COMPUTE + HD_R6_REGS_PRODUCER <= 512 && HD_R6_REGS_COMPUTE % 8 == 0 && HD_R6_REGS_PRODUCER % 8 == 0,
+              "register split exceeds the launch allocation (512 threads x 128 registers)");
+
+constexpr int R6_THREADS  = 512;
+constexpr int R6_STAGES   = 4;
+constexpr int R6_PBUFS    = 3;
+constexpr int R6_P_OFF    = R6_STAGES * U_BYTES;            // 131072
+constexpr int R6_INFO_OFF = R6_P_OFF + R6_PBUFS * U_BYTES;  // 229376
+constexpr int R6_BAR_OFF  = R6_INFO_OFF + R6_STAGES * 64;   // 229632
+constexpr int R6_SMEM_BYTES = R6_BAR_OFF + 256 + 1024;      // + alignment slack = 230912 <= 232448
+
+struct R6Bars
+{
+  uint32_t b;
+  __device__ __forceinline__ uint32_t fullU(int s) const { return b + 8 * s; }        // cell stage s has landed (and its info is written)
+  __device__ __forceinline__ uint32_t emptyU(int s) const { return b + 32 + 8 * s; }  // round 2 is done with it (rounds 0, 1 were before)
+  __device__ __forceinline__ uint32_t pFull0(int i) const { return b + 64 + 8 * i; }  // round 0 has written P[i]
+  __device__ __forceinline__ uint32_t pFull1(int i) const { return b + 88 + 8 * i; }  // round 1 has updated P[i]
+  __device__ __forceinline__ uint32_t pEmpty(int i) const { return b + 112 + 8 * i; } // round 2 has read P[i]
+};
+
+// cell info in shared memory: fbase[6] (48 bytes), cell, flags (r6::CellInfo reordered so that the pair fbase[2r],
+// fbase[2r+1] is one aligned 16-byte load)
+struct R6Info
+{
+  int       cell, flags;
+  long long fA, fB;
+};
+template <int R>
+__device__ __forceinline__ R6Info
+r6_read_info(uint32_t addr)
+{
+  R6Info i;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(i.cell), "=r"(i.flags) : "r"(addr + 48));
+  asm volatile("ld.shared.v2.s64 {%0, %1}, [%2];" : "=l"(i.fA), "=l"(i.fB) : "r"(addr + 16 * R));
+  return i;
+}
+
+__device__ __forceinline__ void
+r6_prefetch_tensor_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void
+r6_prefetch_bulk(const void *ptr, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+
+// mbarrier wait with a watchdog: a protocol error must end the launch with an error (trap), never hang the GPU
+__device__ __forceinline__ void
+r6_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  if (done)
+    return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;)
+    {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar), "r"(parity)
+                   : "memory");
+      if (done)
+        return;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 8000000000ull) // 8 s: beyond the 4 s the halo wait itself allows
+        asm volatile("trap;");
+    }
+}
+
+// --------------------------------------------------------------------------------------------- compute warpgroups
+template <int R, bool FUSED>
+__device__ __forceinline__ void
+r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R6Bars bars, const int t)
+{
+  const int  lane    = t & 31;
+  const bool actA    = p.up_delta[2 * R] != 0, actB = p.up_delta[2 * R + 1] != 0;
+  const bool descend = p.up_delta[0] > 0;
+  auto       release = [&](uint32_t bar) {
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(bar);
+  };
+  r6::ThreadMap<R> tm;
+  tm.init(t);
+  // round 0: the thread's own end layers of the previous cell of the row walk (tasks 0 and 1)
+  double e0[4] = {0.0, 0.0, 0.0, 0.0}, e1[4] = {0.0, 0.0, 0.0, 0.0};
+
+  // trace values of a task, requested from global memory (L2) one task ahead
+  // (round 0, direction 0: only the first cell of a row walk reads its trace from memory — straight into the registers
+  // that otherwise carry the previous cell's end layer, whose old content belongs to the row before)
+  auto request = [&](const R6Info &inf, int j, double(&fa)[4], double(&fb)[4]) {
+    const bool gA = (inf.flags >> (8 + 2 * R)) & 1, gB = (inf.flags >> (9 + 2 * R)) & 1;
+    if (actA && (R != 0 || (inf.flags & 1)))
+      r6::load_trace<R, 0>(p.src, p.ghost, inf.fA, gA, t, j, fa);
+    if (actB)
+      r6::load_trace<R, 1>(p.src, p.ghost, inf.fB, gB, t, j, fb);
+  };
+
+  r6_wait(bars.fullU(0), 0u);
+  R6Info cur = r6_read_info<R>(base + R6_INFO_OFF);
+  if (cur.cell < 0)
+    return;
+  double fa0[4] = {0.0, 0.0, 0.0, 0.0}, fb0[4] = {0.0, 0.0, 0.0, 0.0}; // traces of task 0 of the current cell
+  double fa1[4] = {0.0, 0.0, 0.0, 0.0}, fb1[4] = {0.0, 0.0, 0.0, 0.0}; // traces of task 1 (round 0: e0, e1 stand in for fa0, fa1)
+  request(cur, 0, R == 0 ? e0 : fa0, fb0);
+
+  for (int k = 0;; ++k)
+    {
+      const int      s   = k & (R6_STAGES - 1);
+      const int      pi  = k % R6_PBUFS;
+      const uint32_t pph = uint32_t((k / R6_PBUFS) & 1);
+      const uint32_t ub  = base + uint32_t(s) * U_BYTES;
+      const uint32_t pb  = base + R6_P_OFF + uint32_t(pi) * U_BYTES;
+      if (R == 0)
+        r6_wait(bars.pEmpty(pi), pph ^ 1u);
+      else if (R == 1)
+        r6_wait(bars.pFull0(pi), pph);
+      else
+        r6_wait(bars.pFull1(pi), pph);
+#if HD_R6_UNROLL_TASKS
+      const long long g0    = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
+      R6Info          nxt;
+
+      // ---- task 0 (the traces of task 1 are requested first)
+      request(cur, 1, R == 0 ? e1 : fa1, fb1);
+      if constexpr (R == 0)
+        {
+          double edge[4];
+          r6::task_round0(cf, ub, pb, tm, 0, e0, fb0, descend, edge);
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            e0[b] = edge[b];
+        }
+      else if constexpr (R == 1)
+        r6::task_round1(cf, ub, pb, tm, 0, fa0, fb0);
+      else
+        {
+          double sv[16], q[4][4];
+          if (FUSED)
+            {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                sv[i] = r6_ldg(p.sol + g0 + 256 * i);
+            }
+          r6::task_round2(cf, ub, pb, tm, 0, fa0, fb0, q);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            {
+              const double kv = q[i >> 2][i & 3];
+              if (FUSED)
+                {
+                  p.sol[g0 + 256 * i] = fma(p.fb, kv, sv[i]);
+                  if (p.fa != 0.0)
+                    p.ti_next[g0 + 256 * i] = fma(p.fa, kv, sv[i]);
+                }
+              else
+                p.dst[g0 + 256 * i] = kv;
+            }
+        }
+
+      // ---- task 1 (the next cell's info is in shared memory long before it is needed; its task-0 traces are requested now)
+      r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
+      nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
+      if (nxt.cell >= 0)
+        request(nxt, 0, R == 0 ? e0 : fa0, fb0);
+      if constexpr (R == 0)
+        {
+          double edge[4];
+          r6::task_round0(cf, ub, pb, tm, 1, e1, fb1, descend, edge);
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            e1[b] = edge[b];
+          release(bars.pFull0(pi));
+        }
+      else if constexpr (R == 1)
+        {
+          r6::task_round1(cf, ub, pb, tm, 1, fa1, fb1);
+          release(bars.pFull1(pi));
+        }
+      else
+        {
+          double          sv[16], q[4][4];
+          const long long g1 = g0 + 128;
+          if (FUSED)
+            {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                sv[i] = r6_ldg(p.sol + g1 + 256 * i);
+            }
+          r6::task_round2(cf, ub, pb, tm, 1, fa1, fb1, q);
+          // shared memory of this cell is free again (the values are in registers)
+          __syncwarp();
+          if (lane == 0)
+            {
+              mbar_arrive(bars.pEmpty(pi));
+              mbar_arrive(bars.emptyU(s));
+            }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            {
+              const double kv = q[i >> 2][i & 3];
+              if (FUSED)
+                {
+                  p.sol[g1 + 256 * i] = fma(p.fb, kv, sv[i]);
+                  if (p.fa != 0.0)
+                    p.ti_next[g1 + 256 * i] = fma(p.fa, kv, sv[i]);
+                }
+              else
+                p.dst[g1 + 256 * i] = kv;
+            }
+        }
+#else
+      const long long g0    = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
+      R6Info          nxt;
+      nxt.cell = 0;
+      // both tasks of the cell through ONE copy of the task code (instruction cache: the three rounds run side by side);
+      // the traces of the next task are requested into (nfa, nfb) first and moved over afterwards
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j)
+        {
+          double nfa[4], nfb[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            {
+              nfa[b] = R == 0 ? e1[b] : 0.0; // (round 0: e1 = the end layer the NEXT task needs unless a row walk starts)
+              nfb[b] = 0.0;
+            }
+          if (j == 0)
+            request(cur, 1, nfa, nfb);
+          else
+            {
+              r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
+              nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
+              if (nxt.cell >= 0)
+                request(nxt, 0, nfa, nfb);
+            }
+          if constexpr (R == 0)
+            {
+              double edge[4];
+              r6::task_round0(cf, ub, pb, tm, j, e0, fb0, descend, edge);
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                {
+                  e0[b] = nfa[b];
+                  e1[b] = edge[b];
+                }
+            }
+          else if constexpr (R == 1)
+            r6::task_round1(cf, ub, pb, tm, j, fa0, fb0);
+          else
+            {
+              double          sv[16], q[4][4];
+              const long long g = g0 + 128 * j;
+              if (FUSED)
+                {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    sv[i] = r6_ldg(p.sol + g + 256 * i);
+                }
+              r6::task_round2(cf, ub, pb, tm, j, fa0, fb0, q);
+              if (j == 1)
+                {
+                  // shared memory of this cell is free again (the values are in registers)
+                  __syncwarp();
+                  if (lane == 0)
+                    {
+                      mbar_arrive(bars.pEmpty(pi));
+                      mbar_arrive(bars.emptyU(s));
+                    }
+                }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                {
+                  const double kv = q[i >> 2][i & 3];
+                  if (FUSED)
+                    {
+                      p.sol[g + 256 * i] = fma(p.fb, kv, sv[i]);
+                      if (p.fa != 0.0)
+                        p.ti_next[g + 256 * i] = fma(p.fa, kv, sv[i]);
+                    }
+                  else
+                    p.dst[g + 256 * i] = kv;
+                }
+            }
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            {
+              if (R != 0)
+                fa0[b] = nfa[b];
+              fb0[b] = nfb[b];
+            }
+        }
+      if (R == 0)
+        release(bars.pFull0(pi));
+      else if (R == 1)
+        release(bars.pFull1(pi));
+#endif
+      if (nxt.cell < 0)
+        break;
+      cur = nxt;
+    }
+}
+
+template <bool FUSED, bool HALO>
+__global__ void __launch_bounds__(R6_THREADS, 1)
+  k_rounds_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
+                   const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ FastParams p,
+                   const __grid_constant__ r6::Coef cf)
+{
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw   = smem_u32(smem_raw);
+  const uint32_t base  = (raw + 1023u) & ~1023u;
+  unsigned char *gbase = smem_raw + (base - raw);
+  const R6Bars   bars{base + R6_BAR_OFF};
+
+  const int tid  = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0)
+    {
+      for (int s = 0; s < R6_STAGES; ++s)
+        {
+          mbar_init(bars.fullU(s), 1);
+          mbar_init(bars.emptyU(s), 4);
+        }
+      for (int i = 0; i < R6_PBUFS; ++i)
+        {
+          mbar_init(bars.pFull0(i), 4);
+          mbar_init(bars.pFull1(i), 4);
+          mbar_init(bars.pEmpty(i), 4);
+        }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  __syncthreads();
+
+  if (HALO)
+    {
+      if (p.pass == 3 && p.n_sends > 0 && int(blockIdx.x) < p.n_sender_ctas) // (CTA-uniform)
+        halo_send_cta<R6_THREADS>(p);
+    }
+
+  if (warp < 12)
+    {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 " HD_STR(HD_R6_REGS_COMPUTE) ";");
+      if (warp < 4)
+        r6_compute<0, FUSED>(p, cf, base, bars, tid);
+      else if (warp < 8)
+        r6_compute<1, FUSED>(p, cf, base, bars, tid - 128);
+      else
+        r6_compute<2, FUSED>(p, cf, base, bars, tid - 256);
+      return;
+    }
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 " HD_STR(HD_R6_REGS_PRODUCER) ";");
+  if (warp != 12)
+    return;
+
+  // ======================================================================= producer
+  const int  n0      = p.ncell[0];
+  const bool descend = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
+  const bool ghost0  = p.up_delta[0] != 0 && p.up_kind[0] == HD_SIDE_GHOST;
+  if (lane == 0)
+    {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
+    }
+  bool halo_ready = p.pass != 3;
+  // interior rows: mixed-radix decode that leaves out the ghost layer of every cut direction (see FastParams)
+  auto decode_interior = [&](int i, int(&cr)[6]) {
+#pragma unroll
+    for (int d = 1; d < 6; ++d)
+      {
+        const bool cut = p.cutg[d] >= 0;
+        const int  r   = p.ncell[d] - (cut ? 1 : 0);
+        const int  q   = i % r;
+        i /= r;
+        cr[d] = (cut && p.cutg[d] == 0) ? q + 1 : q;
+      }
+  };
+  auto decode_boundary = [&](int i, int(&cr)[6]) {
+    int dk = 0; // the cut direction whose ghost layer this row lies in (lower cut directions are not at theirs)
+#pragma unroll
+    for (int d = 1; d < 6; ++d)
+      if (dk == 0)
+        {
+          if (i < p.bsize[d])
+            dk = d;
+          else
+            i -= p.bsize[d];
+        }
+#pragma unroll
+    for (int d = 1; d < 6; ++d)
+      {
+        const bool cut = p.cutg[d] >= 0;
+        if (d == dk)
+          cr[d] = p.cutg[d];
+        else
+          {
+            const bool skip = cut && d < dk;
+            const int  r    = p.ncell[d] - (skip ? 1 : 0);
+            const int  q    = i % r;
+            i /= r;
+            cr[d] = (skip && p.cutg[d] == 0) ? q + 1 : q;
+          }
+      }
+  };
+  // work items come from a global counter; the next one is requested while the current row is being loaded
+  int next_item = 0;
+  if (lane == 0)
+    next_item = atomicAdd(p.counters, 1);
+  auto fetch_row = [&](int(&cr)[6], int &sb, int &se) -> bool {
+    for (;;)
+      {
+        int item = 0;
+        if (lane == 0)
+          {
+            item = next_item;
+            if (item < p.n_items)
+              next_item = atomicAdd(p.counters, 1);
+          }
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= p.n_items)
+          return false;
+        cr[0]    = 0;
+        sb       = 0;
+        se       = n0;
+        int mode = p.pass; // 0: all cells of a lattice row, 1: interior list, 2: boundary list
+        if (p.pass == 3)
+          {
+            mode = item >= p.n_int ? 2 : 1;
+            item -= item >= p.n_int ? p.n_int : 0;
+          }
+        if (mode == 0)
+          {
+            int r = item + p.row_begin;
+#pragma unroll
+            for (int d = 1; d < 6; ++d)
+              {
+                cr[d] = r % p.tile[d];
+                r /= p.tile[d];
+              }
+#pragma unroll
+            for (int d = 1; d < 6; ++d)
+              {
+                const int nt = p.ncell[d] / p.tile[d];
+                cr[d] += (r % nt) * p.tile[d];
+                r /= nt;
+              }
+          }
+        else if (mode == 1)
+          {
+            decode_interior(item, cr);
+            if (ghost0)
+              sb = 1;
+          }
+        else if (item < p.n_bnd)
+          decode_boundary(item, cr);
+        else
+          {
+            decode_interior(item - p.n_bnd, cr); // the upwind-most cells of the interior rows (direction 0 cut)
+            se = 1;
+          }
+        if (sb >= se)
+          continue;
+        if (mode == 2 && !halo_ready)
+          {
+            // the ghost faces are written by the neighbour GPUs while this kernel runs; give up after 4 s (error word)
+            if (lane == 0)
+              {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (unsigned todo = p.halo_mask; todo;)
+                  {
+                    const int i = __ffs(todo) - 1;
+                    int       v;
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.halo_flag + i) : "memory");
+                    if (v >= p.halo_target)
+                      {
+                        todo &= todo - 1;
+                        continue;
+                      }
+                    __nanosleep(500);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 4000000000ull)
+                      {
+                        atomicExch(p.counters + 2, 1);
+                        break;
+                      }
+                  }
+              }
+            __syncwarp();
+            halo_ready = true;
+          }
+        return true;
+      }
+  };
+  int c[6], sb = 0, se = 0, k = 0;
+  while (fetch_row(c, sb, se))
+    {
+      for (int step = sb; step < se; ++step, ++k)
+        {
+          c[0]                 = descend ? n0 - 1 - step : step;
+          const long long cell = cell_index(p, c);
+          const int       s    = k & (R6_STAGES - 1);
+          r6_wait(bars.emptyU(s), uint32_t((k / R6_STAGES) & 1) ^ 1u);
+          unsigned char *info = gbase + R6_INFO_OFF + 64 * s;
+          // lanes 0-5: trace base of one direction each
+          r6::FaceBase fbv;
+          fbv.off   = 0;
+          fbv.ghost = false;
+          if (lane < 6)
+            {
+              fbv                                             = r6::face_base(p, c, lane);
+              reinterpret_cast<long long *>(info)[lane] = fbv.off;
+            }
+          const unsigned gmask = __ballot_sync(0xffffffffu, fbv.ghost) & 0x3fu;
+          __syncwarp();
+          if (lane == 0)
+            {
+              reinterpret_cast<int *>(info)[12] = int(cell);
+              reinterpret_cast<int *>(info)[13] = ((step == sb) ? 1 : 0) | int(gmask << 8);
+              const uint32_t dstU = base + s * U_BYTES;
+              mbar_expect_tx(bars.fullU(s), U_BYTES);
+#pragma unroll
+              for (int piece = 0; piece < 4; ++piece)
+                tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), bars.fullU(s));
+              if (FUSED && (p.r6_prefetch & 64))
+                r6_prefetch_bulk(p.sol + cell * CELL, U_BYTES);
+            }
+          else if (lane < 6 && ((p.r6_prefetch >> lane) & 1) && p.up_delta[lane] != 0 && !fbv.ghost)
+            {
+              // face layer of direction `lane` of the upwind neighbour -> L2 (same boxes as the two-role kernel's face loads)
+              const int nb    = int(fbv.off >> 12);
+              const int layer = p.up_delta[lane] < 0 ? 3 : 0;
+              if (lane == 1)
+                r6_prefetch_tensor_3d(&mapT1, 0, layer, nb * 256);
+              else if (lane == 2)
+                r6_prefetch_tensor_3d(&mapT2, 0, layer, nb * 64);
+              else if (lane == 3)
+                r6_prefetch_tensor_3d(&mapT3, 0, layer, nb * 16);
+              else if (lane == 4)
+                r6_prefetch_tensor_3d(&mapT4, 0, layer, nb * 4);
+              else
+                r6_prefetch_bulk(p.src + fbv.off, 8192);
+            }
+        }
+    }
+  // end marker
+  {
+    const int s = k & (R6_STAGES - 1);
+    r6_wait(bars.emptyU(s), uint32_t((k / R6_STAGES) & 1) ^ 1u);
+    if (lane == 0)
+      {
+        reinterpret_cast<int *>(gbase + R6_INFO_OFF + 64 * s)[12] = -1;
+        mbar_arrive(bars.fullU(s));
+        // the last CTA to finish re-arms the row counter for the next launch
+        __threadfence();
+        const int done = atomicAdd(p.counters + 1, 1);
+        if (done == int(gridDim.x) - 1)
+          {
+            p.counters[0] = 0;
+            p.counters[1] = 0;
+            __threadfence();
+          }
+      }
+  }
+}

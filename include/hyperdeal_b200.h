@@ -221,7 +221,9 @@ int hd_advection_ghost_sides(const hd_advection *op, int *needed);
 int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_host, double time);
 /* Select the kernel: 0 = automatic (fastest available), 1 = generic kernel, 2 = pipelined 3D3V k=3 FP64 kernel,
  * 3 = tile kernel (degree 3, 1D1V / 2D2V / 3D3V, periodic or ghost sides), 4 = its row-persistent 3D3V variant,
- * 5 = tile kernel with the partial sums in global memory (degree 3 or 5, even number of directions; EXPERIMENTAL, not yet run on a GPU).
+ * 5 = tile kernel with the partial sums in global memory (degree 3 or 5, even number of directions),
+ * 6 = three-round 3D3V k=3 FP64 kernel (three light compute warps per SM sub-partition, traces read from L2).
+ * With 0 a 3D3V k=3 FP64 mesh runs kernel 6 (HD_FAST_VARIANT=pipe selects 2).
  * HD_ERR_UNSUPPORTED if the kernel does not cover the mesh. */
 int hd_advection_set_kernel(hd_advection *op, int which);
 /* Pipelined 3D3V kernel: L2 residency hints, a bit mask (1: keep the direction-4 outflow layers in L2 for the downwind

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 VEL = np.array([1.0, 0.15, -0.05, 0.1, -0.15, 0.5])
 TOL64 = 1e-12
+FAST_NAMES = ("advect_3d3v_k3", "rounds_3d3v_k3")  # the two 3D3V degree-3 FP64 kernels (hd_advection_set_kernel 2 / 6)
 TOL32 = 1e-5
 
 
@@ -205,7 +206,7 @@ def test_apply_host_pipelined_3d3v(api, ctx, a4, a5, n4, n5):
     mf.copy_in(d_src, src)
     op.apply(d_dst, d_src, 0.0)
     a = mf.copy_out(d_dst)
-    assert op.kernel_name == "advect_3d3v_k3"
+    assert op.kernel_name in FAST_NAMES
     for _ in range(2):  # (second call: staging buffers, streams and events are re-used)
         b = np.full_like(src, np.nan)
         op.apply_host(b, src, 0.0)
@@ -240,6 +241,8 @@ def test_errors_are_reported(api, ctx):
     with pytest.raises(api.HdError):
         op.set_kernel(2)  # the 3D3V kernel does not cover 1D1V
     with pytest.raises(api.HdError):
+        op.set_kernel(6)
+    with pytest.raises(api.HdError):
         api.MatrixFree(ctx, 4, 1, 3, (1,) * 5, (0,) * 5, (1,) * 5)
 
 
@@ -257,32 +260,39 @@ FAST_CASES = [
 ]
 
 
+# kernel 2 = two-role pipelined kernel (advect_3d3v_k3), 6 = three-round kernel (rounds_3d3v_k3, kernel_rounds6d.cuh)
+FAST_KERNELS = {2: "advect_3d3v_k3", 6: "rounds_3d3v_k3"}
+
+
+@pytest.mark.parametrize("kernel", [2, 6])
 @pytest.mark.parametrize("nc,vel,skew", FAST_CASES)
-def test_fast_kernel_matches_oracle(api, ctx, nc, vel, skew):
-    rel, name = _run(api, ctx, 3, 3, nc, 3, skew=skew, vel=vel, kernel=2)
-    assert name == "advect_3d3v_k3"
+def test_fast_kernel_matches_oracle(api, ctx, nc, vel, skew, kernel):
+    rel, name = _run(api, ctx, 3, 3, nc, 3, skew=skew, vel=vel, kernel=kernel)
+    assert name == FAST_KERNELS[kernel]
     assert rel <= TOL64, rel
 
 
 def test_auto_selects_fast_kernel(api, ctx):
     rel, name = _run(api, ctx, 3, 3, (2, 2, 2, 2, 2, 2), 3, skew=0.5, kernel=0)
-    assert name == "advect_3d3v_k3" and rel <= TOL64
+    assert name in FAST_NAMES and rel <= TOL64
 
 
-def test_fast_kernel_many_rows(api, ctx):
+@pytest.mark.parametrize("kernel", [2, 6])
+def test_fast_kernel_many_rows(api, ctx, kernel):
     """4^6 cells: every CTA walks several rows, all ring/parity phases wrap many times."""
-    rel, name = _run(api, ctx, 3, 3, (4, 4, 4, 4, 4, 4), 3, skew=0.5, kernel=2)
-    assert name == "advect_3d3v_k3" and rel <= TOL64
+    rel, name = _run(api, ctx, 3, 3, (4, 4, 4, 4, 4, 4), 3, skew=0.5, kernel=kernel)
+    assert name == FAST_KERNELS[kernel] and rel <= TOL64
 
 
+@pytest.mark.parametrize("kernel", [2, 6])
 @pytest.mark.parametrize("tile", [(2, 2, 2, 2, 0), (4, 2, 3, 1, 2), (3, 0, 2, 2, 4), (1, 1, 1, 1, 1), (5, 7, 5, 5, 3)])
-def test_fast_kernel_row_tiles_are_order_only(api, ctx, tile):
+def test_fast_kernel_row_tiles_are_order_only(api, ctx, tile, kernel):
     """hd_advection_set_row_tile changes the order in which rows of cells are visited (L2 blocking), never the result:
     bit-identical to the lattice order, also for extents the tile does not divide"""
     nc = (3, 4, 2, 6, 3, 4)
     mf = api.MatrixFree(ctx, 3, 3, 3, nc, (0.0,) * 6, (1.0,) * 6)
     op = api.AdvectionOperation(mf, (1.0, 0.15, -0.05, 0.1, -0.15, 0.5), 0.5)
-    op.set_kernel(2)
+    op.set_kernel(kernel)
     src = np.random.default_rng(7).standard_normal(mf.n_dofs)
     d_src, d_a, d_b = (mf.initialize_dof_vector() for _ in range(3))
     mf.copy_in(d_src, src)

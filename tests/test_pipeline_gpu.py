@@ -59,15 +59,17 @@ def test_lsrk_fused_step_matches_oracle(api, ctx, rk):
     assert _rel(mf.copy_out(sol), ref) <= 1e-12
 
 
+@pytest.mark.parametrize("kernel", [2, 6])
 @pytest.mark.parametrize("rk", ["rk45", "rk33"])
-def test_lsrk_fused_fast_kernel(api, ctx, rk):
-    """3D3V k=3: the fused operator+update epilogue of the pipelined kernel."""
+def test_lsrk_fused_fast_kernel(api, ctx, rk, kernel):
+    """3D3V k=3: the fused operator+update epilogue of the two-role (2) and the three-round (6) kernel."""
     nc = (3, 2, 2, 2, 2, 2)
     left, right = (-1.0,) * 6, (1.0,) * 6
     om = O.Mesh(3, 3, nc, left, right, (True,) * 6)
     orc = O.Oracle(om, 3, skew=0.5, velocity=VEL, nthreads=8)
     mf = api.MatrixFree(ctx, 3, 3, 3, nc, left, right)
     op = api.AdvectionOperation(mf, VEL, 0.5)
+    op.set_kernel(kernel)
     sol0 = np.random.default_rng(2).standard_normal(mf.n_dofs)
     dt = 0.002
     ref = sol0
@@ -78,7 +80,7 @@ def test_lsrk_fused_fast_kernel(api, ctx, rk):
     integ = api.LowStorageRungeKuttaIntegrator(mf, Ki, Ti, rk)
     for s in range(2):
         integ.perform_time_step(sol, s * dt, dt, op)
-    assert op.kernel_name == "advect_3d3v_k3_fused_lsrk"
+    assert op.kernel_name == {2: "advect_3d3v_k3_fused_lsrk", 6: "rounds_3d3v_k3_fused_lsrk"}[kernel]
     assert _rel(mf.copy_out(sol), ref) <= 1e-12
 
 
@@ -131,7 +133,9 @@ def test_vector_tools_reference_output(api, ctx):
 
 
 @pytest.mark.parametrize("split_dir,kernel,parts", [(0, 1, False), (2, 1, False), (5, 1, False), (0, 2, False), (1, 2, False), (2, 2, False), (3, 2, False), (4, 2, False), (5, 2, False),
-                                                    (0, 2, True), (1, 2, True), (2, 2, True), (4, 2, True), (5, 2, True), (2, 1, True)])
+                                                    (0, 2, True), (1, 2, True), (2, 2, True), (4, 2, True), (5, 2, True), (2, 1, True),
+                                                    (0, 6, False), (1, 6, False), (2, 6, False), (3, 6, False), (4, 6, False), (5, 6, False),
+                                                    (0, 6, True), (1, 6, True), (2, 6, True), (3, 6, True), (4, 6, True), (5, 6, True)])
 def test_two_bricks_with_ghost_faces(api, ctx, split_dir, kernel, parts):
     """Partition the lattice into two bricks along one direction, exchange packed faces by hand and
     compare with the unpartitioned operator (the ghost path of matrix_free/vector_partitioner.h)."""
@@ -193,7 +197,7 @@ def test_two_bricks_with_ghost_faces(api, ctx, split_dir, kernel, parts):
             op.apply_part(me["dst"], me["src"], 0.0, me["ghost"], api.PART_BOUNDARY)
         else:
             op.apply(me["dst"], me["src"], 0.0, ghosts=me["ghost"])
-        assert op.kernel_name == ("generic" if kernel == 1 else "advect_3d3v_k3")
+        assert op.kernel_name == {1: "generic", 2: "advect_3d3v_k3", 6: "rounds_3d3v_k3"}[kernel]
         out = mf.copy_out(me["dst"])
         expect = np.ascontiguousarray(ref_full[me["sl"]]).reshape(-1)
         assert _rel(out, expect) <= 1e-12
@@ -306,9 +310,10 @@ def test_halo_pack_selective_and_direct(api, ctx, dtype):
     assert np.array_equal(mf.copy_out(d_peer, 64 + n0)[64:], full[o0 : o0 + n0])
 
 
+@pytest.mark.parametrize("kernel", [2, 6])
 @pytest.mark.parametrize("dirs", [(0,), (1,), (2,), (3,), (4,), (5,), (0, 2, 5), (1, 3, 4)])
 @pytest.mark.parametrize("vel", [(1.0, 0.15, -0.05, 0.1, -0.15, 0.5), (-1.0, -0.15, 0.05, -0.1, 0.15, -0.5)])
-def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel):
+def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel, kernel):
     """hd_advection_apply_overlapped: operator + ghost exchange in one kernel.  One brick whose periodic
     neighbour is itself: the halo warp of every CTA stores the brick's own boundary layers into its own ghost
     segments and bumps its own arrival counters, the boundary phase waits for them.  Must equal the plain
@@ -319,6 +324,7 @@ def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel):
     left, right = (-1.0,) * 6, (1.0,) * 6
     mf0 = api.MatrixFree(ctx, 3, 3, 3, nc, left, right)
     op0 = api.AdvectionOperation(mf0, vel, 0.5)
+    op0.set_kernel(kernel)
     u = np.random.default_rng(21).standard_normal(mf0.n_dofs)
     d_src, d_ref = mf0.initialize_dof_vector(), mf0.initialize_dof_vector()
     mf0.copy_in(d_src, u)
@@ -327,6 +333,7 @@ def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel):
     side_kind = [[api.SIDE_GHOST, api.SIDE_GHOST] if d in dirs else [api.SIDE_PERIODIC_LOCAL] * 2 for d in range(6)]
     mf = api.MatrixFree(ctx, 3, 3, 3, nc, left, right, side_kind=side_kind)
     op = api.AdvectionOperation(mf, vel, 0.5)
+    op.set_kernel(kernel)
     needed = op.ghost_sides()
     ghost = torch.full((mf.halo_total,), float("nan"), dtype=torch.float64, device="cuda")
     counters = torch.zeros(12, dtype=torch.int32, device="cuda")
@@ -339,7 +346,7 @@ def test_fused_halo_kernel_self_exchange(api, ctx, dirs, vel):
         op.apply_overlapped(dst.data_ptr(), d_src, 0.0, ghost.data_ptr(), sends, counters.data_ptr(), epoch * op.n_halo_senders)
         torch.cuda.synchronize()
         assert not op.overlap_timed_out()
-        assert op.kernel_name == "advect_3d3v_k3"
+        assert op.kernel_name == {2: "advect_3d3v_k3", 6: "rounds_3d3v_k3"}[kernel]
         assert np.array_equal(dst.cpu().numpy(), ref)
     # configurations the fused kernel does not cover are refused, not silently mis-computed
     mf2 = api.MatrixFree(ctx, 2, 2, 3, (2, 2, 2, 2), (0.0,) * 4, (1.0,) * 4, side_kind=[[api.SIDE_GHOST] * 2] + [[api.SIDE_PERIODIC_LOCAL] * 2] * 3)

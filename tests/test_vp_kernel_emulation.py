@@ -3,7 +3,7 @@
 (tests/vp_emulation_harness.cpp includes it with -DHD_VP_HOST_EMULATION).  A barrier-synchronised kernel computes the same thing in that mode, so its index logic, sweeps and
 coefficients (basis.hpp, the product's own) can be compared with the oracle's literal kernel without a GPU.  This harness
 exists only here; the product library has no CPU path.  What it cannot show: races, launch configuration, shared-memory
-limits — those need the GPU run of tests/test_zz_pending_gpu.py."""
+limits — those need the GPU run of tests/test_zz_vp_device_gpu.py."""
 import ctypes
 import os
 import subprocess

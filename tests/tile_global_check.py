@@ -1,4 +1,4 @@
-"""Child process of tests/test_zz_pending_gpu.py: the global-memory tile kernel (kernel_tile_global.cu, hd_advection_set_kernel 5)
+"""Child process of tests/test_zz_vp_device_gpu.py: the global-memory tile kernel (kernel_tile_global.cu, hd_advection_set_kernel 5)
 against the literal oracle — degree 5 (the 3D3V FP32 case of BASELINE.json configs[2] and smaller relatives) and degree 3, incl.
 the fused LSRK step.  Own process: this kernel has not run on a GPU yet."""
 import os

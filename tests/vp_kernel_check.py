@@ -1,4 +1,4 @@
-"""Child process of tests/test_zz_pending_gpu.py: the general-velocity kernel (kernel_vp.cu) against the literal oracle with
+"""Child process of tests/test_zz_vp_device_gpu.py: the general-velocity kernel (kernel_vp.cu) against the literal oracle with
 the same separable velocity tables.  Runs in its own process so that a fault in this not-yet-validated kernel cannot take
 the CUDA context of the main test session with it.  Prints one 'VPK OK|FAIL' line per case."""
 import os

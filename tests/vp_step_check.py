@@ -1,4 +1,4 @@
-"""Child process of tests/test_zz_pending_gpu.py: the Vlasov-Poisson right-hand side assembled from the device pieces
+"""Child process of tests/test_zz_vp_device_gpu.py: the Vlasov-Poisson right-hand side assembled from the device pieces
 (hd_velocity_space_integration -> hd_poisson_solve -> hd_advection_set_phase_space_velocity -> hd_advection_apply) against the
 oracle (oracle/oracle_vp.py), and the reference's 2D2V Landau-damping golden run with it (diagnostics evaluated by the oracle's
 functions on copies of the device vectors).  Own process: none of this device code has been validated yet."""
