@@ -55,11 +55,13 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic(kernel_name):
+def _traffic(kernel_name, n_gpus=1):
+    """measured DRAM bytes of one launch (ncu), keyed by kernel name; the N > 1 launches (ghost reads, interior/boundary
+    phases, halo stores) have their own entries "<kernel>@N<n>" — never the N = 1 constant"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel_name)
+            return json.load(open(p)).get(kernel_name if n_gpus == 1 else "%s@N%d" % (kernel_name, n_gpus))
         except Exception:
             return None
     return None
@@ -217,12 +219,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=CELLS_PER_DIR, help="cells per direction per GPU (default 8 = the BASELINE workload)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 fused 3D3V kernel")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 two-role pipelined 3D3V kernel, 6 three-round 3D3V kernel")
     ap.add_argument("--layout", default="x24", choices=["x", "xv", "x24"],
                     help="how the N = 8 lattice (16,16,16,8,8,8) is cut: x = x_2,x_1,x_0 in two (bricks of 8^6 cells); xv = x_2,x_1,v_2 in two (16x8x8x8x8x4); "
                          "x24 (default) = x_2 in four, x_1 in two (16x8x4x8x8x8): two cut directions instead of three, rows of cells (along x_0) stay whole")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: direct peer-memory stores over NVLink (default) or NCCL send/recv")
     ap.add_argument("--overlap", default="kernel", choices=["kernel", "parts"], help="N > 1: one launch that waits for the halo flag in-kernel (default) or interior/boundary launches")
+    ap.add_argument("--sustain", type=float, default=3.0, help="also time the step back to back for at least this many seconds (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -249,91 +252,153 @@ def main():
 
     from hyperdeal_b200.partition import BrickPartition, HaloExchange
 
-    # global lattice of the weak-scaling recipe (x_2, x_1, x_0 doubled in turn); how it is cut into equal bricks is ours
-    recipe = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 0))
-    if args.layout == "x" or world < 8:
-        part = recipe
-    else:
-        # never cut x_0 (rows of cells are walked along x_0): the third cut goes through v_2 ("xv") or through x_2 again ("x24")
-        cut = BrickPartition(world, rank, [args.cells] * 6, split_order=(2, 1, 5) if args.layout == "xv" else (2, 1, 2))
-        nloc = [g // c for g, c in zip(recipe.n_cells_global, cut.grid)]
-        part = BrickPartition(world, rank, nloc, grid=cut.grid)
-        assert part.n_cells_global == recipe.n_cells_global
-    nglob, p = list(part.n_cells_global), list(part.grid)
     ctx = api.Context(local_rank)
-    mf = api.MatrixFree(ctx, 3, 3, DEGREE, part.n_cells, (0.0,) * 6, (1.0,) * 6, n_cells_global=part.n_cells_global, cell_offset=part.cell_offset, side_kind=part.side_kind)
-    op = api.AdvectionOperation(mf, VELOCITY, SKEW)
-    op.set_kernel(args.kernel)
-    n_dofs = mf.n_dofs
-    src = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
-    dst = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
-    api.VectorTools.interpolate(mf, src.data_ptr(), api.FN_HYPERRECTANGLE, 0.0)
-    dst.zero_()
-    halo = mf.halo_total
-    send = torch.empty(max(halo, 16), dtype=torch.float64, device="cuda")
-    ghost = torch.zeros(max(halo, 16), dtype=torch.float64, device="cuda")
-    offsets = {(d, s): mf.halo_offset(d, s) for d in range(6) for s in range(2)}
-    sizes = {(d, s): mf.ghost_size(d, s) for d in range(6) for s in range(2)}
-    # upwind flux: only the inflow ghost side of every cut direction is read -> only that one is exchanged
-    exch = HaloExchange(part, offsets, sizes, op.ghost_sides())
-    send_mask = exch.send_mask()
-    halo_bytes = exch.bytes_per_exchange[0] * 8
 
-    # N > 1: direct NVLink variant (pack kernel stores into the neighbours' ghost buffers) unless --halo nccl
-    peer, halo_mode = None, "none"
-    if world > 1:
-        halo_mode = "nccl"
-        if args.halo == "peer":
-            from hyperdeal_b200.partition import PeerHaloExchange
+    def make_partition(cells):
+        # global lattice of the weak-scaling recipe (x_2, x_1, x_0 doubled in turn); how it is cut into equal bricks is ours
+        recipe = BrickPartition(world, rank, list(cells), split_order=(2, 1, 0))
+        if args.layout == "x" or world < 8:
+            return recipe
+        # never cut x_0 (rows of cells are walked along x_0): the third cut goes through v_2 ("xv") or through x_2 again ("x24")
+        cut = BrickPartition(world, rank, list(cells), split_order=(2, 1, 5) if args.layout == "xv" else (2, 1, 2))
+        nloc = [max(1, g // c) for g, c in zip(recipe.n_cells_global, cut.grid)]
+        part = BrickPartition(world, rank, nloc, grid=cut.grid)
+        return part
 
-            try:
-                peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local_rank))
-                halo_mode = "peer"
-            except Exception as e:  # symmetric memory unavailable on this box: NCCL send/recv
-                if rank == 0:
-                    sys.stderr.write("bench: peer-memory halo unavailable (%s: %s), using NCCL send/recv\n" % (type(e).__name__, e))
-            ok = torch.tensor([1 if peer is not None else 0], device="cuda")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0:
-                peer, halo_mode = None, "nccl"
-    main_stream = torch.cuda.current_stream()
-    side_stream = torch.cuda.Stream() if world > 1 else None
-    ev_src, ev_halo = torch.cuda.Event(), torch.cuda.Event()
+    class Problem:
+        """one brick per rank of a periodic lattice + everything one operator application needs (halo plan, peer buffers)"""
 
-    def step():
-        """one operator application; N > 1: start the halo (side stream) -> interior cells -> halo arrived -> boundary cells
-        (the reference's overlapping levels, matrix_free.templates.h:1516-1566)"""
-        if world == 1:
-            op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
-            return
-        if peer is not None and args.overlap == "kernel":
-            # ONE launch: a warp per CTA stores the boundary layers into the neighbours' ghost buffers over NVLink while the
-            # others do the interior cells; the boundary layer starts when the neighbours' arrival counters are complete
-            g, sends, counters, epoch = peer.begin_fused(ctx, op)
-            op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
-            peer.consumed(ctx)
-            return
-        ev_src.record(main_stream)
-        side_stream.wait_event(ev_src)
-        ctx.set_stream(side_stream.cuda_stream)
-        m = 0
-        with torch.cuda.stream(side_stream):
+        def __init__(self, part):
+            self.part = part
+            self.mf = api.MatrixFree(ctx, 3, 3, DEGREE, part.n_cells, (0.0,) * 6, (1.0,) * 6, n_cells_global=part.n_cells_global, cell_offset=part.cell_offset,
+                                     side_kind=part.side_kind)
+            self.op = api.AdvectionOperation(self.mf, VELOCITY, SKEW)
+            self.op.set_kernel(args.kernel)
+            mf, op = self.mf, self.op
+            self.n_dofs = mf.n_dofs
+            self.src = torch.empty(self.n_dofs, dtype=torch.float64, device="cuda")
+            self.dst = torch.zeros(self.n_dofs, dtype=torch.float64, device="cuda")
+            halo = mf.halo_total
+            self.send = torch.empty(max(halo, 16), dtype=torch.float64, device="cuda")
+            self.ghost = torch.zeros(max(halo, 16), dtype=torch.float64, device="cuda")
+            offsets = {(d, s): mf.halo_offset(d, s) for d in range(6) for s in range(2)}
+            sizes = {(d, s): mf.ghost_size(d, s) for d in range(6) for s in range(2)}
+            # upwind flux: only the inflow ghost side of every cut direction is read -> only that one is exchanged
+            self.exch = HaloExchange(part, offsets, sizes, op.ghost_sides())
+            self.send_mask = self.exch.send_mask()
+            self.halo_bytes = self.exch.bytes_per_exchange[0] * 8
+            # N > 1: direct NVLink variant (sender CTAs store into the neighbours' ghost buffers) unless --halo nccl
+            self.peer, self.halo_mode = None, "none"
+            if world > 1:
+                self.halo_mode = "nccl"
+                if args.halo == "peer":
+                    from hyperdeal_b200.partition import PeerHaloExchange
+
+                    try:
+                        self.peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local_rank))
+                        self.halo_mode = "peer"
+                    except Exception as e:  # symmetric memory unavailable on this box: NCCL send/recv
+                        if rank == 0:
+                            sys.stderr.write("bench: peer-memory halo unavailable (%s: %s), using NCCL send/recv\n" % (type(e).__name__, e))
+                    ok = torch.tensor([1 if self.peer is not None else 0], device="cuda")
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if ok.item() == 0:
+                        self.peer, self.halo_mode = None, "nccl"
+            self.main_stream = torch.cuda.current_stream()
+            self.side_stream = torch.cuda.Stream() if world > 1 else None
+            self.ev_src, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
+            self.fused = self.peer is not None and args.overlap == "kernel"
+
+        def step(self):
+            """one operator application; N > 1: start the halo -> interior cells -> halo arrived -> boundary cells
+            (the reference's overlapping levels, matrix_free.templates.h:1516-1566)"""
+            mf, op, src, dst, peer = self.mf, self.op, self.src, self.dst, self.peer
+            if world == 1:
+                op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
+                return
+            if self.fused:
+                # ONE launch: the sender CTAs store the boundary layers into the neighbours' ghost buffers over NVLink while the
+                # others do the interior cells; the boundary layer starts when the neighbours' arrival counters are complete
+                g, sends, counters, epoch = peer.begin_fused(ctx, op)
+                op.apply_overlapped(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), sends, counters, epoch)
+                peer.consumed(ctx)
+                return
+            self.ev_src.record(self.main_stream)
+            self.side_stream.wait_event(self.ev_src)
+            ctx.set_stream(self.side_stream.cuda_stream)
+            m = 0
+            with torch.cuda.stream(self.side_stream):
+                if peer is not None:
+                    g, m = peer.start(mf, ctx, src.data_ptr())
+                else:
+                    mf.halo_pack(src.data_ptr(), self.send.data_ptr(), send_mask=self.send_mask)
+                    HaloExchange.finish(self.exch.start(self.send, self.ghost))
+                    g = self.ghost
+                    self.ev_halo.record(self.side_stream)
+            ctx.set_stream(self.main_stream.cuda_stream)
+            op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_INTERIOR)
             if peer is not None:
-                g, m = peer.start(mf, ctx, src.data_ptr())
+                peer.wait_ready(ctx, m)
             else:
-                mf.halo_pack(src.data_ptr(), send.data_ptr(), send_mask=send_mask)
-                HaloExchange.finish(exch.start(send, ghost))
-                g = ghost
-                ev_halo.record(side_stream)
-        ctx.set_stream(main_stream.cuda_stream)
-        op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_INTERIOR)
-        if peer is not None:
-            peer.wait_ready(ctx, m)
-        else:
-            main_stream.wait_event(ev_halo)
-        op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
-        if peer is not None:
-            peer.consumed(ctx)
+                self.main_stream.wait_event(self.ev_halo)
+            op.apply_part(dst.data_ptr(), src.data_ptr(), 0.0, g.data_ptr(), api.PART_BOUNDARY)
+            if peer is not None:
+                peer.consumed(ctx)
+
+    # ---- N > 1: parity of THIS code path (same layout, halo mode and overlap) on a small lattice, before anything is timed:
+    # every rank's brick against the whole small lattice applied as one periodic brick on its own GPU (the single-brick
+    # operator is pinned against the oracle by tests/test_apply_gpu.py).  Random field; all ranks must agree to 1e-13.
+    parity = None
+    if world > 1:
+        full_part = make_partition([args.cells] * 6)
+        small_local = [max(1, c // 4) for c in full_part.n_cells]
+        spart = BrickPartition(world, rank, small_local, grid=full_part.grid)
+        sp = Problem(spart)
+        mf_all = api.MatrixFree(ctx, 3, 3, DEGREE, spart.n_cells_global, (0.0,) * 6, (1.0,) * 6)
+        op_all = api.AdvectionOperation(mf_all, VELOCITY, SKEW)
+        op_all.set_kernel(args.kernel)
+        u = np.random.default_rng(20240229).standard_normal(mf_all.n_dofs)
+        a_src = torch.from_numpy(u).cuda()
+        a_dst = torch.zeros_like(a_src)
+        op_all.apply(a_dst.data_ptr(), a_src.data_ptr(), 0.0)
+        shape = tuple(reversed(spart.n_cells_global)) + (4096,)
+        sl = tuple(slice(spart.cell_offset[d], spart.cell_offset[d] + spart.n_cells[d]) for d in reversed(range(6)))
+        expect = a_dst.reshape(shape)[sl].contiguous().reshape(-1)
+        sp.src.copy_(a_src.reshape(shape)[sl].contiguous().reshape(-1))
+        rel = 0.0
+        for it in range(3):  # (three applications: both ghost buffers of the double buffer and the epoch counters are exercised)
+            sp.dst.fill_(float("nan"))
+            sp.step()
+            torch.cuda.synchronize()
+            rel = max(rel, float(((sp.dst - expect).abs().max() / expect.abs().max()).item()) if bool(torch.isfinite(sp.dst).all()) else float("inf"))
+        if sp.fused and sp.op.overlap_timed_out():
+            rel = float("inf")
+        t = torch.tensor([rel], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = {"parity_rel": float(t.item()), "tolerance": 1e-13, "layout": args.layout if world >= 8 else "recipe", "gpu_grid": list(spart.grid),
+                  "cells_per_gpu": list(spart.n_cells), "cells_global": list(spart.n_cells_global), "halo": sp.halo_mode,
+                  "overlap": ("kernel" if sp.fused else "parts"), "kernel": sp.op.kernel_name, "field": "standard normal, seed 20240229",
+                  "against": "the whole small lattice as one periodic brick on every rank's own GPU"}
+        if not (parity["parity_rel"] <= 1e-13):
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", **parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            raise SystemExit(3)
+        del sp, mf_all, op_all, a_src, a_dst, expect
+        torch.cuda.empty_cache()
+
+    part = make_partition([args.cells] * 6)
+    nglob, p = list(part.n_cells_global), list(part.grid)
+    prob = Problem(part)
+    mf, op, src, dst, ghost, peer = prob.mf, prob.op, prob.src, prob.dst, prob.ghost, prob.peer
+    n_dofs, halo_bytes, halo_mode, send_mask = prob.n_dofs, prob.halo_bytes, prob.halo_mode, prob.send_mask
+    step = prob.step
+    # synthetic data: a standard normal field (every face term and every rounding path is exercised; zeros — what the
+    # reference benchmark streams — or a smooth wave would let a wrong kernel look right in the checksums below)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    src.normal_(generator=gen)
 
     def barrier():
         if world > 1:
@@ -362,12 +427,12 @@ def main():
     launches = op.launch_count - launches0
     if peer is not None and args.overlap == "kernel" and op.overlap_timed_out():
         raise SystemExit("bench: the in-kernel halo wait timed out on rank %d (halo never signalled)" % rank)
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         # per-launch kernel time for the roofline entry: one un-split launch on this rank's brick (outside the timed region)
         ctx.timer_start()
         op.apply(dst.data_ptr(), src.data_ptr(), 0.0, ghosts=ghost.data_ptr())
         kernel_ms = [ctx.timer_stop()]
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -375,6 +440,32 @@ def main():
     if world > 1 and not (peer is not None and args.overlap == "kernel"):
         launches += args.steps * sum(send_mask)  # pack kernels
     value = n_dofs * world * args.steps / (total_ms * 1e-3) / 1e9
+    # result fingerprint of the device-resident run (random field): compared with the end-to-end result below
+    dst_sample = dst[:: max(1, n_dofs // 65536)].clone()
+    checksum = float(dst_sample.abs().sum().item())
+
+    # ---- sustained regime: the same step back to back for >= --sustain seconds (an LSRK run lives there; the burst number
+    # above is taken at boost clocks)
+    sustained = None
+    if args.sustain > 0:
+        n_s = max(args.steps, int(args.sustain * 1e3 / max(total_ms / args.steps, 1e-3)) + 1)
+        s_sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            s_sampler.start()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record()
+        for _ in range(n_s):
+            step()
+        es1.record()
+        barrier()
+        s_clocks = s_sampler.stop() if rank == 0 else None
+        s_ms = torch.tensor([es0.elapsed_time(es1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(s_ms, op=dist.ReduceOp.MAX)
+        s_total = float(s_ms.item())
+        sustained = {"value": n_dofs * world * n_s / (s_total * 1e-3) / 1e9, "unit": "GDoF/s", "steps": n_s, "seconds": s_total * 1e-3, "ms_per_step": s_total / n_s,
+                     "clocks": s_clocks}
 
     # ---- end to end with HOST buffers: H2D of src and D2H of dst inside the timed region
     e2e = None
@@ -391,8 +482,9 @@ def main():
             op.apply_host_ptr(h_dst.data_ptr(), h_src.data_ptr(), 0.0)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
+        h_sample = h_dst[:: max(1, n_dofs // 65536)].cuda()
         e2e = {"value": n_dofs * e_steps / el / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": n_dofs * 8, "d2h_bytes_per_step": n_dofs * 8, "steps": e_steps,
-               "checksum": float(h_dst[:: max(1, n_dofs // 4096)].sum())}
+               "checksum": float(h_sample.abs().sum().item()), "max_abs_dev_vs_resident": float((h_sample - dst_sample).abs().max().item())}
         del h_src, h_dst
     elif not args.no_e2e:
         # N > 1: every rank copies its brick of src in from pinned host memory, runs the step (halo exchange included) and
@@ -429,8 +521,9 @@ def main():
             el_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
             dist.all_reduce(el_t, op=dist.ReduceOp.MAX)
             el = float(el_t.item())
+            h_sample = h_dst[:: max(1, n_dofs // 65536)].cuda()
             e2e = {"value": n_dofs * world * e_steps / el / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": n_dofs * 8 * world, "d2h_bytes_per_step": n_dofs * 8 * world,
-                   "steps": e_steps, "checksum": float(h_dst[:: max(1, n_dofs // 4096)].sum())}
+                   "steps": e_steps, "checksum": float(h_sample.abs().sum().item()), "max_abs_dev_vs_resident": float((h_sample - dst_sample).abs().max().item())}
             del h_src, h_dst
         else:
             e2e = {"value": None, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "not enough free host memory for %d pinned bricks" % world}
@@ -447,10 +540,16 @@ def main():
             "config": {"workload": "3D3V k=3 FP64 advection apply, Cartesian periodic, %d^6 cells (%.3g DoFs) per GPU, skew 0.5, ECL" % (args.cells, n_dofs),
                        "cells_global": nglob, "cells_per_gpu": list(part.n_cells), "gpu_grid": p, "halo_bytes_sent_per_gpu_per_step": halo_bytes, "halo": halo_mode, "overlap": (args.overlap if peer is not None else "parts") if world > 1 else "none", "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n_dofs * 8 / 2**30),
                        "kernel": name},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name, world),
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this N (profiles/ncu_traffic.json); null = not captured",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": n_dofs * BYTES_PER_DOF, "kernel_ms": k_ms},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "checksum": checksum,
         }
+        if sustained is not None:
+            out["sustained"] = sustained
+        if parity is not None:
+            out["parity"] = parity
+            out["parity_rel"] = parity["parity_rel"]
         if e2e is not None:
             out["e2e"] = e2e
         if not args.no_cpu and world == 1:

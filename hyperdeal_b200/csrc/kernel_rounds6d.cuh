@@ -117,6 +117,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   const int  lane    = t & 31;
   const bool actA    = p.up_delta[2 * R] != 0, actB = p.up_delta[2 * R + 1] != 0;
   const bool descend = p.up_delta[0] > 0;
+  const bool stream  = (p.hints & 4) != 0; // dst written with streaming stores (evict-first in L2): the face layers of src stay longer
   auto       release = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0)
@@ -124,12 +125,9 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   };
   r6::ThreadMap<R> tm;
   tm.init(t);
-  // round 0: the thread's own end layers of the previous cell of the row walk (tasks 0 and 1)
-  double e0[4] = {0.0, 0.0, 0.0, 0.0}, e1[4] = {0.0, 0.0, 0.0, 0.0};
 
-  // trace values of a task, requested from global memory (L2) one task ahead
-  // (round 0, direction 0: only the first cell of a row walk reads its trace from memory — straight into the registers
-  // that otherwise carry the previous cell's end layer, whose old content belongs to the row before)
+  // trace values of a task, requested from global memory (L2).  Round 0, direction 0: only the first cell of a row walk
+  // reads its trace from memory; inside a row it is the thread's own end layer of the previous cell (registers).
   auto request = [&](const R6Info &inf, int j, double(&fa)[4], double(&fb)[4]) {
     const bool gA = (inf.flags >> (8 + 2 * R)) & 1, gB = (inf.flags >> (9 + 2 * R)) & 1;
     if (actA && (R != 0 || (inf.flags & 1)))
@@ -142,9 +140,9 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   R6Info cur = r6_read_info<R>(base + R6_INFO_OFF);
   if (cur.cell < 0)
     return;
-  double fa0[4] = {0.0, 0.0, 0.0, 0.0}, fb0[4] = {0.0, 0.0, 0.0, 0.0}; // traces of task 0 of the current cell
-  double fa1[4] = {0.0, 0.0, 0.0, 0.0}, fb1[4] = {0.0, 0.0, 0.0, 0.0}; // traces of task 1 (round 0: e0, e1 stand in for fa0, fa1)
-  request(cur, 0, R == 0 ? e0 : fa0, fb0);
+  // traces of the task about to run; (round 0) eo = the thread's end layer that the task after it will need
+  double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0}, eo[4] = {0.0, 0.0, 0.0, 0.0};
+  request(cur, 0, fa, fb);
 
   for (int k = 0;; ++k)
     {
@@ -159,147 +157,60 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
         r6_wait(bars.pFull0(pi), pph);
       else
         r6_wait(bars.pFull1(pi), pph);
-#if HD_R6_UNROLL_TASKS
-      const long long g0    = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
-      R6Info          nxt;
-
-      // ---- task 0 (the traces of task 1 are requested first)
-      request(cur, 1, R == 0 ? e1 : fa1, fb1);
-      if constexpr (R == 0)
-        {
-          double edge[4];
-          r6::task_round0(cf, ub, pb, tm, 0, e0, fb0, descend, edge);
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            e0[b] = edge[b];
-        }
-      else if constexpr (R == 1)
-        r6::task_round1(cf, ub, pb, tm, 0, fa0, fb0);
-      else
-        {
-          double sv[16], q[4][4];
-          if (FUSED)
-            {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                sv[i] = r6_ldg(p.sol + g0 + 256 * i);
-            }
-          r6::task_round2(cf, ub, pb, tm, 0, fa0, fb0, q);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            {
-              const double kv = q[i >> 2][i & 3];
-              if (FUSED)
-                {
-                  p.sol[g0 + 256 * i] = fma(p.fb, kv, sv[i]);
-                  if (p.fa != 0.0)
-                    p.ti_next[g0 + 256 * i] = fma(p.fa, kv, sv[i]);
-                }
-              else
-                p.dst[g0 + 256 * i] = kv;
-            }
-        }
-
-      // ---- task 1 (the next cell's info is in shared memory long before it is needed; its task-0 traces are requested now)
-      r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
-      nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
-      if (nxt.cell >= 0)
-        request(nxt, 0, R == 0 ? e0 : fa0, fb0);
-      if constexpr (R == 0)
-        {
-          double edge[4];
-          r6::task_round0(cf, ub, pb, tm, 1, e1, fb1, descend, edge);
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            e1[b] = edge[b];
-          release(bars.pFull0(pi));
-        }
-      else if constexpr (R == 1)
-        {
-          r6::task_round1(cf, ub, pb, tm, 1, fa1, fb1);
-          release(bars.pFull1(pi));
-        }
-      else
-        {
-          double          sv[16], q[4][4];
-          const long long g1 = g0 + 128;
-          if (FUSED)
-            {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                sv[i] = r6_ldg(p.sol + g1 + 256 * i);
-            }
-          r6::task_round2(cf, ub, pb, tm, 1, fa1, fb1, q);
-          // shared memory of this cell is free again (the values are in registers)
-          __syncwarp();
-          if (lane == 0)
-            {
-              mbar_arrive(bars.pEmpty(pi));
-              mbar_arrive(bars.emptyU(s));
-            }
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            {
-              const double kv = q[i >> 2][i & 3];
-              if (FUSED)
-                {
-                  p.sol[g1 + 256 * i] = fma(p.fb, kv, sv[i]);
-                  if (p.fa != 0.0)
-                    p.ti_next[g1 + 256 * i] = fma(p.fa, kv, sv[i]);
-                }
-              else
-                p.dst[g1 + 256 * i] = kv;
-            }
-        }
-#else
-      const long long g0    = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
+      const long long g0 = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
       R6Info          nxt;
       nxt.cell = 0;
-      // both tasks of the cell through ONE copy of the task code (instruction cache: the three rounds run side by side);
-      // the traces of the next task are requested into (nfa, nfb) first and moved over afterwards
+      // both tasks of the cell (HD_R6_UNROLL_TASKS = 0: through ONE copy of the task code — the three rounds run side by
+      // side and share the instruction cache)
+#if HD_R6_UNROLL_TASKS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int j = 0; j < 2; ++j)
         {
-          double nfa[4], nfb[4];
+          // called by the task once it has consumed (fa, fb): request the traces of the task that follows, straight into
+          // the same registers (see rounds6d_tasks.cuh on why not earlier)
+          double          sv[16]; // (round 2, fused LSRK) the `sol` values this task updates
+          const long long g = g0 + 128 * j;
+          auto after_traces = [&]() {
+            if (R == 2 && FUSED)
+              {
+                // requested here, not at the start of the task: a wait for the traces would wait for these loads as well
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-            {
-              nfa[b] = R == 0 ? e1[b] : 0.0; // (round 0: e1 = the end layer the NEXT task needs unless a row walk starts)
-              nfb[b] = 0.0;
-            }
-          if (j == 0)
-            request(cur, 1, nfa, nfb);
-          else
-            {
-              r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
-              nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
-              if (nxt.cell >= 0)
-                request(nxt, 0, nfa, nfb);
-            }
+                for (int i = 0; i < 16; ++i)
+                  sv[i] = r6_ldg(p.sol + g + 256 * i);
+              }
+            if (R == 0)
+              {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  fa[b] = eo[b];
+              }
+            if (j == 0)
+              request(cur, 1, fa, fb);
+            else
+              {
+                r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
+                nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
+                if (nxt.cell >= 0)
+                  request(nxt, 0, fa, fb);
+              }
+          };
           if constexpr (R == 0)
             {
               double edge[4];
-              r6::task_round0(cf, ub, pb, tm, j, e0, fb0, descend, edge);
+              r6::task_round0(cf, ub, pb, tm, j, fa, fb, descend, edge, after_traces);
 #pragma unroll
               for (int b = 0; b < 4; ++b)
-                {
-                  e0[b] = nfa[b];
-                  e1[b] = edge[b];
-                }
+                eo[b] = edge[b];
             }
           else if constexpr (R == 1)
-            r6::task_round1(cf, ub, pb, tm, j, fa0, fb0);
+            r6::task_round1(cf, ub, pb, tm, j, fa, fb, after_traces);
           else
             {
-              double          sv[16], q[4][4];
-              const long long g = g0 + 128 * j;
-              if (FUSED)
-                {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    sv[i] = r6_ldg(p.sol + g + 256 * i);
-                }
-              r6::task_round2(cf, ub, pb, tm, j, fa0, fb0, q);
+              double q[4][4];
+              r6::task_round2(cf, ub, pb, tm, j, fa, fb, q, after_traces);
               if (j == 1)
                 {
                   // shared memory of this cell is free again (the values are in registers)
@@ -320,23 +231,17 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                       if (p.fa != 0.0)
                         p.ti_next[g + 256 * i] = fma(p.fa, kv, sv[i]);
                     }
+                  else if (stream)
+                    __stcs(p.dst + g + 256 * i, kv);
                   else
                     p.dst[g + 256 * i] = kv;
                 }
-            }
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            {
-              if (R != 0)
-                fa0[b] = nfa[b];
-              fb0[b] = nfb[b];
             }
         }
       if (R == 0)
         release(bars.pFull0(pi));
       else if (R == 1)
         release(bars.pFull1(pi));
-#endif
       if (nxt.cell < 0)
         break;
       cur = nxt;

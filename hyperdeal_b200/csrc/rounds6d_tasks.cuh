@@ -284,12 +284,16 @@ namespace r6
     }
   };
 
-  // q[b][a] += sum_j A[a][j] U[b][j] + sum_j B[b][j] U[j][a] + LA[a] fa[b] + LB[b] fb[a]
-  // (the trace terms first: their operands have been in registers since the previous task, the u values are still on
-  // their way from shared memory)
+  // The tile arithmetic is split in two so that the trace values of the NEXT task can be requested in between:
+  //   trace_terms : q[b][a] (+)= LA[a] fa[b] + LB[b] fb[a]        (consumes the traces requested one task ago)
+  //   main_terms  : q[b][a] += sum_j A[a][j] U[b][j] + sum_j B[b][j] U[j][a]
+  // The order matters on the device: global loads are tracked by a handful of COUNTING scoreboards, so a wait for this
+  // task's traces also waits for every younger load on the same scoreboard.  The next request is therefore issued only
+  // after the trace terms — straight into the registers they have just freed — and has the whole main part (128 DFMA
+  // plus the shared-memory traffic of the task) to arrive.
   template <int ROUND, bool INIT>
   HD_R6_FN void
-  tile_fma(const Coef &cf, const double (&U)[4][4], const double (&fa)[4], const double (&fb)[4], double (&q)[4][4])
+  trace_terms(const Coef &cf, const double (&fa)[4], const double (&fb)[4], double (&q)[4][4])
   {
 #pragma unroll
     for (int b = 0; b < 4; ++b)
@@ -301,6 +305,26 @@ namespace r6
 #pragma unroll
       for (int a = 0; a < 4; ++a)
         q[b][a] = r6_fma(cf.LB[ROUND][b], fb[a], q[b][a]);
+  }
+
+  // compiler fence for the order "trace terms, then the next request": the 16 partial sums are operands of a volatile
+  // asm, so they are computed before it, and the (volatile asm) loads of the request stay behind it
+  HD_R6_FN void
+  pin_values(const double (&q)[4][4])
+  {
+#ifndef HD_R6_HOST_EMULATION
+    asm volatile("" ::"d"(q[0][0]), "d"(q[0][1]), "d"(q[0][2]), "d"(q[0][3]), "d"(q[1][0]), "d"(q[1][1]), "d"(q[1][2]), "d"(q[1][3]), "d"(q[2][0]), "d"(q[2][1]),
+                 "d"(q[2][2]), "d"(q[2][3]), "d"(q[3][0]), "d"(q[3][1]), "d"(q[3][2]), "d"(q[3][3])
+                 : "memory");
+#else
+    (void)q;
+#endif
+  }
+
+  template <int ROUND>
+  HD_R6_FN void
+  main_terms(const Coef &cf, const double (&U)[4][4], double (&q)[4][4])
+  {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
@@ -318,10 +342,12 @@ namespace r6
   }
 
   // ---- round 0: directions (0,1); writes P.  `edge[b]` returns the thread's own end layer of direction 0 (the trace the
-  // next cell of the row walk needs: i0 = 0 when the walk descends, else i0 = 3).
+  // next cell of the row walk needs: i0 = 0 when the walk descends, else i0 = 3).  after_traces() is called once fa, fb
+  // have been consumed (it may overwrite them: the request for the next task).
+  template <class F>
   HD_R6_FN void
   task_round0(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<0> &tm, int j, const double (&fa)[4], const double (&fb)[4], bool descend,
-              double (&edge)[4])
+              double (&edge)[4], F &&after_traces)
   {
     double         U[4][4], q[4][4];
     const uint32_t jo = uint32_t(j) * 16384u;
@@ -332,7 +358,10 @@ namespace r6
         U[ch >> 1][(ch & 1) * 2]     = v.x;
         U[ch >> 1][(ch & 1) * 2 + 1] = v.y;
       }
-    tile_fma<0, true>(cf, U, fa, fb, q);
+    trace_terms<0, true>(cf, fa, fb, q);
+    pin_values(q);
+    after_traces();
+    main_terms<0>(cf, U, q);
 #pragma unroll
     for (int b = 0; b < 4; ++b)
       edge[b] = descend ? U[b][0] : U[b][3];
@@ -342,21 +371,25 @@ namespace r6
   }
 
   // ---- round 1: directions (2,3); P updated in place
+  template <class F>
   HD_R6_FN void
-  task_round1(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<1> &tm, int j, const double (&fa)[4], const double (&fb)[4])
+  task_round1(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<1> &tm, int j, const double (&fa)[4], const double (&fb)[4], F &&after_traces)
   {
     double U[4][4], q[4][4];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
-    tile_fma<1, false>(cf, U, fa, fb, q);
+        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+    trace_terms<1, false>(cf, fa, fb, q);
+    pin_values(q);
+    after_traces();
+    main_terms<1>(cf, U, q);
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -366,20 +399,25 @@ namespace r6
 
   // ---- round 2: directions (4,5); returns the finished values K[b][a] of dst index g0 + 256 a + 1024 b,
   // g0 = cell * 4096 + (t & 15) + 16 ((t >> 4) + 8 j)
+  template <class F>
   HD_R6_FN void
-  task_round2(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<2> &tm, int j, const double (&fa)[4], const double (&fb)[4], double (&q)[4][4])
+  task_round2(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<2> &tm, int j, const double (&fa)[4], const double (&fb)[4], double (&q)[4][4],
+              F &&after_traces)
   {
     double U[4][4];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
-    tile_fma<2, false>(cf, U, fa, fb, q);
+        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+    trace_terms<2, false>(cf, fa, fb, q);
+    pin_values(q);
+    after_traces();
+    main_terms<2>(cf, U, q);
   }
 } // namespace r6

@@ -55,6 +55,23 @@ def build(force: bool = False) -> str:
     return so
 
 
+def build_simd(force: bool = False) -> str:
+    """Compile hd_ecl_simd.cpp (the vectorised CPU baseline of bench.py) into oracle/_build/libhdeclsimd.so."""
+    out_dir = os.path.join(_HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libhdeclsimd.so")
+    src = os.path.join(_HERE, "hd_ecl_simd.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        cmd = ["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fno-trapping-math", src, "-o", so + ".tmp"]
+        try:
+            subprocess.check_call(cmd)
+        except subprocess.CalledProcessError:
+            cmd.remove("-march=native")
+            subprocess.check_call(cmd)
+        os.replace(so + ".tmp", so)
+    return so
+
+
 class _Mesh(ctypes.Structure):
     _fields_ = [
         ("dim_x", ctypes.c_int),
@@ -110,6 +127,43 @@ def _lib():
 
 def _ptr(a):
     return a.ctypes.data_as(_DP)
+
+
+_SIMD = None
+
+
+class FastECL:
+    """The vectorised CPU restatement of the reference's ECL kernel (oracle/hd_ecl_simd.cpp) for the benchmark
+    configuration: 3D3V, degree 3, n_q = 4, periodic Cartesian lattice, constant velocity.  Same algorithm and same 1-D
+    data as ``Oracle`` (which pins it in tests/test_ecl_simd_cpu.py); used by bench.py as the CPU baseline."""
+
+    def __init__(self, n_cells, left, right, velocity, skew=0.0, nthreads=1, pin=True):
+        global _SIMD
+        if _SIMD is None:
+            _SIMD = ctypes.CDLL(build_simd())
+            ip = ctypes.POINTER(ctypes.c_int)
+            _SIMD.hde_apply.argtypes = [ip, _DP, _DP, _DP, ctypes.c_double, _DP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, ctypes.c_int, ctypes.c_int]
+            _SIMD.hde_apply.restype = ctypes.c_int
+        assert len(n_cells) == 6
+        self.n_cells = tuple(int(c) for c in n_cells)
+        self.b = basis_1d(3, None, False)
+        self.left = np.ascontiguousarray(left, dtype=np.float64)
+        self.right = np.ascontiguousarray(right, dtype=np.float64)
+        self.velocity = np.ascontiguousarray(velocity, dtype=np.float64)
+        self.skew, self.nthreads, self.pin = float(skew), int(nthreads), bool(pin)
+        self.ndofs = 4096 * int(np.prod(self.n_cells))
+
+    def apply(self, src, dst=None):
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        assert src.size == self.ndofs
+        if dst is None:
+            dst = np.empty_like(src)
+        nc = (ctypes.c_int * 6)(*self.n_cells)
+        b = self.b
+        rc = _SIMD.hde_apply(nc, _ptr(self.left), _ptr(self.right), _ptr(self.velocity), self.skew, _ptr(b.S), _ptr(b.D), _ptr(b.Sinv), _ptr(b.w), _ptr(b.face0),
+                             _ptr(b.face1), _ptr(src), _ptr(dst), self.nthreads, 1 if self.pin else 0)
+        assert rc == 0
+        return dst
 
 
 # --------------------------------------------------------------------------- 1-D basis

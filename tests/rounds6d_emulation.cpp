@@ -110,7 +110,14 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
         }
       const bool descend = L.up_delta[0] > 0;
       const long long nrows = ncells / ncell[0];
-      std::vector<double> tr(128 * 2 * 4);
+      // the walk of ONE persistent CTA over the whole lattice: rows in lattice order, cells of a row in upwind order
+      struct Item
+      {
+        long long cell;
+        bool      first;
+        FaceBase  fbv[6];
+      };
+      std::vector<Item> walk;
       for (long long row = 0; row < nrows; ++row)
         {
           int       c[6];
@@ -122,63 +129,93 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
             }
           for (int step = 0; step < ncell[0]; ++step)
             {
-              c[0]           = descend ? ncell[0] - 1 - step : step;
-              long long cell = 0;
+              c[0] = descend ? ncell[0] - 1 - step : step;
+              Item it;
+              it.cell = 0;
               for (int d = 5; d >= 0; --d)
-                cell = cell * ncell[d] + c[d];
-              FaceBase fbv[6];
+                it.cell = it.cell * ncell[d] + c[d];
+              it.first = step == 0;
               for (int d = 0; d < 6; ++d)
-                fbv[d] = face_base(L, c, d);
-              const bool first = step == 0;
-              // TMA fill: row rr (16 doubles) -> rr * 128, chunk ch -> ch ^ (rr & 7)
-              for (int rr = 0; rr < 256; ++rr)
-                for (int ch = 0; ch < 8; ++ch)
-                  std::memcpy(sm.data() + ub + rr * 128 + ((ch ^ (rr & 7)) << 4), src + cell * CELL + rr * 16 + ch * 2, 16);
-              const double zero[4] = {0, 0, 0, 0};
-              for (int t = 0; t < 128; ++t)
-                for (int j = 0; j < 2; ++j)
-                  {
-                    double fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0}, edge[4];
-                    if (L.up_delta[0] != 0)
-                      {
-                        if (first)
-                          load_trace<0, 0>(src, ghost.data(), fbv[0].off, fbv[0].ghost, t, j, fa);
-                        else
-                          for (int b = 0; b < 4; ++b)
-                            fa[b] = tr[(t * 2 + j) * 4 + b];
-                      }
-                    if (L.up_delta[1] != 0)
-                      load_trace<0, 1>(src, ghost.data(), fbv[1].off, fbv[1].ghost, t, j, fb);
-                    task_round0(cf, ub, pb, tm0[t], j, fa, fb, descend, edge);
-                    for (int b = 0; b < 4; ++b)
-                      tr[(t * 2 + j) * 4 + b] = edge[b];
-                  }
-              (void)zero;
-              for (int t = 0; t < 128; ++t)
-                for (int j = 0; j < 2; ++j)
-                  {
-                    double fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
-                    if (L.up_delta[2] != 0)
-                      load_trace<1, 0>(src, ghost.data(), fbv[2].off, fbv[2].ghost, t, j, fa);
-                    if (L.up_delta[3] != 0)
-                      load_trace<1, 1>(src, ghost.data(), fbv[3].off, fbv[3].ghost, t, j, fb);
-                    task_round1(cf, ub, pb, tm1[t], j, fa, fb);
-                  }
-              for (int t = 0; t < 128; ++t)
-                for (int j = 0; j < 2; ++j)
-                  {
-                    double fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0}, q[4][4];
-                    if (L.up_delta[4] != 0)
-                      load_trace<2, 0>(src, ghost.data(), fbv[4].off, fbv[4].ghost, t, j, fa);
-                    if (L.up_delta[5] != 0)
-                      load_trace<2, 1>(src, ghost.data(), fbv[5].off, fbv[5].ghost, t, j, fb);
-                    task_round2(cf, ub, pb, tm2[t], j, fa, fb, q);
-                    const long long g0 = cell * CELL + (t & 15) + 16 * ((t >> 4) + 8 * j);
-                    for (int b = 0; b < 4; ++b)
-                      for (int a = 0; a < 4; ++a)
-                        dst[g0 + 256 * a + 1024 * b] = q[b][a];
-                  }
+                it.fbv[d] = face_base(L, c, d);
+              walk.push_back(it);
             }
+        }
+      // per-thread pipeline state of the three rounds, exactly as in r6_compute: (fa, fb) = traces of the task about to run,
+      // requested by the previous task's after_traces() callback; round 0: eo = end layer the task after the next needs
+      struct TS
+      {
+        double fa[4], fb[4], eo[4];
+      };
+      std::vector<TS> st[3];
+      for (int R = 0; R < 3; ++R)
+        st[R].assign(128, TS{{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}});
+      auto request = [&](int R, const Item &it, int t, int j, double(&fa)[4], double(&fb)[4]) {
+        const FaceBase &A = it.fbv[2 * R], &B = it.fbv[2 * R + 1];
+        if (R == 0)
+          {
+            if (L.up_delta[0] != 0 && it.first)
+              load_trace<0, 0>(src, ghost.data(), A.off, A.ghost, t, j, fa);
+            if (L.up_delta[1] != 0)
+              load_trace<0, 1>(src, ghost.data(), B.off, B.ghost, t, j, fb);
+          }
+        else if (R == 1)
+          {
+            if (L.up_delta[2] != 0)
+              load_trace<1, 0>(src, ghost.data(), A.off, A.ghost, t, j, fa);
+            if (L.up_delta[3] != 0)
+              load_trace<1, 1>(src, ghost.data(), B.off, B.ghost, t, j, fb);
+          }
+        else
+          {
+            if (L.up_delta[4] != 0)
+              load_trace<2, 0>(src, ghost.data(), A.off, A.ghost, t, j, fa);
+            if (L.up_delta[5] != 0)
+              load_trace<2, 1>(src, ghost.data(), B.off, B.ghost, t, j, fb);
+          }
+      };
+      for (int R = 0; R < 3; ++R)
+        for (int t = 0; t < 128; ++t)
+          request(R, walk[0], t, 0, st[R][t].fa, st[R][t].fb);
+      for (size_t k = 0; k < walk.size(); ++k)
+        {
+          const Item &cur = walk[k];
+          // TMA fill: row rr (16 doubles) -> rr * 128, chunk ch -> ch ^ (rr & 7)
+          for (int rr = 0; rr < 256; ++rr)
+            for (int ch = 0; ch < 8; ++ch)
+              std::memcpy(sm.data() + ub + rr * 128 + ((ch ^ (rr & 7)) << 4), src + cur.cell * CELL + rr * 16 + ch * 2, 16);
+          for (int R = 0; R < 3; ++R)
+            for (int t = 0; t < 128; ++t)
+              for (int j = 0; j < 2; ++j)
+                {
+                  TS & ts    = st[R][t];
+                  auto after = [&]() {
+                    if (R == 0)
+                      for (int b = 0; b < 4; ++b)
+                        ts.fa[b] = ts.eo[b];
+                    if (j == 0)
+                      request(R, cur, t, 1, ts.fa, ts.fb);
+                    else if (k + 1 < walk.size())
+                      request(R, walk[k + 1], t, 0, ts.fa, ts.fb);
+                  };
+                  if (R == 0)
+                    {
+                      double edge[4];
+                      task_round0(cf, ub, pb, tm0[t], j, ts.fa, ts.fb, descend, edge, after);
+                      for (int b = 0; b < 4; ++b)
+                        ts.eo[b] = edge[b];
+                    }
+                  else if (R == 1)
+                    task_round1(cf, ub, pb, tm1[t], j, ts.fa, ts.fb, after);
+                  else
+                    {
+                      double q[4][4];
+                      task_round2(cf, ub, pb, tm2[t], j, ts.fa, ts.fb, q, after);
+                      const long long g0 = cur.cell * CELL + (t & 15) + 16 * ((t >> 4) + 8 * j);
+                      for (int b = 0; b < 4; ++b)
+                        for (int a = 0; a < 4; ++a)
+                          dst[g0 + 256 * a + 1024 * b] = q[b][a];
+                    }
+                }
         }
       return 0;
     }
