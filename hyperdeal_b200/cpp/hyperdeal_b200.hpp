@@ -367,17 +367,21 @@ namespace hyperdeal
     {
       if (s != Number(0))
         throw ExcNotImplemented("vector = s with s != 0");
-      HD_CALL(hd_vector_zero(mesh, ptr));
+      HD_CALL(hd_vector_zero_n(mesh, ptr, n)); // n = the size this vector was allocated with (phase space or x-space)
       return *this;
     }
     void
     copy_locally_owned_data_from(const DeviceVector &src)
     {
-      HD_CALL(hd_vector_copy(mesh, ptr, src.ptr));
+      if (src.n != n)
+        throw ExcMessage("copy_locally_owned_data_from: vectors of different size");
+      HD_CALL(hd_vector_copy_n(mesh, ptr, src.ptr, n));
     }
     void
     copy_from_host(const std::vector<Number> &h)
     {
+      if (std::int64_t(h.size()) > n)
+        throw ExcMessage("copy_from_host: the host vector is larger than the device vector");
       HD_CALL(hd_vector_copy_in(mesh, ptr, h.data(), std::int64_t(h.size())));
     }
     void

@@ -630,7 +630,16 @@ hd_vector_alloc(hd_mesh *m, int do_ghosts, void **ptr)
   HD_CUDA(cudaSetDevice(m->ctx->device));
   const size_t bytes = (size_t)(m->ndofs + (do_ghosts ? m->ghost_total : 0)) * m->elem_size;
   HD_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
-  HD_CUDA(cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream));
+  if (cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream) != cudaSuccess)
+    {
+      cudaFree(*ptr);
+      *ptr = nullptr;
+      return hd::fail(HD_ERR_CUDA, "hd_vector_alloc: cudaMemsetAsync failed");
+    }
+  {
+    std::lock_guard<std::mutex> lock(m->vectors_mutex);
+    m->vectors[*ptr] = m->ndofs + (do_ghosts ? m->ghost_total : 0);
+  }
   return HD_OK;
 }
 
@@ -638,7 +647,25 @@ int
 hd_vector_free(hd_mesh *m, void *ptr)
 {
   HD_REQUIRE(m, "null mesh");
+  {
+    std::lock_guard<std::mutex> lock(m->vectors_mutex);
+    m->vectors.erase(ptr);
+  }
   HD_CUDA(cudaFree(ptr));
+  return HD_OK;
+}
+
+// element count of an operation on `ptr`: n values requested (n < 0: "the owned range of a phase-space vector");
+// a vector this mesh allocated is never accessed beyond its size
+static int
+checked_count(hd_mesh *m, const void *ptr, int64_t n, int64_t *out, const char *what)
+{
+  const int64_t have = m->vector_values(ptr);
+  if (n < 0)
+    n = (have >= 0 && have < m->ndofs) ? have : m->ndofs; // (an x-space vector holds fewer values than the phase-space range)
+  if (have >= 0 && n > have)
+    return hd::fail(HD_ERR_INVALID, std::string(what) + ": " + std::to_string(n) + " values requested, the vector holds " + std::to_string(have));
+  *out = n;
   return HD_OK;
 }
 
@@ -646,6 +673,9 @@ int
 hd_vector_copy_in(hd_mesh *m, void *ptr, const void *host, int64_t n)
 {
   HD_REQUIRE(m && ptr && host && n >= 0, "bad argument");
+  int rc = checked_count(m, ptr, n, &n, "hd_vector_copy_in");
+  if (rc != HD_OK)
+    return rc;
   HD_CUDA(cudaMemcpyAsync(ptr, host, (size_t)n * m->elem_size, cudaMemcpyHostToDevice, m->ctx->stream));
   HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return HD_OK;
@@ -655,25 +685,52 @@ int
 hd_vector_copy_out(hd_mesh *m, const void *ptr, void *host, int64_t n)
 {
   HD_REQUIRE(m && ptr && host && n >= 0, "bad argument");
+  int rc = checked_count(m, ptr, n, &n, "hd_vector_copy_out");
+  if (rc != HD_OK)
+    return rc;
   HD_CUDA(cudaMemcpyAsync(host, ptr, (size_t)n * m->elem_size, cudaMemcpyDeviceToHost, m->ctx->stream));
   HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return HD_OK;
 }
 
 int
-hd_vector_zero(hd_mesh *m, void *ptr)
+hd_vector_zero_n(hd_mesh *m, void *ptr, int64_t n)
 {
   HD_REQUIRE(m && ptr, "bad argument");
-  HD_CUDA(cudaMemsetAsync(ptr, 0, (size_t)m->ndofs * m->elem_size, m->ctx->stream));
+  int rc = checked_count(m, ptr, n, &n, "hd_vector_zero");
+  if (rc != HD_OK)
+    return rc;
+  HD_CUDA(cudaMemsetAsync(ptr, 0, (size_t)n * m->elem_size, m->ctx->stream));
+  return HD_OK;
+}
+
+int
+hd_vector_zero(hd_mesh *m, void *ptr)
+{
+  return hd_vector_zero_n(m, ptr, -1);
+}
+
+int
+hd_vector_copy_n(hd_mesh *m, void *dst, const void *src, int64_t n)
+{
+  HD_REQUIRE(m && dst && src, "bad argument");
+  int64_t nd = n, ns = n;
+  int     rc = checked_count(m, dst, n, &nd, "hd_vector_copy (dst)");
+  if (rc != HD_OK)
+    return rc;
+  rc = checked_count(m, src, n, &ns, "hd_vector_copy (src)");
+  if (rc != HD_OK)
+    return rc;
+  if (nd != ns)
+    return hd::fail(HD_ERR_INVALID, "hd_vector_copy: vectors of different size (" + std::to_string(nd) + " and " + std::to_string(ns) + " values)");
+  HD_CUDA(cudaMemcpyAsync(dst, src, (size_t)nd * m->elem_size, cudaMemcpyDeviceToDevice, m->ctx->stream));
   return HD_OK;
 }
 
 int
 hd_vector_copy(hd_mesh *m, void *dst, const void *src)
 {
-  HD_REQUIRE(m && dst && src, "bad argument");
-  HD_CUDA(cudaMemcpyAsync(dst, src, (size_t)m->ndofs * m->elem_size, cudaMemcpyDeviceToDevice, m->ctx->stream));
-  return HD_OK;
+  return hd_vector_copy_n(m, dst, src, -1);
 }
 
 // ---- advection operator ---------------------------------------------------------------------
@@ -1382,7 +1439,16 @@ hd_vector_alloc_x(hd_mesh *m, void **ptr)
   HD_CUDA(cudaSetDevice(m->ctx->device));
   const size_t bytes = (size_t)hd_mesh_n_dofs_x(m) * m->elem_size;
   HD_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
-  HD_CUDA(cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream));
+  if (cudaMemsetAsync(*ptr, 0, bytes, m->ctx->stream) != cudaSuccess)
+    {
+      cudaFree(*ptr);
+      *ptr = nullptr;
+      return hd::fail(HD_ERR_CUDA, "hd_vector_alloc_x: cudaMemsetAsync failed");
+    }
+  {
+    std::lock_guard<std::mutex> lock(m->vectors_mutex);
+    m->vectors[*ptr] = hd_mesh_n_dofs_x(m);
+  }
   return HD_OK;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -60,6 +62,17 @@ struct hd_mesh
   double *d_basis = nullptr;
   double *d_reduce = nullptr; // 2 doubles for norm reductions
   double *d_wv     = nullptr; // n^dim_v doubles: Gauss-Lobatto JxW of one v-cell (velocity_space_integration)
+  // vectors handed out by hd_vector_alloc / hd_vector_alloc_x: device pointer -> number of values it holds.  The copy / zero
+  // entry points check their element counts against it (pointers the library did not allocate are taken on trust).
+  std::map<const void *, int64_t> vectors;
+  std::mutex                      vectors_mutex;
+  int64_t
+  vector_values(const void *p)
+  {
+    std::lock_guard<std::mutex> lock(vectors_mutex);
+    auto                        it = vectors.find(p);
+    return it == vectors.end() ? -1 : it->second;
+  }
 };
 
 // per-direction collapsed matrices as uploaded to the device (T = Number)

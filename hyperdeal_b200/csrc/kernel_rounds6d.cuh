@@ -8,10 +8,12 @@
 // cell instead of ~2300, and the face layers never pass through shared memory.
 //
 // One persistent CTA per SM, 512 threads = four warpgroups, mbarrier-only pipeline:
-//   warpgroup r = 0,1,2   round r (directions 2r, 2r+1) of the cells this CTA works on, pipelined over consecutive cells:
-//                         while round 2 finishes cell c, round 1 works on c+1 and round 0 on c+2.  The partial sums
-//                         travel through three shared-memory buffers P (round 0 writes, round 1 updates in place, round
-//                         2 reads and writes dst — or the fused LSRK update, time_integrators.templates.h:117-132).
+//   warpgroup r = 0,1,2   round r (directions 2r, 2r+1) of the cells this CTA works on, pipelined over consecutive cells.
+//                         The partial sums travel through three shared-memory buffers P: round 0 writes, round 1 updates in
+//                         place, round 2 computes its own part from u alone and adds P at the end of each task, then writes
+//                         dst — or the fused LSRK update, time_integrators.templates.h:117-132.  So rounds 1 and 2 work on
+//                         the same cell side by side, round 0 is up to two cells ahead, and nobody runs in lock-step (with
+//                         round 2 *starting* from P the three buffers left no slack: 34 % of all warp time was barrier wait).
 //                         The upwind trace values come from global memory (L2) one task ahead of their use; the
 //                         direction-0 trace inside a row walk is the thread's own end layer of the previous cell and
 //                         stays in registers.
@@ -155,8 +157,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
         r6_wait(bars.pEmpty(pi), pph ^ 1u);
       else if (R == 1)
         r6_wait(bars.pFull0(pi), pph);
-      else
-        r6_wait(bars.pFull1(pi), pph);
+      // (round 2 needs the partial sums only at the end of its first task, see task_round2)
       const long long g0 = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
       R6Info          nxt;
       nxt.cell = 0;
@@ -210,7 +211,10 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
           else
             {
               double q[4][4];
-              r6::task_round2(cf, ub, pb, tm, j, fa, fb, q, after_traces);
+              r6::task_round2(cf, ub, pb, tm, j, fa, fb, q, after_traces, [&]() {
+                if (j == 0)
+                  r6_wait(bars.pFull1(pi), pph);
+              });
               if (j == 1)
                 {
                   // shared memory of this cell is free again (the values are in registers)

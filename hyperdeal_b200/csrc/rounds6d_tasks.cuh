@@ -398,26 +398,29 @@ namespace r6
   }
 
   // ---- round 2: directions (4,5); returns the finished values K[b][a] of dst index g0 + 256 a + 1024 b,
-  // g0 = cell * 4096 + (t & 15) + 16 ((t >> 4) + 8 j)
-  template <class F>
+  // g0 = cell * 4096 + (t & 15) + 16 ((t >> 4) + 8 j).  Its own contribution needs only u, so it is computed first and the
+  // partial sums of rounds 0 and 1 are added at the END (before_partial() = wait until round 1 is done with the cell):
+  // rounds 1 and 2 work on the same cell side by side and the three P buffers leave round 0 a whole cell of slack.
+  template <class F, class G>
   HD_R6_FN void
   task_round2(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<2> &tm, int j, const double (&fa)[4], const double (&fb)[4], double (&q)[4][4],
-              F &&after_traces)
+              F &&after_traces, G &&before_partial)
   {
     double U[4][4];
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
+        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+    trace_terms<2, true>(cf, fa, fb, q);
+    pin_values(q);
+    after_traces();
+    main_terms<2>(cf, U, q);
+    before_partial();
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
-        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
-    trace_terms<2, false>(cf, fa, fb, q);
-    pin_values(q);
-    after_traces();
-    main_terms<2>(cf, U, q);
+        q[b][a] += r6_lds64(pb + tm.elem(a, b, j));
   }
 } // namespace r6

@@ -138,6 +138,11 @@ int hd_vector_copy_out(hd_mesh *mesh, const void *device_ptr, void *host, int64_
 int hd_vector_zero(hd_mesh *mesh, void *device_ptr);
 /* dst = src for the owned range (device to device). */
 int hd_vector_copy(hd_mesh *mesh, void *dst, const void *src);
+/* The same with an explicit number of values (n_values < 0: the whole vector — the owned phase-space range, or the
+ * x-space range for a vector from hd_vector_alloc_x).  Vectors allocated by this library are never accessed beyond their
+ * size: a larger n_values — also in hd_vector_copy_in / hd_vector_copy_out — is HD_ERR_INVALID. */
+int hd_vector_zero_n(hd_mesh *mesh, void *device_ptr, int64_t n_values);
+int hd_vector_copy_n(hd_mesh *mesh, void *dst, const void *src, int64_t n_values);
 
 /* ---- advection operator ---------------------------------------------------------------- */
 /* advection::AdvectionOperation::reinit (operators/advection/advection_operation.h:98) with a

@@ -209,7 +209,7 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
                   else
                     {
                       double q[4][4];
-                      task_round2(cf, ub, pb, tm2[t], j, ts.fa, ts.fb, q, after);
+                      task_round2(cf, ub, pb, tm2[t], j, ts.fa, ts.fb, q, after, [] {});
                       const long long g0 = cur.cell * CELL + (t & 15) + 16 * ((t >> 4) + 8 * j);
                       for (int b = 0; b < 4; ++b)
                         for (int a = 0; a < 4; ++a)

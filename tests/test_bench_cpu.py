@@ -18,7 +18,8 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "GDoF/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"] == "advection operator throughput (3D3V, k=3, FP64)" and d["dtype"] == "f64"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "4^6" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "3D3V k=3 FP64 lattice" in d["cpu_baseline"]["sample"]
+    assert isinstance(d["cpu_baseline"]["same_config"], bool)
     assert d["e2e"] == {"value": d["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
