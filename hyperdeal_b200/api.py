@@ -32,12 +32,12 @@ EXPORTS = [
     "hd_last_error", "hd_version", "hd_context_create", "hd_context_destroy", "hd_context_set_stream",
     "hd_context_synchronize", "hd_device_count", "hd_device_malloc", "hd_device_free", "hd_mesh_create", "hd_mesh_destroy", "hd_mesh_n_dofs",
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
-    "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_advection_create",
+    "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_vector_zero_n", "hd_vector_copy_n", "hd_advection_create",
     "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
-    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_potential", "hd_phase_space_diagnostics", "hd_field_energy", "hd_timer_start", "hd_timer_stop",
+    "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_last_solve", "hd_poisson_potential", "hd_phase_space_diagnostics", "hd_field_energy", "hd_timer_start", "hd_timer_stop",
 ]
 
 
@@ -128,6 +128,9 @@ def lib():
     L.hd_poisson_create.argtypes = [c_void_p, POINTER(c_void_p)]
     L.hd_poisson_destroy.argtypes = [c_void_p]
     L.hd_poisson_solve.argtypes = [c_void_p, c_void_p, c_void_p, c_double, c_int, POINTER(c_int)]
+    L.hd_poisson_last_solve.argtypes = [c_void_p, POINTER(c_int), POINTER(c_double)]
+    L.hd_vector_zero_n.argtypes = [c_void_p, c_void_p, c_int64]
+    L.hd_vector_copy_n.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
     L.hd_poisson_potential.argtypes = [c_void_p]
     L.hd_poisson_potential.restype = c_void_p
     L.hd_phase_space_diagnostics.argtypes = [c_void_p, c_void_p, POINTER(c_double)]
@@ -415,10 +418,18 @@ class PoissonSolver:
         self._h = c_void_p()
         _check(lib().hd_poisson_create(matrix_free._h, byref(self._h)))
 
-    def solve(self, rho_x: int, a_v: int, rel_tol: float = 1e-10, max_iterations: int = 10000) -> int:
+    def solve(self, rho_x: int, a_v: int, rel_tol: float = 1e-7, max_iterations: int = 10000) -> int:
+        """CG steps taken; raises HdError (HD_ERR_NO_CONVERGENCE) if rel_tol is not reached — like the reference's SolverCG"""
         it = c_int()
         _check(lib().hd_poisson_solve(self._h, c_void_p(rho_x), c_void_p(a_v), float(rel_tol), int(max_iterations), byref(it)))
         return it.value
+
+    @property
+    def last_solve(self):
+        """(iterations, relative residual) of the last solve"""
+        it, res = c_int(), c_double()
+        _check(lib().hd_poisson_last_solve(self._h, byref(it), byref(res)))
+        return it.value, res.value
 
     @property
     def potential(self) -> int:

@@ -687,11 +687,21 @@ namespace hyperdeal
       PoissonSolver(const PoissonSolver &) = delete;
       PoissonSolver &operator=(const PoissonSolver &) = delete;
       unsigned int
-      solve(DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field, const DeviceVector<Number> &particle_density, const double rel_tol = 1e-10)
+      // poisson.h:593-603: ReductionControl(2 * size, 1e-20, 1e-7); a solve that misses the tolerance throws (HD_CALL turns
+      // HD_ERR_NO_CONVERGENCE into hyperdeal::ExcMessage), as dealii::SolverCG does
+      solve(DerivativeContainer<dim_x, dim_v, Number> &negative_electric_field, const DeviceVector<Number> &particle_density, const double rel_tol = 1e-7)
       {
         int it = 0;
-        HD_CALL(hd_poisson_solve(ps, particle_density.begin(), negative_electric_field.device_table(), rel_tol, 10000, &it));
+        const std::int64_t max_it = 2 * particle_density.size();
+        HD_CALL(hd_poisson_solve(ps, particle_density.begin(), negative_electric_field.device_table(), rel_tol, int(max_it < 100 ? 100 : (max_it > 100000 ? 100000 : max_it)), &it));
         return it;
+      }
+      double
+      last_relative_residual() const
+      {
+        double r = 0.0;
+        HD_CALL(hd_poisson_last_solve(ps, nullptr, &r));
+        return r;
       }
 
     private:

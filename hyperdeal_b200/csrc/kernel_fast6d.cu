@@ -36,6 +36,7 @@
 #include <cstring>
 #include <map>
 #include <type_traits>
+#include <vector>
 
 #include "hd_internal.h"
 #include "rounds6d_tasks.cuh"
@@ -131,6 +132,8 @@ namespace
     // three-round kernel: bit d (1..5) = the producer asks for the upwind face layer of direction d of every cell to be in
     // L2 before the compute warps read it; bit 6 = same for the cell's `sol` values (fused LSRK)
     int           r6_prefetch;
+    // HD_R6_TRACE builds only: timeline of CTA 0 (clock64 per event), long long [13 warps][R6_TRACE_CELLS][8 events]
+    long long *   r6_trace;
   };
 
   struct CellInfo // 32 bytes, one per cell-ring stage
@@ -1224,7 +1227,7 @@ namespace
 
   struct Maps
   {
-    CUtensorMap u, u16, t1, t2, t3, t4;
+    CUtensorMap u, u16, u256, t1, t2, t3, t4;
   };
   struct GhostMaps
   {
@@ -1311,6 +1314,12 @@ namespace
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (r != CUDA_SUCCESS)
             return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(u16) failed with code " + std::to_string((int)r));
+          // and in boxes of 256 rows = one whole cell per TMA instruction (three-round kernel)
+          box[1] = 256;
+          r      = st->encode(&m.u256, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS)
+            return hd::fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled(u256) failed with code " + std::to_string((int)r));
         }
         int rc;
         if ((rc = encode_face_map(st, &m.t1, src, ncells, 1)) != HD_OK)
@@ -1542,6 +1551,7 @@ namespace hd
       }();
       p.hints = op->l2_hints >= 0 ? op->l2_hints : env_hints;
       p.r6_prefetch = 0;
+      p.r6_trace    = nullptr;
     }
     {
       // row tiles (see FastParams::tile); HD_ROW_TILE="t1,t2,t3,t4,t5" overrides the default, 0 = full extent.
@@ -1585,6 +1595,16 @@ namespace hd
           return e ? atoi(e) : 0x7e;
         }();
         p.r6_prefetch = env_pf;
+#ifdef HD_R6_TRACE
+        {
+          // debugging aid (tools/r6_timeline.py): HD_R6_TRACE_FILE=<path> dumps the last launch's timeline of CTA 0
+          static long long *d_trace = nullptr;
+          if (!d_trace)
+            HD_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 13 * R6_TRACE_CELLS * 8));
+          HD_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 13 * R6_TRACE_CELLS * 8, m->ctx->stream));
+          p.r6_trace = d_trace;
+        }
+#endif
         r6::Coef rc6;
         for (int d = 0; d < 6; ++d)
           {
@@ -1604,8 +1624,21 @@ namespace hd
             HD_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, R6_SMEM_BYTES));
             st->attr_set[ridx] = true;
           }
-        rk<<<(unsigned)grid, R6_THREADS, R6_SMEM_BYTES, m->ctx->stream>>>(maps->u, maps->t1, maps->t2, maps->t3, maps->t4, p, rc6);
+        rk<<<(unsigned)grid, R6_THREADS, R6_SMEM_BYTES, m->ctx->stream>>>(maps->u256, maps->t1, maps->t2, maps->t3, maps->t4, p, rc6);
         HD_CUDA(cudaGetLastError());
+#ifdef HD_R6_TRACE
+        if (const char *tf = getenv("HD_R6_TRACE_FILE"))
+          {
+            std::vector<long long> h(13 * R6_TRACE_CELLS * 8);
+            HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
+            HD_CUDA(cudaMemcpy(h.data(), p.r6_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            if (FILE *f = fopen(tf, "wb"))
+              {
+                fwrite(h.data(), sizeof(long long), h.size(), f);
+                fclose(f);
+              }
+          }
+#endif
         op->launches++;
         op->last_kernel = fu.enabled ? "rounds_3d3v_k3_fused_lsrk" : "rounds_3d3v_k3";
         return HD_OK;

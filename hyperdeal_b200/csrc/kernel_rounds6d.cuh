@@ -19,9 +19,13 @@
 //                         stays in registers.
 //   warp 12               producer: takes rows of cells from the global counter (same work lists, row tiles and
 //                         interior/boundary phases as the two-role kernel), computes the trace base offsets of every
-//                         cell (lanes 0-5, one direction each), TMA-loads the cell (128 B swizzle) into a 4-stage ring
-//                         and asks L2 for the face layers the compute warps will read (cp.async.bulk.prefetch).
-//   warps 13-15           only donate their registers (setmaxnreg: compute 152, producer warpgroup 56; 3*152+56 = 512).
+//                         cell (lanes 0-5, one direction each; per row, then one multiply-add per cell) and TMA-loads the
+//                         cell (one 32 KiB box, 128 B swizzle) into a 4-stage ring.  Its per-cell latency sets the pace of
+//                         the ring (measured with the HD_R6_TRACE timeline: 2400 cycles per cell when it also issued the
+//                         prefetches and indexed its coordinates dynamically = local memory; the kernel was producer-bound).
+//   warp 13               prefetch warp: follows the producer through the cell info and asks L2 for the face layers the
+//                         compute warps will read (cp.async.bulk.prefetch[.tensor]).
+//   warps 14-15           only donate their registers (setmaxnreg: compute 152, producer warpgroup 56; 3*152+56 = 512).
 // Shared memory: 4 x 32 KiB (cells) + 3 x 32 KiB (partial sums) + 256 B (cell info) + barriers = 225.5 KiB.
 // Per cell and SM: FP64 pipe 960 warp-DFMA per sub-partition (1920 cycles), shared memory 256 KiB of wavefronts (2048
 // cycles), HBM 64 KiB algorithmic.
@@ -33,27 +37,43 @@
 #define HD_R6_REGS_PRODUCER 56
 #endif
 #ifndef HD_R6_UNROLL_TASKS
-#define HD_R6_UNROLL_TASKS 0 // 1: both tasks of a cell as straight-line code (no register moves for the trace double buffer, twice the code)
+#define HD_R6_UNROLL_TASKS 1 // 1: both tasks of a cell as straight-line code (task index = immediate offsets in every address), 0: one rolled copy
 #endif
 static_assert(3 * HD_R6_REGS_COMPUTE + HD_R6_REGS_PRODUCER <= 512 && HD_R6_REGS_COMPUTE % 8 == 0 && HD_R6_REGS_PRODUCER % 8 == 0,
               "register split exceeds the launch allocation (512 threads x 128 registers)");
 
+constexpr int R6_TRACE_CELLS = 512;
+#ifdef HD_R6_TRACE
+// event e of cell k as seen by warp `w` of CTA 0 (lane 0 only)
+#define R6_TR(w, k, e)                                                                                    \
+  do                                                                                                      \
+    {                                                                                                     \
+      if (p.r6_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (k) < R6_TRACE_CELLS)               \
+        p.r6_trace[((w)*R6_TRACE_CELLS + (k)) * 8 + (e)] = clock64();                                     \
+    }                                                                                                     \
+  while (0)
+#else
+#define R6_TR(w, k, e) ((void)0)
+#endif
 constexpr int R6_THREADS  = 512;
 constexpr int R6_STAGES   = 4;
 constexpr int R6_PBUFS    = 3;
 constexpr int R6_P_OFF    = R6_STAGES * U_BYTES;            // 131072
 constexpr int R6_INFO_OFF = R6_P_OFF + R6_PBUFS * U_BYTES;  // 229376
 constexpr int R6_BAR_OFF  = R6_INFO_OFF + R6_STAGES * 64;   // 229632
-constexpr int R6_SMEM_BYTES = R6_BAR_OFF + 256 + 1024;      // + alignment slack = 230912 <= 232448
+constexpr int R6_SMEM_BYTES = R6_BAR_OFF + 512 + 1024;      // + alignment slack = 231168 <= 232448
 
 struct R6Bars
 {
   uint32_t b;
   __device__ __forceinline__ uint32_t fullU(int s) const { return b + 8 * s; }        // cell stage s has landed (and its info is written)
   __device__ __forceinline__ uint32_t emptyU(int s) const { return b + 32 + 8 * s; }  // round 2 is done with it (rounds 0, 1 were before)
-  __device__ __forceinline__ uint32_t pFull0(int i) const { return b + 64 + 8 * i; }  // round 0 has written P[i]
-  __device__ __forceinline__ uint32_t pFull1(int i) const { return b + 88 + 8 * i; }  // round 1 has updated P[i]
-  __device__ __forceinline__ uint32_t pEmpty(int i) const { return b + 112 + 8 * i; } // round 2 has read P[i]
+  __device__ __forceinline__ uint32_t infoFull(int s) const { return b + 320 + 8 * s; } // the cell info of stage s is written (prefetch warp)
+  __device__ __forceinline__ uint32_t pFull1(int i) const { return b + 64 + 8 * i; }  // round 1 has updated P[i]
+  __device__ __forceinline__ uint32_t pEmpty(int i) const { return b + 88 + 8 * i; }  // round 2 has read P[i]
+  // round 0 -> round 1 is a warp-to-warp, task-to-task dependency: task j of warp w of round 1 reads exactly the rows
+  // (i4 in {2 (w & 1), 2 (w & 1) + 1}, i5 = (w >> 1) + 2 j) that task j of warp w of round 0 writes — one barrier each
+  __device__ __forceinline__ uint32_t pFull0(int i, int w, int j) const { return b + 128 + 8 * ((i * 4 + w) * 2 + j); }
 };
 
 // cell info in shared memory: fbase[6] (48 bytes), cell, flags (r6::CellInfo reordered so that the pair fbase[2r],
@@ -130,12 +150,54 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
 
   // trace values of a task, requested from global memory (L2).  Round 0, direction 0: only the first cell of a row walk
   // reads its trace from memory; inside a row it is the thread's own end layer of the previous cell (registers).
+  // The thread part of the addresses is computed once (r6::face_addr); strides and the task increment are compile-time
+  // constants, so a request is one 64-bit add per side plus the loads with immediate offsets.
+  int thrS[2], thrG[2];
+  {
+    int st;
+    r6::face_addr<R, 0>(false, t, 0, thrS[0], st);
+    r6::face_addr<R, 1>(false, t, 0, thrS[1], st);
+    r6::face_addr<R, 0>(true, t, 0, thrG[0], st);
+    r6::face_addr<R, 1>(true, t, 0, thrG[1], st);
+  }
+  auto load4 = [&](const double *q, auto stride_c, double(&f)[4]) {
+    constexpr int stride = decltype(stride_c)::value;
+    if (stride == 1)
+      {
+        const double2 v0 = r6_ldg128(q), v1 = r6_ldg128(q + 2); // four contiguous doubles, 32-byte aligned
+        f[0] = v0.x;
+        f[1] = v0.y;
+        f[2] = v1.x;
+        f[3] = v1.y;
+      }
+    else
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          f[i] = r6_ldg(q + i * stride);
+      }
+  };
+  constexpr int stepS = r6::trace_task_step(R, false), stepG = r6::trace_task_step(R, true);
+  using SA = std::integral_constant<int, r6::trace_stride(R, 0, false)>;
+  using GA = std::integral_constant<int, r6::trace_stride(R, 0, true)>;
+  using SB = std::integral_constant<int, r6::trace_stride(R, 1, false)>;
+  using GB = std::integral_constant<int, r6::trace_stride(R, 1, true)>;
   auto request = [&](const R6Info &inf, int j, double(&fa)[4], double(&fb)[4]) {
     const bool gA = (inf.flags >> (8 + 2 * R)) & 1, gB = (inf.flags >> (9 + 2 * R)) & 1;
     if (actA && (R != 0 || (inf.flags & 1)))
-      r6::load_trace<R, 0>(p.src, p.ghost, inf.fA, gA, t, j, fa);
+      {
+        if (!gA)
+          load4(p.src + inf.fA + thrS[0] + j * stepS, SA(), fa);
+        else
+          load4(p.ghost + inf.fA + thrG[0] + j * stepG, GA(), fa);
+      }
     if (actB)
-      r6::load_trace<R, 1>(p.src, p.ghost, inf.fB, gB, t, j, fb);
+      {
+        if (!gB)
+          load4(p.src + inf.fB + thrS[1] + j * stepS, SB(), fb);
+        else
+          load4(p.ghost + inf.fB + thrG[1] + j * stepG, GB(), fb);
+      }
   };
 
   r6_wait(bars.fullU(0), 0u);
@@ -145,6 +207,8 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   // traces of the task about to run; (round 0) eo = the thread's end layer that the task after it will need
   double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0}, eo[4] = {0.0, 0.0, 0.0, 0.0};
   request(cur, 0, fa, fb);
+  double U[4][4]; // the u tile of the task about to run (loaded by the task before it)
+  r6::load_u<R>(base, tm, 0, U);
 
   for (int k = 0;; ++k)
     {
@@ -153,11 +217,13 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
       const uint32_t pph = uint32_t((k / R6_PBUFS) & 1);
       const uint32_t ub  = base + uint32_t(s) * U_BYTES;
       const uint32_t pb  = base + R6_P_OFF + uint32_t(pi) * U_BYTES;
+      const int tw = R * 4 + (t >> 5); // (trace builds) this warp's row of the timeline
+      (void)tw;
+      R6_TR(tw, k, 0);
       if (R == 0)
         r6_wait(bars.pEmpty(pi), pph ^ 1u);
-      else if (R == 1)
-        r6_wait(bars.pFull0(pi), pph);
-      // (round 2 needs the partial sums only at the end of its first task, see task_round2)
+      R6_TR(tw, k, 1);
+      // (round 1 waits per task for its own warp's rows, round 2 needs the partial sums only at the end of its first task)
       const long long g0 = (long long)cur.cell * CELL + (t & 15) + 16 * (t >> 4);
       R6Info          nxt;
       nxt.cell = 0;
@@ -192,28 +258,52 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
               request(cur, 1, fa, fb);
             else
               {
+                R6_TR(tw, k, 2);
                 r6_wait(bars.fullU((k + 1) & (R6_STAGES - 1)), uint32_t(((k + 1) / R6_STAGES) & 1));
+                R6_TR(tw, k, 3);
                 nxt = r6_read_info<R>(base + R6_INFO_OFF + 64u * uint32_t((k + 1) & (R6_STAGES - 1)));
                 if (nxt.cell >= 0)
                   request(nxt, 0, fa, fb);
               }
           };
+          // called by the task once it has consumed U: the u tile of the task that follows (its cell has landed: after_traces
+          // of task 1 waited for it)
+          auto after_main = [&]() {
+            if (j == 0)
+              r6::load_u<R>(ub, tm, 1, U);
+            else if (nxt.cell >= 0)
+              r6::load_u<R>(base + uint32_t((k + 1) & (R6_STAGES - 1)) * U_BYTES, tm, 0, U);
+          };
           if constexpr (R == 0)
             {
               double edge[4];
-              r6::task_round0(cf, ub, pb, tm, j, fa, fb, descend, edge, after_traces);
+              r6::task_round0(cf, pb, tm, j, U, fa, fb, descend, edge, after_traces, after_main);
 #pragma unroll
               for (int b = 0; b < 4; ++b)
                 eo[b] = edge[b];
+              release(bars.pFull0(pi, t >> 5, j));
             }
           else if constexpr (R == 1)
-            r6::task_round1(cf, ub, pb, tm, j, fa, fb, after_traces);
+            {
+              r6::task_round1(cf, pb, tm, j, U, fa, fb, after_traces, after_main, [&]() {
+                R6_TR(tw, k, j == 0 ? 4 : 6);
+                r6_wait(bars.pFull0(pi, t >> 5, j), pph);
+                if (j == 0)
+                  R6_TR(tw, k, 5);
+              });
+            }
           else
             {
               double q[4][4];
-              r6::task_round2(cf, ub, pb, tm, j, fa, fb, q, after_traces, [&]() {
+              r6::task_round2(cf, pb, tm, j, U, fa, fb, q, after_traces, after_main, [&]() {
                 if (j == 0)
-                  r6_wait(bars.pFull1(pi), pph);
+                  {
+                    R6_TR(tw, k, 4);
+                    r6_wait(bars.pFull1(pi), pph);
+                    R6_TR(tw, k, 5);
+                  }
+                else
+                  R6_TR(tw, k, 6);
               });
               if (j == 1)
                 {
@@ -242,10 +332,9 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                 }
             }
         }
-      if (R == 0)
-        release(bars.pFull0(pi));
-      else if (R == 1)
+      if (R == 1)
         release(bars.pFull1(pi));
+      R6_TR(tw, k, 7);
       if (nxt.cell < 0)
         break;
       cur = nxt;
@@ -273,11 +362,14 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
       for (int s = 0; s < R6_STAGES; ++s)
         {
           mbar_init(bars.fullU(s), 1);
-          mbar_init(bars.emptyU(s), 4);
+          mbar_init(bars.emptyU(s), 5); // the four warps of round 2 + the prefetch warp (it reads the cell info)
+          mbar_init(bars.infoFull(s), 1);
         }
       for (int i = 0; i < R6_PBUFS; ++i)
         {
-          mbar_init(bars.pFull0(i), 4);
+          for (int w = 0; w < 4; ++w)
+            for (int j = 0; j < 2; ++j)
+              mbar_init(bars.pFull0(i, w, j), 1);
           mbar_init(bars.pFull1(i), 4);
           mbar_init(bars.pEmpty(i), 4);
         }
@@ -304,6 +396,51 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
       return;
     }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 " HD_STR(HD_R6_REGS_PRODUCER) ";");
+  if (warp == 13)
+    {
+      // ===================================================================== prefetch warp
+      // follows the producer through the cell info: asks L2 for the upwind face layers the compute warps will read one to
+      // three cells later (lanes 1-5, one direction each; lanes 1-4 with ONE tensor-prefetch instruction) and, in the fused
+      // LSRK variant, for the cell's `sol` values (lane 0).  Kept off the producer warp: that one sets the pace of the ring.
+      if (lane == 0)
+        {
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
+        }
+      const CUtensorMap *mymap = lane == 1 ? &mapT1 : (lane == 2 ? &mapT2 : (lane == 3 ? &mapT3 : &mapT4));
+      const int          hi    = 1 << (2 * (5 - (lane < 6 ? lane : 5))); // face-layer rows per cell of this lane's map
+      const int          ud    = (lane >= 1 && lane < 6) ? p.up_delta[lane] : 0;
+      const bool         mine  = ud != 0 && ((p.r6_prefetch >> lane) & 1);
+      for (int k = 0;; ++k)
+        {
+          const int s = k & (R6_STAGES - 1);
+          r6_wait(bars.infoFull(s), uint32_t((k / R6_STAGES) & 1));
+          const uint32_t ia = base + R6_INFO_OFF + 64u * uint32_t(s);
+          int            cellk, flags;
+          long long      off = 0;
+          asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(cellk), "=r"(flags) : "r"(ia + 48));
+          if (lane < 6)
+            asm volatile("ld.shared.s64 %0, [%1];" : "=l"(off) : "r"(ia + 8u * uint32_t(lane)));
+          __syncwarp();
+          if (lane == 0)
+            mbar_arrive(bars.emptyU(s)); // the info is in registers
+          if (cellk < 0)
+            break;
+          const bool ghost = (flags >> (8 + lane)) & 1;
+          if (mine && !ghost)
+            {
+              if (lane < 5)
+                r6_prefetch_tensor_3d(mymap, 0, ud < 0 ? 3 : 0, int(off >> 12) * hi);
+              else
+                r6_prefetch_bulk(p.src + off, 8192);
+            }
+          if (FUSED && lane == 0 && (p.r6_prefetch & 64))
+            r6_prefetch_bulk(p.sol + (long long)cellk * CELL, U_BYTES);
+        }
+      return;
+    }
   if (warp != 12)
     return;
 
@@ -314,10 +451,6 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
   if (lane == 0)
     {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT2));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT3));
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT4));
     }
   bool halo_ready = p.pass != 3;
   // interior rows: mixed-radix decode that leaves out the ghost layer of every cut direction (see FastParams)
@@ -452,51 +585,42 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
   int c[6], sb = 0, se = 0, k = 0;
   while (fetch_row(c, sb, se))
     {
+      // per row: cell index of c_0 = 0 and, in lanes 1-5, the trace base of direction `lane` for c_0 = 0 — inside the row it
+      // moves with c_0 (one cell = 4096 values in src, one face cell = 1024 values in the ghost buffer)
+      c[0] = 0;
+      const long long rowcell = cell_index(p, c);
+      r6::FaceBase    rowfb;
+      rowfb.off   = 0;
+      rowfb.ghost = false;
+      if (lane >= 1 && lane < 6)
+        rowfb = r6::face_base(p, c, lane);
       for (int step = sb; step < se; ++step, ++k)
         {
           c[0]                 = descend ? n0 - 1 - step : step;
-          const long long cell = cell_index(p, c);
+          const long long cell = rowcell + c[0];
           const int       s    = k & (R6_STAGES - 1);
+          R6_TR(12, k, 0);
           r6_wait(bars.emptyU(s), uint32_t((k / R6_STAGES) & 1) ^ 1u);
+          R6_TR(12, k, 1);
           unsigned char *info = gbase + R6_INFO_OFF + 64 * s;
           // lanes 0-5: trace base of one direction each
-          r6::FaceBase fbv;
-          fbv.off   = 0;
-          fbv.ghost = false;
+          r6::FaceBase fbv = rowfb;
+          if (lane == 0)
+            fbv = r6::face_base(p, c, 0);
+          else if (lane < 6 && p.up_delta[lane] != 0)
+            fbv.off += (long long)c[0] * (rowfb.ghost ? 1024 : CELL);
           if (lane < 6)
-            {
-              fbv                                             = r6::face_base(p, c, lane);
-              reinterpret_cast<long long *>(info)[lane] = fbv.off;
-            }
+            reinterpret_cast<long long *>(info)[lane] = fbv.off;
           const unsigned gmask = __ballot_sync(0xffffffffu, fbv.ghost) & 0x3fu;
           __syncwarp();
           if (lane == 0)
             {
               reinterpret_cast<int *>(info)[12] = int(cell);
               reinterpret_cast<int *>(info)[13] = ((step == sb) ? 1 : 0) | int(gmask << 8);
-              const uint32_t dstU = base + s * U_BYTES;
+              mbar_arrive(bars.infoFull(s)); // (release: the prefetch warp may read the info now)
               mbar_expect_tx(bars.fullU(s), U_BYTES);
-#pragma unroll
-              for (int piece = 0; piece < 4; ++piece)
-                tma_load_2d(dstU + piece * 8192, &mapU, 0, int(cell * 256 + piece * 64), bars.fullU(s));
-              if (FUSED && (p.r6_prefetch & 64))
-                r6_prefetch_bulk(p.sol + cell * CELL, U_BYTES);
-            }
-          else if (lane < 6 && ((p.r6_prefetch >> lane) & 1) && p.up_delta[lane] != 0 && !fbv.ghost)
-            {
-              // face layer of direction `lane` of the upwind neighbour -> L2 (same boxes as the two-role kernel's face loads)
-              const int nb    = int(fbv.off >> 12);
-              const int layer = p.up_delta[lane] < 0 ? 3 : 0;
-              if (lane == 1)
-                r6_prefetch_tensor_3d(&mapT1, 0, layer, nb * 256);
-              else if (lane == 2)
-                r6_prefetch_tensor_3d(&mapT2, 0, layer, nb * 64);
-              else if (lane == 3)
-                r6_prefetch_tensor_3d(&mapT3, 0, layer, nb * 16);
-              else if (lane == 4)
-                r6_prefetch_tensor_3d(&mapT4, 0, layer, nb * 4);
-              else
-                r6_prefetch_bulk(p.src + fbv.off, 8192);
+              tma_load_2d(base + s * U_BYTES, &mapU, 0, int(cell * 256), bars.fullU(s)); // one box of 256 rows = the cell
+              R6_TR(12, k, 2);
             }
         }
     }
@@ -507,6 +631,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
     if (lane == 0)
       {
         reinterpret_cast<int *>(gbase + R6_INFO_OFF + 64 * s)[12] = -1;
+        mbar_arrive(bars.infoFull(s));
         mbar_arrive(bars.fullU(s));
         // the last CTA to finish re-arms the row counter for the next launch
         __threadfence();

@@ -281,6 +281,12 @@ namespace
     if ((threadIdx.x & 31) == 0)
       atomicAdd(out, s);
   }
+  // z = D^-1 r with the point-Jacobi diagonal of K (the same nd values in every cell of the uniform lattice)
+  __global__ void k_xs_jacobi(const double *r, const double *dinv, double *z, long long n, long long nd)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      z[i] = r[i] * dinv[i % nd];
+  }
   // y = a * x + b * y ;  y += c (scalar shift)
   __global__ void k_xs_axpby(double a, const double *x, double b, double *y, double shift, long long n)
   {
@@ -294,9 +300,11 @@ struct hd_poisson
   hd_mesh * mesh = nullptr;
   XsParams  p;
   double *  d_coef = nullptr, *d_phi = nullptr, *d_r = nullptr, *d_p = nullptr, *d_ap = nullptr, *d_b = nullptr, *d_scalar = nullptr;
+  double *  d_z = nullptr, *d_dinv = nullptr; // preconditioned residual, inverse point-Jacobi diagonal (one cell's worth)
   long long n      = 0;
   size_t    smem_op = 0, smem_grad = 0;
   int       last_iterations = 0;
+  double    last_rel_residual = 0.0;
 };
 
 namespace
@@ -362,7 +370,35 @@ hd_poisson_create(hd_mesh *m, hd_poisson **out)
   HD_CUDA(cudaSetDevice(m->ctx->device));
   HD_CUDA(cudaMalloc(&ps->d_coef, coef.size() * sizeof(double)));
   HD_CUDA(cudaMemcpy(ps->d_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice));
-  double **vecs[] = {&ps->d_phi, &ps->d_r, &ps->d_p, &ps->d_ap, &ps->d_b};
+  {
+    // point-Jacobi diagonal: K = sum_d (1-D SIP block along d) (x) (1-D mass along the others), poisson.h:581-590 takes the
+    // same diagonal (compute_inverse_diagonal) as the smoother's preconditioner
+    const int           n = p.n, blk = 4 * p.n * p.n + p.nq * p.n; // (= xs_coef_block, a device function)
+    std::vector<double> dinv((size_t)p.nd);
+    for (long long i = 0; i < p.nd; ++i)
+      {
+        int idx[3] = {0, 0, 0};
+        long long r = i;
+        for (int d = 0; d < p.dim_x; ++d)
+          {
+            idx[d] = int(r % n);
+            r /= n;
+          }
+        double diag = 0.0;
+        for (int d = 0; d < p.dim_x; ++d)
+          {
+            double t = coef[(size_t)d * blk + idx[d] * n + idx[d]];
+            for (int e = 0; e < p.dim_x; ++e)
+              if (e != d)
+                t *= coef[(size_t)e * blk + 3 * n * n + idx[e] * n + idx[e]];
+            diag += t;
+          }
+        dinv[(size_t)i] = 1.0 / diag;
+      }
+    HD_CUDA(cudaMalloc(&ps->d_dinv, dinv.size() * sizeof(double)));
+    HD_CUDA(cudaMemcpy(ps->d_dinv, dinv.data(), dinv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  double **vecs[] = {&ps->d_phi, &ps->d_r, &ps->d_p, &ps->d_ap, &ps->d_b, &ps->d_z};
   for (double **v : vecs)
     {
       HD_CUDA(cudaMalloc(v, (size_t)ps->n * sizeof(double)));
@@ -387,6 +423,8 @@ hd_poisson_destroy(hd_poisson *ps)
   cudaFree(ps->d_ap);
   cudaFree(ps->d_b);
   cudaFree(ps->d_scalar);
+  cudaFree(ps->d_z);
+  cudaFree(ps->d_dinv);
   delete ps;
   return HD_OK;
 }
@@ -421,18 +459,27 @@ hd_poisson_solve(hd_poisson *ps, const void *rho_x, double *a_v_device, double r
     return rc;
   if ((rc = xs_axpby(ps, 0.0, nullptr, 1.0, ps->d_b, -s * invn)) != HD_OK)
     return rc;
-  // CG on K phi = b, starting from the previous potential (poisson.h:593-603)
+  // Jacobi-preconditioned CG on K phi = b, starting from the previous potential (poisson.h:575-603: SolverCG with a
+  // Chebyshev smoother over the same diagonal as preconditioner, relative residual 1e-7, at most 2 * size iterations)
   k_xs_laplace<<<ncells, 128, ps->smem_op, st>>>(p, ps->d_phi, ps->d_ap);
   HD_CUDA(cudaGetLastError());
   HD_CUDA(cudaMemcpyAsync(ps->d_r, ps->d_b, (size_t)ps->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if ((rc = xs_axpby(ps, -1.0, ps->d_ap, 1.0, ps->d_r)) != HD_OK)
     return rc;
-  HD_CUDA(cudaMemcpyAsync(ps->d_p, ps->d_r, (size_t)ps->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  double rr, bb;
-  if ((rc = xs_reduce(ps, ps->d_r, ps->d_r, &rr)) != HD_OK || (rc = xs_reduce(ps, ps->d_b, ps->d_b, &bb)) != HD_OK)
+  auto precondition = [&]() -> int {
+    k_xs_jacobi<<<blocks, 256, 0, st>>>(ps->d_r, ps->d_dinv, ps->d_z, ps->n, p.nd);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+  };
+  if ((rc = precondition()) != HD_OK)
+    return rc;
+  HD_CUDA(cudaMemcpyAsync(ps->d_p, ps->d_z, (size_t)ps->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  double rr, bb, rz;
+  if ((rc = xs_reduce(ps, ps->d_r, ps->d_r, &rr)) != HD_OK || (rc = xs_reduce(ps, ps->d_b, ps->d_b, &bb)) != HD_OK || (rc = xs_reduce(ps, ps->d_r, ps->d_z, &rz)) != HD_OK)
     return rc;
   const double target = rel_tol * rel_tol * (bb > 0 ? bb : 1.0);
   int          it     = 0;
+  bool         broke  = false;
   while (rr > target && it < max_iterations)
     {
       k_xs_laplace<<<ncells, 128, ps->smem_op, st>>>(p, ps->d_p, ps->d_ap);
@@ -440,25 +487,48 @@ hd_poisson_solve(hd_poisson *ps, const void *rho_x, double *a_v_device, double r
       double pap;
       if ((rc = xs_reduce(ps, ps->d_p, ps->d_ap, &pap)) != HD_OK)
         return rc;
-      if (!(pap > 0))
-        break;
-      const double alpha = rr / pap;
+      if (!(pap > 0) || !(rz > 0))
+        {
+          broke = true; // breakdown or NaN
+          break;
+        }
+      const double alpha = rz / pap;
       if ((rc = xs_axpby(ps, alpha, ps->d_p, 1.0, ps->d_phi)) != HD_OK || (rc = xs_axpby(ps, -alpha, ps->d_ap, 1.0, ps->d_r)) != HD_OK)
         return rc;
-      double rr_new;
-      if ((rc = xs_reduce(ps, ps->d_r, ps->d_r, &rr_new)) != HD_OK)
+      if ((rc = precondition()) != HD_OK)
         return rc;
-      if ((rc = xs_axpby(ps, 1.0, ps->d_r, rr_new / rr, ps->d_p)) != HD_OK)
+      double rz_new;
+      if ((rc = xs_reduce(ps, ps->d_r, ps->d_r, &rr)) != HD_OK || (rc = xs_reduce(ps, ps->d_r, ps->d_z, &rz_new)) != HD_OK)
         return rc;
-      rr = rr_new;
+      if ((rc = xs_axpby(ps, 1.0, ps->d_z, rz_new / rz, ps->d_p)) != HD_OK)
+        return rc;
+      rz = rz_new;
       ++it;
     }
-  ps->last_iterations = it;
+  ps->last_iterations   = it;
+  ps->last_rel_residual = std::sqrt(rr / (bb > 0 ? bb : 1.0));
   if (iterations)
     *iterations = it;
+  // the reference's SolverCG throws when the tolerance is not reached (dealii::SolverControl::NoConvergence): no field table is
+  // written from a potential that did not converge
+  if (broke || !(rr <= target))
+    return hd::fail(HD_ERR_NO_CONVERGENCE, "hd_poisson_solve: CG " + std::string(broke ? "broke down" : "did not converge") + " after " + std::to_string(it) +
+                                             " iterations, relative residual " + std::to_string(ps->last_rel_residual) + " (tolerance " + std::to_string(rel_tol) + ")");
   // negative electric field = grad(phi) at the quadrature points (derivative_container.h:157-190)
   k_xs_gradient<<<ncells, 128, ps->smem_grad, st>>>(p, ps->d_phi, a_v_device);
   HD_CUDA(cudaGetLastError());
+  return HD_OK;
+}
+
+// iteration count and achieved relative residual |r| / |b| of the last solve
+int
+hd_poisson_last_solve(const hd_poisson *ps, int *iterations, double *rel_residual)
+{
+  HD_REQUIRE(ps, "null argument");
+  if (iterations)
+    *iterations = ps->last_iterations;
+  if (rel_residual)
+    *rel_residual = ps->last_rel_residual;
   return HD_OK;
 }
 

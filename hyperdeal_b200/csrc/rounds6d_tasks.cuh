@@ -105,18 +105,21 @@ r6_sts64(uint32_t a, double x)
 // global loads that stay where they are written (volatile asm is not moved across the other volatile asm around it):
 // the trace values of the NEXT task are requested before the arithmetic of the current one.  Plain (coherent) loads:
 // ghost values are written by peer GPUs while the kernel runs.
+#ifndef HD_R6_LDG_MOD
+#define HD_R6_LDG_MOD "" // e.g. ".cg" (cache in L2 only): A/B knob for the trace loads
+#endif
 HD_R6_FN double
 r6_ldg(const double *p)
 {
   double v;
-  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global" HD_R6_LDG_MOD ".f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 HD_R6_FN r6_double2
 r6_ldg128(const double *p)
 {
   double2 v;
-  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm volatile("ld.global" HD_R6_LDG_MOD ".v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 HD_R6_FN double
@@ -158,6 +161,8 @@ namespace r6
 
   // P: anything with ncell[6], up_delta[6] (-1 / +1 / 0: upwind neighbour is the lower / upper cell / none), up_kind[6]
   // (HD_SIDE_* of the brick side the upwind neighbour may lie behind; 1 = HD_SIDE_GHOST) and ghost_off[6]
+  // d may be a run-time value (the producer computes one direction per lane): everything that depends on it is picked
+  // with compile-time indices, so c[] and the parameter arrays are never indexed dynamically (no local memory).
   template <class P>
   HD_R6_FN FaceBase
   face_base(const P &p, const int (&c)[6], int d)
@@ -165,30 +170,42 @@ namespace r6
     FaceBase fbv;
     fbv.off   = 0;
     fbv.ghost = false;
-    if (p.up_delta[d] == 0)
+    int       cd = 0, nd = 1, ud = 0, kd = 0;
+    long long gd = 0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+      if (e == d)
+        {
+          cd = c[e];
+          nd = p.ncell[e];
+          ud = p.up_delta[e];
+          kd = p.up_kind[e];
+          gd = p.ghost_off[e];
+        }
+    if (ud == 0)
       return fbv;
-    const bool at_side = p.up_delta[d] < 0 ? (c[d] == 0) : (c[d] == p.ncell[d] - 1);
-    if (at_side && p.up_kind[d] == 1)
+    const bool at_side = ud < 0 ? (cd == 0) : (cd == nd - 1);
+    if (at_side && kd == 1)
       {
         long long fc = 0;
 #pragma unroll
         for (int e = 5; e >= 0; --e)
           if (e != d)
             fc = fc * p.ncell[e] + c[e];
-        fbv.off   = p.ghost_off[d] + fc * 1024;
+        fbv.off   = gd + fc * 1024;
         fbv.ghost = true;
         return fbv;
       }
-    int n = c[d] + p.up_delta[d];
+    int n = cd + ud;
     if (n < 0)
-      n = p.ncell[d] - 1;
-    if (n >= p.ncell[d])
+      n = nd - 1;
+    if (n >= nd)
       n = 0;
     long long idx = 0;
 #pragma unroll
     for (int e = 5; e >= 0; --e)
       idx = idx * p.ncell[e] + (e == d ? n : c[e]);
-    fbv.off = idx * CELL + (long long)(p.up_delta[d] < 0 ? 3 : 0) * (1 << (2 * d));
+    fbv.off = idx * CELL + (long long)(ud < 0 ? 3 : 0) * (1 << (2 * d));
     return fbv;
   }
 
@@ -217,6 +234,24 @@ namespace r6
             stride = (SIDE == 0 && !ghost) ? 1024 : 256;
           }
       }
+  }
+
+  // the same addressing as compile-time constants (the device loop precomputes the thread part once and gives the loads
+  // immediate offsets): stride of the four values and thread-offset increment from task 0 to task 1
+#ifdef HD_R6_HOST_EMULATION
+#define HD_R6_CONSTEXPR constexpr
+#else
+#define HD_R6_CONSTEXPR __host__ __device__ constexpr
+#endif
+  HD_R6_CONSTEXPR int
+  trace_stride(int round, int side, bool ghost)
+  {
+    return round == 0 ? ((side == 0 && !ghost) ? 4 : 1) : (round == 1 ? ((side == 0 && !ghost) ? 64 : 16) : ((side == 0 && !ghost) ? 1024 : 256));
+  }
+  HD_R6_CONSTEXPR int
+  trace_task_step(int round, bool ghost)
+  {
+    return round == 0 ? (ghost ? 4 * 128 : 16 * 128) : (round == 1 ? (ghost ? 64 * 8 : 256 * 8) : 16 * 8);
   }
 
   // the 4 trace values of one side of a task
@@ -341,23 +376,45 @@ namespace r6
           q[b][a] = r6_fma(cf.B[ROUND][b * 4 + jj], U[jj][a], q[b][a]);
   }
 
+  // The 16 values of u of a task (its 4x4 tile).  They are loaded by the PREVIOUS task, right after its main part (the
+  // registers are free again, and the shared-memory latency disappears behind that task's epilogue): every task function
+  // below takes U loaded and calls after_main() when it is done with it.
+  template <int ROUND>
+  HD_R6_FN void
+  load_u(uint32_t ub, const ThreadMap<ROUND> &tm, int j, double (&U)[4][4])
+  {
+    if (ROUND == 0)
+      {
+        const uint32_t jo = uint32_t(j) * 16384u;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          {
+            const r6_double2 v        = r6_lds128(ub + tm.x[ch] + jo);
+            U[ch >> 1][(ch & 1) * 2]     = v.x;
+            U[ch >> 1][(ch & 1) * 2 + 1] = v.y;
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
+      }
+  }
+
   // ---- round 0: directions (0,1); writes P.  `edge[b]` returns the thread's own end layer of direction 0 (the trace the
   // next cell of the row walk needs: i0 = 0 when the walk descends, else i0 = 3).  after_traces() is called once fa, fb
-  // have been consumed (it may overwrite them: the request for the next task).
-  template <class F>
+  // have been consumed (it may overwrite them: the request for the next task), after_main() once U has been (it loads the
+  // next task's U).
+  template <class F, class H>
   HD_R6_FN void
-  task_round0(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<0> &tm, int j, const double (&fa)[4], const double (&fb)[4], bool descend,
-              double (&edge)[4], F &&after_traces)
+  task_round0(const Coef &cf, uint32_t pb, const ThreadMap<0> &tm, int j, double (&U)[4][4], const double (&fa)[4], const double (&fb)[4], bool descend,
+              double (&edge)[4], F &&after_traces, H &&after_main)
   {
-    double         U[4][4], q[4][4];
+    double         q[4][4];
     const uint32_t jo = uint32_t(j) * 16384u;
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      {
-        const r6_double2 v        = r6_lds128(ub + tm.x[ch] + jo);
-        U[ch >> 1][(ch & 1) * 2]     = v.x;
-        U[ch >> 1][(ch & 1) * 2 + 1] = v.y;
-      }
     trace_terms<0, true>(cf, fa, fb, q);
     pin_values(q);
     after_traces();
@@ -365,31 +422,34 @@ namespace r6
 #pragma unroll
     for (int b = 0; b < 4; ++b)
       edge[b] = descend ? U[b][0] : U[b][3];
+    pin_values(q);
+    after_main();
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch)
       r6_sts128(pb + tm.x[ch] + jo, q[ch >> 1][(ch & 1) * 2], q[ch >> 1][(ch & 1) * 2 + 1]);
   }
 
-  // ---- round 1: directions (2,3); P updated in place
-  template <class F>
+  // ---- round 1: directions (2,3); P updated in place.  Like round 2 it computes its own contribution from u alone and meets
+  // the partial sums only at the end (before_partial() = wait until round 0 has written this task's rows), so that all three
+  // rounds can work on the same cell at the same time and no round ever waits at the START of a task.
+  template <class F, class H, class G>
   HD_R6_FN void
-  task_round1(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<1> &tm, int j, const double (&fa)[4], const double (&fb)[4], F &&after_traces)
+  task_round1(const Coef &cf, uint32_t pb, const ThreadMap<1> &tm, int j, double (&U)[4][4], const double (&fa)[4], const double (&fb)[4], F &&after_traces,
+              H &&after_main, G &&before_partial)
   {
-    double U[4][4], q[4][4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        q[b][a] = r6_lds64(pb + tm.elem(a, b, j));
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
-    trace_terms<1, false>(cf, fa, fb, q);
+    double q[4][4];
+    trace_terms<1, true>(cf, fa, fb, q);
     pin_values(q);
     after_traces();
     main_terms<1>(cf, U, q);
+    pin_values(q);
+    after_main();
+    before_partial();
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        q[b][a] += r6_lds64(pb + tm.elem(a, b, j));
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -401,21 +461,17 @@ namespace r6
   // g0 = cell * 4096 + (t & 15) + 16 ((t >> 4) + 8 j).  Its own contribution needs only u, so it is computed first and the
   // partial sums of rounds 0 and 1 are added at the END (before_partial() = wait until round 1 is done with the cell):
   // rounds 1 and 2 work on the same cell side by side and the three P buffers leave round 0 a whole cell of slack.
-  template <class F, class G>
+  template <class F, class H, class G>
   HD_R6_FN void
-  task_round2(const Coef &cf, uint32_t ub, uint32_t pb, const ThreadMap<2> &tm, int j, const double (&fa)[4], const double (&fb)[4], double (&q)[4][4],
-              F &&after_traces, G &&before_partial)
+  task_round2(const Coef &cf, uint32_t pb, const ThreadMap<2> &tm, int j, double (&U)[4][4], const double (&fa)[4], const double (&fb)[4], double (&q)[4][4],
+              F &&after_traces, H &&after_main, G &&before_partial)
   {
-    double U[4][4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        U[b][a] = r6_lds64(ub + tm.elem(a, b, j));
     trace_terms<2, true>(cf, fa, fb, q);
     pin_values(q);
     after_traces();
     main_terms<2>(cf, U, q);
+    pin_values(q);
+    after_main();
     before_partial();
 #pragma unroll
     for (int b = 0; b < 4; ++b)

@@ -41,7 +41,8 @@ enum
   HD_OK              = 0,
   HD_ERR_INVALID     = -1, /* bad argument / unsupported configuration */
   HD_ERR_CUDA        = -2, /* CUDA runtime or driver failure (incl. no device) */
-  HD_ERR_UNSUPPORTED = -3  /* valid in the reference but not implemented here */
+  HD_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented here */
+  HD_ERR_NO_CONVERGENCE = -4 /* an iterative solve missed its tolerance (the reference: dealii::SolverControl::NoConvergence) */
 };
 
 /* Number type of the DoF vectors (the reference's template parameter `Number`). */
@@ -307,21 +308,26 @@ int64_t hd_mesh_n_dofs_x(const hd_mesh *mesh);
 int     hd_vector_alloc_x(hd_mesh *mesh, void **device_ptr);
 int     hd_velocity_space_integration(hd_mesh *mesh, void *dst_x, const void *src);
 
-/* ---- x-space field solve of the Vlasov-Poisson right-hand side (EXPERIMENTAL: not validated on a GPU yet) ---------------
+/* ---- x-space field solve of the Vlasov-Poisson right-hand side ----------------------------------------------------------
  * Steps 2-4 of examples/vlasov_poisson/include/application.h:529-583 on a periodic Cartesian x-lattice:
  *   rhs = -M (rho - mean), mean removed again;  K phi = rhs with the symmetric-interior-penalty DG Laplacian of
- *   examples/vlasov_poisson/include/poisson.h:166-250, solved by conjugate gradients on the device from the previous potential
- *   (the reference: preconditioned CG to a relative residual of 1e-7, poisson.h:593-603);  a_v = grad(phi) at the quadrature
+ *   examples/vlasov_poisson/include/poisson.h:166-250, solved on the device by conjugate gradients preconditioned with the
+ *   operator's point-Jacobi diagonal, from the previous potential (the reference: CG preconditioned by a Chebyshev smoother
+ *   over the same diagonal, or multigrid, to a relative residual of 1e-7, poisson.h:575-613);  a_v = grad(phi) at the quadrature
  *   points of every x-cell (DerivativeContainer::update, derivative_container.h:157-190) in the layout
  *   hd_advection_set_phase_space_velocity reads: a_v_device[x-cell][x-quadrature point][dim_x] doubles.
- * rho_x: the density of hd_velocity_space_integration (mesh number type).  *iterations (optional) returns the CG steps taken. */
+ * rho_x: the density of hd_velocity_space_integration (mesh number type).  *iterations (optional) returns the CG steps taken.
+ * If the relative residual rel_tol is not reached within max_iterations (or CG breaks down) the call returns
+ * HD_ERR_NO_CONVERGENCE and leaves the gradient table untouched — the reference's SolverCG throws in that case. */
 int hd_poisson_create(hd_mesh *mesh, hd_poisson **out);
 int hd_poisson_destroy(hd_poisson *ps);
 int hd_poisson_solve(hd_poisson *ps, const void *rho_x, double *a_v_device, double rel_tol, int max_iterations, int *iterations);
+/* CG steps and achieved relative residual |r| / |b| of the last hd_poisson_solve (either pointer may be NULL) */
+int hd_poisson_last_solve(const hd_poisson *ps, int *iterations, double *rel_residual);
 /* potential of the last solve: device pointer to hd_mesh_n_dofs_x doubles (x-space layout), owned by the solver */
 const double *hd_poisson_potential(const hd_poisson *ps);
 
-/* Diagnostics of the Vlasov-Poisson driver (examples/vlasov_poisson/include/diagnostics.h; EXPERIMENTAL like the field solve):
+/* Diagnostics of the Vlasov-Poisson driver (examples/vlasov_poisson/include/diagnostics.h):
  * phase_space_diagnostics (:34-86) at the Gauss points of the OWNED cells: out = {sum f JxW (mass), sum f^2 JxW (the caller
  * all-reduces and takes the square root: L2 norm), sum |v|^2 f JxW (kinetic energy), sum v_d f JxW for d < dim_v (momentum), 0..};
  * compute_electric_energy (:88-143): out[d] = sum_q (a_v[.][q][d])^2 JxW over the x-lattice, d < dim_x, from the gradient

@@ -25,8 +25,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nloc = (3, 2, 2, 2, 2, 2)
-    for kernel, split_order in ((0, (2, 1, 0)), (0, (0, 1, 2)), (1, (2, 1, 0))):
-        part = BrickPartition(world, rank, nloc, split_order=split_order)
+    # kernel 6 = three-round 3D3V kernel (the automatic choice), 2 = two-role pipelined kernel, 1 = generic kernel;
+    # "x24" = the layout bench.py uses at 8 GPUs (x_2 cut in four, x_1 in two, rows of cells along x_0 whole), at world 4
+    # its 4-GPU restriction (x_2 in four); bricks one cell thick in the cut direction included
+    cases = [(6, (2, 1, 0), None, nloc), (2, (2, 1, 0), None, nloc), (6, (0, 1, 2), None, nloc), (1, (2, 1, 0), None, nloc)]
+    if world == 8:
+        cases += [(6, None, (1, 2, 4, 1, 1, 1), (4, 2, 1, 2, 2, 2)), (2, None, (1, 2, 4, 1, 1, 1), (4, 2, 2, 2, 2, 2))]
+    elif world == 4:
+        cases += [(6, None, (1, 1, 4, 1, 1, 1), (4, 2, 1, 2, 2, 2)), (6, None, (1, 2, 2, 1, 1, 1), (4, 2, 2, 2, 2, 2))]
+    for kernel, split_order, grid, nloc in cases:
+        part = BrickPartition(world, rank, nloc, split_order=split_order) if grid is None else BrickPartition(world, rank, nloc, grid=grid)
         ctx = api.Context(local)
         left, right = (0.0,) * 6, (1.0,) * 6
         mf = api.MatrixFree(ctx, 3, 3, 3, nloc, left, right, n_cells_global=part.n_cells_global, cell_offset=part.cell_offset, side_kind=part.side_kind)
@@ -35,6 +43,7 @@ def main():
         # whole lattice on this GPU
         mf_all = api.MatrixFree(ctx, 3, 3, 3, part.n_cells_global, left, right)
         op_all = api.AdvectionOperation(mf_all, VEL, 0.5)
+        op_all.set_kernel(kernel)
         u = np.random.default_rng(1234).standard_normal(mf_all.n_dofs)
         a_src, a_dst = mf_all.initialize_dof_vector(), mf_all.initialize_dof_vector()
         mf_all.copy_in(a_src, u)
@@ -73,7 +82,7 @@ def main():
             peer.consumed(ctx)
         torch.cuda.synchronize()
         rel = max(rel, float(np.max(np.abs(dst.cpu().numpy() - expect)) / np.max(np.abs(expect))))
-        if op.kernel_name.startswith("advect_3d3v"):
+        if op.kernel_name.startswith(("advect_3d3v", "rounds_3d3v")):
             # fused variant: ONE kernel per step packs, sends over NVLink, does the interior, waits, does the boundary
             dst.zero_()
             for it in range(5):

@@ -144,11 +144,11 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
       // requested by the previous task's after_traces() callback; round 0: eo = end layer the task after the next needs
       struct TS
       {
-        double fa[4], fb[4], eo[4];
+        double fa[4], fb[4], eo[4], U[4][4];
       };
       std::vector<TS> st[3];
       for (int R = 0; R < 3; ++R)
-        st[R].assign(128, TS{{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}});
+        st[R].assign(128, TS{});
       auto request = [&](int R, const Item &it, int t, int j, double(&fa)[4], double(&fb)[4]) {
         const FaceBase &A = it.fbv[2 * R], &B = it.fbv[2 * R + 1];
         if (R == 0)
@@ -176,13 +176,31 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
       for (int R = 0; R < 3; ++R)
         for (int t = 0; t < 128; ++t)
           request(R, walk[0], t, 0, st[R][t].fa, st[R][t].fb);
+      // the emulated shared memory holds TWO cell stages (the current cell and the next one: a task loads the u tile of the
+      // task after it, which may belong to the next cell) and one P buffer
+      std::vector<unsigned char> sm2(3 * U_BYTES);
+      r6emu::smem = sm2.data();
+      auto fill = [&](size_t k) {
+        // TMA fill: row rr (16 doubles) -> rr * 128, chunk ch -> ch ^ (rr & 7)
+        const uint32_t st_off = uint32_t(k & 1) * U_BYTES;
+        for (int rr = 0; rr < 256; ++rr)
+          for (int ch = 0; ch < 8; ++ch)
+            std::memcpy(sm2.data() + st_off + rr * 128 + ((ch ^ (rr & 7)) << 4), src + walk[k].cell * CELL + rr * 16 + ch * 2, 16);
+      };
+      const uint32_t pbuf = 2 * U_BYTES;
+      fill(0);
+      for (int t = 0; t < 128; ++t)
+        {
+          load_u<0>(0, tm0[t], 0, st[0][t].U);
+          load_u<1>(0, tm1[t], 0, st[1][t].U);
+          load_u<2>(0, tm2[t], 0, st[2][t].U);
+        }
       for (size_t k = 0; k < walk.size(); ++k)
         {
           const Item &cur = walk[k];
-          // TMA fill: row rr (16 doubles) -> rr * 128, chunk ch -> ch ^ (rr & 7)
-          for (int rr = 0; rr < 256; ++rr)
-            for (int ch = 0; ch < 8; ++ch)
-              std::memcpy(sm.data() + ub + rr * 128 + ((ch ^ (rr & 7)) << 4), src + cur.cell * CELL + rr * 16 + ch * 2, 16);
+          const uint32_t ucur = uint32_t(k & 1) * U_BYTES, unext = uint32_t((k + 1) & 1) * U_BYTES;
+          if (k + 1 < walk.size())
+            fill(k + 1);
           for (int R = 0; R < 3; ++R)
             for (int t = 0; t < 128; ++t)
               for (int j = 0; j < 2; ++j)
@@ -197,19 +215,31 @@ hd_r6_emulate(const double *src, double *dst, const int *ncell, const double *le
                     else if (k + 1 < walk.size())
                       request(R, walk[k + 1], t, 0, ts.fa, ts.fb);
                   };
+                  auto after_main = [&]() {
+                    const bool     more = j == 0 || k + 1 < walk.size();
+                    const uint32_t ub2  = j == 0 ? ucur : unext;
+                    if (!more)
+                      return;
+                    if (R == 0)
+                      load_u<0>(ub2, tm0[t], 1 - j, ts.U);
+                    else if (R == 1)
+                      load_u<1>(ub2, tm1[t], 1 - j, ts.U);
+                    else
+                      load_u<2>(ub2, tm2[t], 1 - j, ts.U);
+                  };
                   if (R == 0)
                     {
                       double edge[4];
-                      task_round0(cf, ub, pb, tm0[t], j, ts.fa, ts.fb, descend, edge, after);
+                      task_round0(cf, pbuf, tm0[t], j, ts.U, ts.fa, ts.fb, descend, edge, after, after_main);
                       for (int b = 0; b < 4; ++b)
                         ts.eo[b] = edge[b];
                     }
                   else if (R == 1)
-                    task_round1(cf, ub, pb, tm1[t], j, ts.fa, ts.fb, after);
+                    task_round1(cf, pbuf, tm1[t], j, ts.U, ts.fa, ts.fb, after, after_main, [] {});
                   else
                     {
                       double q[4][4];
-                      task_round2(cf, ub, pb, tm2[t], j, ts.fa, ts.fb, q, after, [] {});
+                      task_round2(cf, pbuf, tm2[t], j, ts.U, ts.fa, ts.fb, q, after, after_main, [] {});
                       const long long g0 = cur.cell * CELL + (t & 15) + 16 * ((t >> 4) + 8 * j);
                       for (int b = 0; b < 4; ++b)
                         for (int a = 0; a < 4; ++a)

@@ -68,8 +68,11 @@ def test_shim_header_is_self_contained(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+# ..._04, _08 and _q5..._02 run the reference with UseECL = false / DoBuffering = true (its face-centric loop,
+# advection_operation.h:574-1130) — served by the same ECL-style kernels here, and their .out files equal the ECL twins'.
 GOLDEN = ["adv_2D_2D_k3.hyperrectangle_01", "adv_2D_2D_k3.hyperrectangle_03", "adv_2D_2D_k3.hyperrectangle_05", "adv_2D_2D_k3.hyperrectangle_07",
-          "adv_2D_2D_k3_q5.hyperrectangle_01", "adv_1D_1D_k3.hyperrectangle_01_rk47"]
+          "adv_2D_2D_k3_q5.hyperrectangle_01", "adv_1D_1D_k3.hyperrectangle_01_rk47",
+          "adv_2D_2D_k3.hyperrectangle_02", "adv_2D_2D_k3.hyperrectangle_04", "adv_2D_2D_k3.hyperrectangle_08", "adv_2D_2D_k3_q5.hyperrectangle_02"]
 
 
 def _check(lines, gold, name):

@@ -22,6 +22,6 @@ def test_partitioned_operator_matches_single_gpu(world):
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "mgpu_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
-    assert res.stdout.count("MGPU OK") == 3, res.stdout
+    assert res.stdout.count("MGPU OK") == (4 if world == 2 else 6) and "MGPU FAIL" not in res.stdout, res.stdout

@@ -250,7 +250,9 @@ def _run_example_gpu(api, ctx, json_path, n_points):
     return lines
 
 
-GOLDEN = ["adv_2D_2D_k3.hyperrectangle_%02d" % i for i in (1, 3, 5, 7)] + ["adv_2D_2D_k3_q5.hyperrectangle_01", "adv_2D_2D_k3_q5.hyperrectangle_03", "adv_1D_1D_k3.hyperrectangle_01", "adv_1D_1D_k3.hyperrectangle_01_rk33", "adv_1D_1D_k3.hyperrectangle_02"]
+# (2D2V _04/_06/_08, _q5..._04 and 1D1V _04 are the reference's UseECL = false / DoBuffering = true runs: one ECL-style kernel serves both loop types here)
+GOLDEN = ["adv_2D_2D_k3.hyperrectangle_%02d" % i for i in (1, 3, 5, 7)] + ["adv_2D_2D_k3_q5.hyperrectangle_01", "adv_2D_2D_k3_q5.hyperrectangle_03", "adv_1D_1D_k3.hyperrectangle_01", "adv_1D_1D_k3.hyperrectangle_01_rk33", "adv_1D_1D_k3.hyperrectangle_02"] + \
+         ["adv_2D_2D_k3.hyperrectangle_%02d" % i for i in (2, 4, 6, 8)] + ["adv_2D_2D_k3_q5.hyperrectangle_04", "adv_1D_1D_k3.hyperrectangle_04"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)

@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, GPU call F: all three rounds meet the partial sums at the END of their tasks
+mkdir -p gpurun_out
+echo "== parity" > gpurun_out/f_tests.log
+timeout 900 python -m pytest tests/test_apply_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q -k "fast_kernel or auto_selects or fused_fast or two_bricks or self_exchange" >> gpurun_out/f_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/f_tests.log
+tail -3 gpurun_out/f_tests.log
+ROUNDS=2 timeout 1200 python tools/r6_ab.py rounds_lex=HD_ROW_TILE=0,0,0,0,0 rounds= pipe=HD_FAST_VARIANT=pipe unroll=lib=r6_unroll,HD_ROW_TILE=0,0,0,0,0 \
+  x0only=AB_VEL=1.0,0,0,0,0,0 x045=AB_VEL=1.0,0,0,0,-0.15,0.5,HD_ROW_TILE=0,0,0,0,0 > gpurun_out/f_ab.log 2>&1
+tail -6 gpurun_out/f_ab.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rounds -s 3 -c 1 -f -o gpurun_out/r02f_rounds python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --sustain 0 > gpurun_out/f_ncu.log 2>&1
+tail -1 gpurun_out/f_ncu.log | cut -c1-100
