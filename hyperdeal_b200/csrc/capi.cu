@@ -5,6 +5,7 @@
 #include <new>
 
 #include "hd_internal.h"
+#include "rounds6d_tasks.cuh"
 
 namespace hd
 {
@@ -253,6 +254,201 @@ namespace
             atomicAdd(out + 0, s_norm);
             atomicAdd(out + 1, s_err);
           }
+      }
+  }
+
+  // ---- streaming versions of the two VectorTools kernels for degree 3 (n = 4 nodes per direction) ------------------------
+  // k_interpolate4: a thread writes whole lines of 4 nodal values along x_0 (32 bytes, two 16-byte stores; a warp writes
+  // 1 KiB contiguously): value = t_0[i_0] * prod_{d>=1} t_d[i_d] with the 1-D factor tables of the cell in shared memory
+  // and all index arithmetic on compile-time extents.  Write-only, 8 B/DoF.
+  template <typename T, int DIM>
+  __global__ void __launch_bounds__(256)
+    k_interpolate4(T *__restrict__ vec, LatticeParams lp, const double *__restrict__ nodes, int fn_id, double time, int cells_per_cta)
+  {
+    extern __shared__ double tab[]; // [cell][direction][node]
+    constexpr int   N = 4, LINES = 1 << (2 * (DIM - 1));
+    const long long cell0 = (long long)blockIdx.x * cells_per_cta;
+    long long       nloc  = lp.ncells - cell0;
+    if (nloc > cells_per_cta)
+      nloc = cells_per_cta;
+    for (int e = threadIdx.x; e < nloc * DIM * N; e += blockDim.x)
+      {
+        const int lc = e / (DIM * N), d = (e / N) % DIM, id = e % N;
+        long long r  = cell0 + lc;
+        for (int k = 0; k < d; ++k)
+          r /= lp.ncell[k];
+        const int    c = int(r % lp.ncell[d]);
+        const double x = lp.left[d] + lp.h[d] * ((c + lp.cell_offset[d]) + nodes[id]);
+        tab[e]         = builtin_factor(fn_id, d, x, time);
+      }
+    __syncthreads();
+    const int total = int(nloc) * LINES;
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+      {
+        const int     lc = i / LINES, line = i % LINES;
+        const double *t  = tab + lc * DIM * N;
+        double        f  = 1.0;
+#pragma unroll
+        for (int d = 1; d < DIM; ++d)
+          f *= t[d * N + ((line >> (2 * (d - 1))) & 3)];
+        // same order of multiplications as the generic kernel: ((t0 * t1) * t2) ... — so that the values are bit-identical
+        double v[N];
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+          {
+            double r = t[a];
+#pragma unroll
+            for (int d = 1; d < DIM; ++d)
+              r *= t[d * N + ((line >> (2 * (d - 1))) & 3)];
+            v[a] = r;
+          }
+        (void)f;
+        T *o = vec + (cell0 + lc) * (long long)(LINES * N) + (long long)line * N;
+        if (sizeof(T) == 8)
+          {
+            reinterpret_cast<double2 *>(o)[0] = make_double2(v[0], v[1]);
+            reinterpret_cast<double2 *>(o)[1] = make_double2(v[2], v[3]);
+          }
+        else
+          *reinterpret_cast<float4 *>(o) = make_float4(float(v[0]), float(v[1]), float(v[2]), float(v[3]));
+      }
+  }
+
+  // k_norm_error_3d3v: 3D3V, n = n_q = 4.  The cell sits in shared memory in the swizzled row layout of the three-round
+  // operator kernel (rounds6d_tasks.cuh) and the six S sweeps (nodal values -> quadrature points) run as three passes of
+  // two directions on a 4x4 register tile per thread, with that kernel's conflict-free thread maps; the third pass keeps
+  // its tile in registers and goes straight into the quadrature sums.  A CTA walks over cells and reduces once at the end.
+  // Read-only, 8 B/DoF; 24 FMA per value for the sweeps.
+  template <typename T>
+  __global__ void __launch_bounds__(256)
+    k_norm_error_3d3v(const T *__restrict__ vec, LatticeParams lp, const double *__restrict__ basis, int fn_id, double time, double *__restrict__ out)
+  {
+    __shared__ __align__(1024) unsigned char cellbuf[32768];
+    __shared__ double                        ftab[6][4], wtab[6][4], Ssm[16];
+    __shared__ double                        red[2][8];
+    const int      tid = threadIdx.x, t = tid & 127, j = tid >> 7;
+    const uint32_t ub  = (uint32_t)__cvta_generic_to_shared(cellbuf);
+    const double * xq = basis + 4, *w = xq + 4, *S = w + 4;
+    if (tid < 16)
+      Ssm[tid] = S[tid];
+    if (tid < 24)
+      wtab[tid / 4][tid % 4] = lp.h[tid / 4] * w[tid % 4];
+    r6::ThreadMap<0> tm0;
+    r6::ThreadMap<1> tm1;
+    r6::ThreadMap<2> tm2;
+    tm0.init(t);
+    tm1.init(t);
+    tm2.init(t);
+    double s_norm = 0.0, s_err = 0.0;
+    // y[b][a] = sum_j S[a][j] x[b][j], then z[b][a] = sum_j S[b][j] y[j][a]
+    auto sweep2 = [&](double(&x)[4][4]) {
+      double y[4][4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          y[b][a] = Ssm[a * 4 + 0] * x[b][0] + Ssm[a * 4 + 1] * x[b][1] + Ssm[a * 4 + 2] * x[b][2] + Ssm[a * 4 + 3] * x[b][3];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          x[b][a] = Ssm[b * 4 + 0] * y[0][a] + Ssm[b * 4 + 1] * y[1][a] + Ssm[b * 4 + 2] * y[2][a] + Ssm[b * 4 + 3] * y[3][a];
+    };
+    for (long long cell = blockIdx.x; cell < lp.ncells; cell += gridDim.x)
+      {
+        __syncthreads(); // the previous cell's tables and buffer are no longer read
+        if (tid < 24)
+          {
+            const int d = tid / 4, q = tid % 4;
+            long long r = cell;
+            for (int k = 0; k < d; ++k)
+              r /= lp.ncell[k];
+            const int c = int(r % lp.ncell[d]);
+            ftab[d][q]  = builtin_factor(fn_id, d, lp.left[d] + lp.h[d] * ((c + lp.cell_offset[d]) + xq[q]), time);
+          }
+        // coalesced load of the cell into the swizzled layout: chunk g (16 bytes) of row g / 8
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+          {
+            const int      g   = tid + 256 * m;
+            const uint32_t row = uint32_t(g >> 3), ch = uint32_t(g & 7);
+            const T *      sp  = vec + cell * 4096 + 2 * g;
+            r6_sts128(ub + row * 128u + ((ch ^ (row & 7u)) << 4), double(sp[0]), double(sp[1]));
+          }
+        __syncthreads();
+        double x[4][4];
+        // pass 0: directions (0,1) — the thread's row
+        {
+          const uint32_t jo = uint32_t(j) * 16384u;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            {
+              const double2 v            = r6_lds128(ub + tm0.x[ch] + jo);
+              x[ch >> 1][(ch & 1) * 2]     = v.x;
+              x[ch >> 1][(ch & 1) * 2 + 1] = v.y;
+            }
+          sweep2(x);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            r6_sts128(ub + tm0.x[ch] + jo, x[ch >> 1][(ch & 1) * 2], x[ch >> 1][(ch & 1) * 2 + 1]);
+        }
+        __syncthreads();
+        // pass 1: directions (2,3)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            x[b][a] = r6_lds64(ub + tm1.elem(a, b, j));
+        sweep2(x);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            r6_sts64(ub + tm1.elem(a, b, j), x[b][a]);
+        __syncthreads();
+        // pass 2: directions (4,5), then the quadrature sums at the points (q0,q1 | q2,q3 | a, b)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            x[b][a] = r6_lds64(ub + tm2.elem(a, b, j));
+        sweep2(x);
+        const int    q0 = t & 3, q1 = (t >> 2) & 3, E = (t >> 4) + 8 * j, q2 = E & 3, q3 = E >> 2;
+        const double wc = ((wtab[0][q0] * wtab[1][q1]) * wtab[2][q2]) * wtab[3][q3];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            {
+              // same multiplication order as the generic kernel: f = (((((f0 f1) f2) f3) f4) f5), jxw likewise
+              const double f   = ((((ftab[0][q0] * ftab[1][q1]) * ftab[2][q2]) * ftab[3][q3]) * ftab[4][a]) * ftab[5][b];
+              const double jxw = (wc * wtab[4][a]) * wtab[5][b];
+              const double u   = x[b][a];
+              s_norm += u * u * jxw;
+              s_err += (u - f) * (u - f) * jxw;
+            }
+      }
+    for (int off = 16; off > 0; off >>= 1)
+      {
+        s_norm += __shfl_down_sync(0xffffffffu, s_norm, off);
+        s_err += __shfl_down_sync(0xffffffffu, s_err, off);
+      }
+    if ((tid & 31) == 0)
+      {
+        red[0][tid >> 5] = s_norm;
+        red[1][tid >> 5] = s_err;
+      }
+    __syncthreads();
+    if (tid == 0)
+      {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < 8; ++i)
+          {
+            a += red[0][i];
+            b += red[1][i];
+          }
+        atomicAdd(out + 0, a);
+        atomicAdd(out + 1, b);
       }
   }
 
@@ -1496,6 +1692,35 @@ hd_interpolate_builtin(hd_mesh *m, void *vec, int fn_id, double time)
   HD_REQUIRE(m && vec, "null argument");
   HD_CUDA(cudaSetDevice(m->ctx->device));
   const LatticeParams lp  = lattice(m);
+  if (m->n == 4 && (m->dim == 2 || m->dim == 4 || m->dim == 6))
+    {
+      // degree 3: the streaming kernel (>= 4096 nodal values per CTA)
+      const int       cpb  = m->nd >= 4096 ? 1 : int(4096 / m->nd);
+      const size_t    smem = (size_t)cpb * m->dim * 4 * sizeof(double);
+      const long long g    = (m->ncells + cpb - 1) / cpb;
+#define HD_INTERP4(T, DIM) k_interpolate4<T, DIM><<<(unsigned)g, 256, smem, m->ctx->stream>>>(static_cast<T *>(vec), lp, m->d_basis, fn_id, time, cpb)
+      if (m->d.number_type == HD_F64)
+        {
+          if (m->dim == 2)
+            HD_INTERP4(double, 2);
+          else if (m->dim == 4)
+            HD_INTERP4(double, 4);
+          else
+            HD_INTERP4(double, 6);
+        }
+      else
+        {
+          if (m->dim == 2)
+            HD_INTERP4(float, 2);
+          else if (m->dim == 4)
+            HD_INTERP4(float, 4);
+          else
+            HD_INTERP4(float, 6);
+        }
+#undef HD_INTERP4
+      HD_CUDA(cudaGetLastError());
+      return HD_OK;
+    }
   const int           cpb = m->nd >= 1024 ? 1 : int(1024 / m->nd); // >= 1024 nodal values per CTA
   const size_t        smem = (size_t)cpb * m->dim * m->n * sizeof(double);
   const long long     g    = (m->ncells + cpb - 1) / cpb;
@@ -1521,7 +1746,17 @@ hd_norm_and_error_builtin(hd_mesh *m, const void *vec, int fn_id, double time, d
   if (smem > m->ctx->smem_optin)
     return hd::fail(HD_ERR_UNSUPPORTED, "norm_and_error: cell does not fit into shared memory");
   HD_CUDA(cudaMemsetAsync(m->d_reduce, 0, 2 * sizeof(double), m->ctx->stream));
-  if (m->d.number_type == HD_F64)
+  if (m->dim == 6 && m->n == 4 && m->nq == 4)
+    {
+      // 3D3V degree 3 (the benchmark lattice): the register-tile kernel, a few CTAs per SM walking over the cells
+      const long long want = (long long)m->ctx->sm_count * 2; // (124 registers x 256 threads: two resident CTAs per SM)
+      const unsigned  g    = (unsigned)(m->ncells < want ? m->ncells : want);
+      if (m->d.number_type == HD_F64)
+        k_norm_error_3d3v<double><<<g, 256, 0, m->ctx->stream>>>(static_cast<const double *>(vec), lp, m->d_basis, fn_id, time, m->d_reduce);
+      else
+        k_norm_error_3d3v<float><<<g, 256, 0, m->ctx->stream>>>(static_cast<const float *>(vec), lp, m->d_basis, fn_id, time, m->d_reduce);
+    }
+  else if (m->d.number_type == HD_F64)
     {
       if (smem > 48 * 1024)
         HD_CUDA(cudaFuncSetAttribute(k_norm_error<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

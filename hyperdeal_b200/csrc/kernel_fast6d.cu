@@ -132,7 +132,7 @@ namespace
     // three-round kernel: bit d (1..5) = the producer asks for the upwind face layer of direction d of every cell to be in
     // L2 before the compute warps read it; bit 6 = same for the cell's `sol` values (fused LSRK)
     int           r6_prefetch;
-    // HD_R6_TRACE builds only: timeline of CTA 0 (clock64 per event), long long [13 warps][R6_TRACE_CELLS][8 events]
+    // HD_R6_TRACE builds only: timeline of CTA 0 (clock64 per event), long long [13 warps][R6_TRACE_CELLS][16 events]
     long long *   r6_trace;
   };
 
@@ -1600,8 +1600,8 @@ namespace hd
           // debugging aid (tools/r6_timeline.py): HD_R6_TRACE_FILE=<path> dumps the last launch's timeline of CTA 0
           static long long *d_trace = nullptr;
           if (!d_trace)
-            HD_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 13 * R6_TRACE_CELLS * 8));
-          HD_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 13 * R6_TRACE_CELLS * 8, m->ctx->stream));
+            HD_CUDA(cudaMalloc(&d_trace, sizeof(long long) * 13 * R6_TRACE_CELLS * 16));
+          HD_CUDA(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 13 * R6_TRACE_CELLS * 16, m->ctx->stream));
           p.r6_trace = d_trace;
         }
 #endif
@@ -1624,12 +1624,12 @@ namespace hd
             HD_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, R6_SMEM_BYTES));
             st->attr_set[ridx] = true;
           }
-        rk<<<(unsigned)grid, R6_THREADS, R6_SMEM_BYTES, m->ctx->stream>>>(maps->u256, maps->t1, maps->t2, maps->t3, maps->t4, p, rc6);
+        rk<<<(unsigned)grid, R6_THREADS, R6_SMEM_BYTES, m->ctx->stream>>>(maps->u256, maps->t1, maps->t2, maps->t3, maps->t4, gmaps->g1, p, rc6);
         HD_CUDA(cudaGetLastError());
 #ifdef HD_R6_TRACE
         if (const char *tf = getenv("HD_R6_TRACE_FILE"))
           {
-            std::vector<long long> h(13 * R6_TRACE_CELLS * 8);
+            std::vector<long long> h(13 * R6_TRACE_CELLS * 16);
             HD_CUDA(cudaStreamSynchronize(m->ctx->stream));
             HD_CUDA(cudaMemcpy(h.data(), p.r6_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
             if (FILE *f = fopen(tf, "wb"))

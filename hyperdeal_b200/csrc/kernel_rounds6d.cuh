@@ -9,7 +9,7 @@
 //
 // One persistent CTA per SM, 512 threads = four warpgroups, mbarrier-only pipeline:
 //   warpgroup r = 0,1,2   round r (directions 2r, 2r+1) of the cells this CTA works on, pipelined over consecutive cells.
-//                         The partial sums travel through three shared-memory buffers P: round 0 writes, round 1 updates in
+//                         The partial sums travel through two shared-memory buffers P: round 0 writes, round 1 updates in
 //                         place, round 2 computes its own part from u alone and adds P at the end of each task, then writes
 //                         dst — or the fused LSRK update, time_integrators.templates.h:117-132.  So rounds 1 and 2 work on
 //                         the same cell side by side, round 0 is up to two cells ahead, and nobody runs in lock-step (with
@@ -26,7 +26,8 @@
 //   warp 13               prefetch warp: follows the producer through the cell info and asks L2 for the face layers the
 //                         compute warps will read (cp.async.bulk.prefetch[.tensor]).
 //   warps 14-15           only donate their registers (setmaxnreg: compute 152, producer warpgroup 56; 3*152+56 = 512).
-// Shared memory: 4 x 32 KiB (cells) + 3 x 32 KiB (partial sums) + 256 B (cell info) + barriers = 225.5 KiB.
+// Shared memory: 4 x 32 KiB (cells) + 2 x 32 KiB (partial sums) + 4 x 8 KiB (direction-1 face layer of every cell stage)
+// + 256 B (cell info) + barriers = 225.5 KiB.
 // Per cell and SM: FP64 pipe 960 warp-DFMA per sub-partition (1920 cycles), shared memory 256 KiB of wavefronts (2048
 // cycles), HBM 64 KiB algorithmic.
 
@@ -37,7 +38,7 @@
 #define HD_R6_REGS_PRODUCER 56
 #endif
 #ifndef HD_R6_UNROLL_TASKS
-#define HD_R6_UNROLL_TASKS 1 // 1: both tasks of a cell as straight-line code (task index = immediate offsets in every address), 0: one rolled copy
+#define HD_R6_UNROLL_TASKS 1 // 1: both tasks unrolled (35 KB of hot loops, 2.04e9 instructions per apply, ~20 % of the stall samples are instruction fetch), 0: one rolled copy (17 KB, 2.42e9 instructions); A/B within one box: profiles/r02_rounds_ab.txt
 #endif
 static_assert(3 * HD_R6_REGS_COMPUTE + HD_R6_REGS_PRODUCER <= 512 && HD_R6_REGS_COMPUTE % 8 == 0 && HD_R6_REGS_PRODUCER % 8 == 0,
               "register split exceeds the launch allocation (512 threads x 128 registers)");
@@ -49,7 +50,7 @@ constexpr int R6_TRACE_CELLS = 512;
   do                                                                                                      \
     {                                                                                                     \
       if (p.r6_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (k) < R6_TRACE_CELLS)               \
-        p.r6_trace[((w)*R6_TRACE_CELLS + (k)) * 8 + (e)] = clock64();                                     \
+        p.r6_trace[((w)*R6_TRACE_CELLS + (k)) * 16 + (e)] = clock64();                                     \
     }                                                                                                     \
   while (0)
 #else
@@ -57,9 +58,10 @@ constexpr int R6_TRACE_CELLS = 512;
 #endif
 constexpr int R6_THREADS  = 512;
 constexpr int R6_STAGES   = 4;
-constexpr int R6_PBUFS    = 3;
+constexpr int R6_PBUFS    = 2;
 constexpr int R6_P_OFF    = R6_STAGES * U_BYTES;            // 131072
-constexpr int R6_INFO_OFF = R6_P_OFF + R6_PBUFS * U_BYTES;  // 229376
+constexpr int R6_F1_OFF   = R6_P_OFF + R6_PBUFS * U_BYTES;  // 196608: direction-1 face layer of every cell stage (8 KiB each)
+constexpr int R6_INFO_OFF = R6_F1_OFF + R6_STAGES * F_BYTES; // 229376
 constexpr int R6_BAR_OFF  = R6_INFO_OFF + R6_STAGES * 64;   // 229632
 constexpr int R6_SMEM_BYTES = R6_BAR_OFF + 512 + 1024;      // + alignment slack = 231168 <= 232448
 
@@ -104,20 +106,14 @@ r6_prefetch_bulk(const void *ptr, uint32_t bytes)
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
 
-// mbarrier wait with a watchdog: a protocol error must end the launch with an error (trap), never hang the GPU
+// mbarrier wait with a watchdog: a protocol error must end the launch with an error (trap), never hang the GPU.  Kept to
+// a handful of instructions (the three rounds share a 32 KB instruction cache): every failed try_wait has already slept
+// for the hardware's time slice, so a retry count stands in for a clock (2^26 retries are seconds).
 __device__ __forceinline__ void
 r6_wait(uint32_t bar, uint32_t parity)
 {
   uint32_t done;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(done)
-               : "r"(bar), "r"(parity)
-               : "memory");
-  if (done)
-    return;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;)
+  for (uint32_t it = 0;; ++it)
     {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done)
@@ -125,8 +121,7 @@ r6_wait(uint32_t bar, uint32_t parity)
                    : "memory");
       if (done)
         return;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 8000000000ull) // 8 s: beyond the 4 s the halo wait itself allows
+      if (it > (1u << 26))
         asm volatile("trap;");
     }
 }
@@ -139,7 +134,11 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   const int  lane    = t & 31;
   const bool actA    = p.up_delta[2 * R] != 0, actB = p.up_delta[2 * R + 1] != 0;
   const bool descend = p.up_delta[0] > 0;
-  const bool stream  = (p.hints & 4) != 0; // dst written with streaming stores (evict-first in L2): the face layers of src stay longer
+#ifdef HD_R6_STREAM_STORES
+  constexpr bool stream = true; // dst written with streaming stores (evict-first in L2); measured: no gain (profiles/r02_rounds_ab.txt)
+#else
+  constexpr bool stream = false;
+#endif
   auto       release = [&](uint32_t bar) {
     __syncwarp();
     if (lane == 0)
@@ -164,11 +163,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
     constexpr int stride = decltype(stride_c)::value;
     if (stride == 1)
       {
-        const double2 v0 = r6_ldg128(q), v1 = r6_ldg128(q + 2); // four contiguous doubles, 32-byte aligned
-        f[0] = v0.x;
-        f[1] = v0.y;
-        f[2] = v1.x;
-        f[3] = v1.y;
+        r6_ldg256(q, f); // four contiguous doubles, 32-byte aligned: one 256-bit load
       }
     else
       {
@@ -191,7 +186,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
         else
           load4(p.ghost + inf.fA + thrG[0] + j * stepG, GA(), fa);
       }
-    if (actB)
+    if (actB && R != 0) // (round 0: staged in shared memory, see load_tile)
       {
         if (!gB)
           load4(p.src + inf.fB + thrS[1] + j * stepS, SB(), fb);
@@ -208,7 +203,22 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
   double fa[4] = {0.0, 0.0, 0.0, 0.0}, fb[4] = {0.0, 0.0, 0.0, 0.0}, eo[4] = {0.0, 0.0, 0.0, 0.0};
   request(cur, 0, fa, fb);
   double U[4][4]; // the u tile of the task about to run (loaded by the task before it)
-  r6::load_u<R>(base, tm, 0, U);
+  // round 0: the direction-1 traces of the task come from the face layer the producer staged with the cell (32-byte rows,
+  // 32 B swizzle: the two 16-byte halves of row r are swapped when bit 2 of r is set) — two conflict-free LDS.128
+  auto load_tile = [&](int stage, int j) {
+    r6::load_u<R>(base + uint32_t(stage) * U_BYTES, tm, j, U);
+    if (R == 0 && actB)
+      {
+        const uint32_t r32 = uint32_t(t) + 128u * uint32_t(j), fl = (r32 >> 2) & 1u;
+        const uint32_t tb  = base + R6_F1_OFF + uint32_t(stage) * F_BYTES + r32 * 32u;
+        const double2  v0 = r6_lds128(tb + ((0u ^ fl) << 4)), v1 = r6_lds128(tb + ((1u ^ fl) << 4));
+        fb[0] = v0.x;
+        fb[1] = v0.y;
+        fb[2] = v1.x;
+        fb[3] = v1.y;
+      }
+  };
+  load_tile(0, 0);
 
   for (int k = 0;; ++k)
     {
@@ -241,6 +251,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
           double          sv[16]; // (round 2, fused LSRK) the `sol` values this task updates
           const long long g = g0 + 128 * j;
           auto after_traces = [&]() {
+            R6_TR(tw, k, 8 + 4 * j); // trace terms done
             if (R == 2 && FUSED)
               {
                 // requested here, not at the start of the task: a wait for the traces would wait for these loads as well
@@ -265,14 +276,16 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                 if (nxt.cell >= 0)
                   request(nxt, 0, fa, fb);
               }
+            R6_TR(tw, k, 9 + 4 * j); // next request issued
           };
           // called by the task once it has consumed U: the u tile of the task that follows (its cell has landed: after_traces
           // of task 1 waited for it)
           auto after_main = [&]() {
+            R6_TR(tw, k, 10 + 4 * j); // main terms done
             if (j == 0)
-              r6::load_u<R>(ub, tm, 1, U);
+              load_tile(s, 1);
             else if (nxt.cell >= 0)
-              r6::load_u<R>(base + uint32_t((k + 1) & (R6_STAGES - 1)) * U_BYTES, tm, 0, U);
+              load_tile((k + 1) & (R6_STAGES - 1), 0);
           };
           if constexpr (R == 0)
             {
@@ -331,6 +344,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                     p.dst[g + 256 * i] = kv;
                 }
             }
+          R6_TR(tw, k, 11 + 4 * j); // task done (results stored)
         }
       if (R == 1)
         release(bars.pFull1(pi));
@@ -344,8 +358,8 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
 template <bool FUSED, bool HALO>
 __global__ void __launch_bounds__(R6_THREADS, 1)
   k_rounds_3d3v_k3(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ CUtensorMap mapT2,
-                   const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ FastParams p,
-                   const __grid_constant__ r6::Coef cf)
+                   const __grid_constant__ CUtensorMap mapT3, const __grid_constant__ CUtensorMap mapT4, const __grid_constant__ CUtensorMap mapG1,
+                   const __grid_constant__ FastParams p, const __grid_constant__ r6::Coef cf)
 {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw   = smem_u32(smem_raw);
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
       const CUtensorMap *mymap = lane == 1 ? &mapT1 : (lane == 2 ? &mapT2 : (lane == 3 ? &mapT3 : &mapT4));
       const int          hi    = 1 << (2 * (5 - (lane < 6 ? lane : 5))); // face-layer rows per cell of this lane's map
       const int          ud    = (lane >= 1 && lane < 6) ? p.up_delta[lane] : 0;
-      const bool         mine  = ud != 0 && ((p.r6_prefetch >> lane) & 1);
+      const bool         mine  = ud != 0 && lane >= 2 && ((p.r6_prefetch >> lane) & 1); // (direction 1 is staged by the producer)
       for (int k = 0;; ++k)
         {
           const int s = k & (R6_STAGES - 1);
@@ -448,8 +462,10 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
   const int  n0      = p.ncell[0];
   const bool descend = p.up_delta[0] > 0; // upwind neighbour is the upper cell: walk downwards
   const bool ghost0  = p.up_delta[0] != 0 && p.up_kind[0] == HD_SIDE_GHOST;
+  const bool act1    = p.up_delta[1] != 0;
   if (lane == 0)
     {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
     }
   bool halo_ready = p.pass != 3;
@@ -611,15 +627,32 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
             fbv.off += (long long)c[0] * (rowfb.ghost ? 1024 : CELL);
           if (lane < 6)
             reinterpret_cast<long long *>(info)[lane] = fbv.off;
-          const unsigned gmask = __ballot_sync(0xffffffffu, fbv.ghost) & 0x3fu;
+          const unsigned  gmask  = __ballot_sync(0xffffffffu, fbv.ghost) & 0x3fu;
+          const long long off1   = __shfl_sync(0xffffffffu, fbv.off, 1); // lane 1's direction-1 trace base
+          const bool      ghost1 = (gmask >> 1) & 1u;
           __syncwarp();
           if (lane == 0)
             {
               reinterpret_cast<int *>(info)[12] = int(cell);
               reinterpret_cast<int *>(info)[13] = ((step == sb) ? 1 : 0) | int(gmask << 8);
               mbar_arrive(bars.infoFull(s)); // (release: the prefetch warp may read the info now)
-              mbar_expect_tx(bars.fullU(s), U_BYTES);
+#ifdef HD_R6_DEBUG_SKIP_F1 // timing experiment only (wrong results): what does fetching the direction-1 face layer cost?
+              const bool f1 = false;
+#else
+              const bool f1 = act1;
+#endif
+              mbar_expect_tx(bars.fullU(s), U_BYTES + (f1 ? F_BYTES : 0));
               tma_load_2d(base + s * U_BYTES, &mapU, 0, int(cell * 256), bars.fullU(s)); // one box of 256 rows = the cell
+              if (f1)
+                {
+                  // the upwind face layer of direction 1 (256 pieces of 32 bytes, one per row of the neighbour cell — the one
+                  // trace no warp can read from global memory in a coalesced way) lands next to the cell
+                  const uint32_t dstF = base + R6_F1_OFF + s * F_BYTES;
+                  if (ghost1)
+                    tma_load_2d(dstF, &mapG1, 0, int(off1 >> 2), bars.fullU(s)); // ghost segment viewed as rows of 4 doubles
+                  else
+                    tma_load_3d(dstF, &mapT1, 0, p.up_delta[1] < 0 ? 3 : 0, int(off1 >> 12) * 256, bars.fullU(s));
+                }
               R6_TR(12, k, 2);
             }
         }

@@ -70,6 +70,12 @@ r6_ldg128(const double *p)
 {
   return r6_double2{p[0], p[1]};
 }
+HD_R6_FN void
+r6_ldg256(const double *p, double (&f)[4])
+{
+  for (int i = 0; i < 4; ++i)
+    f[i] = p[i];
+}
 HD_R6_FN double
 r6_fma(double a, double b, double c)
 {
@@ -121,6 +127,13 @@ r6_ldg128(const double *p)
   double2 v;
   asm volatile("ld.global" HD_R6_LDG_MOD ".v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
+}
+// four contiguous doubles, 32-byte aligned, as ONE 256-bit load (LDG.E.ENL2.256 on sm_100a): the lanes of round 0 read
+// 32 bytes each from 32 different 128-byte lines, and the L1TEX data pipe is charged per line and instruction
+HD_R6_FN void
+r6_ldg256(const double *p, double (&f)[4])
+{
+  asm volatile("ld.global" HD_R6_LDG_MOD ".v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(f[0]), "=d"(f[1]), "=d"(f[2]), "=d"(f[3]) : "l"(p));
 }
 HD_R6_FN double
 r6_fma(double a, double b, double c)
@@ -264,12 +277,7 @@ namespace r6
     const double *p = (ghost ? ghosts : src) + fbase + thr;
     if (ROUND == 0 && (SIDE == 1 || ghost))
       {
-        // four contiguous doubles, 32-byte aligned
-        const r6_double2 v0 = r6_ldg128(p), v1 = r6_ldg128(p + 2);
-        f[0] = v0.x;
-        f[1] = v0.y;
-        f[2] = v1.x;
-        f[3] = v1.y;
+        r6_ldg256(p, f); // four contiguous doubles, 32-byte aligned
       }
     else
       {
@@ -460,7 +468,7 @@ namespace r6
   // ---- round 2: directions (4,5); returns the finished values K[b][a] of dst index g0 + 256 a + 1024 b,
   // g0 = cell * 4096 + (t & 15) + 16 ((t >> 4) + 8 j).  Its own contribution needs only u, so it is computed first and the
   // partial sums of rounds 0 and 1 are added at the END (before_partial() = wait until round 1 is done with the cell):
-  // rounds 1 and 2 work on the same cell side by side and the three P buffers leave round 0 a whole cell of slack.
+  // rounds 1 and 2 work on the same cell side by side and round 0 may already be on the next one (two P buffers).
   template <class F, class H, class G>
   HD_R6_FN void
   task_round2(const Coef &cf, uint32_t pb, const ThreadMap<2> &tm, int j, double (&U)[4][4], const double (&fa)[4], const double (&fb)[4], double (&q)[4][4],
