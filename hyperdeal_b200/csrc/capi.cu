@@ -1153,9 +1153,12 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
       if (part == HD_PART_INTERIOR)
         return HD_OK;
       const bool tile = op->kernel_choice == 3 || (op->kernel_choice == 0 && hd::tile_preferred(op));
+      // degree 5 (n = 6; BASELINE.json configs[2] is 3D3V degree 5 in FP32): the global-memory tile kernel beats the
+      // generic one (95 against 79 GDoF/s on 6^3 x 4^3 cells, profiles/r02a_zoo_tg.txt) wherever it applies
+      const bool tg = op->kernel_choice == 5 || (op->kernel_choice == 0 && m->n == 6 && hd::tile_global_supported(op));
       if (op->kernel_choice == 4)
         rc = hd::launch_tile_row(op, dst, src, ghosts, time, fu);
-      else if (op->kernel_choice == 5)
+      else if (tg)
         rc = hd::launch_tile_global(op, dst, src, ghosts, time, fu);
       else
         rc = tile ? hd::launch_tile(op, dst, src, ghosts, time, fu) : hd::launch_generic(op, dst, src, ghosts, time, fu);

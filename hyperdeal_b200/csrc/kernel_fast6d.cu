@@ -132,6 +132,14 @@ namespace
     // three-round kernel: bit d (1..5) = the producer asks for the upwind face layer of direction d of every cell to be in
     // L2 before the compute warps read it; bit 6 = same for the cell's `sol` values (fused LSRK)
     int           r6_prefetch;
+    // three-round kernel, pass 3 (fused halo) without an interior/boundary split: ONE list of all rows in the usual tiled
+    // lattice order; a row that reads a ghost side whose halo has not arrived yet is put on a device-wide deferred queue
+    // and taken up again once the main list is exhausted.  Only the ghost rows met during the first ~ms are ever deferred,
+    // everything else runs in lattice order with its L2 / TLB locality.
+    // counters: [0] next row, [1] finished CTAs, [2] time-out flag, [3] deferred rows queued, [4] deferred rows taken,
+    // [5] CTAs that have exhausted the main list
+    int           defer;
+    int *         defer_queue; // nrows entries, 0 = empty slot, else row item + 1 (self-cleaning)
     // HD_R6_TRACE builds only: timeline of CTA 0 (clock64 per event), long long [13 warps][R6_TRACE_CELLS][16 events]
     long long *   r6_trace;
   };
@@ -1241,6 +1249,8 @@ namespace
     std::map<const void *, GhostMaps> ghost_cache;
     bool                         attr_set[8] = {false, false, false, false, false, false, false, false};
     int *                        d_counters  = nullptr;
+    int *                        d_defer     = nullptr; // deferred-row queue of the fused-halo pass (three-round kernel)
+    int                          defer_rows  = 0;
   };
 
   int
@@ -1280,8 +1290,8 @@ namespace
       }
     if (!st->d_counters)
       {
-        HD_CUDA(cudaMalloc(&st->d_counters, 4 * sizeof(int)));
-        HD_CUDA(cudaMemset(st->d_counters, 0, 4 * sizeof(int)));
+        HD_CUDA(cudaMalloc(&st->d_counters, 8 * sizeof(int)));
+        HD_CUDA(cudaMemset(st->d_counters, 0, 8 * sizeof(int)));
       }
     *out = st;
     return HD_OK;
@@ -1552,6 +1562,8 @@ namespace hd
       p.hints = op->l2_hints >= 0 ? op->l2_hints : env_hints;
       p.r6_prefetch = 0;
       p.r6_trace    = nullptr;
+      p.defer       = 0;
+      p.defer_queue = nullptr;
     }
     {
       // row tiles (see FastParams::tile); HD_ROW_TILE="t1,t2,t3,t4,t5" overrides the default, 0 = full extent.
@@ -1595,6 +1607,30 @@ namespace hd
           return e ? atoi(e) : 0x7e;
         }();
         p.r6_prefetch = env_pf;
+        {
+          static const int env_defer = [] {
+            const char *e = getenv("HD_R6_DEFER");
+            return e ? atoi(e) : 0; // default: interior list, then boundary list (1-GPU self exchange: 4.95 ms against 5.08 ms with the queue, profiles/r02_fused_halo_selftest.txt)
+          }();
+          const bool ghost0 = p.up_delta[0] != 0 && p.up_kind[0] == HD_SIDE_GHOST;
+          if (part == 3 && env_defer && !ghost0)
+            {
+              if (st->defer_rows < p.nrows)
+                {
+                  cudaFree(st->d_defer);
+                  st->d_defer = nullptr;
+                  HD_CUDA(cudaMalloc(&st->d_defer, sizeof(int) * (size_t)p.nrows));
+                  HD_CUDA(cudaMemsetAsync(st->d_defer, 0, sizeof(int) * (size_t)p.nrows, m->ctx->stream));
+                  st->defer_rows = p.nrows;
+                }
+              p.defer       = 1;
+              p.defer_queue = st->d_defer;
+              p.n_items     = p.nrows;
+              grid          = p.nrows < m->ctx->sm_count ? p.nrows : m->ctx->sm_count;
+              // (rows are decoded in the tiled lattice order of pass 0: the tile extents were set above for a full launch)
+              p.row_begin = 0;
+            }
+        }
 #ifdef HD_R6_TRACE
         {
           // debugging aid (tools/r6_timeline.py): HD_R6_TRACE_FILE=<path> dumps the last launch's timeline of CTA 0
@@ -1675,7 +1711,10 @@ namespace hd
   {
     FastState *st = static_cast<FastState *>(op->fast_state);
     if (st)
-      cudaFree(st->d_counters);
+      {
+        cudaFree(st->d_counters);
+        cudaFree(st->d_defer);
+      }
     delete st;
     op->fast_state = nullptr;
   }

@@ -468,7 +468,9 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT1));
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU));
     }
-  bool halo_ready = p.pass != 3;
+  bool     halo_ready = p.pass != 3;
+  unsigned seen       = 0; // (deferring pass 3) ghost sides whose arrival counter this producer has already seen at its target
+  bool     deferred_phase = false;
   // interior rows: mixed-radix decode that leaves out the ghost layer of every cut direction (see FastParams)
   auto decode_interior = [&](int i, int(&cr)[6]) {
 #pragma unroll
@@ -516,19 +518,144 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
     for (;;)
       {
         int item = 0;
-        if (lane == 0)
+        if (!deferred_phase)
           {
-            item = next_item;
-            if (item < p.n_items)
-              next_item = atomicAdd(p.counters, 1);
+            if (lane == 0)
+              {
+                item = next_item;
+                if (item < p.n_items)
+                  next_item = atomicAdd(p.counters, 1);
+              }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= p.n_items)
+              {
+                if (!(p.pass == 3 && p.defer))
+                  return false;
+                // main list exhausted: on to the deferred rows
+                deferred_phase = true;
+                if (lane == 0)
+                  {
+                    __threadfence();
+                    atomicAdd(p.counters + 5, 1);
+                  }
+              }
           }
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= p.n_items)
-          return false;
+        if (deferred_phase)
+          {
+            // take the next deferred row; the queue is complete once every CTA has exhausted the main list
+            int ok = 0;
+            if (lane == 0)
+              {
+                item = atomicAdd(p.counters + 4, 1);
+                for (;;)
+                  {
+                    int produced, done;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(produced) : "l"(p.counters + 3) : "memory");
+                    if (item < produced)
+                      {
+                        ok = 1;
+                        break;
+                      }
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(p.counters + 5) : "memory");
+                    if (done >= int(gridDim.x))
+                      {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(produced) : "l"(p.counters + 3) : "memory");
+                        ok = item < produced;
+                        break;
+                      }
+                    __nanosleep(200);
+                  }
+              }
+            ok   = __shfl_sync(0xffffffffu, ok, 0);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (!ok)
+              return false;
+          }
         cr[0]    = 0;
         sb       = 0;
         se       = n0;
         int mode = p.pass; // 0: all cells of a lattice row, 1: interior list, 2: boundary list
+        if (p.pass == 3 && p.defer)
+          {
+            // the usual tiled lattice order; ghost rows whose halo is not there yet go to the deferred queue
+            const bool second = deferred_phase;
+            if (second)
+              {
+                // item = index into the deferred queue (taken from counters[4] by next_deferred below)
+                int row = 0;
+                if (lane == 0)
+                  {
+                    volatile int *slot = p.defer_queue + item;
+                    while ((row = *slot) == 0)
+                      __nanosleep(100);
+                    *slot = 0; // leave the queue clean for the next launch
+                    row -= 1;
+                  }
+                item = __shfl_sync(0xffffffffu, row, 0);
+              }
+            int r = item;
+#pragma unroll
+            for (int d = 1; d < 6; ++d)
+              {
+                cr[d] = r % p.tile[d];
+                r /= p.tile[d];
+              }
+#pragma unroll
+            for (int d = 1; d < 6; ++d)
+              {
+                const int nt = p.ncell[d] / p.tile[d];
+                cr[d] += (r % nt) * p.tile[d];
+                r /= nt;
+              }
+            unsigned need = 0;
+#pragma unroll
+            for (int e = 1; e < 6; ++e)
+              if (p.cutg[e] >= 0 && cr[e] == p.cutg[e])
+                need |= 1u << (2 * e + (p.up_delta[e] < 0 ? 0 : 1));
+            need &= ~seen;
+            if (need)
+              {
+                unsigned got = 0;
+                if (lane == 0)
+                  {
+                    unsigned long long t0, t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (unsigned todo = need; todo;)
+                      {
+                        const int i = __ffs(todo) - 1;
+                        int       v;
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.halo_flag + i) : "memory");
+                        if (v >= p.halo_target)
+                          {
+                            got |= 1u << i;
+                            todo &= todo - 1;
+                            continue;
+                          }
+                        if (!second)
+                          break; // first pass over the list: do not wait, defer the row
+                        __nanosleep(500);
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 4000000000ull)
+                          {
+                            atomicExch(p.counters + 2, 1);
+                            break;
+                          }
+                      }
+                    if (got)
+                      asm volatile("fence.proxy.async;" ::: "memory"); // the TMA (async proxy) reads the direction-1 ghosts
+                    if (!second && (need & ~got))
+                      {
+                        const int idx = atomicAdd(p.counters + 3, 1);
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.defer_queue + idx), "r"(item + 1) : "memory");
+                      }
+                  }
+                got = __shfl_sync(0xffffffffu, got, 0);
+                seen |= got;
+                if (!second && (need & ~got))
+                  continue; // deferred
+              }
+            return true;
+          }
         if (p.pass == 3)
           {
             mode = item >= p.n_int ? 2 : 1;
@@ -591,6 +718,7 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
                         break;
                       }
                   }
+                asm volatile("fence.proxy.async;" ::: "memory"); // the TMA (async proxy) reads the direction-1 ghosts
               }
             __syncwarp();
             halo_ready = true;
@@ -673,6 +801,9 @@ __global__ void __launch_bounds__(R6_THREADS, 1)
           {
             p.counters[0] = 0;
             p.counters[1] = 0;
+            p.counters[3] = 0;
+            p.counters[4] = 0;
+            p.counters[5] = 0;
             __threadfence();
           }
       }
