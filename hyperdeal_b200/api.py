@@ -36,7 +36,11 @@ EXPORTS = [
     "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
     "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
-    "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step",
+    "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step", "hd_lsrk_stage_fused", "hd_lsrk_stage_overlapped",
+    "hd_multi_create", "hd_multi_destroy", "hd_multi_n_gpus", "hd_multi_mesh", "hd_multi_context", "hd_multi_n_dofs", "hd_multi_synchronize", "hd_multi_vector_alloc",
+    "hd_multi_vector_free", "hd_multi_vector_copy_in", "hd_multi_vector_copy_out", "hd_multi_interpolate_builtin", "hd_multi_norm_and_error_builtin",
+    "hd_multi_advection_create", "hd_multi_advection_destroy", "hd_multi_advection_set_dirichlet_builtin", "hd_multi_advection_kernel_name", "hd_multi_advection_apply",
+    "hd_multi_lsrk_create", "hd_multi_lsrk_destroy", "hd_multi_lsrk_step",
     "hd_interpolate_builtin", "hd_norm_and_error_builtin", "hd_mesh_n_dofs_x", "hd_vector_alloc_x", "hd_velocity_space_integration", "hd_poisson_create", "hd_poisson_destroy", "hd_poisson_solve", "hd_poisson_last_solve", "hd_poisson_potential", "hd_phase_space_diagnostics", "hd_field_energy", "hd_timer_start", "hd_timer_stop",
 ]
 
@@ -131,6 +135,33 @@ def lib():
     L.hd_poisson_last_solve.argtypes = [c_void_p, POINTER(c_int), POINTER(c_double)]
     L.hd_vector_zero_n.argtypes = [c_void_p, c_void_p, c_int64]
     L.hd_vector_copy_n.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
+    L.hd_lsrk_stage_fused.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double]
+    L.hd_lsrk_stage_overlapped.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(HaloSend), c_int, c_void_p, c_int, c_double, c_double]
+    L.hd_multi_create.argtypes = [c_int, POINTER(c_int), POINTER(MeshDesc), POINTER(c_int), POINTER(c_void_p)]
+    L.hd_multi_destroy.argtypes = [c_void_p]
+    L.hd_multi_n_gpus.argtypes = [c_void_p]
+    L.hd_multi_mesh.argtypes = [c_void_p, c_int]
+    L.hd_multi_mesh.restype = c_void_p
+    L.hd_multi_context.argtypes = [c_void_p, c_int]
+    L.hd_multi_context.restype = c_void_p
+    L.hd_multi_n_dofs.argtypes = [c_void_p]
+    L.hd_multi_n_dofs.restype = c_int64
+    L.hd_multi_synchronize.argtypes = [c_void_p]
+    L.hd_multi_vector_alloc.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.hd_multi_vector_free.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.hd_multi_vector_copy_in.argtypes = [c_void_p, POINTER(c_void_p), c_void_p]
+    L.hd_multi_vector_copy_out.argtypes = [c_void_p, POINTER(c_void_p), c_void_p]
+    L.hd_multi_interpolate_builtin.argtypes = [c_void_p, POINTER(c_void_p), c_int, c_double]
+    L.hd_multi_norm_and_error_builtin.argtypes = [c_void_p, POINTER(c_void_p), c_int, c_double, POINTER(c_double)]
+    L.hd_multi_advection_create.argtypes = [c_void_p, c_double, POINTER(c_double), POINTER(c_void_p)]
+    L.hd_multi_advection_destroy.argtypes = [c_void_p]
+    L.hd_multi_advection_set_dirichlet_builtin.argtypes = [c_void_p, c_int]
+    L.hd_multi_advection_kernel_name.argtypes = [c_void_p]
+    L.hd_multi_advection_kernel_name.restype = c_char_p
+    L.hd_multi_advection_apply.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_double]
+    L.hd_multi_lsrk_create.argtypes = [c_void_p, c_char_p, POINTER(c_void_p)]
+    L.hd_multi_lsrk_destroy.argtypes = [c_void_p]
+    L.hd_multi_lsrk_step.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_double, c_double]
     L.hd_poisson_potential.argtypes = [c_void_p]
     L.hd_poisson_potential.restype = c_void_p
     L.hd_phase_space_diagnostics.argtypes = [c_void_p, c_void_p, POINTER(c_double)]
@@ -477,3 +508,95 @@ class VectorTools:
     def norm_and_error(matrix_free: MatrixFree, vec: int, fn_id: int = FN_HYPERRECTANGLE, time: float = 0.0):
         n2, e2 = VectorTools.norm_and_error_sums(matrix_free, vec, fn_id, time)
         return math.sqrt(n2), math.sqrt(e2)
+
+
+class MultiGpu:
+    """Single-process multi-GPU lattice (hd_multi_*): the phase-space lattice is cut into a Cartesian grid of bricks, one per
+    GPU (the reference's PartitionX x PartitionV process grid, examples/advection/include/application.h:150-176 +
+    base/mpi.h create_rectangular_comm); ghost faces move over NVLink peer stores.  Vectors are tuples of per-brick
+    device pointers; copy_in/copy_out take the GLOBAL lattice in the single-brick ordering."""
+
+    def __init__(self, n_gpus, dim_x, dim_v, degree, n_cells_global, left, right, grid, periodic=True, dtype=np.float64, devices=None):
+        dim = dim_x + dim_v
+        self.n, self.dim, self.dtype = n_gpus, dim, np.dtype(dtype)
+        d = MeshDesc()
+        d.dim_x, d.dim_v, d.degree, d.n_points, d.collocation = dim_x, dim_v, degree, degree + 1, 0
+        d.number_type = HD_F64 if self.dtype == np.float64 else HD_F32
+        if isinstance(periodic, bool):
+            periodic = (periodic,) * dim
+        for i in range(HD_MAX_DIM):
+            d.left[i] = left[i] if i < dim else 0.0
+            d.right[i] = right[i] if i < dim else 1.0
+            d.n_cells[i] = d.n_cells_global[i] = n_cells_global[i] if i < dim else 1
+            d.cell_offset[i] = 0
+            for s in range(2):
+                d.side_kind[i][s] = SIDE_PERIODIC_LOCAL if (i >= dim or periodic[i]) else SIDE_DIRICHLET
+        g = (c_int * HD_MAX_DIM)(*[grid[i] if i < dim else 1 for i in range(HD_MAX_DIM)])
+        dev = (c_int * n_gpus)(*devices) if devices is not None else None
+        self._h = c_void_p()
+        _check(lib().hd_multi_create(n_gpus, dev, byref(d), g, byref(self._h)))
+        self.n_dofs = lib().hd_multi_n_dofs(self._h)
+        self._ops, self._rks = [], []
+
+    def _arr(self, ptrs):
+        return (c_void_p * self.n)(*ptrs)
+
+    def initialize_dof_vector(self):
+        a = (c_void_p * self.n)()
+        _check(lib().hd_multi_vector_alloc(self._h, a))
+        return tuple(a)
+
+    def free(self, vec):
+        _check(lib().hd_multi_vector_free(self._h, self._arr(vec)))
+
+    def copy_in(self, vec, host):
+        h = np.ascontiguousarray(host, dtype=self.dtype)
+        assert h.size == self.n_dofs
+        _check(lib().hd_multi_vector_copy_in(self._h, self._arr(vec), h.ctypes.data_as(c_void_p)))
+
+    def copy_out(self, vec):
+        h = np.empty(self.n_dofs, dtype=self.dtype)
+        _check(lib().hd_multi_vector_copy_out(self._h, self._arr(vec), h.ctypes.data_as(c_void_p)))
+        return h
+
+    def interpolate(self, vec, fn_id=FN_HYPERRECTANGLE, time=0.0):
+        _check(lib().hd_multi_interpolate_builtin(self._h, self._arr(vec), fn_id, float(time)))
+
+    def norm_and_error(self, vec, fn_id=FN_HYPERRECTANGLE, time=0.0):
+        out = (c_double * 2)()
+        _check(lib().hd_multi_norm_and_error_builtin(self._h, self._arr(vec), fn_id, float(time), out))
+        return math.sqrt(out[0]), math.sqrt(out[1])
+
+    def advection(self, velocity, skew=0.5):
+        h = c_void_p()
+        v = (c_double * HD_MAX_DIM)(*[velocity[i] if i < self.dim else 0.0 for i in range(HD_MAX_DIM)])
+        _check(lib().hd_multi_advection_create(self._h, float(skew), v, byref(h)))
+        self._ops.append(h)
+        return h
+
+    def kernel_name(self, op):
+        return lib().hd_multi_advection_kernel_name(op).decode()
+
+    def apply(self, op, dst, src, time=0.0):
+        _check(lib().hd_multi_advection_apply(op, self._arr(dst), self._arr(src), float(time)))
+
+    def lsrk(self, rk_type="rk45"):
+        h = c_void_p()
+        _check(lib().hd_multi_lsrk_create(self._h, rk_type.encode(), byref(h)))
+        self._rks.append(h)
+        return h
+
+    def lsrk_step(self, rk, op, solution, Ki, Ti, t, dt):
+        _check(lib().hd_multi_lsrk_step(rk, op, self._arr(solution), self._arr(Ki), self._arr(Ti), float(t), float(dt)))
+
+    def synchronize(self):
+        _check(lib().hd_multi_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            for h in self._rks:
+                lib().hd_multi_lsrk_destroy(h)
+            for h in self._ops:
+                lib().hd_multi_advection_destroy(h)
+            lib().hd_multi_destroy(self._h)
+            self._h, self._ops, self._rks = c_void_p(), [], []

@@ -85,6 +85,14 @@ namespace hyperdeal
         dim_x     = prm.get_int("General/DimX", 0);
         dim_v     = prm.get_int("General/DimV", 0);
         degree    = prm.get_int("General/DegreeX", 0);
+        // process grid of the reference run (parameters.h:62-63); here: bricks = GPUs of this process.  The environment
+        // overrides the file the way `mpirun -np N` does for the reference's tests (tests/*.mpirun=N.out)
+        partition_x = prm.get_int("General/PartitionX", 1);
+        partition_v = prm.get_int("General/PartitionV", 1);
+        if (const char *e = std::getenv("HD_PARTITION_X"))
+          partition_x = std::atoi(e);
+        if (const char *e = std::getenv("HD_PARTITION_V"))
+          partition_v = std::atoi(e);
       }
       bool                        do_collocation;
       TimeLoopParamters<double>   time_loop_parameters;
@@ -99,6 +107,7 @@ namespace hyperdeal
       unsigned int                n_subdivisions_x[3], n_subdivisions_v[3];
       std::string                 case_name;
       int                         dim_x, dim_v, degree;
+      int                         partition_x = 1, partition_v = 1;
     };
 
     // examples/advection/include/application.h:60-640
@@ -214,6 +223,108 @@ namespace hyperdeal
       std::unique_ptr<AdvectionOperation<dim_x, dim_v, degree, n_points, Number, VectorType, VelocityField>> advection_operation;
       TimeLoop<Number, VectorType>                                                                       time_loop;
     };
+
+    // the same application on PartitionX x PartitionV GPUs of this process (hyperdeal::multi, hd_multi_*): identical
+    // set-up sequence, time step and diagnostics; every stage = one ghost exchange over NVLink + one fused kernel per GPU
+    template <int dim_x, int dim_v, int degree, int n_points, typename Number>
+    class MultiApplication
+    {
+    public:
+      static const int dim = dim_x + dim_v;
+      using VectorType     = multi::DistributedDeviceVector<Number>;
+
+      explicit MultiApplication(DynamicConvergenceTable &table)
+        : table(table)
+      {}
+
+      void
+      reinit(Parameters &param)
+      {
+        this->param = &param;
+        if (param.case_name != "hyperrectangle")
+          throw ExcNotImplemented("case " + param.case_name + " (Cartesian lattices only)");
+        if (std::getenv("HD_DRIVER_UNFUSED") || std::getenv("HD_DRIVER_HOST_FUNCTIONS"))
+          throw ExcNotImplemented("HD_DRIVER_UNFUSED / HD_DRIVER_HOST_FUNCTIONS on more than one GPU");
+        CartesianLattice<dim_x> lx;
+        CartesianLattice<dim_v> lv;
+        for (int d = 0; d < dim_x; ++d)
+          {
+            lx.left[d]    = -1.0;
+            lx.right[d]   = +1.0;
+            lx.n_cells[d] = param.n_subdivisions_x[d] << param.n_refinements_x;
+          }
+        for (int d = 0; d < dim_v; ++d)
+          {
+            lv.left[d]    = -1.0;
+            lv.right[d]   = +1.0;
+            lv.n_cells[d] = param.n_subdivisions_v[d] << param.n_refinements_v;
+          }
+        lx.periodic = param.periodic_x;
+        lv.periodic = param.periodic_v;
+        lx.degree = lv.degree = degree;
+        lx.n_points = lv.n_points = n_points;
+        lx.collocation = lv.collocation = param.do_collocation;
+        matrix_free.reset(new multi::MatrixFree<dim_x, dim_v, Number>(lx, lv, param.partition_x, param.partition_v));
+        matrix_free->reinit();
+        matrix_free->initialize_dof_vector(vct_Ki);
+        matrix_free->initialize_dof_vector(vct_Ti);
+        matrix_free->initialize_dof_vector(vct_solution);
+        analytical_solution.reset(new hyperrectangle::ExactSolution<dim, Number>());
+        multi::interpolate<dim_x, dim_v, Number>(analytical_solution, *matrix_free, vct_solution);
+        boundary_descriptor.reset(new BoundaryDescriptor<dim, Number>());
+        boundary_descriptor->dirichlet_bc[0].reset(new hyperrectangle::ExactSolution<dim, Number>());
+        boundary_descriptor->dirichlet_bc[1].reset(new hyperrectangle::ExactSolution<dim, Number>());
+        const auto transport_direction = hyperrectangle::ExactSolution<dim, Number>().get_transport_direction();
+        advection_operation.reset(new multi::AdvectionOperation<dim_x, dim_v, Number>(*matrix_free));
+        advection_operation->reinit(boundary_descriptor, transport_direction, param.advection_operation_parameters);
+
+        // application.h:369-392 (the critical time step depends on the global lattice only)
+        auto &       tl                 = param.time_loop_parameters;
+        const auto & d                  = matrix_free->get_mesh_desc();
+        Number       v_max[2]           = {0, 0};
+        for (int i = 0; i < dim; ++i)
+          v_max[i < dim_x ? 0 : 1] = std::max<Number>(v_max[i < dim_x ? 0 : 1], std::abs(transport_direction[i] / ((d.right[i] - d.left[i]) / d.n_cells_global[i])));
+        const Number critical_time_step = std::min(Number(1.0) / v_max[0], Number(1.0) / v_max[1]);
+        const Number dt                 = std::min<Number>(tl.time_step, param.cfl_number * critical_time_step / std::pow(degree, 1.5));
+        tl.time_step                    = (tl.final_time - tl.start_time) / std::ceil((tl.final_time - tl.start_time) / dt);
+        time_loop.reinit(tl);
+      }
+
+      void
+      solve()
+      {
+        multi::LowStorageRungeKuttaIntegrator<Number> time_integrator(matrix_free->get_multi(), vct_Ki, vct_Ti, param->rk_type);
+        std::array<Number, 2>                         error;
+        const auto &                                  tl = param->time_loop_parameters;
+        const unsigned int time_steps = time_loop.loop(
+          vct_solution,
+          [&](auto &solution, const auto cur_time, const auto time_step, const auto &) { time_integrator.perform_time_step(solution, cur_time, time_step, *advection_operation); },
+          [&](const VectorType &src, VectorType &dst, const Number cur_time) { advection_operation->apply(dst, src, cur_time); },
+          [&](const Number cur_time) {
+            if (!param->dignostics_enabled ||
+                (cur_time != tl.start_time && static_cast<int>((cur_time + 0.00000000001 - tl.start_time) / param->dignostics_tick) ==
+                                                static_cast<int>((cur_time + 0.00000000001 - tl.start_time - tl.time_step) / param->dignostics_tick)))
+              return;
+            analytical_solution->set_time(cur_time);
+            error = multi::norm_and_error<dim_x, dim_v, Number>(analytical_solution, *matrix_free, vct_solution);
+            printf("   Time:%10.3e, norm: %17.10e, error: %17.10e\n", cur_time, error[0], error[1]);
+          });
+        table.set("info->time_steps", time_steps);
+        table.set("info->n_dofs", double(matrix_free->n_dofs()));
+        table.set("info->n_gpus", double(matrix_free->n_bricks()));
+        printf("   bricks: %d, kernel: %s\n", matrix_free->n_bricks(), advection_operation->kernel_name().c_str());
+      }
+
+    private:
+      DynamicConvergenceTable &                                     table;
+      Parameters *                                                  param = nullptr;
+      std::unique_ptr<multi::MatrixFree<dim_x, dim_v, Number>>      matrix_free;
+      VectorType                                                    vct_Ki, vct_Ti, vct_solution;
+      std::shared_ptr<dealii::Function<dim, Number>>                analytical_solution;
+      std::shared_ptr<BoundaryDescriptor<dim, Number>>              boundary_descriptor;
+      std::unique_ptr<multi::AdvectionOperation<dim_x, dim_v, Number>> advection_operation;
+      TimeLoop<Number, VectorType>                                  time_loop;
+    };
   } // namespace advection
 } // namespace hyperdeal
 
@@ -243,6 +354,13 @@ namespace
   void
   run_application(const hyperdeal::DeviceCommunicator &comm, hyperdeal::DynamicConvergenceTable &table, hyperdeal::advection::Parameters &param)
   {
+    if (param.partition_x * param.partition_v > 1)
+      {
+        hyperdeal::advection::MultiApplication<dim_x, dim_v, degree, n_points, double> app(table);
+        app.reinit(param);
+        app.solve();
+        return;
+      }
     hyperdeal::advection::Application<dim_x, dim_v, degree, n_points, double> app(comm, table);
     app.reinit(param);
     app.solve();

@@ -935,6 +935,269 @@ namespace hyperdeal
       return {{Number(std::sqrt(out[0])), Number(std::sqrt(out[1]))}};
     }
   } // namespace VectorTools
+
+  // ---- more than one GPU in ONE process (hd_multi_*) ----------------------------------------------------------------
+  // The reference runs PartitionX x PartitionV MPI ranks (examples/advection/include/application.h:150-176; the process
+  // grid of base/mpi.h create_rectangular_comm) and partitions the x- and the v-triangulation among the rows and columns
+  // of that grid.  Here the same two numbers cut the Cartesian lattice into bricks, one per GPU of this process; ghost
+  // faces travel over NVLink peer stores inside the library.  The classes below carry the same member names as their
+  // single-GPU counterparts so a driver's set-up / time loop reads the same.
+  namespace multi
+  {
+    // cut `parts` ways: the slowest direction first, each direction as far as its cell count allows
+    template <int dim>
+    std::array<int, dim>
+    brick_grid(const CartesianLattice<dim> &lattice, int parts)
+    {
+      std::array<int, dim> g;
+      g.fill(1);
+      for (int d = dim - 1; d >= 0 && parts > 1; --d)
+        {
+          int a = parts, b = int(lattice.n_cells[d]);
+          while (b)
+            {
+              const int t = a % b;
+              a           = b;
+              b           = t;
+            }
+          g[d] = a; // gcd(parts, n_cells[d])
+          parts /= a;
+        }
+      if (parts != 1)
+        throw ExcMessage("the lattice cannot be cut into the requested number of bricks");
+      return g;
+    }
+
+    template <typename Number>
+    class DistributedDeviceVector;
+
+    template <int dim_x, int dim_v, typename Number = double>
+    class MatrixFree
+    {
+    public:
+      static const int dim = dim_x + dim_v;
+      MatrixFree(const CartesianLattice<dim_x> &matrix_free_x, const CartesianLattice<dim_v> &matrix_free_v, const int partition_x, const int partition_v)
+        : lattice_x(matrix_free_x)
+        , lattice_v(matrix_free_v)
+        , size_x(partition_x)
+        , size_v(partition_v)
+      {}
+      ~MatrixFree()
+      {
+        if (mm)
+          hd_multi_destroy(mm);
+      }
+      MatrixFree(const MatrixFree &) = delete;
+      MatrixFree &operator=(const MatrixFree &) = delete;
+
+      void
+      reinit()
+      {
+        if (lattice_x.degree != lattice_v.degree || lattice_x.n_points != lattice_v.n_points || lattice_x.collocation != lattice_v.collocation)
+          throw ExcNotImplemented("different degree / quadrature in x and v");
+        hd_mesh_desc d{};
+        d.dim_x       = dim_x;
+        d.dim_v       = dim_v;
+        d.degree      = lattice_x.degree;
+        d.n_points    = lattice_x.n_points;
+        d.collocation = lattice_x.collocation;
+        d.number_type = internal::number_type<Number>();
+        int grid[HD_MAX_DIM];
+        for (int i = 0; i < HD_MAX_DIM; ++i)
+          {
+            d.left[i]           = 0.0;
+            d.right[i]          = 1.0;
+            d.n_cells_global[i] = d.n_cells[i] = 1;
+            d.cell_offset[i]                   = 0;
+            d.side_kind[i][0] = d.side_kind[i][1] = HD_SIDE_PERIODIC_LOCAL;
+            grid[i]                               = 1;
+          }
+        const auto gx = brick_grid<dim_x>(lattice_x, size_x);
+        const auto gv = brick_grid<dim_v>(lattice_v, size_v);
+        for (int i = 0; i < dim; ++i)
+          {
+            const bool in_x     = i < dim_x;
+            const int  j        = in_x ? i : i - dim_x;
+            d.left[i]           = in_x ? lattice_x.left[j] : lattice_v.left[j];
+            d.right[i]          = in_x ? lattice_x.right[j] : lattice_v.right[j];
+            d.n_cells_global[i] = d.n_cells[i] = in_x ? lattice_x.n_cells[j] : lattice_v.n_cells[j];
+            const bool periodic                = in_x ? lattice_x.periodic : lattice_v.periodic;
+            d.side_kind[i][0] = d.side_kind[i][1] = periodic ? HD_SIDE_PERIODIC_LOCAL : HD_SIDE_DIRICHLET;
+            grid[i]                               = in_x ? gx[j] : gv[j];
+          }
+        if (mm)
+          hd_multi_destroy(mm);
+        mm = nullptr;
+        HD_CALL(hd_multi_create(size_x * size_v, nullptr, &d, grid, &mm));
+        desc = d;
+      }
+      void
+      initialize_dof_vector(DistributedDeviceVector<Number> &vec, const unsigned int = 0, const bool = true, const bool = true) const
+      {
+        vec.reinit(mm);
+      }
+      hd_multi *          get_multi() const { return mm; }
+      const hd_mesh_desc &get_mesh_desc() const { return desc; } // the GLOBAL lattice
+      std::int64_t        n_dofs() const { return hd_multi_n_dofs(mm); }
+      int                 n_bricks() const { return hd_multi_n_gpus(mm); }
+
+    private:
+      CartesianLattice<dim_x> lattice_x;
+      CartesianLattice<dim_v> lattice_v;
+      const int               size_x, size_v;
+      hd_multi *              mm = nullptr;
+      hd_mesh_desc            desc{};
+    };
+
+    // one device pointer per brick
+    template <typename Number>
+    class DistributedDeviceVector
+    {
+    public:
+      DistributedDeviceVector() = default;
+      ~DistributedDeviceVector() { clear(); }
+      DistributedDeviceVector(const DistributedDeviceVector &) = delete;
+      DistributedDeviceVector &operator=(const DistributedDeviceVector &) = delete;
+      void
+      reinit(hd_multi *m)
+      {
+        clear();
+        mm = m;
+        ptrs.assign(hd_multi_n_gpus(mm), nullptr);
+        HD_CALL(hd_multi_vector_alloc(mm, ptrs.data()));
+      }
+      void
+      clear()
+      {
+        if (!ptrs.empty())
+          hd_multi_vector_free(mm, ptrs.data());
+        ptrs.clear();
+      }
+      void *const *bricks() const { return ptrs.data(); }
+      std::int64_t size() const { return hd_multi_n_dofs(mm); }
+      // host transfers in the ordering of the single-GPU lattice
+      void
+      copy_from_host(const std::vector<Number> &h)
+      {
+        if (std::int64_t(h.size()) != size())
+          throw ExcMessage("copy_from_host: size mismatch");
+        HD_CALL(hd_multi_vector_copy_in(mm, ptrs.data(), h.data()));
+      }
+      void
+      copy_to_host(std::vector<Number> &h) const
+      {
+        h.resize(size());
+        HD_CALL(hd_multi_vector_copy_out(mm, ptrs.data(), h.data()));
+      }
+
+    private:
+      hd_multi *          mm = nullptr;
+      std::vector<void *> ptrs;
+    };
+
+    // advection::AdvectionOperation on all bricks (constant velocity; Dirichlet data from a device-side Function)
+    template <int dim_x, int dim_v, typename Number>
+    class AdvectionOperation
+    {
+    public:
+      static const int dim = dim_x + dim_v;
+      explicit AdvectionOperation(const MatrixFree<dim_x, dim_v, Number> &data)
+        : data(data)
+      {}
+      ~AdvectionOperation()
+      {
+        if (op)
+          hd_multi_advection_destroy(op);
+      }
+      void
+      reinit(const std::shared_ptr<advection::BoundaryDescriptor<dim, Number>> boundary_descriptor, const dealii_compat::Tensor<1, dim, Number> &transport_direction,
+             const advection::AdvectionOperationParamters &                   additional_data)
+      {
+        double velocity[HD_MAX_DIM] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < dim; ++i)
+          velocity[i] = transport_direction[i];
+        if (op)
+          hd_multi_advection_destroy(op);
+        op = nullptr;
+        HD_CALL(hd_multi_advection_create(data.get_multi(), additional_data.factor_skew, velocity, &op));
+        const auto &d = data.get_mesh_desc();
+        bool        dirichlet = false;
+        for (int i = 0; i < dim; ++i)
+          dirichlet |= d.side_kind[i][0] == HD_SIDE_DIRICHLET;
+        if (dirichlet)
+          {
+            int id = -1;
+            for (const auto &bc : boundary_descriptor->dirichlet_bc)
+              id = bc.second->device_function_id();
+            if (id < 0)
+              throw ExcNotImplemented("multi-GPU Dirichlet data from a host-only Function");
+            HD_CALL(hd_multi_advection_set_dirichlet_builtin(op, id));
+          }
+      }
+      void
+      apply(DistributedDeviceVector<Number> &dst, const DistributedDeviceVector<Number> &src, const Number current_time)
+      {
+        HD_CALL(hd_multi_advection_apply(op, dst.bricks(), src.bricks(), double(current_time)));
+      }
+      hd_multi_advection *handle() const { return op; }
+      std::string         kernel_name() const { return hd_multi_advection_kernel_name(op); }
+
+    private:
+      const MatrixFree<dim_x, dim_v, Number> &data;
+      hd_multi_advection *                    op = nullptr;
+    };
+
+    template <typename Number>
+    class LowStorageRungeKuttaIntegrator
+    {
+    public:
+      using VectorType = DistributedDeviceVector<Number>;
+      LowStorageRungeKuttaIntegrator(hd_multi *mm, VectorType &vec_Ki, VectorType &vec_Ti, const std::string type)
+        : vec_Ki(vec_Ki)
+        , vec_Ti(vec_Ti)
+      {
+        HD_CALL(hd_multi_lsrk_create(mm, type.c_str(), &rk));
+      }
+      ~LowStorageRungeKuttaIntegrator()
+      {
+        if (rk)
+          hd_multi_lsrk_destroy(rk);
+      }
+      template <int dim_x, int dim_v>
+      void
+      perform_time_step(VectorType &solution, const Number &current_time, const Number &time_step, AdvectionOperation<dim_x, dim_v, Number> &op)
+      {
+        HD_CALL(hd_multi_lsrk_step(rk, op.handle(), solution.bricks(), vec_Ki.bricks(), vec_Ti.bricks(), double(current_time), double(time_step)));
+      }
+
+    private:
+      VectorType &   vec_Ki;
+      VectorType &   vec_Ti;
+      hd_multi_lsrk *rk = nullptr;
+    };
+
+    template <int dim_x, int dim_v, typename Number>
+    void
+    interpolate(const std::shared_ptr<dealii_compat::Function<dim_x + dim_v, Number>> f, const MatrixFree<dim_x, dim_v, Number> &matrix_free, DistributedDeviceVector<Number> &dst)
+    {
+      const int id = f->device_function_id();
+      if (id < 0)
+        throw ExcNotImplemented("multi-GPU interpolation of a host-only Function");
+      HD_CALL(hd_multi_interpolate_builtin(matrix_free.get_multi(), dst.bricks(), id, double(f->get_time())));
+    }
+
+    template <int dim_x, int dim_v, typename Number>
+    std::array<Number, 2>
+    norm_and_error(const std::shared_ptr<dealii_compat::Function<dim_x + dim_v, Number>> f, const MatrixFree<dim_x, dim_v, Number> &matrix_free, const DistributedDeviceVector<Number> &src)
+    {
+      const int id = f->device_function_id();
+      if (id < 0)
+        throw ExcNotImplemented("norm_and_error against a host-only Function");
+      double out[2];
+      HD_CALL(hd_multi_norm_and_error_builtin(matrix_free.get_multi(), src.bricks(), id, double(f->get_time()), out));
+      return {{Number(std::sqrt(out[0])), Number(std::sqrt(out[1]))}};
+    }
+  } // namespace multi
 } // namespace hyperdeal
 
 #ifndef HYPERDEAL_B200_NO_DEALII_ALIAS

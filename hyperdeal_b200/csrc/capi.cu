@@ -1619,6 +1619,68 @@ hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *
   return HD_OK;
 }
 
+// stage time t + c_i dt and the update factors of stage i (time_integrators.templates.h:117-132, :174-182)
+static void
+lsrk_stage_factors(const hd_lsrk *rk, int stage, double dt, double *c, double *fb, double *fa)
+{
+  const int S = (int)rk->bi.size();
+  double    sum_prev_b = 0.0;
+  *c                   = 0.0;
+  for (int s = 1; s <= stage; ++s)
+    {
+      *c = sum_prev_b + rk->ai[s - 1];
+      sum_prev_b += rk->bi[s - 1];
+    }
+  *fb = rk->bi[stage] * dt;
+  *fa = (stage == S - 1) ? 0.0 : rk->ai[stage] * dt;
+}
+
+int
+hd_lsrk_stage_fused(hd_lsrk *rk, hd_advection *op, int stage, void *solution, const void *ti_cur, void *ti_next, const void *ghosts, double t, double dt)
+{
+  HD_REQUIRE(rk && op && solution && ti_cur && ti_next, "null argument");
+  HD_REQUIRE(stage >= 0 && stage < (int)rk->bi.size(), "bad stage");
+  HD_REQUIRE(ti_cur != ti_next && ti_cur != solution && ti_next != solution, "solution, ti_cur and ti_next must be three different vectors");
+  hd_mesh *m = rk->mesh;
+  HD_REQUIRE(m == op->mesh, "integrator and operator belong to different meshes");
+  HD_REQUIRE(!op->d_av, "fused stages need a constant velocity (the phase-space field changes at every stage: hd_lsrk_stage_update)");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  double      c;
+  FusedUpdate fu;
+  fu.enabled = 1;
+  fu.sol     = solution;
+  fu.ti_next = ti_next;
+  lsrk_stage_factors(rk, stage, dt, &c, &fu.fb, &fu.fa);
+  return apply_impl(op, nullptr, ti_cur, ghosts, t + c * dt, fu);
+}
+
+int
+hd_lsrk_stage_overlapped(hd_lsrk *rk, hd_advection *op, int stage, void *solution, const void *ti_cur, void *ti_next, const void *ghosts,
+                         const hd_halo_send *sends, int n_sends, const void *arrival_counters, int target, double t, double dt)
+{
+  HD_REQUIRE(rk && op && solution && ti_cur && ti_next && ghosts && arrival_counters && target > 0, "null argument");
+  HD_REQUIRE(stage >= 0 && stage < (int)rk->bi.size(), "bad stage");
+  HD_REQUIRE(ti_cur != ti_next && ti_cur != solution && ti_next != solution, "solution, ti_cur and ti_next must be three different vectors");
+  hd_mesh *m = rk->mesh;
+  HD_REQUIRE(m == op->mesh, "integrator and operator belong to different meshes");
+  HD_REQUIRE(!op->d_av, "fused stages need a constant velocity");
+  HD_CUDA(cudaSetDevice(m->ctx->device));
+  const bool fast = op->kernel_choice == 2 || op->kernel_choice == 6 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
+  if (!fast)
+    return hd::fail(HD_ERR_UNSUPPORTED, "hd_lsrk_stage_overlapped needs one of the 3D3V degree-3 FP64 kernels; use hd_halo_pack + hd_lsrk_stage_fused");
+  for (int d = 0; d < m->dim; ++d)
+    for (int sd = 0; sd < 2; ++sd)
+      if (m->d.side_kind[d][sd] == HD_SIDE_DIRICHLET)
+        return hd::fail(HD_ERR_UNSUPPORTED, "hd_lsrk_stage_overlapped: Dirichlet sides are not supported");
+  double      c;
+  FusedUpdate fu;
+  fu.enabled = 1;
+  fu.sol     = solution;
+  fu.ti_next = ti_next;
+  lsrk_stage_factors(rk, stage, dt, &c, &fu.fb, &fu.fa);
+  return hd::launch_fast6d(op, nullptr, ti_cur, ghosts, t + c * dt, fu, 3, sends, n_sends, arrival_counters, target);
+}
+
 // ---- VectorTools ------------------------------------------------------------------------------
 int64_t
 hd_mesh_n_dofs_x(const hd_mesh *m)

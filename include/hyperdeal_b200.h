@@ -290,6 +290,55 @@ int hd_lsrk_stage_update(hd_mesh *mesh, void *solution, void *next_Ti, const voi
  * are the two registers the reference's constructor takes; for single-GPU meshes only. */
 int hd_lsrk_step(hd_lsrk *rk, hd_advection *op, void *solution, void *vec_Ki, void *vec_Ti, double t, double dt);
 
+/* One fused LSRK stage on a brick whose ghost faces the CALLER has filled (multi-GPU time stepping: one ghost exchange of the
+ * current Ti per stage, then this call): K = op(ti_cur, t + c_stage dt) is never stored,
+ *   solution += b_stage dt K ;  ti_next = solution_old + a_stage dt K   (not written in the last stage).
+ * solution, ti_cur and ti_next are three different vectors (the neighbours still read ti_cur: ping-pong Ti between the two
+ * registers of the reference's constructor, as hd_lsrk_step does).  ghosts = ghost faces of ti_cur, NULL on an unpartitioned mesh. */
+int hd_lsrk_stage_fused(hd_lsrk *rk, hd_advection *op, int stage, void *solution, const void *ti_cur, void *ti_next, const void *ghosts, double t, double dt);
+/* The same with the ghost exchange INSIDE the kernel (3D3V degree-3 FP64 kernels; arguments as hd_advection_apply_overlapped):
+ * sender CTAs store ti_cur's boundary layers into the neighbours' ghost buffers, interior cells run meanwhile. */
+int hd_lsrk_stage_overlapped(hd_lsrk *rk, hd_advection *op, int stage, void *solution, const void *ti_cur, void *ti_next, const void *ghosts,
+                             const hd_halo_send *sends, int n_sends, const void *arrival_counters, int target, double t, double dt);
+
+/* ---- several GPUs in ONE process (the C++ host's route; one process per GPU goes through hd_halo_pack_ex / *_overlapped) ----
+ * The reference builds its process grid PartitionX x PartitionV in C++ (performance/util/driver.h:133-161,
+ * examples/advection/advection.cc:82-88) and exchanges ghost faces inside LinearAlgebra::SharedMPI::Vector
+ * (matrix_free/vector_partitioner.h:1387-1692).  hd_multi is that for one box: the lattice of global_desc (n_cells_global,
+ * left/right, degree..., side_kind = kind of the DOMAIN boundary per direction: HD_SIDE_PERIODIC_LOCAL or a Dirichlet kind;
+ * n_cells / cell_offset are ignored) is cut into grid[d] equal bricks per direction, brick i (coordinates: i in mixed radix
+ * over grid, direction 0 fastest) lives on devices[i] (NULL: device i), peer access is enabled between all of them, ghost
+ * faces travel as direct stores of the sender's pack kernel into the receiver's ghost buffer, ordered by CUDA events.
+ * Vectors are arrays of n_gpus device pointers (one per brick, the brick's own lattice layout). */
+typedef struct hd_multi           hd_multi;
+typedef struct hd_multi_advection hd_multi_advection;
+typedef struct hd_multi_lsrk      hd_multi_lsrk;
+int         hd_multi_create(int n_gpus, const int *devices, const hd_mesh_desc *global_desc, const int *grid, hd_multi **out);
+int         hd_multi_destroy(hd_multi *mm);
+int         hd_multi_n_gpus(const hd_multi *mm);
+hd_mesh *   hd_multi_mesh(hd_multi *mm, int brick);
+hd_context *hd_multi_context(hd_multi *mm, int brick);
+int64_t     hd_multi_n_dofs(const hd_multi *mm);
+int         hd_multi_synchronize(hd_multi *mm);
+int         hd_multi_vector_alloc(hd_multi *mm, void **ptrs);
+int         hd_multi_vector_free(hd_multi *mm, void *const *ptrs);
+/* scatter / gather between the bricks and ONE host vector in the layout of the unpartitioned lattice */
+int hd_multi_vector_copy_in(hd_multi *mm, void *const *ptrs, const void *host_global);
+int hd_multi_vector_copy_out(hd_multi *mm, void *const *ptrs, void *host_global);
+int hd_multi_interpolate_builtin(hd_multi *mm, void *const *vec, int fn_id, double time);
+/* out = the two SUMS over all bricks (as hd_norm_and_error_builtin: the caller takes the square roots) */
+int hd_multi_norm_and_error_builtin(hd_multi *mm, void *const *vec, int fn_id, double time, double out[2]);
+int hd_multi_advection_create(hd_multi *mm, double skew_factor, const double *velocity, hd_multi_advection **out);
+int hd_multi_advection_destroy(hd_multi_advection *op);
+int hd_multi_advection_set_dirichlet_builtin(hd_multi_advection *op, int fn_id);
+const char *hd_multi_advection_kernel_name(const hd_multi_advection *op);
+/* ghost exchange + AdvectionOperation::apply on every brick (asynchronous on the bricks' streams) */
+int hd_multi_advection_apply(hd_multi_advection *op, void *const *dst, void *const *src, double time);
+int hd_multi_lsrk_create(hd_multi *mm, const char *type, hd_multi_lsrk **out);
+int hd_multi_lsrk_destroy(hd_multi_lsrk *rk);
+/* perform_time_step on all bricks: per stage one ghost exchange of Ti and one fused operator + update launch per brick */
+int hd_multi_lsrk_step(hd_multi_lsrk *rk, hd_multi_advection *op, void *const *solution, void *const *vec_Ki, void *const *vec_Ti, double t, double dt);
+
 /* ---- VectorTools ------------------------------------------------------------------------ */
 /* VectorTools::interpolate (numerics/vector_tools.h:88): nodal values at the GLL points. */
 int hd_interpolate_builtin(hd_mesh *mesh, void *vec, int fn_id, double time);

@@ -95,6 +95,34 @@ def test_cpp_advection_driver_reproduces_golden(drivers, golden_dir, name):
     _check(_parse_stdout(r.stdout), O.parse_golden(os.path.join(golden_dir, name + ".out")), name)
 
 
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+# the reference's own multi-rank tests are the same parameter files run under mpirun -np N with the same expected output
+# (examples/advection/tests/*.mpirun=N.out style); here PartitionX x PartitionV GPUs of one process (hd_multi_*)
+@pytest.mark.gpu
+@pytest.mark.parametrize("px,pv", [(2, 1), (1, 2), (2, 2), (4, 1), (4, 2)])
+@pytest.mark.parametrize("name", ["adv_2D_2D_k3.hyperrectangle_01", "adv_2D_2D_k3.hyperrectangle_03", "adv_2D_2D_k3_q5.hyperrectangle_01", "adv_1D_1D_k3.hyperrectangle_01_rk47"])
+def test_cpp_advection_driver_multi_gpu_golden(drivers, golden_dir, name, px, pv):
+    if _n_gpus() < px * pv:
+        pytest.skip("needs %d GPUs" % (px * pv))
+    env = dict(os.environ, HD_PARTITION_X=str(px), HD_PARTITION_V=str(pv))
+    r = subprocess.run([drivers["advection"], os.path.join(golden_dir, name + ".json")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "bricks: %d" % (px * pv) in r.stdout
+    _check(_parse_stdout(r.stdout), O.parse_golden(os.path.join(golden_dir, name + ".out")), name)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_multi_gpu_driver_fails_loudly_without_gpu(drivers, golden_dir):
+    r = subprocess.run([drivers["advection"], os.path.join(golden_dir, "adv_2D_2D_k3.hyperrectangle_01.json")], capture_output=True, text=True,
+                       env=dict(os.environ, HD_PARTITION_X="2"))
+    assert r.returncode == 1 and "Exception on processing" in r.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"HD_DRIVER_UNFUSED": "1"}, {"HD_DRIVER_HOST_FUNCTIONS": "1"}, {"HD_DRIVER_UNFUSED": "1", "HD_DRIVER_HOST_FUNCTIONS": "1"}])
 def test_cpp_driver_reference_call_structure(drivers, golden_dir, env):
