@@ -434,6 +434,24 @@ class LowStorageRungeKuttaIntegrator:
             fa = 0.0 if stage == len(b) - 1 else a[stage] * time_step
             _check(L.hd_lsrk_stage_update(mf._h, c_void_p(solution), c_void_p(self.Ti), c_void_p(self.Ki), b[stage] * time_step, fa))
 
+    def perform_time_step_partitioned(self, solution: int, current_time: float, time_step: float, op, peer, ctx):
+        """One time step of a brick of a multi-GPU lattice (one process per GPU): per stage ONE kernel
+        (hd_lsrk_stage_overlapped) that packs and sends the boundary layers of the current Ti over NVLink, applies the
+        operator and the stage update; `peer` is the partition.PeerHaloExchange of this brick.  The reference does the
+        same per stage through update_ghost_values + the ECL loop + the update loops (time_integrators.templates.h:93-184)."""
+        L = lib()
+        _check(L.hd_vector_copy(self.mf._h, c_void_p(self.Ti), c_void_p(solution)))
+        cur, nxt = self.Ti, self.Ki
+        for stage in range(self.n_stages()):
+            g, sends, counters, target = peer.begin_fused(ctx, op)
+            arr = (HaloSend * max(len(sends), 1))()
+            for i, (d, s, dp, cp) in enumerate(sends):
+                arr[i].dir, arr[i].side, arr[i].dst, arr[i].arrival_counter = int(d), int(s), c_void_p(dp), c_void_p(cp)
+            _check(L.hd_lsrk_stage_overlapped(self._h, op._h, stage, c_void_p(solution), c_void_p(cur), c_void_p(nxt), c_void_p(g.data_ptr()), arr, len(sends),
+                                              c_void_p(counters), int(target), float(current_time), float(time_step)))
+            peer.consumed(ctx)
+            cur, nxt = nxt, cur
+
     def close(self):
         if self._h:
             lib().hd_lsrk_destroy(self._h)

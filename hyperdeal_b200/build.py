@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhdgpu.so")
 SOURCES = ["capi.cu", "kernels_generic.cu", "kernel_fast6d.cu", "kernel_vp.cu", "poisson_x.cu", "vp_diagnostics.cu", "kernel_tile_global.cu", "multi_gpu.cu"]
-HEADERS = ["hd_internal.h", "basis.hpp", "rounds6d_tasks.cuh", "kernel_rounds6d.cuh", os.path.join("..", "..", "include", "hyperdeal_b200.h")]
+HEADERS = ["hd_internal.h", "basis.hpp", "rounds6d_tasks.cuh", "kernel_rounds6d.cuh", "kernel_vp_tile.cuh", os.path.join("..", "..", "include", "hyperdeal_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

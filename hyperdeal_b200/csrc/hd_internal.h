@@ -110,6 +110,7 @@ struct hd_advection
   // speed-independent coefficient block
   const void *d_av      = nullptr;
   void *      d_vp_coef = nullptr;
+  std::vector<double> h_vp_coef; // host copy (the tile kernels take their matrices as a kernel parameter)
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
   int   row_tile[5] = {-1, -1, -1, -1, -1}; // pipelined kernel: row tile per direction 1..5 (-1 = default, 0 = full extent)

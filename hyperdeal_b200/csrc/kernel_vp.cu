@@ -268,6 +268,35 @@ namespace
       }
   }
 
+#include "kernel_vp_tile.cuh"
+
+  // the tile kernels' coefficient block from the generic one ([dim][Ca | Cabs | La0 | La1 | Labs0 | Labs1]) and the basis
+  inline void
+  vp_tile_coefficients(const hd::Basis1D &b, const int dim, const std::vector<double> &coef, VpTileCoef &cf)
+  {
+    const int blk = 2 * 16 + 4 * 4;
+    for (int d = 0; d < 4; ++d)
+      for (int i = 0; i < 16; ++i)
+        {
+          cf.Ca[d][i]   = d < dim ? coef[(size_t)d * blk + i] : 0.0;
+          cf.Cabs[d][i] = d < dim ? coef[(size_t)d * blk + 16 + i] : 0.0;
+          if (i < 4)
+            {
+              cf.La0[d][i]   = d < dim ? coef[(size_t)d * blk + 32 + i] : 0.0;
+              cf.La1[d][i]   = d < dim ? coef[(size_t)d * blk + 36 + i] : 0.0;
+              cf.Labs0[d][i] = d < dim ? coef[(size_t)d * blk + 40 + i] : 0.0;
+              cf.Labs1[d][i] = d < dim ? coef[(size_t)d * blk + 44 + i] : 0.0;
+            }
+        }
+    for (int i = 0; i < 16; ++i)
+      {
+        cf.S[i]    = (double)b.S[i];
+        cf.Sinv[i] = (double)b.Sinv[i];
+      }
+    for (int i = 0; i < 4; ++i)
+      cf.xq[i] = (double)b.xq[i];
+  }
+
 #ifndef HD_VP_HOST_EMULATION
   template <typename T>
   __global__ void __launch_bounds__(256) k_apply_vp(const VpParams p)
@@ -305,7 +334,7 @@ namespace hd
   vp_upload_coefficients(hd_advection *op)
   {
     hd_mesh *           m = op->mesh;
-    std::vector<double> h;
+    std::vector<double> &h = op->h_vp_coef;
     vp_coefficients(m->basis, m->dim, m->h, op->skew, h);
     HD_CUDA(cudaSetDevice(m->ctx->device));
     if (!op->d_vp_coef)
@@ -347,10 +376,47 @@ namespace hd
     p.fb      = fu.fb;
     p.fa      = fu.fa;
     p.fused   = fu.enabled;
+    const bool f64 = m->d.number_type == HD_F64;
+    // degree 3 with 4 quadrature points in 1D1V / 2D2V: the register-tile kernels (kernel_vp_tile.cuh); kernel choice 1
+    // (hd_advection_set_kernel) keeps the generic one for A/B runs and as the cross-check of the tests
+    if (m->n == 4 && m->nq == 4 && (m->dim == 2 || m->dim == 4) && op->kernel_choice != 1 && !op->h_vp_coef.empty())
+      {
+        VpTileCoef cf;
+        vp_tile_coefficients(m->basis, m->dim, op->h_vp_coef, cf);
+        if (m->dim == 2)
+          {
+            const unsigned grid = (unsigned)((m->ncells + 127) / 128);
+            if (f64)
+              k_vp_tile_1d1v<double><<<grid, 128, 0, m->ctx->stream>>>(p, cf);
+            else
+              k_vp_tile_1d1v<float><<<grid, 128, 0, m->ctx->stream>>>(p, cf);
+            op->last_kernel = "vp_tile_1d1v";
+          }
+        else
+          {
+            constexpr int  WARPS = 2;
+            const size_t   smem  = (size_t)WARPS * VPT_WARP * sizeof(double);
+            const unsigned grid  = (unsigned)((m->ncells + 2 * WARPS - 1) / (2 * WARPS));
+            static bool    attr  = false;
+            if (!attr)
+              {
+                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<double, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<float, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr = true;
+              }
+            if (f64)
+              k_vp_tile_2d2v<double, WARPS><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+            else
+              k_vp_tile_2d2v<float, WARPS><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+            op->last_kernel = "vp_tile_2d2v";
+          }
+        HD_CUDA(cudaGetLastError());
+        op->launches++;
+        return HD_OK;
+      }
     const size_t smem = (6 * (size_t)cap + 2 * (size_t)m->n * m->n) * sizeof(double);
     if (smem > m->ctx->smem_optin)
       return hd::fail(HD_ERR_UNSUPPORTED, "general-velocity kernel: the cell does not fit into shared memory six times");
-    const bool f64 = m->d.number_type == HD_F64;
     if (smem > 48 * 1024)
       {
         if (f64)

@@ -172,7 +172,7 @@ class PeerHaloExchange:
 
     COUNT, READY, ACK = 0, 16, 32  # word offsets of the three flag groups (slot = 2*d+side inside each)
 
-    def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6):
+    def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6, dtype=None):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -180,7 +180,9 @@ class PeerHaloExchange:
         self.part = part
         group = group if group is not None else dist.group.WORLD
         n = max(int(total), 16)
-        self.ghosts = [symm.empty(n, dtype=torch.float64, device=device) for _ in range(2)]
+        dtype = torch.float64 if dtype is None else dtype  # the lattice's number type (hd_mesh_desc.number_type)
+        esize = torch.empty(0, dtype=dtype).element_size()
+        self.ghosts = [symm.empty(n, dtype=dtype, device=device) for _ in range(2)]
         self.flags = symm.empty(64, dtype=torch.int32, device=device)
         for g in self.ghosts:
             g.zero_()
@@ -190,7 +192,7 @@ class PeerHaloExchange:
         self.flag_handle = symm.rendezvous(self.flags, group)
         self.plan = HaloExchange(part, offsets, sizes, needed)
         self.mask = self.plan.send_mask(max_dim)
-        self.bytes_sent = self.plan.bytes_per_exchange[0] * 8
+        self.bytes_sent = self.plan.bytes_per_exchange[0] * esize
         self.flag_ptrs = [int(x) for x in self.flag_handle.buffer_ptrs]
         self.my_flags = self.flag_ptrs[part.rank]
         self.peer_dst, self.fused_sends = [], []
@@ -198,7 +200,7 @@ class PeerHaloExchange:
             ptrs, sends = [0] * (2 * max_dim), []
             for s in self.plan.sends:
                 # my boundary layer (d, side) is the ghost segment (d, 1 - side) of the neighbour behind that side
-                ptrs[2 * s.d + s.side] = int(h.buffer_ptrs[s.peer]) + 8 * offsets[(s.d, 1 - s.side)]
+                ptrs[2 * s.d + s.side] = int(h.buffer_ptrs[s.peer]) + esize * offsets[(s.d, 1 - s.side)]
                 sends.append((s.d, s.side, ptrs[2 * s.d + s.side], self.flag_ptrs[s.peer] + 4 * (self.COUNT + 2 * s.d + (1 - s.side))))
             self.peer_dst.append(ptrs)
             self.fused_sends.append(sends)

@@ -2,8 +2,8 @@
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_check.py
 Every rank owns one brick of a periodic 3D3V k=3 lattice, exchanges upwind ghost faces over NCCL
 (hyperdeal_b200.partition), applies the operator in two parts (interior overlapped with the exchange, then the
-boundary layer) and compares its brick with the same operator applied to the WHOLE lattice on its own GPU
-(single brick, periodic wrap) — which tests/test_apply_gpu.py pins against the oracle.  Prints one 'MGPU OK' line."""
+boundary layer; split and fused-halo variants; three complete fused rk45 steps) and compares its brick with the same
+operator / integrator applied to the WHOLE lattice on its own GPU (single brick, periodic wrap) — which tests/test_apply_gpu.py pins against the oracle.  Prints one 'MGPU OK' line."""
 import os
 import sys
 
@@ -92,6 +92,21 @@ def main():
             torch.cuda.synchronize()
             assert not op.overlap_timed_out()
             rel = max(rel, float(np.max(np.abs(dst.cpu().numpy() - expect)) / np.max(np.abs(expect))))
+            # complete rk45 steps: per stage ONE kernel per GPU (pack + NVLink stores + operator + stage update,
+            # hd_lsrk_stage_overlapped) against the single-GPU fused integrator on the whole lattice
+            a_ki, a_ti = mf_all.initialize_dof_vector(), mf_all.initialize_dof_vector()
+            rk_all = api.LowStorageRungeKuttaIntegrator(mf_all, a_ki, a_ti, "rk45")
+            sol, ki, ti = src.clone(), torch.zeros_like(src), torch.zeros_like(src)
+            rk = api.LowStorageRungeKuttaIntegrator(mf, ki.data_ptr(), ti.data_ptr(), "rk45")
+            time, dt = 0.0, 2e-3
+            for it in range(3):
+                rk_all.perform_time_step(a_src, time, dt, op_all)
+                rk.perform_time_step_partitioned(sol.data_ptr(), time, dt, op, peer, ctx)
+                time += dt
+            torch.cuda.synchronize()
+            assert not op.overlap_timed_out()
+            exp_sol = np.ascontiguousarray(mf_all.copy_out(a_src).reshape(ref_all.shape)[sl]).reshape(-1)
+            rel = max(rel, float(np.max(np.abs(sol.cpu().numpy() - exp_sol)) / np.max(np.abs(exp_sol))))
         t = torch.tensor([rel], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:

@@ -26,7 +26,41 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(so)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
     lib.hd_vp_emulate.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, dp, dp, ctypes.c_double]
+    lib.hd_vp_tile_emulate.argtypes = [dp, dp, dp, ctypes.c_int, ip, dp, dp, ctypes.c_double]
     return lib
+
+
+TILE_CASES = [
+    # dx cells          skew
+    (1, (3, 4), 0.0),
+    (1, (2, 3), 0.5),
+    (1, (1, 1), 0.0),
+    (1, (5, 2), 0.3),
+    (2, (2, 3, 2, 2), 0.0),
+    (2, (3, 2, 2, 3), 0.5),
+    (2, (1, 1, 1, 1), 0.0),       # one cell: every neighbour is the cell itself; the second half of the warp idles
+    (2, (3, 1, 1, 3), 0.3),       # odd number of cells
+    (2, (4, 2, 3, 2), 1.0),
+]
+
+
+@pytest.mark.parametrize("dx,nc,skew", TILE_CASES)
+def test_tile_kernel_source_matches_literal_oracle(emu, dx, nc, skew):
+    """kernel_vp_tile.cuh (degree 3, n_points 4; 1D1V thread-per-cell, 2D2V warp phases) against the oracle's literal kernel"""
+    dim = 2 * dx
+    left, right = (0.0,) * dx + (-1.3,) * dx, (2.0,) * dx + (1.7,) * dx  # v = 0 lies inside a cell
+    vp = V.VlasovPoissonOracle(dx, dx, 3, nc, left, right, nthreads=2)
+    rng = np.random.default_rng(23)
+    a_v = np.ascontiguousarray(rng.standard_normal(vp.adv.a_v_table.shape))
+    orc = O.Oracle(vp.mesh, 3, skew=skew, a_x_table=vp.v_at_q, a_v_table=a_v, nthreads=2)
+    f = np.ascontiguousarray(rng.standard_normal(orc.ndofs))
+    ref = orc.apply(f)
+    out = np.full_like(f, np.nan)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    rc = emu.hd_vp_tile_emulate(f.ctypes.data_as(dp), out.ctypes.data_as(dp), a_v.ctypes.data_as(dp), dx, (ctypes.c_int * dim)(*nc),
+                                (ctypes.c_double * dim)(*left), (ctypes.c_double * dim)(*right), float(skew))
+    assert rc == 0
+    assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
 
 
 CASES = [

@@ -68,6 +68,82 @@ hd_vp_emulate(const double *src, double *dst, const double *a_v, int dim_x, int 
     }
 }
 
+// the degree-3 register-tile kernels (kernel_vp_tile.cuh): 1D1V one "thread" per cell; 2D2V the five phases of a warp, run
+// lane by lane with the warp's shared-memory block emulated (a __syncwarp separates the phases on the device)
+extern "C" int
+hd_vp_tile_emulate(const double *src, double *dst, const double *a_v, int dim_x, const int *ncell, const double *left, const double *right, double skew)
+{
+  try
+    {
+      hd::Basis1D b;
+      b.init(3, 4, false);
+      const int dim = 2 * dim_x;
+      if (dim != 2 && dim != 4)
+        return -2;
+      VpParams  p;
+      double    h[HD_MAX_DIM];
+      long long ncells = 1;
+      for (int d = 0; d < HD_MAX_DIM; ++d)
+        {
+          p.ncell[d]       = d < dim ? ncell[d] : 1;
+          p.cell_offset[d] = 0;
+          p.left[d]        = d < dim ? left[d] : 0.0;
+          h[d] = p.h[d] = d < dim ? (right[d] - left[d]) / ncell[d] : 1.0;
+          if (d < dim)
+            ncells *= ncell[d];
+        }
+      std::vector<double> coef;
+      vp_coefficients(b, dim, h, skew, coef);
+      VpTileCoef cf;
+      vp_tile_coefficients(b, dim, coef, cf);
+      p.src = src;
+      p.dst = dst;
+      p.coef = nullptr;
+      p.basis = nullptr;
+      p.a_v = a_v;
+      p.dim_x = p.dim_v = dim_x;
+      p.n = p.nq = 4;
+      p.nd = dim == 2 ? 16 : 256;
+      p.ncells = ncells;
+      p.cap = 0;
+      p.sol = p.ti_next = nullptr;
+      p.fb = p.fa = 0.0;
+      p.fused = 0;
+      if (dim == 2)
+        {
+          for (long long cell = 0; cell < ncells; ++cell)
+            vpt2_cell<double>(p, cf, cell);
+          return 0;
+        }
+      std::vector<double> sm(VPT_WARP, std::nan(""));
+      for (long long cell0 = 0; cell0 < ncells; cell0 += 2)
+        {
+          Vpt4Lane L[32];
+          double   R[32][4][4];
+          auto     cb   = [&](int lane) { return sm.data() + (lane >> 4) * VPT_CELL; };
+          auto     mine = [&](int lane) { return std::min(cell0 + (lane >> 4), ncells - 1); };
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase1<double>(p, cf, L[lane], cb(lane), lane & 15, mine(lane));
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase2a(L[lane], cb(lane), lane & 15);
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase1b<double>(p, cf, L[lane], cb(lane), lane & 15);
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase2b(p, cf, L[lane], cb(lane), lane & 15, R[lane]);
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase2c(L[lane], cb(lane), lane & 15, R[lane]);
+          for (int lane = 0; lane < 32; ++lane)
+            if (cell0 + (lane >> 4) < ncells)
+              vpt4_phase3<double>(p, cf, L[lane], cb(lane), lane & 15);
+        }
+      return 0;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}
+
 // ---- x-space field solve (poisson_x.cu): operator, mass matrix and gradient bodies, one sequential "thread" per cell
 #include "../hyperdeal_b200/csrc/poisson_x.cu"
 

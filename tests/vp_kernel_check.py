@@ -17,11 +17,22 @@ CASES = [
     # dx dv cells                   nq    skew  dtype
     (1, 1, (3, 4), None, 0.0, np.float64),
     (1, 1, (2, 3), None, 0.5, np.float64),
+    (1, 1, (131, 5), None, 0.3, np.float64),            # more than one CTA of the thread-per-cell kernel, ragged tail
     (2, 2, (2, 3, 2, 2), None, 0.0, np.float64),
+    (2, 2, (3, 1, 1, 3), None, 0.5, np.float64),        # odd number of cells: half a warp without a cell
+    (2, 2, (5, 4, 3, 4), None, 1.0, np.float64),
     (2, 2, (2, 2, 3, 2), 5, 0.3, np.float64),
     (3, 3, (2, 1, 2, 2, 2, 1), None, 0.0, np.float64),
     (2, 2, (3, 2, 2, 2), None, 0.0, np.float32),
+    (1, 1, (7, 3), None, 0.0, np.float32),
 ]
+
+
+def expected_kernel(dx, nq):
+    """degree 3 with 4 quadrature points in 1D1V / 2D2V: the register-tile kernels (kernel_vp_tile.cuh); else the generic one"""
+    if nq in (None, 4) and dx in (1, 2):
+        return "vp_tile_1d1v" if dx == 1 else "vp_tile_2d2v"
+    return "vp_generic"
 
 
 def main():
@@ -46,17 +57,22 @@ def main():
         op.set_phase_space_velocity(d_av.data_ptr())
         d_src, d_dst = mf.initialize_dof_vector(), mf.initialize_dof_vector()
         mf.copy_in(d_src, f)
-        op.apply(d_dst, d_src, 0.0)
-        out = mf.copy_out(d_dst).astype(np.float64)
-        rel = float(np.max(np.abs(out - ref)) / np.max(np.abs(ref)))
         tol = 1e-12 if dtype == np.float64 else 1e-5
-        ok = rel <= tol and op.kernel_name == "vp_generic"
-        bad += not ok
-        print("VPK %s dx=%d dv=%d cells=%s nq=%s skew=%g %s kernel=%s rel=%.3e" % ("OK" if ok else "FAIL", dx, dv, nc, nq, skew, np.dtype(dtype).name, op.kernel_name, rel), flush=True)
+        for choice in (0, 1):  # automatic choice, then the generic kernel
+            op.set_kernel(choice)
+            mf.copy_in(d_dst, np.zeros(orc.ndofs))
+            op.apply(d_dst, d_src, 0.0)
+            out = mf.copy_out(d_dst).astype(np.float64)
+            rel = float(np.max(np.abs(out - ref)) / np.max(np.abs(ref)))
+            want = expected_kernel(dx, nq) if choice == 0 else "vp_generic"
+            ok = rel <= tol and op.kernel_name == want
+            bad += not ok
+            print("VPK %s dx=%d dv=%d cells=%s nq=%s skew=%g %s kernel=%s rel=%.3e" % ("OK" if ok else "FAIL", dx, dv, nc, nq, skew, np.dtype(dtype).name, op.kernel_name, rel), flush=True)
+        op.set_kernel(0)
         # back to the constant velocity: the shipped kernels again
         op.set_phase_space_velocity(None)
         op.apply(d_dst, d_src, 0.0)
-        assert op.kernel_name != "vp_generic"
+        assert not op.kernel_name.startswith("vp_")
     sys.exit(1 if bad else 0)
 
 
