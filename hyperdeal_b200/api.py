@@ -434,6 +434,25 @@ class LowStorageRungeKuttaIntegrator:
             fa = 0.0 if stage == len(b) - 1 else a[stage] * time_step
             _check(L.hd_lsrk_stage_update(mf._h, c_void_p(solution), c_void_p(self.Ti), c_void_p(self.Ki), b[stage] * time_step, fa))
 
+    def perform_time_step_staged(self, solution: int, current_time: float, time_step: float, op, prepare):
+        """Fused stages with a right-hand side that depends on the stage vector (Vlasov-Poisson): before every stage
+        `prepare(ti_ptr, stage_time)` refreshes the operator's velocity field from the current stage vector (rho -> Poisson ->
+        grad(phi) table), then ONE kernel applies the operator and the stage update (hd_lsrk_stage_fused).  Same numbers as
+        perform_time_step with a callable; one streaming kernel less per stage."""
+        L = lib()
+        b, a = self.coefficients()
+        _check(L.hd_vector_copy(self.mf._h, c_void_p(self.Ti), c_void_p(solution)))
+        cur, nxt = self.Ti, self.Ki
+        sum_prev_b = 0.0
+        for stage in range(len(b)):
+            c = 0.0
+            if stage > 0:
+                c = sum_prev_b + a[stage - 1]
+                sum_prev_b += b[stage - 1]
+            prepare(cur, current_time + c * time_step)
+            _check(L.hd_lsrk_stage_fused(self._h, op._h, stage, c_void_p(solution), c_void_p(cur), c_void_p(nxt), None, float(current_time), float(time_step)))
+            cur, nxt = nxt, cur
+
     def perform_time_step_partitioned(self, solution: int, current_time: float, time_step: float, op, peer, ctx):
         """One time step of a brick of a multi-GPU lattice (one process per GPU): per stage ONE kernel
         (hd_lsrk_stage_overlapped) that packs and sends the boundary layers of the current Ti over NVLink, applies the

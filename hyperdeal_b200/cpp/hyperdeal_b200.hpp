@@ -809,6 +809,33 @@ namespace hyperdeal
       HD_CALL(hd_lsrk_step(rk, op.handle(), solution.begin(), vec_Ki.begin(), vec_Ti.begin(), double(current_time), double(time_step)));
     }
 
+    // staged fused path for a right-hand side that depends on the stage vector (Vlasov-Poisson, application.h:516-600):
+    // `prepare(stage_vector, stage_time)` refreshes the operator's velocity field (rho -> Poisson -> grad(phi)), then ONE
+    // kernel applies the operator and the stage update (hd_lsrk_stage_fused); the stage vector alternates between vec_Ti
+    // and vec_Ki.  Same numbers as the std::function path, one streaming kernel less per stage.
+    template <int dim_x, int dim_v, int degree, int n_points, typename VelocityField>
+    void
+    perform_time_step(VectorType &solution, const Number &current_time, const Number &time_step,
+                      advection::AdvectionOperation<dim_x, dim_v, degree, n_points, Number, VectorType, VelocityField> &op,
+                      const std::function<void(const VectorType &, const Number)> &                                       prepare)
+    {
+      vec_Ti.copy_locally_owned_data_from(solution);
+      VectorType *cur = &vec_Ti, *nxt = &vec_Ki;
+      double      sum_previous_bi = 0.0;
+      for (unsigned int stage = 0; stage < bi.size(); ++stage)
+        {
+          double c_i = 0.0;
+          if (stage > 0)
+            {
+              c_i = sum_previous_bi + ai[stage - 1];
+              sum_previous_bi += bi[stage - 1];
+            }
+          prepare(*cur, Number(current_time + c_i * time_step));
+          HD_CALL(hd_lsrk_stage_fused(rk, op.handle(), int(stage), solution.begin(), cur->begin(), nxt->begin(), nullptr, double(current_time), double(time_step)));
+          std::swap(cur, nxt);
+        }
+    }
+
     unsigned int n_stages() const { return bi.size(); }
 
   private:

@@ -124,10 +124,21 @@ namespace hyperdeal
         LowStorageRungeKuttaIntegrator<Number, VectorType> time_integrator(vct_Ki, vct_Ti, rk_type, true);
         bool                                               clear_diag_file = true;
         unsigned int                                       n_total_poisson_iterations = 0;
+        // HD_DRIVER_UNFUSED=1: the reference's call structure (std::function right-hand side, stage update as its own kernel)
+        const bool unfused = std::getenv("HD_DRIVER_UNFUSED") != nullptr;
 
         const unsigned int time_steps = time_loop.loop(
           vct_solution,
-          [&](auto &solution, const auto cur_time, const auto time_step, const auto &runnable) { time_integrator.perform_time_step(solution, cur_time, time_step, runnable); },
+          [&](auto &solution, const auto cur_time, const auto time_step, const auto &runnable) {
+            if (unfused)
+              time_integrator.perform_time_step(solution, cur_time, time_step, runnable);
+            else
+              // per stage: refresh the field from the stage vector, then one kernel for operator + stage update
+              time_integrator.perform_time_step(solution, cur_time, time_step, *advection_operation, [&](const VectorType &src, const Number) {
+                VectorTools::velocity_space_integration<degree, n_points>(*matrix_free, particle_density, src, 0, 0, 2);
+                n_total_poisson_iterations += poisson_solver->solve(*negative_electric_field, particle_density);
+              });
+          },
           [&](const VectorType &src, VectorType &dst, const Number cur_time) {
             // steps 1-5 of application.h:516-600
             VectorTools::velocity_space_integration<degree, n_points>(*matrix_free, particle_density, src, 0, 0, 2);

@@ -1643,7 +1643,8 @@ hd_lsrk_stage_fused(hd_lsrk *rk, hd_advection *op, int stage, void *solution, co
   HD_REQUIRE(ti_cur != ti_next && ti_cur != solution && ti_next != solution, "solution, ti_cur and ti_next must be three different vectors");
   hd_mesh *m = rk->mesh;
   HD_REQUIRE(m == op->mesh, "integrator and operator belong to different meshes");
-  HD_REQUIRE(!op->d_av, "fused stages need a constant velocity (the phase-space field changes at every stage: hd_lsrk_stage_update)");
+  // (a phase-space velocity field is allowed here: the caller refreshes it from ti_cur before every stage — the
+  // Vlasov-Poisson right-hand side, examples/vlasov_poisson/include/application.h:516-600)
   HD_CUDA(cudaSetDevice(m->ctx->device));
   double      c;
   FusedUpdate fu;

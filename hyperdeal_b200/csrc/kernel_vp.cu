@@ -309,6 +309,29 @@ namespace
 
 #ifndef HD_VP_HOST_EMULATION
 
+namespace
+{
+  template <int WARPS, int MINB>
+  int
+  launch_vp_tile_2d2v(hd_mesh *m, const VpParams &p, const VpTileCoef &cf, const bool f64)
+  {
+    const size_t   smem = (size_t)WARPS * VPT_WARP * sizeof(double);
+    const unsigned grid = (unsigned)((m->ncells + 2 * WARPS - 1) / (2 * WARPS));
+    if (smem > 48 * 1024) // (per device, so not cached in a static)
+      {
+        if (f64)
+          HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<double, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+          HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<float, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      }
+    if (f64)
+      k_vp_tile_2d2v<double, WARPS, MINB><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+    else
+      k_vp_tile_2d2v<float, WARPS, MINB><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+    return HD_OK;
+  }
+} // namespace
+
 namespace hd
 {
   bool
@@ -379,7 +402,7 @@ namespace hd
     const bool f64 = m->d.number_type == HD_F64;
     // degree 3 with 4 quadrature points in 1D1V / 2D2V: the register-tile kernels (kernel_vp_tile.cuh); kernel choice 1
     // (hd_advection_set_kernel) keeps the generic one for A/B runs and as the cross-check of the tests
-    if (m->n == 4 && m->nq == 4 && (m->dim == 2 || m->dim == 4) && op->kernel_choice != 1 && !op->h_vp_coef.empty())
+    if (m->n == 4 && m->nq == 4 && (m->dim == 2 || m->dim == 4) && op->kernel_choice != 1 && !op->h_vp_coef.empty() && m->ncells < (1ll << 31))
       {
         VpTileCoef cf;
         vp_tile_coefficients(m->basis, m->dim, op->h_vp_coef, cf);
@@ -394,20 +417,27 @@ namespace hd
           }
         else
           {
-            constexpr int  WARPS = 2;
-            const size_t   smem  = (size_t)WARPS * VPT_WARP * sizeof(double);
-            const unsigned grid  = (unsigned)((m->ncells + 2 * WARPS - 1) / (2 * WARPS));
-            static bool    attr  = false;
-            if (!attr)
-              {
-                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<double, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_2d2v<float, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr = true;
-              }
-            if (f64)
-              k_vp_tile_2d2v<double, WARPS><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+            // CTA shape (warps, minimum CTAs per SM -> register cap), HD_VP_TILE_VARIANT.  Shared memory (21 KiB per warp)
+            // would allow 10 warps per SM, but more than 8 warps (two per SM sub-partition) cap the registers at 168 and the
+            // kernel spills; measured on 32^4 cells (profiles/r02_vp_tile_variants.txt): 0 (default) 2 warps x 4 CTAs, 254
+            // registers: 94.0 GDoF/s; 1: 2 x 5 (168 + spills): 83.5; 2: 5 x 2: 76.4; 3: 3 x 3: 82.5; 4: 4 x 2: 93.4
+            static const int variant = [] {
+              const char *e = getenv("HD_VP_TILE_VARIANT");
+              return e ? atoi(e) : 0;
+            }();
+            int rc;
+            if (variant == 1)
+              rc = launch_vp_tile_2d2v<2, 5>(m, p, cf, f64);
+            else if (variant == 2)
+              rc = launch_vp_tile_2d2v<5, 2>(m, p, cf, f64);
+            else if (variant == 3)
+              rc = launch_vp_tile_2d2v<3, 3>(m, p, cf, f64);
+            else if (variant == 4)
+              rc = launch_vp_tile_2d2v<4, 2>(m, p, cf, f64);
             else
-              k_vp_tile_2d2v<float, WARPS><<<grid, WARPS * 32, smem, m->ctx->stream>>>(p, cf);
+              rc = launch_vp_tile_2d2v<2, 4>(m, p, cf, f64);
+            if (rc != HD_OK)
+              return rc;
             op->last_kernel = "vp_tile_2d2v";
           }
         HD_CUDA(cudaGetLastError());

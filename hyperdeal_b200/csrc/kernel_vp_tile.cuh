@@ -16,12 +16,14 @@
 //     V role: lane = (x0, x1), tile over (v0, v1)
 // exchanging tiles through its private shared-memory buffers (tile stride 18 doubles: the 128-bit X-tile accesses and the
 // 64-bit V-tile accesses are both conflict-free).  Only __syncwarp — no block barrier, warps drift freely.
-//     phase 1 : X: W = S S u -> BW;  one neighbour face tile per lane: S S -> BF;  P0/Q0 = Ca_0/Cabs_0 u + traces -> BP/BQ;
+//     phase 0 : coalesced fetch of the cell, the 16 face tiles of the v-neighbours and the x-traces -> BU, BF, TX
+//     phase 1 : X: W = S S u -> BW (over BU);  face tiles: S S in place;  P0/Q0 = Ca_0/Cabs_0 u + traces -> BP/BQ;
 //               Ma/Mabs entries -> BM
 //     phase 2a: V: OX  = Ma_0 P0 + Mabs_0 Q0                       (v0 sweep)
-//     phase 1': X: P1/Q1 (x1 sweep) -> BP/BQ
+//     phase 1b: X: P1/Q1 (x1 sweep) -> BP/BQ
 //     phase 2b: V: OX += Ma_1 P1 + Mabs_1 Q1;  R = sum_d (G_d Ca_d + |G_d| Cabs_d) W + traces;  R -> BP, OX -> BQ
-//     phase 3 : X: out = Sinv Sinv R + OX -> dst (or the fused LSRK update), 128 B per lane
+//     phase 3 : X: out = Sinv Sinv R + OX -> buffer 0
+//     phase 4 : coalesced store of the cell (or the fused LSRK update)
 // 1D1V: one thread per cell, the whole 4x4 cell in registers.
 //
 // The phase functions are plain host/device code (lane and buffers as arguments): tests/vp_emulation_harness.cpp runs them
@@ -43,7 +45,7 @@ struct VpTileCoef
 
 constexpr int VPT_TS   = 18;          // tile stride (doubles)
 constexpr int VPT_BUF  = 16 * VPT_TS; // one cell buffer
-constexpr int VPT_CELL = 4 * VPT_BUF + 64; // BW, BF, BP, BQ + BM (Ma_0, Mabs_0, Ma_1, Mabs_1)
+constexpr int VPT_CELL = 4 * VPT_BUF + 64 + 128; // BU/BW, BF, BP, BQ + BM (Ma_0, Mabs_0, Ma_1, Mabs_1) + TX (traces: 2 sides x 64)
 constexpr int VPT_WARP = 2 * VPT_CELL;
 
 // out[b][a] (+)= sum_j M[a * 4 + j] in[b][j]: sweep along the fast tile index
@@ -176,60 +178,174 @@ vpt_neighbours(const VpParams &p, const long long cell, const int cd, const long
   hi = cd == p.ncell[d] - 1 ? cell - (long long)(p.ncell[d] - 1) * cstr : cell + cstr;
 }
 
+// two consecutive values from global memory / to global memory (one 16-byte access for double)
+template <typename T>
+HD_VPT_FN void
+vpt_load2(const T *p, double &a, double &b)
+{
+#ifdef HD_VP_HOST_EMULATION
+  a = double(p[0]);
+  b = double(p[1]);
+#else
+  if (sizeof(T) == 8)
+    {
+      const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+      a               = v.x;
+      b               = v.y;
+    }
+  else
+    {
+      const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+      a              = v.x;
+      b              = v.y;
+    }
+#endif
+}
+
+template <typename T>
+HD_VPT_FN void
+vpt_store2(T *p, const double a, const double b)
+{
+#ifdef HD_VP_HOST_EMULATION
+  p[0] = T(a);
+  p[1] = T(b);
+#else
+  if (sizeof(T) == 8)
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+  else
+    *reinterpret_cast<float2 *>(p) = make_float2(float(a), float(b));
+#endif
+}
+
+// two consecutive doubles in shared memory (16-byte aligned: even index)
+HD_VPT_FN void
+vpt_sm_store2(double *q, const double a, const double b)
+{
+#ifdef HD_VP_HOST_EMULATION
+  q[0] = a;
+  q[1] = b;
+#else
+  *reinterpret_cast<double2 *>(q) = make_double2(a, b);
+#endif
+}
+
+HD_VPT_FN void
+vpt_sm_load2(const double *q, double &a, double &b)
+{
+#ifdef HD_VP_HOST_EMULATION
+  a = q[0];
+  b = q[1];
+#else
+  const double2 v = *reinterpret_cast<const double2 *>(q);
+  a               = v.x;
+  b               = v.y;
+#endif
+}
+
 // per-lane state that lives across the phases of the 2D2V kernel
 struct Vpt4Lane
 {
   double    U[4][4];  // X role: the lane's tile of u
   double    OX[4][4]; // V role: x-direction part of the result
+  double    x1[2][2][2]; // this lane's share of the x_1 traces (fetched in phase 0, staged in phase 1b): [side][piece][2 values]
   long long cell;
   int       c[4];
   long long cstr[4];
 };
 
 // ---- 2D2V ---------------------------------------------------------------------------------------------------------------
-// `cb` = the shared-memory block of this lane's cell (VPT_CELL doubles), t = lane within the cell (0..15)
+// `cb` = the shared-memory block of this lane's cell (VPT_CELL doubles), t = lane within the cell (0..15).
+// Phase 0: the 16 lanes of a cell fetch everything the cell needs from global memory with COALESCED accesses (consecutive
+// lanes = consecutive 16-byte pieces) and lay it out tile by tile in shared memory: the cell (16 tiles), the 16 face tiles of
+// the four v-neighbours, the x_0 traces (64 values per side, 8 bytes out of every 32) — a lane reading "its" 128-byte tile
+// directly costs one L1 wavefront per lane and request, which made the first version of this kernel L1-bound (ncu:
+// l1tex data pipe 96 %, 8x sector amplification).
 template <typename T>
 HD_VPT_FN void
-vpt4_phase1(const VpParams &p, const VpTileCoef &cf, Vpt4Lane &L, double *cb, const int t, const long long cell)
+vpt4_phase0(const VpParams &p, Vpt4Lane &L, double *cb, const int t, const long long cell)
 {
-  double *BW = cb, *BF = cb + VPT_BUF, *BP = cb + 2 * VPT_BUF, *BQ = cb + 3 * VPT_BUF, *BM = cb + 4 * VPT_BUF;
+  double * BU = cb, *BF = cb + VPT_BUF, *TX = cb + 4 * VPT_BUF + 64;
   const T *src = static_cast<const T *>(p.src);
   L.cell       = cell;
   {
-    long long r = cell, m = 1;
+    // (32-bit decode: a lattice of 2 KiB cells has far fewer than 2^31 of them; checked at launch)
+    unsigned  r = (unsigned)cell;
+    long long m = 1;
 #pragma unroll
     for (int d = 0; d < 4; ++d)
       {
-        L.c[d] = int(r % p.ncell[d]);
-        r /= p.ncell[d];
-        L.cstr[d] = m;
+        const unsigned nc = (unsigned)p.ncell[d], q = r / nc;
+        L.c[d]            = int(r - q * nc);
+        r                 = q;
+        L.cstr[d]         = m;
         m *= p.ncell[d];
       }
   }
-  vpt_load16(src + cell * 256 + 16 * t, L.U);
-  // the neighbour face tile of this lane: face f = (v-direction, side), o = index along the other v-direction
-  double F[4][4];
-  {
-    const int f = t >> 2, o = t & 3, dv = f >> 1, side = f & 1;
-    long long lo, hi;
-    // (selects, not L.c[2 + dv]: a dynamically indexed member would put the whole lane state into local memory)
-    const int       cd = dv == 0 ? L.c[2] : L.c[3], nc = dv == 0 ? p.ncell[2] : p.ncell[3];
-    const long long cs = dv == 0 ? L.cstr[2] : L.cstr[3];
-    lo                 = cd == 0 ? cell + (long long)(nc - 1) * cs : cell - cs;
-    hi                 = cd == nc - 1 ? cell - (long long)(nc - 1) * cs : cell + cs;
-    const int layer = side ? 0 : 3; // the neighbour's layer that touches the shared face
-    const int tvn   = dv == 0 ? layer + 4 * o : o + 4 * layer;
-    vpt_load16(src + (side ? hi : lo) * 256 + 16 * tvn, F);
-  }
-  // x_0 traces of the lane's tile: 4 values (x1) per side
-  long long lo0, hi0;
-  vpt_neighbours(p, cell, L.c[0], L.cstr[0], 0, lo0, hi0);
+  long long nb[4][2]; // [direction][side]
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    vpt_neighbours(p, cell, L.c[d], L.cstr[d], d, nb[d][0], nb[d][1]);
+  double u[8][2], f[8][2], tx[4][2];
+  // the cell: piece k = 16 i + t holds values 2k, 2k + 1
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    vpt_load2(src + cell * 256 + 2 * (16 * i + t), u[i][0], u[i][1]);
+  // face tiles: tile ft = 2 i + (t >> 3) = (face f = i >> 1, o = ft & 3); face f = (v-direction f >> 1, side f & 1)
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    {
+      const int ft = 2 * i + (t >> 3), o = ft & 3, dv = i >> 2, side = (i >> 1) & 1;
+      const int layer = side ? 0 : 3; // the neighbour's layer that touches the shared face
+      const int tvn   = dv == 0 ? layer + 4 * o : o + 4 * layer;
+      vpt_load2(src + nb[2 + dv][side] * 256 + 16 * tvn + 2 * (t & 7), f[i][0], f[i][1]);
+    }
+  // x_0 traces: value k = 16 i + t of a side belongs to tile k >> 2, b = k & 3 (element 3 + 4 b resp. 4 b of that tile)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    {
+      const int k = 16 * i + t;
+      tx[i][0]    = double(src[nb[0][0] * 256 + 16 * (k >> 2) + 3 + 4 * (k & 3)]);
+      tx[i][1]    = double(src[nb[0][1] * 256 + 16 * (k >> 2) + 4 * (k & 3)]);
+    }
+  // x_1 traces: piece k = 16 i + t (i = 0, 1) = values 2 (k & 1), +1 of the 4 that tile k >> 1 contributes (elements 12..15 of
+  // the lower neighbour's tile, 0..3 of the upper one's); kept in registers until phase 1b
+#pragma unroll
+  for (int side = 0; side < 2; ++side)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      {
+        const int k = 16 * i + t;
+        vpt_load2(src + nb[1][side] * 256 + 16 * (k >> 1) + (side ? 0 : 12) + 2 * (k & 1), L.x1[side][i][0], L.x1[side][i][1]);
+      }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    {
+      const int k = 16 * i + t;
+      vpt_sm_store2(BU + (k >> 3) * VPT_TS + 2 * (k & 7), u[i][0], u[i][1]);
+      vpt_sm_store2(BF + (k >> 3) * VPT_TS + 2 * (k & 7), f[i][0], f[i][1]);
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    {
+      TX[16 * i + t]      = tx[i][0];
+      TX[64 + 16 * i + t] = tx[i][1];
+    }
+}
+
+template <typename T>
+HD_VPT_FN void
+vpt4_phase1(const VpParams &p, const VpTileCoef &cf, Vpt4Lane &L, double *cb, const int t)
+{
+  double *BW = cb, *BF = cb + VPT_BUF, *BP = cb + 2 * VPT_BUF, *BQ = cb + 3 * VPT_BUF, *BM = cb + 4 * VPT_BUF, *TX = BM + 64;
+  double  F[4][4];
+  vpt_load_x(BW, t, L.U); // (the staged cell; W overwrites it tile by tile below)
+  vpt_load_x(BF, t, F);
   double tl[4], th[4];
 #pragma unroll
   for (int b = 0; b < 4; ++b)
     {
-      tl[b] = double(src[lo0 * 256 + 16 * t + 3 + 4 * b]);
-      th[b] = double(src[hi0 * 256 + 16 * t + 4 * b]);
+      tl[b] = TX[4 * t + b];
+      th[b] = TX[64 + 4 * t + b];
     }
   // Ma / Mabs of both x-directions: entry (i, j) = t of each (the same for all cells with this v-coordinate)
   {
@@ -290,20 +406,31 @@ vpt4_phase2a(Vpt4Lane &L, const double *cb, const int t)
   vpt_sweep_a<true>(M, A, L.OX);
 }
 
-template <typename T>
+// phase 1b, first half: the x_1 traces fetched in phase 0 go to the (now free) trace buffer; a __syncwarp follows
 HD_VPT_FN void
-vpt4_phase1b(const VpParams &p, const VpTileCoef &cf, Vpt4Lane &L, double *cb, const int t)
+vpt4_phase1b_stage(const Vpt4Lane &L, double *cb, const int t)
 {
-  double * BP  = cb + 2 * VPT_BUF, *BQ = cb + 3 * VPT_BUF;
-  const T *src = static_cast<const T *>(p.src);
-  long long lo1, hi1;
-  vpt_neighbours(p, L.cell, L.c[1], L.cstr[1], 1, lo1, hi1);
-  double tl[4], th[4];
+  double *TX = cb + 4 * VPT_BUF + 64;
+#pragma unroll
+  for (int side = 0; side < 2; ++side)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      {
+        const int k = 16 * i + t;
+        vpt_sm_store2(TX + 64 * side + 4 * (k >> 1) + 2 * (k & 1), L.x1[side][i][0], L.x1[side][i][1]);
+      }
+}
+
+HD_VPT_FN void
+vpt4_phase1b(const VpTileCoef &cf, Vpt4Lane &L, double *cb, const int t)
+{
+  double *BP = cb + 2 * VPT_BUF, *BQ = cb + 3 * VPT_BUF, *TX = cb + 4 * VPT_BUF + 64;
+  double  tl[4], th[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
     {
-      tl[a] = double(src[lo1 * 256 + 16 * t + 12 + a]);
-      th[a] = double(src[hi1 * 256 + 16 * t + a]);
+      tl[a] = TX[4 * t + a];
+      th[a] = TX[64 + 4 * t + a];
     }
   double A[4][4], B[4][4];
   vpt_sweep_b<false>(cf.Ca[1], L.U, A);
@@ -425,16 +552,53 @@ vpt_store_result(const VpParams &p, const long long g, const double (&O)[4][4])
     }
 }
 
-template <typename T>
+// X role: the result tile goes to shared memory (buffer 0: W is no longer needed) for the coalesced store of phase 4
 HD_VPT_FN void
-vpt4_phase3(const VpParams &p, const VpTileCoef &cf, const Vpt4Lane &L, const double *cb, const int t)
+vpt4_phase3(const VpTileCoef &cf, double *cb, const int t)
 {
   double A[4][4], B[4][4], O[4][4];
   vpt_load_x(cb + 2 * VPT_BUF, t, A);
   vpt_load_x(cb + 3 * VPT_BUF, t, O);
   vpt_sweep_a<false>(cf.Sinv, A, B);
   vpt_sweep_b<true>(cf.Sinv, B, O);
-  vpt_store_result<T>(p, L.cell * 256 + 16 * t, O);
+  vpt_store_x(cb, t, O);
+}
+
+// coalesced store (or the fused LSRK update): piece k = 16 i + t holds values 2k, 2k + 1 of the cell
+template <typename T>
+HD_VPT_FN void
+vpt4_phase4(const VpParams &p, const Vpt4Lane &L, const double *cb, const int t)
+{
+  T *             dst = static_cast<T *>(p.dst), *sol = static_cast<T *>(p.sol), *tin = static_cast<T *>(p.ti_next);
+  const long long g0  = L.cell * 256;
+  if (p.fused)
+    {
+      double s[8][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        vpt_load2(sol + g0 + 2 * (16 * i + t), s[i][0], s[i][1]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        {
+          const int k = 16 * i + t;
+          double    v0, v1;
+          vpt_sm_load2(cb + (k >> 3) * VPT_TS + 2 * (k & 7), v0, v1);
+          vpt_store2(sol + g0 + 2 * k, s[i][0] + p.fb * v0, s[i][1] + p.fb * v1);
+          if (p.fa != 0.0)
+            vpt_store2(tin + g0 + 2 * k, s[i][0] + p.fa * v0, s[i][1] + p.fa * v1);
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        {
+          const int k = 16 * i + t;
+          double    v0, v1;
+          vpt_sm_load2(cb + (k >> 3) * VPT_TS + 2 * (k & 7), v0, v1);
+          vpt_store2(dst + g0 + 2 * k, v0, v1);
+        }
+    }
 }
 
 // ---- 1D1V: one thread per cell; tile U[v0][x0] ------------------------------------------------------------------------------
@@ -443,7 +607,7 @@ HD_VPT_FN void
 vpt2_cell(const VpParams &p, const VpTileCoef &cf, const long long cell)
 {
   const T * src = static_cast<const T *>(p.src);
-  const int c0 = int(cell % p.ncell[0]), c1 = int(cell / p.ncell[0]);
+  const int c1 = int((unsigned)cell / (unsigned)p.ncell[0]), c0 = int((unsigned)cell - (unsigned)c1 * (unsigned)p.ncell[0]);
   long long lo0, hi0, lo1, hi1;
   vpt_neighbours(p, cell, c0, 1, 0, lo0, hi0);
   vpt_neighbours(p, cell, c1, p.ncell[0], 1, lo1, hi1);
@@ -517,9 +681,10 @@ vpt2_cell(const VpParams &p, const VpTileCoef &cf, const long long cell)
 }
 
 #ifndef HD_VP_HOST_EMULATION
-// 2D2V: WARPS warps per CTA, two cells per warp
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_vp_tile_2d2v(const VpParams p, const __grid_constant__ VpTileCoef cf)
+// 2D2V: WARPS warps per CTA, two cells per warp; MINB CTAs per SM bound the register allocation (12 warps per SM = 168
+// registers, no spills)
+template <typename T, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_vp_tile_2d2v(const VpParams p, const __grid_constant__ VpTileCoef cf)
 {
   extern __shared__ double sm[];
   const int       lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 15;
@@ -530,19 +695,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_vp_tile_2d2v(const VpParams p, c
   const bool      live = cell < p.ncells;
   const long long mine = live ? cell : p.ncells - 1;
   Vpt4Lane        L;
-  vpt4_phase1<T>(p, cf, L, cb, t, mine);
+  vpt4_phase0<T>(p, L, cb, t, mine);
+  __syncwarp();
+  vpt4_phase1<T>(p, cf, L, cb, t);
   __syncwarp();
   vpt4_phase2a(L, cb, t);
+  vpt4_phase1b_stage(L, cb, t);
   __syncwarp();
-  vpt4_phase1b<T>(p, cf, L, cb, t);
+  vpt4_phase1b(cf, L, cb, t);
   __syncwarp();
   double R[4][4];
   vpt4_phase2b(p, cf, L, cb, t, R);
   __syncwarp();
   vpt4_phase2c(L, cb, t, R);
   __syncwarp();
+  vpt4_phase3(cf, cb, t);
+  __syncwarp();
   if (live)
-    vpt4_phase3<T>(p, cf, L, cb, t);
+    vpt4_phase4<T>(p, L, cb, t);
 }
 
 template <typename T>

@@ -27,15 +27,18 @@ def test_vlasov_poisson_right_hand_side_and_golden_run_on_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "vp_step_check.py")], capture_output=True, text=True, timeout=180)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("VPS OK") == 6 and "VPS FAIL" not in r.stdout and "VPD FAIL" not in r.stdout
+    assert r.stdout.count("VPS OK") == 7 and "VPS FAIL" not in r.stdout and "VPD FAIL" not in r.stdout
 
 
-def test_cpp_vlasov_poisson_driver_reproduces_golden(drivers, golden_dir, tmp_path):
+@pytest.mark.parametrize("env", [{}, {"HD_DRIVER_UNFUSED": "1"}], ids=["fused_stages", "reference_call_structure"])
+def test_cpp_vlasov_poisson_driver_reproduces_golden(drivers, golden_dir, tmp_path, env):
     """examples/vlasov_poisson re-hosted (hyperdeal_b200/cpp/vlasov_poisson.cc) on the reference's 2D2V Landau-damping case:
-    time_history_diagnostic.out against examples/vlasov_poisson/tests/vp_2D_2D_k3.hyperrectangle_01.out"""
+    time_history_diagnostic.out against examples/vlasov_poisson/tests/vp_2D_2D_k3.hyperrectangle_01.out — with the fused
+    stages (field refresh + ONE kernel for operator and stage update) and with the reference's std::function call structure"""
     from oracle import oracle_vp as V
 
-    r = subprocess.run([drivers["vlasov_poisson"], os.path.join(golden_dir, "vp_2D_2D_k3.hyperrectangle_01.json")], capture_output=True, text=True, timeout=180, cwd=str(tmp_path))
+    r = subprocess.run([drivers["vlasov_poisson"], os.path.join(golden_dir, "vp_2D_2D_k3.hyperrectangle_01.json")], capture_output=True, text=True, timeout=180, cwd=str(tmp_path),
+                       env=dict(os.environ, **env))
     assert r.returncode == 0, r.stderr
     rows = V.parse_vp_golden(str(tmp_path / "time_history_diagnostic.out"))
     gold = V.parse_vp_golden(os.path.join(golden_dir, "vp_2D_2D_k3.hyperrectangle_01.out"))

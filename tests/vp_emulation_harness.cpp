@@ -123,18 +123,25 @@ hd_vp_tile_emulate(const double *src, double *dst, const double *a_v, int dim_x,
           auto     cb   = [&](int lane) { return sm.data() + (lane >> 4) * VPT_CELL; };
           auto     mine = [&](int lane) { return std::min(cell0 + (lane >> 4), ncells - 1); };
           for (int lane = 0; lane < 32; ++lane)
-            vpt4_phase1<double>(p, cf, L[lane], cb(lane), lane & 15, mine(lane));
+            vpt4_phase0<double>(p, L[lane], cb(lane), lane & 15, mine(lane));
           for (int lane = 0; lane < 32; ++lane)
-            vpt4_phase2a(L[lane], cb(lane), lane & 15);
+            vpt4_phase1<double>(p, cf, L[lane], cb(lane), lane & 15);
           for (int lane = 0; lane < 32; ++lane)
-            vpt4_phase1b<double>(p, cf, L[lane], cb(lane), lane & 15);
+            {
+              vpt4_phase2a(L[lane], cb(lane), lane & 15);
+              vpt4_phase1b_stage(L[lane], cb(lane), lane & 15);
+            }
+          for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase1b(cf, L[lane], cb(lane), lane & 15);
           for (int lane = 0; lane < 32; ++lane)
             vpt4_phase2b(p, cf, L[lane], cb(lane), lane & 15, R[lane]);
           for (int lane = 0; lane < 32; ++lane)
             vpt4_phase2c(L[lane], cb(lane), lane & 15, R[lane]);
           for (int lane = 0; lane < 32; ++lane)
+            vpt4_phase3(cf, cb(lane), lane & 15);
+          for (int lane = 0; lane < 32; ++lane)
             if (cell0 + (lane >> 4) < ncells)
-              vpt4_phase3<double>(p, cf, L[lane], cb(lane), lane & 15);
+              vpt4_phase4<double>(p, L[lane], cb(lane), lane & 15);
         }
       return 0;
     }

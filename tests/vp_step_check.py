@@ -53,7 +53,27 @@ def main():
     if not ok:
         sys.exit(1)  # no point in the long run
 
-    # ---- the golden run (rk45, 104 steps): unfused LSRK with the device right-hand side
+    # ---- fused stages (hd_lsrk_stage_fused with the field refreshed per stage) = the unfused std::function structure
+    def refresh(src, t):
+        api.VectorTools.velocity_space_integration(mf, d_rho, src)
+        ps.solve(d_rho, a_v.data_ptr(), rel_tol=1e-11, max_iterations=2000)
+
+    s1, s2, Ki, Ti = (mf.initialize_dof_vector() for _ in range(4))
+    mf.copy_in(s1, f0)
+    mf.copy_in(s2, f0)
+    integ = api.LowStorageRungeKuttaIntegrator(mf, Ki, Ti, "rk45")
+    for step in range(2):
+        integ.perform_time_step(s1, step * 1e-2, 1e-2, rhs)
+        integ.perform_time_step_staged(s2, step * 1e-2, 1e-2, op, refresh)
+    a, b = mf.copy_out(s1), mf.copy_out(s2)
+    rel = float(np.max(np.abs(a - b)) / np.max(np.abs(a)))
+    ok = rel <= 1e-13
+    bad += not ok
+    print("VPS %s fused stages against the unfused integrator: rel=%.3e (kernel %s)" % ("OK" if ok else "FAIL", rel, op.kernel_name), flush=True)
+    for v in (s1, s2, Ki, Ti):
+        api._check(api.lib().hd_vector_free(mf._h, api.c_void_p(v)))
+
+    # ---- the golden run (rk45, 104 steps): fused stages with the device right-hand side
     rows, _ = V.run_vlasov_poisson_example(os.path.join(GOLDEN, "vp_2D_2D_k3.hyperrectangle_01.json"), n_points=4, nthreads=4, max_steps=0)
     gold = V.parse_vp_golden(os.path.join(GOLDEN, "vp_2D_2D_k3.hyperrectangle_01.out"))
     T, n_steps = 0.5, 104
@@ -63,7 +83,7 @@ def main():
     integ = api.LowStorageRungeKuttaIntegrator(mf, Ki, Ti, "rk45")
     out_rows = []
     for step in range(1, n_steps + 1):
-        integ.perform_time_step(sol, (step - 1) * dt, dt, rhs)
+        integ.perform_time_step_staged(sol, (step - 1) * dt, dt, op, refresh)
         t = step * dt
         if int((t + 1e-11) / 0.1) != int((t + 1e-11 - dt) / 0.1):
             f = mf.copy_out(sol)

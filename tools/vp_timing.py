@@ -67,7 +67,12 @@ def run(name):
     t_apply = timeit(lambda: op.apply(K, f, 0.0))
     L = api.lib()
     t_update = timeit(lambda: api._check(L.hd_lsrk_stage_update(mf._h, api.c_void_p(sol), api.c_void_p(f), api.c_void_p(K), 1e-6, 1e-6)))
+    Ki, Ti = mf.initialize_dof_vector(), mf.initialize_dof_vector()
+    rk = api.LowStorageRungeKuttaIntegrator(mf, Ki, Ti, "rk45")
+    mf.copy_in(Ti, np.full(mf.n_dofs, 1.0))
+    t_fused = timeit(lambda: api._check(L.hd_lsrk_stage_fused(rk._h, op._h, 1, api.c_void_p(sol), api.c_void_p(Ti), api.c_void_p(Ki), None, 0.0, 1e-9)))
     total = t_rho + t_poisson + t_apply + t_update
+    total_fused = t_rho + t_poisson + t_fused
     it, res = ps.last_solve
     es = 8
     print("VP %-9s %s cells, %.3e DoFs, kernel %s" % (name, "x".join(map(str, nc)), mf.n_dofs, op.kernel_name))
@@ -75,7 +80,9 @@ def run(name):
     print("   Poisson solve         %9.3f ms  (warm start: %d CG iterations, relative residual %.2e; cold start: %d iterations; %d x-space DoFs)" % (t_poisson, it, res, it_cold, mf.n_dofs_x))
     print("   operator (general a)  %9.3f ms  (%6.1f GDoF/s, %5.0f GB/s algorithmic)" % (t_apply, mf.n_dofs / t_apply / 1e6, mf.n_dofs * 2 * es / t_apply / 1e6))
     print("   LSRK stage update     %9.3f ms  (%5.0f GB/s)" % (t_update, mf.n_dofs * 4 * es / t_update / 1e6))
-    print("   whole stage           %9.3f ms  = %6.2f GDoF/s" % (total, mf.n_dofs / total / 1e6), flush=True)
+    print("   whole stage           %9.3f ms  = %6.2f GDoF/s" % (total, mf.n_dofs / total / 1e6))
+    print("   operator + update, one kernel (hd_lsrk_stage_fused) %9.3f ms (%5.0f GB/s algorithmic at 32 B/DoF)" % (t_fused, mf.n_dofs * 4 * es / t_fused / 1e6))
+    print("   whole stage, fused    %9.3f ms  = %6.2f GDoF/s" % (total_fused, mf.n_dofs / total_fused / 1e6), flush=True)
 
 
 if __name__ == "__main__":
