@@ -37,6 +37,14 @@ def test_product_arm_needs_a_gpu():
     assert "CUDA" in (r.stderr + r.stdout)
 
 
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+@pytest.mark.parametrize("workload", ["k5f32", "vp2d2v"])
+def test_secondary_workloads_need_a_gpu(workload):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert "CUDA" in (r.stderr + r.stdout)
+
+
 def test_tools_and_entry_points_compile():
     """every script under tools/, bench.py and __graft_entry__.py at least byte-compiles (they only run on a GPU box)"""
     import glob
