@@ -692,6 +692,8 @@ hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
             off += m->ghost_cnt[d][s];
             m->has_ghosts = true;
           }
+        if (desc->side_kind[d][s] == HD_SIDE_DIRICHLET || desc->side_kind[d][s] == HD_SIDE_DIRICHLET_HOM)
+          m->has_dirichlet = true;
       }
   m->ghost_total = off;
   try
@@ -1041,6 +1043,11 @@ hd_advection_destroy(hd_advection *op)
   if (!op)
     return HD_OK;
   hd::fast6d_release(op);
+  if (op->shadow_op)
+    hd_advection_destroy(op->shadow_op);
+  if (op->shadow_mesh)
+    hd_mesh_destroy(op->shadow_mesh);
+  cudaFree(op->d_shadow_ghost);
   cudaFree(op->d_coef);
   cudaFree(op->d_vp_coef);
   cudaFree(op->d_stage_src);
@@ -1127,6 +1134,69 @@ hd_advection_launch_count(const hd_advection *op)
   return op ? op->launches : 0;
 }
 
+static int apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part);
+
+// Dirichlet sides on the specialised kernels.  At a Dirichlet face the upwind flux sees u+ = -u- + 2 g
+// (advection_operation.h:490-519); in the collapsed form (basis.hpp) that is the INTERIOR formula with the neighbour trace
+// -u_face + 2 ghat.  So a lattice with Dirichlet sides is served by any kernel that knows ghost sides: a small kernel writes
+// those traces of the inflow sides into an internal ghost buffer (k_dirichlet_source in ghost mode, one CTA per boundary
+// face cell), then the operator runs on a shadow description of the same lattice whose inflow Dirichlet sides are
+// HD_SIDE_GHOST (outflow sides read nothing: beta = 0).  Single-brick lattices only (a brick with real ghost sides keeps
+// the generic kernel + lifting kernel); hd_advection_set_kernel(op, 1) forces that path too.
+static bool
+dirichlet_shadow(hd_advection *op)
+{
+  if (op->shadow_state != 0)
+    return op->shadow_state > 0;
+  op->shadow_state = -1;
+  hd_mesh *m = op->mesh;
+  if (m->has_ghosts)
+    return false;
+  hd_mesh_desc d   = m->d;
+  bool         any = false;
+  for (int k = 0; k < m->dim; ++k)
+    for (int s = 0; s < 2; ++s)
+      if (d.side_kind[k][s] == HD_SIDE_DIRICHLET || d.side_kind[k][s] == HD_SIDE_DIRICHLET_HOM)
+        {
+          d.side_kind[k][s] = ((op->nb_mask[k] >> s) & 1) ? HD_SIDE_GHOST : HD_SIDE_PERIODIC_LOCAL;
+          any               = true;
+        }
+  if (!any)
+    return false;
+  if (hd_mesh_create(m->ctx, &d, &op->shadow_mesh) != HD_OK)
+    return false;
+  if (hd_advection_create(op->shadow_mesh, op->skew, op->a, &op->shadow_op) != HD_OK)
+    return false;
+  hd_advection *sh = op->shadow_op;
+  // worth it only if the shadow lattice gets one of the specialised kernels
+  const bool special = hd::fast6d_supported(sh) || hd::tile_preferred(sh) || (op->shadow_mesh->n == 6 && hd::tile_global_supported(sh));
+  if (!special)
+    return false;
+  const size_t bytes = (size_t)hd_halo_total(op->shadow_mesh) * m->elem_size;
+  if (cudaMalloc(&op->d_shadow_ghost, bytes ? bytes : 256) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+  op->shadow_state = 1;
+  return true;
+}
+
+static int
+apply_dirichlet_as_ghosts(hd_advection *op, void *dst, const void *src, double time, const FusedUpdate &fu)
+{
+  int rc = hd::launch_dirichlet_ghosts(op, op->shadow_mesh, op->d_shadow_ghost, src, time);
+  if (rc != HD_OK)
+    return rc;
+  hd_advection *sh  = op->shadow_op;
+  sh->kernel_choice = op->kernel_choice;
+  const int64_t before = sh->launches;
+  rc = apply_impl(sh, dst, src, op->d_shadow_ghost, time, fu, HD_PART_ALL);
+  op->launches += sh->launches - before;
+  op->last_kernel = sh->last_kernel;
+  return rc;
+}
+
 static int
 apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, double time, const FusedUpdate &fu, int part = HD_PART_ALL)
 {
@@ -1144,6 +1214,8 @@ apply_impl(hd_advection *op, void *dst, const void *src, const void *ghosts, dou
         return HD_OK;
       return hd::launch_vp(op, dst, src, time, fu);
     }
+  if (m->has_dirichlet && part == HD_PART_ALL && op->kernel_choice != 1 && dirichlet_shadow(op))
+    return apply_dirichlet_as_ghosts(op, dst, src, time, fu);
   bool fast = op->kernel_choice == 2 || op->kernel_choice == 6 || (op->kernel_choice == 0 && hd::fast6d_supported(op));
   if (fast)
     rc = hd::launch_fast6d(op, dst, src, ghosts, time, fu, part);

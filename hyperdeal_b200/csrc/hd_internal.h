@@ -58,6 +58,7 @@ struct hd_mesh
   int64_t      ghost_cnt[HD_MAX_DIM][2];
   int64_t      ghost_total = 0;
   bool         has_ghosts  = false;
+  bool         has_dirichlet = false;
   // device copies (double) of nodes[n], xq[nq], w[nq], S[nq*n]
   double *d_basis = nullptr;
   double *d_reduce = nullptr; // 2 doubles for norm reductions
@@ -111,6 +112,12 @@ struct hd_advection
   const void *d_av      = nullptr;
   void *      d_vp_coef = nullptr;
   std::vector<double> h_vp_coef; // host copy (the tile kernels take their matrices as a kernel parameter)
+  // Dirichlet lattices on the fast kernels: the same lattice with its inflow Dirichlet sides declared HD_SIDE_GHOST, an
+  // operator on it, and the ghost buffer that receives -u_face + 2 g before every application (capi.cu: apply_dirichlet_as_ghosts)
+  hd_mesh *     shadow_mesh  = nullptr;
+  hd_advection *shadow_op    = nullptr;
+  void *        d_shadow_ghost = nullptr;
+  int           shadow_state = 0; // 0 = not tried, 1 = in use, -1 = not applicable
   // fast-kernel private state (tensor maps etc.)
   void *fast_state = nullptr;
   int   row_tile[5] = {-1, -1, -1, -1, -1}; // pipelined kernel: row tile per direction 1..5 (-1 = default, 0 = full extent)
@@ -161,4 +168,5 @@ namespace hd
   int  launch_vp(hd_advection *op, void *dst, const void *src, double time, const FusedUpdate &fu);
   // dirichlet source term (kernels_generic.cu)
   int launch_dirichlet_source(hd_advection *op, void *dst, double time, const FusedUpdate &fu);
+  int launch_dirichlet_ghosts(hd_advection *op, const hd_mesh *ghost_mesh, void *ghosts, const void *src, double time);
 } // namespace hd

@@ -249,6 +249,11 @@ namespace
     T *           ti_next;
     double        fb, fa;
     int           fused;
+    // ghost mode (Dirichlet sides served by the ghost-side code of the fast kernels): instead of lifting 2 beta l ghat
+    // into the cell, write the trace the upwind flux would see behind the face, -u_face + 2 ghat, into a ghost segment
+    const T *src_for_ghost;
+    T *      ghost_out; // start of this side's segment, [n_face_cells][n^(dim-1)]
+    int      homogeneous;
   };
 
   __device__ double
@@ -302,7 +307,9 @@ namespace
     for (int q = threadIdx.x; q < nqf; q += blockDim.x)
       {
         double val;
-        if (p.g)
+        if (p.homogeneous)
+          val = 0.0;
+        else if (p.g)
           val = p.g[fc * nqf + q];
         else
           {
@@ -358,6 +365,18 @@ namespace
     for (int e = 0; e < p.dir; ++e)
       stride_d *= n;
     const long long nd = (long long)nf * n;
+    if (p.ghost_out)
+      {
+        // u+ = -u- + 2 g at a Dirichlet face (advection_operation.h:490-519) as the neighbour trace of the interior formula
+        const int layer = p.side ? n - 1 : 0;
+        for (int i = threadIdx.x; i < nf; i += blockDim.x)
+          {
+            const int    lo = i % stride_d, hi = i / stride_d;
+            const double u  = double(p.src_for_ghost[cell * nd + ((long long)hi * n + layer) * stride_d + lo]);
+            p.ghost_out[fc * nf + i] = T(2.0 * in[i] - u);
+          }
+        return;
+      }
     for (int i = threadIdx.x; i < nd; i += blockDim.x)
       {
         const int    lo = i % stride_d, rest = i / stride_d, id = rest % n, hi = rest / n;
@@ -1127,23 +1146,29 @@ namespace hd
     return launch_n<float>(op, dst, src, ghosts, fu);
   }
 
+  // ghost_mesh == nullptr: lift the boundary data into dst (generic-kernel path).  Otherwise: fill the ghost segments of
+  // `ghost_mesh` (the same lattice with its inflow Dirichlet sides declared HD_SIDE_GHOST) in `ghosts` from src and g.
   template <typename T>
   static int
-  dirichlet_t(hd_advection *op, void *dst, double time, const FusedUpdate &fu)
+  dirichlet_t(hd_advection *op, void *dst, double time, const FusedUpdate &fu, const hd_mesh *ghost_mesh = nullptr, void *ghosts = nullptr, const void *src = nullptr)
   {
     hd_mesh *m = op->mesh;
     for (int d = 0; d < m->dim; ++d)
       for (int side = 0; side < 2; ++side)
         {
-          if (m->d.side_kind[d][side] != HD_SIDE_DIRICHLET)
+          const bool hom = m->d.side_kind[d][side] == HD_SIDE_DIRICHLET_HOM;
+          if (m->d.side_kind[d][side] != HD_SIDE_DIRICHLET && !(ghost_mesh && hom))
             continue;
           if (!((op->nb_mask[d] >> side) & 1))
             continue; // outflow side: beta = 0
           DirParams<T> p;
           p.dst   = static_cast<T *>(dst);
           p.g     = op->d_g[d][side];
-          if (!p.g && op->dirichlet_fn < 0)
+          if (!hom && !p.g && op->dirichlet_fn < 0)
             return hd::fail(HD_ERR_INVALID, "inhomogeneous Dirichlet side without boundary data");
+          p.homogeneous   = hom ? 1 : 0;
+          p.src_for_ghost = static_cast<const T *>(src);
+          p.ghost_out     = ghost_mesh ? static_cast<T *>(ghosts) + ghost_mesh->ghost_off[d][side] : nullptr;
           p.basis = m->d_basis;
           p.lift  = reinterpret_cast<const char *>(op->d_coef) + op->coef_bytes + sizeof(double) * m->n * (2 * d + side);
           p.dim   = m->dim;
@@ -1191,5 +1216,14 @@ namespace hd
     if (op->mesh->d.number_type == HD_F64)
       return dirichlet_t<double>(op, dst, time, fu);
     return dirichlet_t<float>(op, dst, time, fu);
+  }
+
+  int
+  launch_dirichlet_ghosts(hd_advection *op, const hd_mesh *ghost_mesh, void *ghosts, const void *src, double time)
+  {
+    FusedUpdate fu;
+    if (op->mesh->d.number_type == HD_F64)
+      return dirichlet_t<double>(op, nullptr, time, fu, ghost_mesh, ghosts, src);
+    return dirichlet_t<float>(op, nullptr, time, fu, ghost_mesh, ghosts, src);
   }
 } // namespace hd

@@ -104,9 +104,12 @@ def test_generic_kernel_velocity_signs(api, ctx, vel):
     assert rel <= TOL64, rel
 
 
+# Dirichlet lattices: kernel 0 = the automatic choice, which serves them on the specialised kernels through synthesised ghost
+# traces (-u_face + 2 g, capi.cu: apply_dirichlet_as_ghosts); kernel 1 = the generic kernel with boundary matrices + lifting kernel
+@pytest.mark.parametrize("kernel,expect", [(0, "tile"), (1, "generic")])
 @pytest.mark.parametrize("bc_kind", [1, 2])
 @pytest.mark.parametrize("skew", [0.0, 0.5])
-def test_dirichlet_matches_oracle(api, ctx, bc_kind, skew):
+def test_dirichlet_matches_oracle(api, ctx, bc_kind, skew, kernel, expect):
     # the reference's Dirichlet goldens (adv_2D_2D_k3.hyperrectangle_03/07) use this mesh class
     dx, dv, nc = 2, 2, (3, 2, 2, 3)
     om, mf = _mesh_pair(api, ctx, dx, dv, nc, 3, periodic=False)
@@ -123,11 +126,32 @@ def test_dirichlet_matches_oracle(api, ctx, bc_kind, skew):
     ref = orc.apply(src, time=0.37)
     op = A.AdvectionOperation(mf, vel, skew)
     op.set_dirichlet_builtin(A.FN_HYPERRECTANGLE)
+    op.set_kernel(kernel)
     d_src, d_dst = mf.initialize_dof_vector(), mf.initialize_dof_vector()
     mf.copy_in(d_src, src)
     op.apply(d_dst, d_src, 0.37)
     out = mf.copy_out(d_dst)
     assert _rel(out, ref) <= TOL64
+    assert op.kernel_name == expect
+
+
+@pytest.mark.parametrize("dx,dv,nc,k,dtype,periodic,vel,expect", [
+    # 3D3V degree 3 FP64, all sides Dirichlet: the three-round kernel (ghost traces in all six directions, x_0 included)
+    (3, 3, (3, 2, 2, 2, 2, 2), 3, np.float64, False, None, "rounds_3d3v_k3"),
+    (3, 3, (2, 2, 2, 2, 2, 2), 3, np.float64, False, (-1.0, -0.15, 0.05, -0.1, 0.15, -0.5), "rounds_3d3v_k3"),
+    # mixed: periodic x, Dirichlet v; one direction without transport
+    (3, 3, (2, 2, 2, 2, 2, 2), 3, np.float64, (True, True, True, False, False, False), (1.0, 0.15, -0.05, 0.0, -0.15, 0.5), "rounds_3d3v_k3"),
+    (3, 3, (2, 2, 2, 2, 2, 2), 3, np.float32, False, None, "tile"),
+    (2, 2, (3, 2, 2, 3), 3, np.float32, False, None, "tile"),
+    (3, 3, (2, 1, 2, 1, 2, 1), 5, np.float32, False, None, "tile_global"),
+    (1, 1, (4, 3), 3, np.float64, False, None, "generic"),   # no specialised kernel preferred in 1D1V: lifting-kernel path
+])
+def test_dirichlet_on_specialised_kernels(api, ctx, dx, dv, nc, k, dtype, periodic, vel, expect):
+    rel, name = _run(api, ctx, dx, dv, nc, k, periodic=periodic, dtype=dtype, vel=vel, skew=0.5)
+    assert name == expect
+    assert rel <= (TOL64 if dtype == np.float64 else TOL32), rel
+    rel1, name1 = _run(api, ctx, dx, dv, nc, k, periodic=periodic, dtype=dtype, vel=vel, skew=0.5, kernel=1)
+    assert name1 == "generic" and rel1 <= (TOL64 if dtype == np.float64 else TOL32)
 
 
 def test_dirichlet_uploaded_values(api, ctx):

@@ -72,6 +72,28 @@ if sel in ("all", "row"):
     torch.cuda.empty_cache()
     apply_case("apply 3D3V k=3 f64, 8^6 cells", 3, 3, 3, [8] * 6, np.float64)
     torch.cuda.empty_cache()
+if sel in ("apply2d",):
+    apply_case("apply 2D2V k=3 f64, 64x64x32x32 cells (configs[0])", 2, 2, 3, [64, 64, 32, 32], np.float64)
+if sel in ("dirichlet",):
+    # Dirichlet lattices: automatic choice (specialised kernel fed with synthesised ghost traces) against the generic kernel + lifting kernel
+    def dirichlet_case(name, dx, dv, k, nc, dtype, kernel):
+        dim = dx + dv
+        mf = api.MatrixFree(ctx, dx, dv, k, nc, (0.0,) * dim, (1.0,) * dim, periodic=False, dtype=dtype)
+        op = api.AdvectionOperation(mf, V[:dim], 0.5)
+        op.set_dirichlet_builtin(api.FN_HYPERRECTANGLE)
+        op.set_kernel(kernel)
+        tdt = torch.float64 if dtype == np.float64 else torch.float32
+        src = torch.empty(mf.n_dofs, dtype=tdt, device="cuda"); dst = torch.empty_like(src)
+        api.VectorTools.interpolate(mf, src.data_ptr(), api.FN_HYPERRECTANGLE, 0.0)
+        ms = timeit(lambda: op.apply(dst.data_ptr(), src.data_ptr(), 0.1))
+        report("%s [%s]" % (name, op.kernel_name), ms, mf.n_dofs, 2 * src.element_size())
+        del src, dst
+        op.close(); mf.close()
+        torch.cuda.empty_cache()
+    dirichlet_case("apply 3D3V k=3 f64, 8^6 cells, Dirichlet on all sides", 3, 3, 3, [8] * 6, np.float64, 0)
+    dirichlet_case("apply 3D3V k=3 f64, 8^6 cells, Dirichlet on all sides, generic kernel", 3, 3, 3, [8] * 6, np.float64, 1)
+    dirichlet_case("apply 2D2V k=3 f64, 64x64x32x32 cells, Dirichlet on all sides", 2, 2, 3, [64, 64, 32, 32], np.float64, 0)
+    dirichlet_case("apply 2D2V k=3 f64, 64x64x32x32 cells, Dirichlet on all sides, generic kernel", 2, 2, 3, [64, 64, 32, 32], np.float64, 1)
 if sel in ("tg",):  # the not yet validated global-memory tile kernel on BASELINE.json configs[2]
     apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), global-memory tile kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=5)
     torch.cuda.empty_cache()
