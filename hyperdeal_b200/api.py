@@ -23,6 +23,7 @@ HD_MAX_DIM = 6
 HD_F64, HD_F32 = 0, 1
 SIDE_PERIODIC_LOCAL, SIDE_GHOST, SIDE_DIRICHLET, SIDE_DIRICHLET_HOM = 0, 1, 2, 3
 FN_ZERO, FN_HYPERRECTANGLE = 0, 1
+EVAL_ALL, EVAL_CELL, EVAL_ALL_WITHOUT_NEIGHBOR_LOAD = 0, 1, 2
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -34,7 +35,7 @@ EXPORTS = [
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_vector_zero_n", "hd_vector_copy_n", "hd_advection_create",
     "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
-    "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_dirichlet_values",
+    "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_evaluation_level", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step", "hd_lsrk_stage_fused", "hd_lsrk_stage_overlapped",
     "hd_multi_create", "hd_multi_destroy", "hd_multi_n_gpus", "hd_multi_mesh", "hd_multi_context", "hd_multi_n_dofs", "hd_multi_synchronize", "hd_multi_vector_alloc",
@@ -116,6 +117,7 @@ def lib():
     L.hd_advection_set_halo_senders.argtypes = [c_void_p, c_int]
     L.hd_advection_apply_host.argtypes = [c_void_p, c_void_p, c_void_p, c_double]
     L.hd_advection_set_kernel.argtypes = [c_void_p, c_int]
+    L.hd_advection_set_evaluation_level.argtypes = [c_void_p, c_int]
     L.hd_advection_set_l2_hints.argtypes = [c_void_p, c_int]
     L.hd_advection_set_row_tile.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_advection_set_dirichlet_values.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int64]
@@ -365,6 +367,10 @@ class AdvectionOperation:
 
     def apply_host_ptr(self, dst_ptr: int, src_ptr: int, time: float = 0.0):
         _check(lib().hd_advection_apply_host(self._h, c_void_p(dst_ptr), c_void_p(src_ptr), float(time)))
+
+    def set_evaluation_level(self, level: int):
+        """AdvectionOperationEvaluationLevel (advection_operation.h:37-42): EVAL_ALL, EVAL_CELL, EVAL_ALL_WITHOUT_NEIGHBOR_LOAD"""
+        _check(lib().hd_advection_set_evaluation_level(self._h, int(level)))
 
     def set_kernel(self, which: int):
         _check(lib().hd_advection_set_kernel(self._h, which))

@@ -484,7 +484,7 @@ namespace hyperdeal
       dealii_compat::Tensor<1, dim, Number> transport_direction;
     };
 
-    enum class AdvectionOperationEvaluationLevel // advection_operation.h:44-50; only `all` has a device path
+    enum class AdvectionOperationEvaluationLevel // advection_operation.h:37-42 (hd_advection_set_evaluation_level)
     {
       cell,
       all_without_neighbor_load,
@@ -549,8 +549,9 @@ namespace hyperdeal
       void
       apply(VectorType &dst, const VectorType &src, const Number time, Timers * = nullptr)
       {
-        if (eval_level != AdvectionOperationEvaluationLevel::all)
-          throw ExcNotImplemented("partial evaluation levels (profiling variants of the CPU kernel)");
+        HD_CALL(hd_advection_set_evaluation_level(op, eval_level == AdvectionOperationEvaluationLevel::all  ? HD_EVAL_ALL :
+                                                      eval_level == AdvectionOperationEvaluationLevel::cell ? HD_EVAL_CELL :
+                                                                                                               HD_EVAL_ALL_WITHOUT_NEIGHBOR_LOAD));
         if (host_sampled_bc)
           upload_dirichlet_values(time);
         HD_CALL(hd_advection_apply(op, dst.begin(), src.begin(), nullptr, double(time)));

@@ -283,14 +283,17 @@ namespace hd
     // L0/L1 = neighbour lifting vectors (zero for the outflow side);
     // G0/G1 = 2*beta_f*l_f, the lifting of the Dirichlet datum g.
     void
-    direction_matrices(LD a, LD h, LD s, std::vector<LD> C[4], std::vector<LD> &L0, std::vector<LD> &L1) const
+    // level: the reference's AdvectionOperationEvaluationLevel (advection_operation.h:37-42) — 0 = all, 1 = cell (no face
+    // integrals at all: alpha = beta = 0), 2 = all_without_neighbor_load (the neighbour's trace is not read: beta-part of
+    // the interior faces dropped, the own-side face term alpha kept)
+    direction_matrices(LD a, LD h, LD s, std::vector<LD> C[4], std::vector<LD> &L0, std::vector<LD> &L1, const int level = 0) const
     {
       LD alpha[2], beta[2];
       for (int f = 0; f < 2; ++f)
         {
           const LD an = a * (f ? 1 : -1);
-          alpha[f]    = -(an / 2 + fabsl(a) / 2 - s * an) / h;
-          beta[f]     = -(an - fabsl(a)) / 2 / h;
+          alpha[f]    = level == 1 ? LD(0) : -(an / 2 + fabsl(a) / 2 - s * an) / h;
+          beta[f]     = level == 1 ? LD(0) : -(an - fabsl(a)) / 2 / h;
         }
       for (int var = 0; var < 4; ++var)
         {
@@ -311,8 +314,8 @@ namespace hd
       L1.resize(n);
       for (int i = 0; i < n; ++i)
         {
-          L0[i] = beta[0] * l0[i];
-          L1[i] = beta[1] * l1[i];
+          L0[i] = level == 2 ? LD(0) : beta[0] * l0[i];
+          L1[i] = level == 2 ? LD(0) : beta[1] * l1[i];
         }
     }
   };

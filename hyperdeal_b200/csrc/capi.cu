@@ -957,24 +957,12 @@ namespace
 } // namespace
 extern "C" {
 
-int
-hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advection **out)
+// collapsed matrices of every direction for op->a, op->skew, op->eval_level: host copies + the device blob of the generic kernel
+static int
+build_coefficients(hd_advection *op)
 {
-  HD_REQUIRE(m && velocity && out, "null argument");
-  hd_advection *op = new (std::nothrow) hd_advection;
-  HD_REQUIRE(op, "out of memory");
-  op->mesh = m;
-  op->skew = skew;
-  for (int d = 0; d < HD_MAX_DIM; ++d)
-    {
-      op->a[d]       = d < m->dim ? velocity[d] : 0.0;
-      op->nb_mask[d] = 0;
-      for (int s = 0; s < 2; ++s)
-        {
-          op->d_g[d][s]     = nullptr;
-          op->g_count[d][s] = 0;
-        }
-    }
+  hd_mesh *    m    = op->mesh;
+  const double skew = op->skew;
   hd::Basis1D &b = m->basis;
   b.set_skew((hd::LD)skew);
   const int           n = m->n;
@@ -982,7 +970,7 @@ hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advectio
   for (int d = 0; d < m->dim; ++d)
     {
       std::vector<hd::LD> C[4], L0, L1;
-      b.direction_matrices((hd::LD)velocity[d], (hd::LD)m->h[d], (hd::LD)skew, C, L0, L1);
+      b.direction_matrices((hd::LD)op->a[d], (hd::LD)m->h[d], (hd::LD)skew, C, L0, L1, op->eval_level);
       for (int v = 0; v < 4; ++v)
         {
           op->hC[d][v].resize(n * n);
@@ -1023,7 +1011,6 @@ hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advectio
         f64 ? fill_coef<double, 6>(op, blob) : fill_coef<float, 6>(op, blob);
         break;
       default:
-        delete op;
         return hd::fail(HD_ERR_UNSUPPORTED, "degree must be in 1..5");
     }
   // layout: [DirCoef block, padded to 8 bytes][double lifts[dim][2][n]]
@@ -1031,10 +1018,51 @@ hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advectio
   blob.resize(op->coef_bytes + lifts.size() * sizeof(double));
   std::memcpy(blob.data() + op->coef_bytes, lifts.data(), lifts.size() * sizeof(double));
   HD_CUDA(cudaSetDevice(m->ctx->device));
+  cudaFree(op->d_coef);
+  op->d_coef = nullptr;
   HD_CUDA(cudaMalloc(&op->d_coef, blob.size()));
   HD_CUDA(cudaMemcpy(op->d_coef, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  return HD_OK;
+}
+
+int
+hd_advection_create(hd_mesh *m, double skew, const double *velocity, hd_advection **out)
+{
+  HD_REQUIRE(m && velocity && out, "null argument");
+  hd_advection *op = new (std::nothrow) hd_advection;
+  HD_REQUIRE(op, "out of memory");
+  op->mesh = m;
+  op->skew = skew;
+  for (int d = 0; d < HD_MAX_DIM; ++d)
+    {
+      op->a[d]       = d < m->dim ? velocity[d] : 0.0;
+      op->nb_mask[d] = 0;
+      for (int s = 0; s < 2; ++s)
+        {
+          op->d_g[d][s]     = nullptr;
+          op->g_count[d][s] = 0;
+        }
+    }
+  const int rc = build_coefficients(op);
+  if (rc != HD_OK)
+    {
+      delete op;
+      return rc;
+    }
   *out = op;
   return HD_OK;
+}
+
+int
+hd_advection_set_evaluation_level(hd_advection *op, int level)
+{
+  HD_REQUIRE(op && level >= HD_EVAL_ALL && level <= HD_EVAL_ALL_WITHOUT_NEIGHBOR_LOAD, "bad argument");
+  HD_REQUIRE(!op->mesh->has_dirichlet || level == HD_EVAL_ALL, "partial evaluation levels are profiling variants for periodic / ghosted lattices");
+  if (level == op->eval_level)
+    return HD_OK;
+  HD_CUDA(cudaStreamSynchronize(op->mesh->ctx->stream)); // the coefficient blob may still be in use
+  op->eval_level = level;
+  return build_coefficients(op);
 }
 
 int

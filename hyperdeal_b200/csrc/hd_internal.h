@@ -94,6 +94,7 @@ struct hd_advection
   size_t      coef_bytes  = 0;
   int         nb_mask[HD_MAX_DIM]; // bit0: lower neighbour trace needed, bit1: upper
   int         kernel_choice = 0;
+  int         eval_level    = 0; // HD_EVAL_*
   const char *last_kernel   = "none";
   int64_t     launches      = 0;
   // host copies of the collapsed matrices in double (for the specialised kernels)

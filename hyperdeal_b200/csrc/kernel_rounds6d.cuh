@@ -257,7 +257,11 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                 // requested here, not at the start of the task: a wait for the traces would wait for these loads as well
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
+#ifdef HD_R6_FUSED_CS
+                  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(sv[i]) : "l"(p.sol + g + 256 * i)); // read once: evict-first, keeps the face layers of src in L2
+#else
                   sv[i] = r6_ldg(p.sol + g + 256 * i);
+#endif
               }
             if (R == 0)
               {
@@ -334,9 +338,15 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                   const double kv = q[i >> 2][i & 3];
                   if (FUSED)
                     {
+#ifdef HD_R6_FUSED_CS
+                      __stcs(p.sol + g + 256 * i, fma(p.fb, kv, sv[i]));
+                      if (p.fa != 0.0)
+                        __stcs(p.ti_next + g + 256 * i, fma(p.fa, kv, sv[i]));
+#else
                       p.sol[g + 256 * i] = fma(p.fb, kv, sv[i]);
                       if (p.fa != 0.0)
                         p.ti_next[g + 256 * i] = fma(p.fa, kv, sv[i]);
+#endif
                     }
                   else if (stream)
                     __stcs(p.dst + g + 256 * i, kv);

@@ -303,7 +303,23 @@ namespace
         nqf *= nq;
         nf *= n;
       }
-    // g at face quadrature points
+    // g at face quadrature points.  The built-in hyperrectangle solution is a product of one factor per direction
+    // (cases/hyperrectangle.h:46-57): 1-D factor tables first, then products — dim * nq instead of dim * nq^(dim-1)
+    // sin/cos evaluations per face cell, which dominated this kernel (3D3V: 6 x 1024 per face cell)
+    double *   fac       = sm + 2 * cap; // [dim][nq]
+    const bool separable = !p.homogeneous && !p.g && p.fn_id == HD_FN_HYPERRECTANGLE;
+    if (separable)
+      {
+        for (int i = threadIdx.x; i < dim * nq; i += blockDim.x)
+          {
+            const int    e = i / nq, q = i % nq;
+            const double adv[6] = {1.0, 0.15, -0.05, 0.0, 0.0, 0.0};
+            const double PI     = 3.14159265358979323846;
+            const double x = e == p.dir ? p.left[e] + p.h[e] * (c[e] + p.cell_offset[e] + (p.side ? 1.0 : 0.0)) : p.left[e] + p.h[e] * (c[e] + p.cell_offset[e] + xq[q]);
+            fac[i]         = e == 0 ? sin(2.0 * (x - p.time * adv[e]) * PI) : cos(2.0 * (x - p.time * adv[e]) * PI);
+          }
+        __syncthreads();
+      }
     for (int q = threadIdx.x; q < nqf; q += blockDim.x)
       {
         double val;
@@ -311,6 +327,23 @@ namespace
           val = 0.0;
         else if (p.g)
           val = p.g[fc * nqf + q];
+        else if (separable)
+          {
+            // same order of the products as builtin_fn: r = f_0, then r *= f_e for e = 1..dim-1
+            int    rr = q;
+            double r  = 1.0;
+            for (int e = 0; e < dim; ++e)
+              {
+                int qe = 0;
+                if (e != p.dir)
+                  {
+                    qe = rr % nq;
+                    rr /= nq;
+                  }
+                r = e == 0 ? fac[qe] : r * fac[e * nq + qe];
+              }
+            val = r;
+          }
         else
           {
             double x[HD_MAX_DIM];
@@ -1196,7 +1229,7 @@ namespace hd
           int mx = m->n > m->nq ? m->n : m->nq, cap = 1;
           for (int e = 0; e < m->dim - 1; ++e)
             cap *= mx;
-          const size_t smem = 2 * sizeof(double) * cap;
+          const size_t smem = 2 * sizeof(double) * cap + sizeof(double) * HD_MAX_DIM * mx;
           if (smem > 48 * 1024)
             {
               if (smem > m->ctx->smem_optin)

@@ -232,6 +232,14 @@ int hd_advection_apply_host(hd_advection *op, void *dst_host, const void *src_ho
  * With 0 a 3D3V k=3 FP64 mesh runs kernel 6 (HD_FAST_VARIANT=pipe selects 2).
  * HD_ERR_UNSUPPORTED if the kernel does not cover the mesh. */
 int hd_advection_set_kernel(hd_advection *op, int which);
+/* AdvectionOperationEvaluationLevel (the template parameter of AdvectionOperation::apply, advection_operation.h:37-42,
+ * 134-209): profiling variants that attribute the operator's time.  HD_EVAL_CELL = cell integrals only;
+ * HD_EVAL_ALL_WITHOUT_NEIGHBOR_LOAD = face integrals with the neighbour's trace not read (taken as zero here; the reference
+ * leaves it undefined); HD_EVAL_ALL = the operator (default).  Periodic / ghosted lattices only. */
+#define HD_EVAL_ALL 0
+#define HD_EVAL_CELL 1
+#define HD_EVAL_ALL_WITHOUT_NEIGHBOR_LOAD 2
+int hd_advection_set_evaluation_level(hd_advection *op, int level);
 /* Pipelined 3D3V kernel: L2 residency hints, a bit mask (1: keep the direction-4 outflow layers in L2 for the downwind
  * neighbour, 2: evict-first on the far face loads, 4: streaming stores; -1 = default = environment HD_L2_HINTS, else 0).
  * A tuning knob, results do not depend on it; only effective in builds with -DHD_HINTS=1 (off by default: measured

@@ -64,6 +64,8 @@ struct hdo_op
   const double *a_v_table;     // [n_cells_x][nq^dim_x][dim_v]   a_v(x-cell, q_x)
   int           bc_kind; // boundary faces: 0 none expected, 1 Dirichlet g (fn_id), 2 homogeneous
   int           fn_id;   // 0: hyperrectangle ExactSolution (examples/advection/cases/hyperrectangle.h:29-66)
+  int           eval_level; // AdvectionOperationEvaluationLevel (:37-42): 0 all, 1 cell (faces skipped, :407),
+                            // 2 all_without_neighbor_load (:422-423: phi_p not read; taken as zero here)
 };
 
 // examples/advection/cases/hyperrectangle.h:46-57
@@ -295,7 +297,7 @@ namespace
       }
 
     // --- 3) faces (:406-526)
-    for (int face = 0; face < 2 * dim; ++face)
+    for (int face = 0; face < 2 * dim && op.eval_level != 1; ++face)
       {
         const int     d        = face / 2;
         const int     side     = face % 2;
@@ -394,7 +396,7 @@ namespace
               const double u_minus = um[i];
               double       u_plus;
               if (!is_boundary)
-                u_plus = up[i];
+                u_plus = op.eval_level == 2 ? 0.0 : up[i];
               else if (op.bc_kind == 2)
                 u_plus = -u_minus; // DirichletHomogenous (:494-495)
               else

@@ -104,6 +104,7 @@ class _Op(ctypes.Structure):
         ("a_v_table", _DP),
         ("bc_kind", ctypes.c_int),
         ("fn_id", ctypes.c_int),
+        ("eval_level", ctypes.c_int),
     ]
 
 
@@ -353,7 +354,8 @@ HYPERRECTANGLE_VELOCITY = (1.0, 0.15, -0.05, 0.0, 0.0, 0.0)
 class Oracle:
     """CPU restatement of MatrixFree + AdvectionOperation + VectorTools on a Cartesian mesh."""
 
-    def __init__(self, mesh: Mesh, degree: int, nq: int | None = None, collocation=False, skew=0.0, velocity=None, a_x_table=None, a_v_table=None, bc_kind=1, nthreads=1):
+    def __init__(self, mesh: Mesh, degree: int, nq: int | None = None, collocation=False, skew=0.0, velocity=None, a_x_table=None, a_v_table=None, bc_kind=1, nthreads=1,
+                 eval_level=0):
         self.mesh = mesh
         self.degree = degree
         self.b = basis_1d(degree, nq, collocation)
@@ -383,6 +385,7 @@ class Oracle:
             op.a_const = _ptr(self.velocity)
         op.bc_kind = bc_kind
         op.fn_id = 0
+        op.eval_level = int(eval_level)  # AdvectionOperationEvaluationLevel: 0 all, 1 cell, 2 all_without_neighbor_load
         self._op = op
         self._mesh = mesh.c_struct()
 

@@ -329,3 +329,40 @@ def test_fast_kernel_row_tiles_are_order_only(api, ctx, tile, kernel):
     assert np.abs(a).max() > 0
     for p in (d_src, d_a, d_b):
         mf.free_vector(p)
+
+
+# AdvectionOperationEvaluationLevel (advection_operation.h:37-42): cell integrals only / faces without the neighbour's trace
+@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("dx,dv,nc,k,dtype,kernel,expect", [
+    (3, 3, (3, 2, 2, 2, 2, 2), 3, np.float64, 0, "rounds_3d3v_k3"),
+    (3, 3, (2, 2, 2, 2, 2, 2), 3, np.float64, 2, "advect_3d3v_k3"),
+    (2, 2, (3, 2, 4, 2), 3, np.float64, 0, "tile"),
+    (2, 2, (3, 2, 4, 2), 3, np.float64, 1, "generic"),
+    (2, 1, (2, 3, 2), 2, np.float64, 0, "generic"),
+    (3, 3, (2, 1, 2, 1, 2, 1), 5, np.float32, 0, "tile_global"),
+])
+def test_evaluation_levels_match_oracle(api, ctx, level, dx, dv, nc, k, dtype, kernel, expect):
+    dim = dx + dv
+    om, mf = _mesh_pair(api, ctx, dx, dv, nc, k, dtype=dtype)
+    vel = VEL[:dim]
+    orc = O.Oracle(om, k, skew=0.5, velocity=vel, nthreads=8, eval_level=level)
+    src = np.random.default_rng(5).standard_normal(orc.ndofs)
+    if dtype == np.float32:
+        src = src.astype(np.float32).astype(np.float64)
+    ref = orc.apply(src, time=0.0)
+    full = O.Oracle(om, k, skew=0.5, velocity=vel, nthreads=8).apply(src, time=0.0)
+    assert _rel(ref, full) > 1e-3  # the levels are different operators
+    op = api.AdvectionOperation(mf, vel, 0.5)
+    op.set_kernel(kernel)
+    op.set_evaluation_level(level)
+    d_src, d_dst = mf.initialize_dof_vector(), mf.initialize_dof_vector()
+    mf.copy_in(d_src, src)
+    op.apply(d_dst, d_src, 0.0)
+    tol = TOL64 if dtype == np.float64 else TOL32
+    assert _rel(mf.copy_out(d_dst), ref) <= tol
+    assert op.kernel_name == expect
+    assert op.ghost_sides() == [0] * 12  # no neighbour is read at these levels
+    # and back to the full operator
+    op.set_evaluation_level(api.EVAL_ALL)
+    op.apply(d_dst, d_src, 0.0)
+    assert _rel(mf.copy_out(d_dst), full) <= tol

@@ -94,6 +94,21 @@ if sel in ("dirichlet",):
     dirichlet_case("apply 3D3V k=3 f64, 8^6 cells, Dirichlet on all sides, generic kernel", 3, 3, 3, [8] * 6, np.float64, 1)
     dirichlet_case("apply 2D2V k=3 f64, 64x64x32x32 cells, Dirichlet on all sides", 2, 2, 3, [64, 64, 32, 32], np.float64, 0)
     dirichlet_case("apply 2D2V k=3 f64, 64x64x32x32 cells, Dirichlet on all sides, generic kernel", 2, 2, 3, [64, 64, 32, 32], np.float64, 1)
+if sel in ("levels",):
+    # attribution of the operator's time with the reference's evaluation levels (advection_operation.h:37-42)
+    for kern, kname in ((0, "three-round kernel"), (2, "two-role kernel")):
+        mf = api.MatrixFree(ctx, 3, 3, 3, [8] * 6, (0.0,) * 6, (1.0,) * 6)
+        op = api.AdvectionOperation(mf, V, 0.5)
+        op.set_kernel(kern)
+        src = torch.empty(mf.n_dofs, dtype=torch.float64, device="cuda"); dst = torch.empty_like(src)
+        api.VectorTools.interpolate(mf, src.data_ptr(), api.FN_HYPERRECTANGLE, 0.0)
+        for level, lname in ((api.EVAL_ALL, "all"), (api.EVAL_ALL_WITHOUT_NEIGHBOR_LOAD, "all_without_neighbor_load"), (api.EVAL_CELL, "cell")):
+            op.set_evaluation_level(level)
+            ms = timeit(lambda: op.apply(dst.data_ptr(), src.data_ptr(), 0.0))
+            report("apply 3D3V k=3 f64, 8^6 cells, %s, level %s" % (kname, lname), ms, mf.n_dofs, 16)
+        del src, dst
+        op.close(); mf.close()
+        torch.cuda.empty_cache()
 if sel in ("tg",):  # the not yet validated global-memory tile kernel on BASELINE.json configs[2]
     apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), global-memory tile kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=5)
     torch.cuda.empty_cache()
