@@ -37,6 +37,11 @@
 #ifndef HD_R6_REGS_PRODUCER
 #define HD_R6_REGS_PRODUCER 56
 #endif
+#ifndef HD_R6_FUSED_CS
+#define HD_R6_FUSED_CS 1 // fused LSRK epilogue: `sol` read and `sol` / `Ti_next` written with .cs (evict-first) accesses, so that the
+                         // streams do not push the face layers of src out of L2: DRAM reads 25.4 -> 23.9 GB, 8.58 -> 8.43 ms per stage
+                         // (profiles/r02y_fused_stream_ab.txt, r02y_rounds_fused_cs_ncu_summary.json)
+#endif
 #ifndef HD_R6_UNROLL_TASKS
 #define HD_R6_UNROLL_TASKS 1 // 1: both tasks unrolled (35 KB of hot loops, 2.04e9 instructions per apply, ~20 % of the stall samples are instruction fetch), 0: one rolled copy (17 KB, 2.42e9 instructions); A/B within one box: profiles/r02_rounds_ab.txt
 #endif
@@ -257,7 +262,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                 // requested here, not at the start of the task: a wait for the traces would wait for these loads as well
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-#ifdef HD_R6_FUSED_CS
+#if HD_R6_FUSED_CS
                   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(sv[i]) : "l"(p.sol + g + 256 * i)); // read once: evict-first, keeps the face layers of src in L2
 #else
                   sv[i] = r6_ldg(p.sol + g + 256 * i);
@@ -338,7 +343,7 @@ r6_compute(const FastParams &p, const r6::Coef &cf, const uint32_t base, const R
                   const double kv = q[i >> 2][i & 3];
                   if (FUSED)
                     {
-#ifdef HD_R6_FUSED_CS
+#if HD_R6_FUSED_CS
                       __stcs(p.sol + g + 256 * i, fma(p.fb, kv, sv[i]));
                       if (p.fa != 0.0)
                         __stcs(p.ti_next + g + 256 * i, fma(p.fa, kv, sv[i]));

@@ -297,6 +297,32 @@ namespace
       cf.xq[i] = (double)b.xq[i];
   }
 
+  inline void
+  vp_tile6_coefficients(const hd::Basis1D &b, const std::vector<double> &coef, VpTile6Coef &cf)
+  {
+    const int blk = 2 * 16 + 4 * 4;
+    for (int d = 0; d < 6; ++d)
+      for (int i = 0; i < 16; ++i)
+        {
+          cf.Ca[d][i]   = coef[(size_t)d * blk + i];
+          cf.Cabs[d][i] = coef[(size_t)d * blk + 16 + i];
+          if (i < 4)
+            {
+              cf.La0[d][i]   = coef[(size_t)d * blk + 32 + i];
+              cf.La1[d][i]   = coef[(size_t)d * blk + 36 + i];
+              cf.Labs0[d][i] = coef[(size_t)d * blk + 40 + i];
+              cf.Labs1[d][i] = coef[(size_t)d * blk + 44 + i];
+            }
+        }
+    for (int i = 0; i < 16; ++i)
+      {
+        cf.S[i]    = (double)b.S[i];
+        cf.Sinv[i] = (double)b.Sinv[i];
+      }
+    for (int i = 0; i < 4; ++i)
+      cf.xq[i] = (double)b.xq[i];
+  }
+
 #ifndef HD_VP_HOST_EMULATION
   template <typename T>
   __global__ void __launch_bounds__(256) k_apply_vp(const VpParams p)
@@ -402,6 +428,29 @@ namespace hd
     const bool f64 = m->d.number_type == HD_F64;
     // degree 3 with 4 quadrature points in 1D1V / 2D2V: the register-tile kernels (kernel_vp_tile.cuh); kernel choice 1
     // (hd_advection_set_kernel) keeps the generic one for A/B runs and as the cross-check of the tests
+    if (m->n == 4 && m->nq == 4 && m->dim == 6 && op->kernel_choice != 1 && !op->h_vp_coef.empty() && m->ncells < (1ll << 31))
+      {
+        VpTile6Coef cf;
+        vp_tile6_coefficients(m->basis, op->h_vp_coef, cf);
+        const size_t smem = (size_t)VPT6_SMEM * sizeof(double);
+        if (smem <= m->ctx->smem_optin)
+          {
+            if (f64)
+              {
+                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_3d3v<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_vp_tile_3d3v<double><<<(unsigned)m->ncells, 256, smem, m->ctx->stream>>>(p, cf);
+              }
+            else
+              {
+                HD_CUDA(cudaFuncSetAttribute(k_vp_tile_3d3v<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_vp_tile_3d3v<float><<<(unsigned)m->ncells, 256, smem, m->ctx->stream>>>(p, cf);
+              }
+            HD_CUDA(cudaGetLastError());
+            op->launches++;
+            op->last_kernel = "vp_tile_3d3v";
+            return HD_OK;
+          }
+      }
     if (m->n == 4 && m->nq == 4 && (m->dim == 2 || m->dim == 4) && op->kernel_choice != 1 && !op->h_vp_coef.empty() && m->ncells < (1ll << 31))
       {
         VpTileCoef cf;

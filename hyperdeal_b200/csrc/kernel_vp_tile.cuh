@@ -680,6 +680,460 @@ vpt2_cell(const VpParams &p, const VpTileCoef &cf, const long long cell)
   vpt_store_result<T>(p, cell * 16, O);
 }
 
+// ---- 3D3V ---------------------------------------------------------------------------------------------------------------
+// One CTA of 256 threads per cell (4096 values).  The six directions form three pairs, (x0,x1), (x2,v0), (v1,v2), and a
+// thread owns the 4x4 tile over one pair — three views of the same shared-memory buffer:
+//     P0: thread = tile number tau = (x2,v0,v1,v2),  tile over (x0,x1): 16 contiguous values (stride-18 padding as in 2D2V)
+//     P1: thread = (e01 = x0 + 4 x1, w = v1 + 4 v2), tile over (x2,v0)
+//     P2: thread = c = x0 + 4 x1 + 16 x2 + 64 v0,    tile over (v1,v2)
+// (all three conflict-free on buffers of 256 tiles x 18 doubles).  Four cell buffers B0..B3 (u / S_x u, two temporaries, the
+// x-part of the result) and six face buffers (the layers of the v-neighbours, S_x-transformed in shared memory).  Phases,
+// separated by __syncthreads (x-direction d pairs C(x_d) with M(v_d); the views are chosen so that u dies early):
+//     0  coalesced fetch: cell -> B0, six v-face layers -> BF, Ma/Mabs of the three v-coordinates -> BM
+//     A  [P1] T1/T2 = Ca_2/Cabs_2(x2) u + traces -> B1/B2;            face tiles: S(x0) S(x1) in place
+//     B  [P2] OUT  = Ma_2(v2) T1 + Mabs_2(v2) T2 -> B3;               face lines: S(x2) in place
+//     C  [P0] U <- B0;  T1/T2 = Ca_0/Cabs_0(x0) U + traces;  B0 <- S(x0) S(x1) U
+//     D  [P1] OUT += Ma_0(v0) T1 + Mabs_0(v0) T2
+//     E  [P0] T1/T2 = Ca_1/Cabs_1(x1) U + traces
+//     F  [P2] OUT += Ma_1(v1) T1 + Mabs_1(v1) T2
+//     G  [P1] W = S(x2) B0 -> B0;  R = (G_0 Ca_3 + |G_0| Cabs_3)(v0) W + traces -> B1      (G_0 varies along the tile's x2 index)
+//     H  [P2] R += (G_1 Ca_4 + |G_1| Cabs_4)(v1) W + (G_2 Ca_5 + |G_2| Cabs_5)(v2) W + traces  (G scalar per thread)
+//     I  [P1] R = Sinv(x2) R
+//     J  [P0] out = Sinv(x0) Sinv(x1) R + OUT -> B2
+//     K  coalesced store of B2 (or the fused LSRK update)
+// ~110 DFMA per DoF.  The phase functions take the thread index and the shared-memory block as arguments:
+// tests/vp_emulation_harness.cpp runs them thread by thread on the CPU against the oracle.
+
+struct VpTile6Coef
+{
+  double Ca[6][16], Cabs[6][16]; // [direction][out * 4 + in]
+  double La0[6][4], La1[6][4], Labs0[6][4], Labs1[6][4];
+  double S[16], Sinv[16];
+  double xq[4];
+};
+
+constexpr int VPT6_BUF  = 256 * VPT_TS;                 // one cell buffer (doubles)
+constexpr int VPT6_FACE = 64 * VPT_TS;                  // one face layer
+constexpr int VPT6_BM   = 4 * VPT6_BUF + 6 * VPT6_FACE; // offset of the Ma/Mabs block: [d][2][16]
+constexpr int VPT6_SMEM = VPT6_BM + 96;                 // doubles
+
+// tile element (a, b) of thread T in view P -> index into a cell buffer
+template <int P>
+HD_VPT_FN int
+vpt6_addr(const int T, const int a, const int b)
+{
+  if (P == 0)
+    return T * VPT_TS + a + 4 * b;
+  if (P == 1)
+    return (a + 4 * b + 16 * (T >> 4)) * VPT_TS + (T & 15);
+  return ((T >> 4) + 16 * (a + 4 * b)) * VPT_TS + (T & 15);
+}
+
+template <int P>
+HD_VPT_FN void
+vpt6_load(const double *buf, const int T, double (&A)[4][4])
+{
+  if (P == 0)
+    vpt_load_x(buf, T, A);
+  else
+    {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          A[b][a] = buf[vpt6_addr<P>(T, a, b)];
+    }
+}
+
+template <int P>
+HD_VPT_FN void
+vpt6_store(double *buf, const int T, const double (&A)[4][4])
+{
+  if (P == 0)
+    vpt_store_x(buf, T, A);
+  else
+    {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          buf[vpt6_addr<P>(T, a, b)] = A[b][a];
+    }
+}
+
+struct Vpt6Cell // per-CTA (identical in all threads): the cell, its coordinates and neighbours
+{
+  long long cell;
+  int       c[6];
+  long long nb[6][2]; // [direction][side]
+};
+
+HD_VPT_FN void
+vpt6_decode(const VpParams &p, const long long cell, Vpt6Cell &C)
+{
+  C.cell = cell;
+  unsigned  r = (unsigned)cell;
+  long long m = 1;
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+    {
+      const unsigned nc = (unsigned)p.ncell[d], q = r / nc;
+      C.c[d]            = int(r - q * nc);
+      r                 = q;
+      vpt_neighbours(p, cell, C.c[d], m, d, C.nb[d][0], C.nb[d][1]);
+      m *= p.ncell[d];
+    }
+}
+
+// phase 0
+template <typename T_>
+HD_VPT_FN void
+vpt6_phase0(const VpParams &p, const VpTile6Coef &cf, const Vpt6Cell &C, double *sm, const int T)
+{
+  const T_ *src = static_cast<const T_ *>(p.src);
+  double *  B0 = sm, *BF = sm + 4 * VPT6_BUF, *BM = sm + VPT6_BM;
+  // the cell: piece k = 256 i + T = values 2k, 2k + 1
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    {
+      const int k = 256 * i + T;
+      double    a, b;
+      vpt_load2(src + C.cell * 4096 + 2 * k, a, b);
+      vpt_sm_store2(B0 + (k >> 3) * VPT_TS + 2 * (k & 7), a, b);
+    }
+  // the six v-face layers: piece k = 256 i + T (i < 12): face f = k / 512 = (v-direction f >> 1, side f & 1), face tile tf =
+  // x2 + 4 o1 + 16 o2 (o1, o2 = the other two v-indices, ascending), part = k & 7
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+    {
+      const int k = 256 * i + T, f = i >> 1, dv = f >> 1, side = f & 1, rem = k & 511, tf = rem >> 3, part = rem & 7;
+      const int layer = side ? 0 : 3, x2 = tf & 3, o1 = (tf >> 2) & 3, o2 = tf >> 4;
+      const int taun  = dv == 0 ? x2 + 4 * layer + 16 * o1 + 64 * o2 : (dv == 1 ? x2 + 4 * o1 + 16 * layer + 64 * o2 : x2 + 4 * o1 + 16 * o2 + 64 * layer);
+      const long long nbc = dv == 0 ? C.nb[3][side] : (dv == 1 ? C.nb[4][side] : C.nb[5][side]);
+      double    a, b;
+      vpt_load2(src + nbc * 4096 + 16 * taun + 2 * part, a, b);
+      vpt_sm_store2(BF + f * VPT6_FACE + tf * VPT_TS + 2 * part, a, b);
+    }
+  // Ma / Mabs of the three v-coordinates: BM[d][0 | 1][i * 4 + j]
+  if (T < 48)
+    {
+      const int d = T >> 4, i = (T >> 2) & 3, j = T & 3;
+      const int cd = d == 0 ? C.c[3] : (d == 1 ? C.c[4] : C.c[5]);
+      const double left = d == 0 ? p.left[3] : (d == 1 ? p.left[4] : p.left[5]), h = d == 0 ? p.h[3] : (d == 1 ? p.h[4] : p.h[5]);
+      const int off = d == 0 ? p.cell_offset[3] : (d == 1 ? p.cell_offset[4] : p.cell_offset[5]);
+      double ma = 0.0, mabs = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        {
+          const double g = left + h * ((cd + off) + cf.xq[q]);
+          const double s = cf.Sinv[i * 4 + q] * cf.S[q * 4 + j];
+          ma += s * g;
+          mabs += s * fabs(g);
+        }
+      BM[d * 32 + (T & 15)]      = ma;
+      BM[d * 32 + 16 + (T & 15)] = mabs;
+    }
+}
+
+// T1/T2 = Ca_d/Cabs_d U + lifted traces, sweep along the tile's fast (ALONG_A) or slow index; tl/th indexed by the other one
+template <bool ALONG_A>
+HD_VPT_FN void
+vpt6_cpart(const VpTile6Coef &cf, const int d, const double (&U)[4][4], const double (&tl)[4], const double (&th)[4], double (&A)[4][4], double (&B)[4][4])
+{
+  if (ALONG_A)
+    {
+      vpt_sweep_a<false>(cf.Ca[d], U, A);
+      vpt_sweep_a<false>(cf.Cabs[d], U, B);
+    }
+  else
+    {
+      vpt_sweep_b<false>(cf.Ca[d], U, A);
+      vpt_sweep_b<false>(cf.Cabs[d], U, B);
+    }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      {
+        const int o = ALONG_A ? a : b, t = ALONG_A ? b : a; // o: index along the sweep direction, t: index of the trace value
+        A[b][a] += cf.La0[d][o] * tl[t] + cf.La1[d][o] * th[t];
+        B[b][a] += cf.Labs0[d][o] * tl[t] + cf.Labs1[d][o] * th[t];
+      }
+}
+
+// S(x0) S(x1) on the face tiles (384 tiles: 2 per thread, the second one for T < 128 only)
+HD_VPT_FN void
+vpt6_face_s01(const VpTile6Coef &cf, double *sm, const int T)
+{
+  double *BF = sm + 4 * VPT6_BUF;
+#pragma unroll 1
+  for (int tt = T; tt < 384; tt += 256)
+    {
+      double *fb = BF + (tt >> 6) * VPT6_FACE;
+      double  A[4][4], B[4][4];
+      vpt_load_x(fb, tt & 63, A);
+      vpt_sweep_a<false>(cf.S, A, B);
+      vpt_sweep_b<false>(cf.S, B, A);
+      vpt_store_x(fb, tt & 63, A);
+    }
+}
+
+// S(x2) on the face lines: thread T = (e01, oo): the 4 values x2 = 0..3 at face tile x2 + 4 oo, element e01, of every face
+HD_VPT_FN void
+vpt6_face_s2(const VpTile6Coef &cf, double *sm, const int T)
+{
+  double *  BF = sm + 4 * VPT6_BUF;
+  const int e01 = T & 15, oo = T >> 4;
+#pragma unroll
+  for (int f = 0; f < 6; ++f)
+    {
+      double *q = BF + f * VPT6_FACE + (4 * oo) * VPT_TS + e01;
+      double  v[4], o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = q[j * VPT_TS];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o[i] = cf.S[i * 4 + 0] * v[0] + cf.S[i * 4 + 1] * v[1] + cf.S[i * 4 + 2] * v[2] + cf.S[i * 4 + 3] * v[3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        q[j * VPT_TS] = o[j];
+    }
+}
+
+// The x-traces (raw values of the x-neighbours, global memory through L2) of a phase are requested one or two phases before
+// they are used — with one CTA per SM nothing else hides their latency.  tr[0][.] = lower, tr[1][.] = upper neighbour.
+//   direction 2 (phase A, P1 view): layers x2 = 3 / 0 at (e01; v0 = b; w)
+//   direction 0 (phase C, P0 view): elements 3 + 4 b / 4 b of the neighbour's tile T
+//   direction 1 (phase E, P0 view): elements 12 + a / a
+template <typename T_, int D>
+HD_VPT_FN void
+vpt6_request_traces(const VpParams &p, const Vpt6Cell &C, const int T, double (&tr)[2][4])
+{
+  const T_ *src = static_cast<const T_ *>(p.src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    {
+      if (D == 2)
+        {
+          tr[0][i] = double(src[C.nb[2][0] * 4096 + (T & 15) + 48 + 64 * i + 256 * (T >> 4)]);
+          tr[1][i] = double(src[C.nb[2][1] * 4096 + (T & 15) + 64 * i + 256 * (T >> 4)]);
+        }
+      else if (D == 0)
+        {
+          tr[0][i] = double(src[C.nb[0][0] * 4096 + 16 * T + 3 + 4 * i]);
+          tr[1][i] = double(src[C.nb[0][1] * 4096 + 16 * T + 4 * i]);
+        }
+      else
+        {
+          tr[0][i] = double(src[C.nb[1][0] * 4096 + 16 * T + 12 + i]);
+          tr[1][i] = double(src[C.nb[1][1] * 4096 + 16 * T + i]);
+        }
+    }
+}
+
+HD_VPT_FN void
+vpt6_phaseA(const VpTile6Coef &cf, double *sm, const int T, const double (&tr)[2][4])
+{
+  double *B0 = sm, *B1 = sm + VPT6_BUF, *B2 = sm + 2 * VPT6_BUF;
+  double  U[4][4], A[4][4], B[4][4];
+  const double(&tl)[4] = tr[0], (&th)[4] = tr[1];
+  vpt6_load<1>(B0, T, U);
+  vpt6_cpart<true>(cf, 2, U, tl, th, A, B); // x2 = the fast index of a P1 tile
+  vpt6_store<1>(B1, T, A);
+  vpt6_store<1>(B2, T, B);
+  vpt6_face_s01(cf, sm, T);
+}
+
+// OUT (+)= Ma_d T1 + Mabs_d T2 in view P, sweep along the fast (ALONG_A) or the slow index
+template <int P, bool ALONG_A, bool ADD>
+HD_VPT_FN void
+vpt6_mpart(double *sm, const int d, const int T)
+{
+  double *B1 = sm + VPT6_BUF, *B2 = sm + 2 * VPT6_BUF, *B3 = sm + 3 * VPT6_BUF, *BM = sm + VPT6_BM + d * 32;
+  double  A[4][4], O[4][4], M[16];
+  if (ADD)
+    vpt6_load<P>(B3, T, O);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    M[i] = BM[i];
+  vpt6_load<P>(B1, T, A);
+  if (ALONG_A)
+    {
+      if (ADD)
+        vpt_sweep_a<true>(M, A, O);
+      else
+        vpt_sweep_a<false>(M, A, O);
+    }
+  else
+    {
+      if (ADD)
+        vpt_sweep_b<true>(M, A, O);
+      else
+        vpt_sweep_b<false>(M, A, O);
+    }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    M[i] = BM[16 + i];
+  vpt6_load<P>(B2, T, A);
+  if (ALONG_A)
+    vpt_sweep_a<true>(M, A, O);
+  else
+    vpt_sweep_b<true>(M, A, O);
+  vpt6_store<P>(B3, T, O);
+}
+
+// phases C and E share the thread's U tile (registers)
+HD_VPT_FN void
+vpt6_phaseC(const VpTile6Coef &cf, double *sm, const int T, double (&U)[4][4], const double (&tr)[2][4])
+{
+  double *B0 = sm, *B1 = sm + VPT6_BUF, *B2 = sm + 2 * VPT6_BUF;
+  double  A[4][4], B[4][4];
+  const double(&tl)[4] = tr[0], (&th)[4] = tr[1];
+  vpt6_load<0>(B0, T, U);
+  vpt6_cpart<true>(cf, 0, U, tl, th, A, B);
+  vpt6_store<0>(B1, T, A);
+  vpt6_store<0>(B2, T, B);
+  vpt_sweep_a<false>(cf.S, U, A);
+  vpt_sweep_b<false>(cf.S, A, B);
+  vpt6_store<0>(B0, T, B);
+}
+
+HD_VPT_FN void
+vpt6_phaseE(const VpTile6Coef &cf, double *sm, const int T, const double (&U)[4][4], const double (&tr)[2][4])
+{
+  double *B1 = sm + VPT6_BUF, *B2 = sm + 2 * VPT6_BUF;
+  double  A[4][4], B[4][4];
+  const double(&tl)[4] = tr[0], (&th)[4] = tr[1];
+  vpt6_cpart<false>(cf, 1, U, tl, th, A, B);
+  vpt6_store<0>(B1, T, A);
+  vpt6_store<0>(B2, T, B);
+}
+
+HD_VPT_FN void
+vpt6_phaseG(const VpParams &p, const VpTile6Coef &cf, const Vpt6Cell &C, double *sm, const int T)
+{
+  double *  B0 = sm, *B1 = sm + VPT6_BUF, *BF = sm + 4 * VPT6_BUF;
+  const int e01 = T & 15, w = T >> 4;
+  double    W01[4][4], W[4][4], A[4][4], B[4][4];
+  vpt6_load<1>(B0, T, W01);
+  vpt_sweep_a<false>(cf.S, W01, W); // S(x2): x2 = the fast index
+  vpt6_store<1>(B0, T, W);
+  vpt_sweep_b<false>(cf.Ca[3], W, A); // v0 = the slow index
+  vpt_sweep_b<false>(cf.Cabs[3], W, B);
+  const long long cx = C.c[0] + (long long)p.ncell[0] * (C.c[1] + (long long)p.ncell[1] * C.c[2]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    {
+      const double g  = p.a_v[(cx * 64 + e01 + 16 * a) * 3 + 0], ga = fabs(g);
+      const double fl = BF[0 * VPT6_FACE + (a + 4 * w) * VPT_TS + e01], fh = BF[1 * VPT6_FACE + (a + 4 * w) * VPT_TS + e01];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        A[b][a] = g * (A[b][a] + cf.La0[3][b] * fl + cf.La1[3][b] * fh) + ga * (B[b][a] + cf.Labs0[3][b] * fl + cf.Labs1[3][b] * fh);
+    }
+  vpt6_store<1>(B1, T, A);
+}
+
+HD_VPT_FN void
+vpt6_phaseH(const VpParams &p, const VpTile6Coef &cf, const Vpt6Cell &C, double *sm, const int T)
+{
+  double *  B0 = sm, *B1 = sm + VPT6_BUF, *BF = sm + 4 * VPT6_BUF;
+  const int e01 = T & 15, x2 = (T >> 4) & 3, v0 = T >> 6;
+  double    W[4][4], R[4][4], M[16];
+  vpt6_load<2>(B0, T, W);
+  vpt6_load<2>(B1, T, R);
+  const long long cx = C.c[0] + (long long)p.ncell[0] * (C.c[1] + (long long)p.ncell[1] * C.c[2]);
+  const double    g1 = p.a_v[(cx * 64 + (T & 63)) * 3 + 1], g2 = p.a_v[(cx * 64 + (T & 63)) * 3 + 2];
+  const double    a1 = fabs(g1), a2 = fabs(g2);
+  // v1 = the fast index: faces 2 (lower), 3 (upper) of the v1-neighbours at (x..; v0; v2 = b)
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    M[i] = g1 * cf.Ca[4][i] + a1 * cf.Cabs[4][i];
+  vpt_sweep_a<true>(M, W, R);
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    {
+      const double fl = BF[2 * VPT6_FACE + (x2 + 4 * v0 + 16 * b) * VPT_TS + e01], fh = BF[3 * VPT6_FACE + (x2 + 4 * v0 + 16 * b) * VPT_TS + e01];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        R[b][a] += (g1 * cf.La0[4][a] + a1 * cf.Labs0[4][a]) * fl + (g1 * cf.La1[4][a] + a1 * cf.Labs1[4][a]) * fh;
+    }
+  // v2 = the slow index: faces 4, 5 at (x..; v0; v1 = a)
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    M[i] = g2 * cf.Ca[5][i] + a2 * cf.Cabs[5][i];
+  vpt_sweep_b<true>(M, W, R);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    {
+      const double fl = BF[4 * VPT6_FACE + (x2 + 4 * v0 + 16 * a) * VPT_TS + e01], fh = BF[5 * VPT6_FACE + (x2 + 4 * v0 + 16 * a) * VPT_TS + e01];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        R[b][a] += (g2 * cf.La0[5][b] + a2 * cf.Labs0[5][b]) * fl + (g2 * cf.La1[5][b] + a2 * cf.Labs1[5][b]) * fh;
+    }
+  vpt6_store<2>(B1, T, R);
+}
+
+HD_VPT_FN void
+vpt6_phaseI(const VpTile6Coef &cf, double *sm, const int T)
+{
+  double *B1 = sm + VPT6_BUF;
+  double  R[4][4], A[4][4];
+  vpt6_load<1>(B1, T, R);
+  vpt_sweep_a<false>(cf.Sinv, R, A);
+  vpt6_store<1>(B1, T, A);
+}
+
+HD_VPT_FN void
+vpt6_phaseJ(const VpTile6Coef &cf, double *sm, const int T)
+{
+  double *B1 = sm + VPT6_BUF, *B2 = sm + 2 * VPT6_BUF, *B3 = sm + 3 * VPT6_BUF;
+  double  R[4][4], A[4][4], O[4][4];
+  vpt6_load<0>(B1, T, R);
+  vpt6_load<0>(B3, T, O);
+  vpt_sweep_a<false>(cf.Sinv, R, A);
+  vpt_sweep_b<true>(cf.Sinv, A, O);
+  vpt6_store<0>(B2, T, O);
+}
+
+// fused LSRK update: the thread's `sol` values are requested two phases before the store (phase I), see phase K
+template <typename T_>
+HD_VPT_FN void
+vpt6_request_sol(const VpParams &p, const Vpt6Cell &C, const int T, double (&sv)[8][2])
+{
+  const T_ *sol = static_cast<const T_ *>(p.sol);
+  if (p.fused)
+    {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        vpt_load2(sol + C.cell * 4096 + 2 * (256 * i + T), sv[i][0], sv[i][1]);
+    }
+}
+
+template <typename T_>
+HD_VPT_FN void
+vpt6_phaseK(const VpParams &p, const Vpt6Cell &C, const double *sm, const int T, const double (&sv)[8][2])
+{
+  const double *  B2  = sm + 2 * VPT6_BUF;
+  T_ *            dst = static_cast<T_ *>(p.dst), *sol = static_cast<T_ *>(p.sol), *tin = static_cast<T_ *>(p.ti_next);
+  const long long g0  = C.cell * 4096;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    {
+      const int k = 256 * i + T;
+      double    v0, v1;
+      vpt_sm_load2(B2 + (k >> 3) * VPT_TS + 2 * (k & 7), v0, v1);
+      if (p.fused)
+        {
+          vpt_store2(sol + g0 + 2 * k, sv[i][0] + p.fb * v0, sv[i][1] + p.fb * v1);
+          if (p.fa != 0.0)
+            vpt_store2(tin + g0 + 2 * k, sv[i][0] + p.fa * v0, sv[i][1] + p.fa * v1);
+        }
+      else
+        vpt_store2(dst + g0 + 2 * k, v0, v1);
+    }
+}
+
 #ifndef HD_VP_HOST_EMULATION
 // 2D2V: WARPS warps per CTA, two cells per warp; MINB CTAs per SM bound the register allocation (12 warps per SM = 168
 // registers, no spills)
@@ -721,5 +1175,44 @@ __global__ void __launch_bounds__(128) k_vp_tile_1d1v(const VpParams p, const __
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell < p.ncells)
     vpt2_cell<T>(p, cf, cell);
+}
+// 3D3V: one cell per CTA of 256 threads
+template <typename T_>
+__global__ void __launch_bounds__(256, 1) k_vp_tile_3d3v(const VpParams p, const __grid_constant__ VpTile6Coef cf)
+{
+  extern __shared__ double sm[];
+  const int T = threadIdx.x;
+  Vpt6Cell  C;
+  vpt6_decode(p, blockIdx.x, C);
+  double trA[2][4], trC[2][4], trE[2][4], sv[8][2];
+  vpt6_request_traces<T_, 2>(p, C, T, trA);
+  vpt6_phase0<T_>(p, cf, C, sm, T);
+  __syncthreads();
+  vpt6_request_traces<T_, 0>(p, C, T, trC);
+  vpt6_phaseA(cf, sm, T, trA);
+  __syncthreads();
+  vpt6_mpart<2, false, false>(sm, 2, T); // B: OUT = Ma_2(v2) ..., v2 = the slow index of a P2 tile
+  vpt6_face_s2(cf, sm, T);
+  __syncthreads();
+  double U[4][4];
+  vpt6_request_traces<T_, 1>(p, C, T, trE);
+  vpt6_phaseC(cf, sm, T, U, trC);
+  __syncthreads();
+  vpt6_mpart<1, false, true>(sm, 0, T); // D: v0 = the slow index of a P1 tile
+  __syncthreads();
+  vpt6_phaseE(cf, sm, T, U, trE);
+  __syncthreads();
+  vpt6_mpart<2, true, true>(sm, 1, T); // F: v1 = the fast index of a P2 tile
+  __syncthreads();
+  vpt6_phaseG(p, cf, C, sm, T);
+  __syncthreads();
+  vpt6_phaseH(p, cf, C, sm, T);
+  __syncthreads();
+  vpt6_request_sol<T_>(p, C, T, sv);
+  vpt6_phaseI(cf, sm, T);
+  __syncthreads();
+  vpt6_phaseJ(cf, sm, T);
+  __syncthreads();
+  vpt6_phaseK<T_>(p, C, sm, T, sv);
 }
 #endif

@@ -73,4 +73,4 @@ def test_general_velocity_kernel_matches_oracle():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "vp_kernel_check.py")], capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("VPK OK") == 20 and "VPK FAIL" not in r.stdout
+    assert r.stdout.count("VPK OK") == 24 and "VPK FAIL" not in r.stdout

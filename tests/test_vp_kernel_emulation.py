@@ -41,12 +41,15 @@ TILE_CASES = [
     (2, (1, 1, 1, 1), 0.0),       # one cell: every neighbour is the cell itself; the second half of the warp idles
     (2, (3, 1, 1, 3), 0.3),       # odd number of cells
     (2, (4, 2, 3, 2), 1.0),
+    (3, (2, 1, 2, 2, 2, 1), 0.0),
+    (3, (2, 3, 2, 1, 2, 2), 0.5),
+    (3, (1, 1, 1, 1, 1, 1), 0.3),
 ]
 
 
 @pytest.mark.parametrize("dx,nc,skew", TILE_CASES)
 def test_tile_kernel_source_matches_literal_oracle(emu, dx, nc, skew):
-    """kernel_vp_tile.cuh (degree 3, n_points 4; 1D1V thread-per-cell, 2D2V warp phases) against the oracle's literal kernel"""
+    """kernel_vp_tile.cuh (degree 3, n_points 4; 1D1V thread-per-cell, 2D2V warp phases, 3D3V CTA phases) against the oracle's literal kernel"""
     dim = 2 * dx
     left, right = (0.0,) * dx + (-1.3,) * dx, (2.0,) * dx + (1.7,) * dx  # v = 0 lies inside a cell
     vp = V.VlasovPoissonOracle(dx, dx, 3, nc, left, right, nthreads=2)

@@ -2,6 +2,7 @@
 // Includes the source of the general-velocity kernel with the host-emulation switch: the per-cell body then runs as ONE
 // sequential "thread" per cell with barriers as no-ops, which computes what the barrier-synchronised CUDA kernel computes.
 #define HD_VP_HOST_EMULATION
+#include <array>
 #include "../hyperdeal_b200/csrc/kernel_vp.cu"
 
 // test harness entry point (tests only): every cell of a periodic lattice, one sequential "thread" per cell
@@ -78,7 +79,7 @@ hd_vp_tile_emulate(const double *src, double *dst, const double *a_v, int dim_x,
       hd::Basis1D b;
       b.init(3, 4, false);
       const int dim = 2 * dim_x;
-      if (dim != 2 && dim != 4)
+      if (dim != 2 && dim != 4 && dim != 6)
         return -2;
       VpParams  p;
       double    h[HD_MAX_DIM];
@@ -103,7 +104,7 @@ hd_vp_tile_emulate(const double *src, double *dst, const double *a_v, int dim_x,
       p.a_v = a_v;
       p.dim_x = p.dim_v = dim_x;
       p.n = p.nq = 4;
-      p.nd = dim == 2 ? 16 : 256;
+      p.nd = dim == 2 ? 16 : (dim == 4 ? 256 : 4096);
       p.ncells = ncells;
       p.cap = 0;
       p.sol = p.ti_next = nullptr;
@@ -113,6 +114,66 @@ hd_vp_tile_emulate(const double *src, double *dst, const double *a_v, int dim_x,
         {
           for (long long cell = 0; cell < ncells; ++cell)
             vpt2_cell<double>(p, cf, cell);
+          return 0;
+        }
+      if (dim == 6)
+        {
+          // 3D3V: the phases of one CTA (256 threads), thread by thread; __syncthreads separates them on the device
+          VpTile6Coef cf6;
+          vp_tile6_coefficients(b, coef, cf6);
+          std::vector<double> sm6(VPT6_SMEM, std::nan(""));
+          std::vector<std::array<std::array<double, 4>, 4>> Us(256);
+          for (long long cell = 0; cell < ncells; ++cell)
+            {
+              Vpt6Cell C;
+              vpt6_decode(p, cell, C);
+              double *sm = sm6.data();
+              auto    U  = [&](int T) -> double(&)[4][4] { return *reinterpret_cast<double(*)[4][4]>(Us[T].data()); };
+              struct Tr
+              {
+                double a[2][4], c[2][4], e[2][4], sv[8][2];
+              };
+              std::vector<Tr> tr(256);
+              for (int T = 0; T < 256; ++T)
+                {
+                  vpt6_request_traces<double, 2>(p, C, T, tr[T].a);
+                  vpt6_phase0<double>(p, cf6, C, sm, T);
+                }
+              for (int T = 0; T < 256; ++T)
+                {
+                  vpt6_request_traces<double, 0>(p, C, T, tr[T].c);
+                  vpt6_phaseA(cf6, sm, T, tr[T].a);
+                }
+              for (int T = 0; T < 256; ++T)
+                {
+                  vpt6_mpart<2, false, false>(sm, 2, T);
+                  vpt6_face_s2(cf6, sm, T);
+                }
+              for (int T = 0; T < 256; ++T)
+                {
+                  vpt6_request_traces<double, 1>(p, C, T, tr[T].e);
+                  vpt6_phaseC(cf6, sm, T, U(T), tr[T].c);
+                }
+              for (int T = 0; T < 256; ++T)
+                vpt6_mpart<1, false, true>(sm, 0, T);
+              for (int T = 0; T < 256; ++T)
+                vpt6_phaseE(cf6, sm, T, U(T), tr[T].e);
+              for (int T = 0; T < 256; ++T)
+                vpt6_mpart<2, true, true>(sm, 1, T);
+              for (int T = 0; T < 256; ++T)
+                vpt6_phaseG(p, cf6, C, sm, T);
+              for (int T = 0; T < 256; ++T)
+                vpt6_phaseH(p, cf6, C, sm, T);
+              for (int T = 0; T < 256; ++T)
+                {
+                  vpt6_request_sol<double>(p, C, T, tr[T].sv);
+                  vpt6_phaseI(cf6, sm, T);
+                }
+              for (int T = 0; T < 256; ++T)
+                vpt6_phaseJ(cf6, sm, T);
+              for (int T = 0; T < 256; ++T)
+                vpt6_phaseK<double>(p, C, sm, T, tr[T].sv);
+            }
           return 0;
         }
       std::vector<double> sm(VPT_WARP, std::nan(""));

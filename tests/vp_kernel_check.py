@@ -23,15 +23,17 @@ CASES = [
     (2, 2, (5, 4, 3, 4), None, 1.0, np.float64),
     (2, 2, (2, 2, 3, 2), 5, 0.3, np.float64),
     (3, 3, (2, 1, 2, 2, 2, 1), None, 0.0, np.float64),
+    (3, 3, (2, 2, 2, 2, 2, 2), None, 0.5, np.float64),
+    (3, 3, (1, 2, 1, 2, 1, 2), None, 0.3, np.float32),
     (2, 2, (3, 2, 2, 2), None, 0.0, np.float32),
     (1, 1, (7, 3), None, 0.0, np.float32),
 ]
 
 
 def expected_kernel(dx, nq):
-    """degree 3 with 4 quadrature points in 1D1V / 2D2V: the register-tile kernels (kernel_vp_tile.cuh); else the generic one"""
-    if nq in (None, 4) and dx in (1, 2):
-        return "vp_tile_1d1v" if dx == 1 else "vp_tile_2d2v"
+    """degree 3 with 4 quadrature points: the register-tile kernels (kernel_vp_tile.cuh); else the generic one"""
+    if nq in (None, 4):
+        return {1: "vp_tile_1d1v", 2: "vp_tile_2d2v", 3: "vp_tile_3d3v"}[dx]
     return "vp_generic"
 
 
