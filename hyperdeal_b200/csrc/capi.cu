@@ -634,6 +634,8 @@ hd_timer_stop(hd_context *ctx, double *ms)
 }
 
 // ---- mesh ---------------------------------------------------------------------------------
+static int mesh_device_setup(hd_mesh *m, const std::vector<double> &hb);
+
 int
 hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
 {
@@ -717,7 +719,22 @@ hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
     hb.push_back((double)v);
   for (auto v : m->basis.Sinv)
     hb.push_back((double)v);
-  HD_CUDA(cudaSetDevice(ctx->device));
+  // (device allocations: a failure past this point frees what was allocated — mesh_device_setup returns, the caller destroys)
+  const int rc = mesh_device_setup(m, hb);
+  if (rc != HD_OK)
+    {
+      hd_mesh_destroy(m);
+      return rc;
+    }
+  *out = m;
+  return HD_OK;
+}
+
+static int
+mesh_device_setup(hd_mesh *m, const std::vector<double> &hb)
+{
+  const hd_mesh_desc *desc = &m->d;
+  HD_CUDA(cudaSetDevice(m->ctx->device));
   HD_CUDA(cudaMalloc(&m->d_basis, hb.size() * sizeof(double)));
   HD_CUDA(cudaMemcpy(m->d_basis, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
   HD_CUDA(cudaMalloc(&m->d_reduce, 2 * sizeof(double)));
@@ -735,7 +752,6 @@ hd_mesh_create(hd_context *ctx, const hd_mesh_desc *desc, hd_mesh **out)
     HD_CUDA(cudaMalloc(&m->d_wv, wv.size() * sizeof(double)));
     HD_CUDA(cudaMemcpy(m->d_wv, wv.data(), wv.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
-  *out = m;
   return HD_OK;
 }
 
@@ -1548,7 +1564,7 @@ hd_halo_pack_ex(hd_mesh *m, const void *src, void *send, const int *send_mask, v
         const int nfi = (int)m->nf, sdi = (int)stride_d, nfci = (int)nfc;
         // An SM only hosts kernels of one shared-memory carve-out at a time: ask for the operator kernel's (maximum shared
         // memory), otherwise pack CTAs and the persistent operator CTAs exclude each other and nothing overlaps.
-        static bool carveout_set = false;
+        bool &carveout_set = m->ctx->pack_carveout_set; // (a per-device attribute: per context, not a process-wide static)
         if (!carveout_set)
           {
             cudaFuncSetAttribute(k_halo_pack<double, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

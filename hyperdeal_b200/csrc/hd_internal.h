@@ -40,6 +40,7 @@ struct hd_context
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
   int          sm_count = 0;
   size_t       smem_optin = 0;
+  bool         pack_carveout_set = false; // k_halo_pack's shared-memory carve-out has been set on this device
 };
 
 struct hd_mesh

@@ -204,22 +204,25 @@ hd_phase_space_diagnostics(hd_mesh *m, const void *vec, double out[6])
   const size_t     smem = (2 * (size_t)p.cap + 6 * 128) * sizeof(double);
   if (smem > m->ctx->smem_optin)
     return hd::fail(HD_ERR_UNSUPPORTED, "phase_space_diagnostics: cell does not fit into shared memory");
+  if (smem > 48 * 1024)
+    {
+      if (m->d.number_type == HD_F64)
+        HD_CUDA(cudaFuncSetAttribute(k_phase_space_diagnostics<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else
+        HD_CUDA(cudaFuncSetAttribute(k_phase_space_diagnostics<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+  // (no early return while d_out is alive)
   double *d_out = nullptr;
   HD_CUDA(cudaMalloc(&d_out, 6 * sizeof(double)));
-  HD_CUDA(cudaMemsetAsync(d_out, 0, 6 * sizeof(double), m->ctx->stream));
-  if (m->d.number_type == HD_F64)
+  cudaError_t e = cudaMemsetAsync(d_out, 0, 6 * sizeof(double), m->ctx->stream);
+  if (e == cudaSuccess)
     {
-      if (smem > 48 * 1024)
-        HD_CUDA(cudaFuncSetAttribute(k_phase_space_diagnostics<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_phase_space_diagnostics<double><<<(unsigned)m->ncells, 128, smem, m->ctx->stream>>>(p, static_cast<const double *>(vec), d_out);
+      if (m->d.number_type == HD_F64)
+        k_phase_space_diagnostics<double><<<(unsigned)m->ncells, 128, smem, m->ctx->stream>>>(p, static_cast<const double *>(vec), d_out);
+      else
+        k_phase_space_diagnostics<float><<<(unsigned)m->ncells, 128, smem, m->ctx->stream>>>(p, static_cast<const float *>(vec), d_out);
+      e = cudaGetLastError();
     }
-  else
-    {
-      if (smem > 48 * 1024)
-        HD_CUDA(cudaFuncSetAttribute(k_phase_space_diagnostics<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_phase_space_diagnostics<float><<<(unsigned)m->ncells, 128, smem, m->ctx->stream>>>(p, static_cast<const float *>(vec), d_out);
-    }
-  cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out, d_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream);
   if (e == cudaSuccess)
