@@ -13,6 +13,7 @@
 // Everything is built on the single-brick C ABI; nothing here launches a kernel of its own.
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "hd_internal.h"
@@ -32,6 +33,10 @@ struct hd_multi
   std::vector<bool>               done_valid[2];
   long long                       exchanges = 0;
   int                             dim = 0;
+  // fused halo (3D3V degree-3 FP64 kernels): arrival counters of every brick, slot 2 * d + side (peer-written), and the
+  // number of fused applications so far (the counters are never reset: target = applications * sender CTAs)
+  std::vector<int *> counters;
+  long long          fused_apps = 0;
 };
 
 struct hd_multi_advection
@@ -39,6 +44,7 @@ struct hd_multi_advection
   hd_multi *                  mm = nullptr;
   std::vector<hd_advection *> op;
   std::vector<std::array<int, 2 * HD_MAX_DIM>> needed; // per brick: ghost sides its operator reads
+  bool                                         fused = false; // the operator kernel packs and sends the halo itself
 };
 
 struct hd_multi_lsrk
@@ -142,6 +148,51 @@ namespace
       }
     return HD_OK;
   }
+  // One operator application (or fused LSRK stage: rk != nullptr) on all bricks with the halo INSIDE the operator kernel
+  // (hd_advection_apply_overlapped / hd_lsrk_stage_overlapped): the first CTAs of brick j's kernel pack its boundary
+  // layers, store them into the receivers' ghost buffers over NVLink and bump the receivers' arrival counters; the
+  // kernel's boundary phase waits for its own counters.  The kernels of all bricks are launched back to back from this
+  // thread (asynchronously), so every kernel finds its senders running.  Buffer reuse is ordered by events as in exchange().
+  int
+  fused_step(hd_multi *mm, hd_multi_advection *mop, hd_multi_lsrk *mrk, int stage, void *const *dst, void *const *src, void *const *solution, void *const *ti_next,
+             double t, double dt)
+  {
+    const int n      = mm->n;
+    const int buf    = int(mm->exchanges & 1);
+    const int target = int((mm->fused_apps + 1) * hd_advection_n_halo_senders(mop->op[0]));
+    for (int j = 0; j < n; ++j)
+      {
+        hd_halo_send sends[2 * HD_MAX_DIM];
+        int          n_sends = 0;
+        HD_CUDA(cudaSetDevice(mm->device[j]));
+        for (int d = 0; d < mm->dim; ++d)
+          for (int s = 0; s < 2; ++s)
+            {
+              if (mm->grid[d] == 1)
+                continue;
+              const int i = neighbour(mm, j, d, s);
+              if (i < 0 || !mop->needed[i][2 * d + (1 - s)])
+                continue;
+              sends[n_sends].dir  = d;
+              sends[n_sends].side = s;
+              sends[n_sends].dst  = static_cast<char *>(mm->ghost[buf][i]) + (size_t)hd_halo_offset(mm->mesh[i], d, 1 - s) * mm->mesh[i]->elem_size;
+              sends[n_sends].arrival_counter = mm->counters[i] + (2 * d + (1 - s));
+              ++n_sends;
+              if (mm->done_valid[buf][i])
+                HD_CUDA(cudaStreamWaitEvent(mm->stream[j], mm->ev_done[buf][i], 0));
+            }
+        int rc;
+        if (mrk)
+          rc = hd_lsrk_stage_overlapped(mrk->rk[j], mop->op[j], stage, solution[j], src[j], ti_next[j], mm->ghost[buf][j], sends, n_sends, mm->counters[j], target, t, dt);
+        else
+          rc = hd_advection_apply_overlapped(mop->op[j], dst[j], src[j], mm->ghost[buf][j], t, sends, n_sends, mm->counters[j], target);
+        if (rc != HD_OK)
+          return rc;
+      }
+    mm->exchanges++;
+    mm->fused_apps++;
+    return mark_done(mm, buf);
+  }
 } // namespace
 
 extern "C" {
@@ -155,6 +206,7 @@ multi_init_bricks(hd_multi *mm, const hd_mesh_desc *global)
   mm->stream.assign(n_gpus, nullptr);
   mm->coords.resize(n_gpus);
   mm->ev_packed.assign(n_gpus, nullptr);
+  mm->counters.assign(n_gpus, nullptr);
   for (int b = 0; b < 2; ++b)
     {
       mm->ghost[b].assign(n_gpus, nullptr);
@@ -203,6 +255,8 @@ multi_init_bricks(hd_multi *mm, const hd_mesh_desc *global)
           HD_CUDA(cudaEventCreateWithFlags(&mm->ev_done[b][i], cudaEventDisableTiming));
         }
       HD_CUDA(cudaEventCreateWithFlags(&mm->ev_packed[i], cudaEventDisableTiming));
+      HD_CUDA(cudaMalloc(&mm->counters[i], 64 * sizeof(int)));
+      HD_CUDA(cudaMemset(mm->counters[i], 0, 64 * sizeof(int)));
     }
   return HD_OK;
 }
@@ -286,6 +340,7 @@ hd_multi_destroy(hd_multi *mm)
         }
       if (mm->ev_packed[i])
         cudaEventDestroy(mm->ev_packed[i]);
+      cudaFree(mm->counters[i]);
       hd_mesh_destroy(mm->mesh[i]);
       hd_context_destroy(mm->ctx[i]);
       if (mm->stream[i])
@@ -466,6 +521,21 @@ hd_multi_advection_create(hd_multi *mm, double skew_factor, const double *veloci
   mop->needed.resize(mm->n);
   for (int i = 0; i < mm->n; ++i)
     hd_advection_ghost_sides(mop->op[i], mop->needed[i].data());
+  // the fused halo needs one of the 3D3V degree-3 FP64 kernels, ghost (not Dirichlet) sides, and every brick sending
+  // something (a kernel that waits for counters nobody bumps would wait for its time-out); HD_MULTI_FUSED=0 keeps the
+  // pack kernels + events of exchange()
+  {
+    const char *e = getenv("HD_MULTI_FUSED");
+    bool ok = (!e || atoi(e) != 0) && mm->n > 1 && hd_advection_n_halo_senders(mop->op[0]) > 0 && !mm->mesh[0]->has_dirichlet;
+    for (int i = 0; i < mm->n && ok; ++i)
+      {
+        bool any = false;
+        for (int k = 0; k < 2 * HD_MAX_DIM; ++k)
+          any |= mop->needed[i][k] != 0;
+        ok = any && !mm->mesh[i]->has_dirichlet;
+      }
+    mop->fused = ok;
+  }
   *out = mop;
   return HD_OK;
 }
@@ -505,6 +575,8 @@ hd_multi_advection_apply(hd_multi_advection *mop, void *const *dst, void *const 
 {
   HD_REQUIRE(mop && dst && src, "null argument");
   hd_multi *mm  = mop->mm;
+  if (mop->fused)
+    return fused_step(mm, mop, nullptr, 0, dst, src, nullptr, nullptr, time, 0.0);
   const int buf = int(mm->exchanges & 1);
   int       rc  = exchange(mm, mop->needed, src, buf);
   if (rc != HD_OK)
@@ -565,6 +637,13 @@ hd_multi_lsrk_step(hd_multi_lsrk *mrk, hd_multi_advection *mop, void *const *sol
     }
   for (int stage = 0; stage < mrk->stages; ++stage)
     {
+      if (mop->fused)
+        {
+          if ((rc = fused_step(mm, mop, mrk, stage, nullptr, cur.data(), solution, nxt.data(), t, dt)) != HD_OK)
+            return rc;
+          cur.swap(nxt);
+          continue;
+        }
       const int buf = int(mm->exchanges & 1);
       if ((rc = exchange(mm, mop->needed, cur.data(), buf)) != HD_OK)
         return rc;

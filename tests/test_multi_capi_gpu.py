@@ -29,9 +29,17 @@ CASES = [
 ]
 
 
+# fused = the operator kernels pack and send the halo themselves (3D3V degree-3 FP64 lattices; the default there);
+# HD_MULTI_FUSED=0 = pack kernels + CUDA events (every other lattice, and the cross-check)
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_halo", "pack_kernels"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_%dd%dv_k%d_%s%s" % (c[0], c[1], c[2], c[3], "x".join(map(str, c[5])), "" if c[6] else "_dirichlet"))
-def test_multi_matches_single(case):
+def test_multi_matches_single(case, fused, monkeypatch):
     from hyperdeal_b200 import api
+
+    if not fused:
+        if not (case[1] == 3 and case[3] == 3):
+            pytest.skip("the fused halo only exists for 3D3V degree 3: same code path as the other parametrisation")
+        monkeypatch.setenv("HD_MULTI_FUSED", "0")
 
     n, dim_x, dim_v, degree, cells, grid, periodic, vel = case
     if _n_gpus() < n:
