@@ -163,30 +163,6 @@ CPU_NOTE = ("CPU restatement of hyper.deal's literal ECL algorithm (advection_op
             "the hyper.deal binary itself needs deal.II + MPI, which this image does not have")
 
 
-def _nvlink_counters(index):
-    """cumulative NVLink payload counters of one GPU in bytes (NVML field values, all links): (tx, rx) or None"""
-    try:
-        import pynvml
-
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        TX, RX = pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX
-        v = pynvml.nvmlDeviceGetFieldValues(h, [(TX, 0xFFFFFFFF), (RX, 0xFFFFFFFF)])  # scopeId UINT_MAX: sum over the links
-        if all(x.nvmlReturn == 0 for x in v):
-            return tuple(int(x.value.ullVal) * 1024 for x in v)  # KiB
-        # per-link counters (drivers that do not serve the aggregate scope)
-        tot, seen = [0, 0], False
-        for link in range(18):
-            v = pynvml.nvmlDeviceGetFieldValues(h, [(TX, link), (RX, link)])
-            for i, x in enumerate(v):
-                if x.nvmlReturn == 0:
-                    tot[i] += int(x.value.ullVal) * 1024
-                    seen = True
-        return tuple(tot) if seen else None
-    except Exception:
-        return None
-
-
 def _cpu_problem():
     """(FastECL, src, dst, same_config): the benchmark lattice itself — 8^6 cells, 8 GiB per vector — if the host has the
     memory for two such vectors, else the largest lattice of the same family that fits (halved along v)."""
@@ -455,7 +431,7 @@ def main():
                     from hyperdeal_b200.partition import PeerHaloExchange
 
                     try:
-                        self.peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local_rank))
+                        self.peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local_rank), ctx=ctx)
                         self.halo_mode = "peer"
                     except Exception as e:  # symmetric memory unavailable on this box: NCCL send/recv
                         if rank == 0:
@@ -568,7 +544,6 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    nvl0 = _nvlink_counters(local_rank) if world > 1 else None
     launches0 = op.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -585,7 +560,6 @@ def main():
             step()
     ev1.record()
     barrier()
-    nvl1 = _nvlink_counters(local_rank) if world > 1 else None
     launches = op.launch_count - launches0
     if peer is not None and args.overlap == "kernel" and op.overlap_timed_out():
         raise SystemExit("bench: the in-kernel halo wait timed out on rank %d (halo never signalled)" % rank)
@@ -709,14 +683,6 @@ def main():
         }
         if sustained is not None:
             out["sustained"] = sustained
-        if world > 1:
-            # NVLink payload bytes of rank 0's GPU over the timed region (NVML counters; ncu's nvl* metrics need a multi-rank
-            # capture): to be compared with config.halo_bytes_sent_per_gpu_per_step
-            if nvl0 is not None and nvl1 is not None:
-                out["nvlink"] = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / args.steps, "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / args.steps,
-                                 "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX of GPU %d, all links, timed region (includes flags and acknowledgements)" % local_rank}
-            else:
-                out["nvlink"] = None
         if parity is not None:
             out["parity"] = parity
             out["parity_rel"] = parity["parity_rel"]

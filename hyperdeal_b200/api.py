@@ -35,7 +35,8 @@ EXPORTS = [
     "hd_mesh_n_cells", "hd_mesh_dofs_per_cell", "hd_mesh_ghost_size", "hd_mesh_basis", "hd_vector_alloc",
     "hd_vector_free", "hd_vector_copy", "hd_vector_copy_in", "hd_vector_copy_out", "hd_vector_zero", "hd_vector_zero_n", "hd_vector_copy_n", "hd_advection_create",
     "hd_advection_destroy", "hd_advection_set_phase_space_velocity", "hd_advection_apply", "hd_advection_apply_part", "hd_advection_apply_overlapped", "hd_advection_overlap_status", "hd_advection_n_ctas", "hd_advection_n_halo_senders", "hd_advection_set_halo_senders", "hd_stream_write_flag", "hd_stream_wait_flag", "hd_advection_ghost_sides", "hd_advection_apply_host", "hd_advection_set_kernel", "hd_advection_set_l2_hints", "hd_advection_set_row_tile",
-    "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_evaluation_level", "hd_advection_set_dirichlet_values",
+    "hd_advection_kernel_name", "hd_advection_launch_count", "hd_advection_set_evaluation_level",
+    "hd_ipc_export", "hd_ipc_open", "hd_ipc_close", "hd_advection_set_dirichlet_values",
     "hd_advection_set_dirichlet_builtin", "hd_halo_pack", "hd_halo_pack_ex", "hd_halo_offset", "hd_halo_total", "hd_lsrk_create",
     "hd_lsrk_destroy", "hd_lsrk_n_stages", "hd_lsrk_coefficients", "hd_lsrk_stage_update", "hd_lsrk_step", "hd_lsrk_stage_fused", "hd_lsrk_stage_overlapped",
     "hd_multi_create", "hd_multi_destroy", "hd_multi_n_gpus", "hd_multi_mesh", "hd_multi_context", "hd_multi_n_dofs", "hd_multi_synchronize", "hd_multi_vector_alloc",
@@ -109,6 +110,11 @@ def lib():
     L.hd_advection_apply_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, POINTER(HaloSend), c_int, c_void_p, c_int]
     L.hd_advection_overlap_status.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_stream_write_flag.argtypes = [c_void_p, c_void_p, c_int]
+    L.hd_device_malloc.argtypes = [c_void_p, ctypes.c_size_t, POINTER(c_void_p)]
+    L.hd_device_free.argtypes = [c_void_p, c_void_p]
+    L.hd_ipc_export.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.hd_ipc_open.argtypes = [c_void_p, c_void_p, POINTER(c_void_p)]
+    L.hd_ipc_close.argtypes = [c_void_p, c_void_p]
     L.hd_stream_wait_flag.argtypes = [c_void_p, c_void_p, c_int]
     L.hd_advection_ghost_sides.argtypes = [c_void_p, POINTER(c_int)]
     L.hd_halo_pack_ex.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_void_p), c_void_p, POINTER(c_int)]

@@ -1325,6 +1325,40 @@ hd_advection_apply_overlapped(hd_advection *op, void *dst, const void *src, cons
   return hd::launch_fast6d(op, dst, src, ghosts, time, fu, 3, sends, n_sends, arrival_counters, target);
 }
 
+// ---- peer-mapped memory across processes (CUDA IPC) ------------------------------------------------------------
+int
+hd_ipc_export(hd_context *ctx, const void *ptr, void *handle)
+{
+  HD_REQUIRE(ctx && ptr && handle, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == HD_IPC_HANDLE_BYTES, "IPC handle size");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  HD_CUDA(cudaStreamSynchronize(ctx->stream)); // (hd_device_malloc zeroes on the stream)
+  cudaIpcMemHandle_t h;
+  HD_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+  std::memcpy(handle, &h, sizeof(h));
+  return HD_OK;
+}
+
+int
+hd_ipc_open(hd_context *ctx, const void *handle, void **ptr)
+{
+  HD_REQUIRE(ctx && handle && ptr, "null argument");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  HD_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return HD_OK;
+}
+
+int
+hd_ipc_close(hd_context *ctx, void *ptr)
+{
+  HD_REQUIRE(ctx, "null context");
+  HD_CUDA(cudaSetDevice(ctx->device));
+  HD_CUDA(cudaIpcCloseMemHandle(ptr));
+  return HD_OK;
+}
+
 int
 hd_advection_n_ctas(const hd_advection *op)
 {

@@ -89,6 +89,12 @@ def ghost_layout(n_cells_local, dofs_1d: int, side_kind):
     return offsets, sizes, off
 
 
+def ctypes_ptr(p):
+    import ctypes
+
+    return ctypes.c_void_p(int(p))
+
+
 @dataclass
 class _Msg:
     d: int
@@ -172,41 +178,111 @@ class PeerHaloExchange:
 
     COUNT, READY, ACK = 0, 16, 32  # word offsets of the three flag groups (slot = 2*d+side inside each)
 
-    def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6, dtype=None):
+    def __init__(self, part: BrickPartition, offsets, sizes, total: int, needed, device, group=None, max_dim: int = 6, dtype=None, transport=None, ctx=None):
+        """transport: "symm" = torch.distributed symmetric memory (the default), "ipc" = plain device allocations exchanged
+        through CUDA IPC handles (hd_device_malloc / hd_ipc_export / hd_ipc_open; needs `ctx`, the api.Context of this
+        rank) — what an MPI host would do; HD_PEER_TRANSPORT overrides the default."""
+        import os
+
         import torch
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
 
         self.part = part
         group = group if group is not None else dist.group.WORLD
         n = max(int(total), 16)
         dtype = torch.float64 if dtype is None else dtype  # the lattice's number type (hd_mesh_desc.number_type)
         esize = torch.empty(0, dtype=dtype).element_size()
-        self.ghosts = [symm.empty(n, dtype=dtype, device=device) for _ in range(2)]
-        self.flags = symm.empty(64, dtype=torch.int32, device=device)
-        for g in self.ghosts:
-            g.zero_()
-        self.flags.zero_()
-        torch.cuda.synchronize()
-        self.handles = [symm.rendezvous(g, group) for g in self.ghosts]
-        self.flag_handle = symm.rendezvous(self.flags, group)
+        transport = transport or os.environ.get("HD_PEER_TRANSPORT", "symm")
+        if transport == "ipc" and ctx is None:
+            raise ValueError("the ipc transport needs the api.Context of this rank")
+        self.transport = transport
         self.plan = HaloExchange(part, offsets, sizes, needed)
+        if transport == "ipc":
+            ghost_ptrs, self.flag_ptrs = self._ipc_setup(ctx, n * esize, group)
+        else:
+            import torch.distributed._symmetric_memory as symm
+
+            self.ghosts = [symm.empty(n, dtype=dtype, device=device) for _ in range(2)]
+            self.flags = symm.empty(64, dtype=torch.int32, device=device)
+            for g in self.ghosts:
+                g.zero_()
+            self.flags.zero_()
+            torch.cuda.synchronize()
+            self.handles = [symm.rendezvous(g, group) for g in self.ghosts]
+            self.flag_handle = symm.rendezvous(self.flags, group)
+            ghost_ptrs = [[int(x) for x in h.buffer_ptrs] for h in self.handles]
+            self.flag_ptrs = [int(x) for x in self.flag_handle.buffer_ptrs]
         self.mask = self.plan.send_mask(max_dim)
         self.bytes_sent = self.plan.bytes_per_exchange[0] * esize
-        self.flag_ptrs = [int(x) for x in self.flag_handle.buffer_ptrs]
         self.my_flags = self.flag_ptrs[part.rank]
         self.peer_dst, self.fused_sends = [], []
-        for h in self.handles:
+        for bptrs in ghost_ptrs:
             ptrs, sends = [0] * (2 * max_dim), []
             for s in self.plan.sends:
                 # my boundary layer (d, side) is the ghost segment (d, 1 - side) of the neighbour behind that side
-                ptrs[2 * s.d + s.side] = int(h.buffer_ptrs[s.peer]) + esize * offsets[(s.d, 1 - s.side)]
+                ptrs[2 * s.d + s.side] = bptrs[s.peer] + esize * offsets[(s.d, 1 - s.side)]
                 sends.append((s.d, s.side, ptrs[2 * s.d + s.side], self.flag_ptrs[s.peer] + 4 * (self.COUNT + 2 * s.d + (1 - s.side))))
             self.peer_dst.append(ptrs)
             self.fused_sends.append(sends)
         self.step = 0
         self.fused_steps = 0
         dist.barrier(group=group)  # every rank has zeroed its flags before anyone signals
+
+    class _Raw:
+        """a device allocation that is not a torch tensor: the callers only ask for data_ptr()"""
+
+        def __init__(self, ptr):
+            self.ptr = int(ptr)
+
+        def data_ptr(self):
+            return self.ptr
+
+    def _ipc_setup(self, ctx, ghost_bytes, group):
+        """two ghost buffers + one flag block per rank from hd_device_malloc; handles all-gathered; the allocations of the
+        ranks this brick talks to are mapped with hd_ipc_open.  Returns ([ptrs of buffer 0 by rank, ptrs of buffer 1], flag ptrs)."""
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import api
+
+        L = api.lib()
+        self._ctx, self._own, self._opened = ctx, [], []
+        mine = []
+        for nbytes in (ghost_bytes, ghost_bytes, 256):
+            p = ctypes.c_void_p()
+            api._check(L.hd_device_malloc(ctx._h, int(nbytes), ctypes.byref(p)))
+            h = ctypes.create_string_buffer(64)
+            api._check(L.hd_ipc_export(ctx._h, p, h))
+            self._own.append(p.value)
+            mine.append(bytes(h.raw))
+        everyone = [None] * self.part.world
+        dist.all_gather_object(everyone, mine, group=group)
+        peers = {m.peer for m in self.plan.sends} | {m.peer for m in self.plan.recvs}
+        table = [[0] * self.part.world for _ in range(3)]
+        for r in range(self.part.world):
+            for k in range(3):
+                if r == self.part.rank:
+                    table[k][r] = self._own[k]
+                elif r in peers:
+                    p = ctypes.c_void_p()
+                    api._check(L.hd_ipc_open(ctx._h, everyone[r][k], ctypes.byref(p)))
+                    self._opened.append(p.value)
+                    table[k][r] = p.value
+        self.ghosts = [PeerHaloExchange._Raw(self._own[0]), PeerHaloExchange._Raw(self._own[1])]
+        return [table[0], table[1]], table[2]
+
+    def close(self):
+        """ipc transport: unmap the peers' allocations and free this rank's (call after a barrier: nobody may still write)"""
+        if getattr(self, "_own", None):
+            from . import api
+
+            L = api.lib()
+            for p in self._opened:
+                L.hd_ipc_close(self._ctx._h, ctypes_ptr(p))
+            for p in self._own:
+                L.hd_device_free(self._ctx._h, ctypes_ptr(p))
+            self._own, self._opened = [], []
 
     def _next(self, ctx):
         self.step += 1

@@ -216,6 +216,15 @@ int hd_advection_overlap_status(hd_advection *op, int *timed_out);
  * memory of another GPU) and "wait until *flag >= value".  These carry the halo handshake between GPUs: data-ready
  * flags forward, buffer-consumed flags backward (the role MPI_Isend/Irecv completion + the shared-memory window
  * barriers play in matrix_free/vector_partitioner.h:1482-1592). */
+/* Peer-mapped device memory for hosts that run one PROCESS per GPU (the MPI / torch.distributed route): plain device
+ * allocations exported through CUDA IPC handles, the counterpart of the MPI-3 shared-memory window of the reference
+ * (matrix_free/vector_partitioner.h:552-640).  hd_device_malloc (above) returns zeroed memory; hd_ipc_export writes the 64-byte
+ * handle of an allocation made by hd_device_malloc; hd_ipc_open maps another process' allocation into this one
+ * (peer access over NVLink); the mapping is closed with hd_ipc_close, the allocation freed with hd_device_free. */
+#define HD_IPC_HANDLE_BYTES 64
+int hd_ipc_export(hd_context *ctx, const void *ptr, void *handle);
+int hd_ipc_open(hd_context *ctx, const void *handle, void **ptr);
+int hd_ipc_close(hd_context *ctx, void *ptr);
 int hd_stream_write_flag(hd_context *ctx, void *flag_device, int value);
 int hd_stream_wait_flag(hd_context *ctx, void *flag_device, int value);
 /* needed[2*dir+side] = 1 if the operator reads ghost side (dir, side): with the upwind flux only the inflow side

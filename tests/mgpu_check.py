@@ -72,7 +72,7 @@ def main():
         # direct variant: the pack kernel stores into the neighbours' ghost buffers over NVLink (peer-mapped pointers)
         from hyperdeal_b200.partition import PeerHaloExchange
 
-        peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local))
+        peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local), ctx=ctx)
         dst.zero_()
         for it in range(4):  # split variant: pack kernel, stream flags, two operator launches (all on one stream)
             g, m = peer.start(mf, ctx, src.data_ptr())

@@ -26,7 +26,7 @@ send = torch.empty(halo, dtype=torch.float64, device="cuda"); ghost = torch.zero
 offsets = {(d, s): mf.halo_offset(d, s) for d in range(6) for s in range(2)}
 sizes = {(d, s): mf.ghost_size(d, s) for d in range(6) for s in range(2)}
 ex = HaloExchange(part, offsets, sizes, op.ghost_sides())
-peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local))
+peer = PeerHaloExchange(part, offsets, sizes, halo, op.ghost_sides(), torch.device("cuda", local), ctx=ctx)
 mask = ex.send_mask()
 
 def timeit(name, fn, reps=5):
