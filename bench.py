@@ -111,6 +111,12 @@ class ClockSampler:
                 break
             time.sleep(0.002)
 
+    def begin(self):
+        """forget what was sampled so far: the timed region starts now (the polling thread keeps running)"""
+        del self.sm[:]
+        self.reasons.clear()
+        del self.samples[:]
+
     def start(self):
         if self.nvml is not None:
             self.thread = threading.Thread(target=self._poll, daemon=True)
@@ -543,12 +549,17 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    barrier()
-    launches0 = op.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    # The clock sampler is set up BEFORE the barrier: nvmlInit takes tens of milliseconds on an 8-GPU box and a different
+    # time in every process; done after the barrier it let the ranks enter the timed loop milliseconds apart, and since
+    # every kernel waits for its neighbours' halo the whole skew landed in the 10 timed steps (N = 8: 5.4 instead of 4.9 ms).
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler is not None:
+        sampler.begin()
+    launches0 = op.launch_count
     kernel_ms = []
     ev0.record()
     for _ in range(args.steps):
@@ -585,11 +596,13 @@ def main():
     sustained = None
     if args.sustain > 0:
         n_s = max(args.steps, int(args.sustain * 1e3 / max(total_ms / args.steps, 1e-3)) + 1)
-        s_sampler = ClockSampler(local_rank)
-        barrier()
-        if rank == 0:
+        s_sampler = ClockSampler(local_rank) if rank == 0 else None
+        if s_sampler is not None:
             s_sampler.start()
         es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if s_sampler is not None:
+            s_sampler.begin()
         es0.record()
         for _ in range(n_s):
             step()
