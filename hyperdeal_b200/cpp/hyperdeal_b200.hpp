@@ -73,6 +73,10 @@ namespace hyperdeal
     {
       using boundary_id = unsigned int;
     }
+    namespace numbers
+    {
+      constexpr types::boundary_id internal_face_boundary_id = static_cast<types::boundary_id>(-1);
+    }
 
     template <int rank, int dim, typename Number = double>
     class Tensor;
@@ -156,6 +160,132 @@ namespace hyperdeal
   private:
     hd_context *ctx = nullptr;
   };
+
+  // ---- internal::MatrixFreeFunctions::ShapeInfo (matrix_free/shape_info.h:26-231) ------------------------------------
+  // Host tables of the phase-space element: which nodal values of a cell lie on each of its 2 * dim faces, in the order
+  // the reference's face evaluators enumerate them.  The device kernels do not read these tables (on a Cartesian lattice a
+  // face layer is "the cell index with one digit fixed"); they are here for callers of get_shape_info().
+  // Ordering, restated from its definition: inside a dim_s-dimensional subspace the face of direction e lists the other
+  // digits in natural order, except for the middle direction of a 3-D subspace, whose local coordinate system is (z, x):
+  // the index along z runs fastest.  An x-face then takes all v-digits as the slow part, a v-face all x-digits as the fast part.
+  namespace internal
+  {
+    namespace MatrixFreeFunctions
+    {
+      template <typename Number>
+      struct ShapeInfo
+      {
+        template <int dim_x, int dim_v>
+        void
+        reinit(const unsigned int degree)
+        {
+          const unsigned int n = degree + 1, dim = dim_x + dim_v;
+          const auto         ipow = [](unsigned int b, unsigned int e) {
+            unsigned int r = 1;
+            while (e--)
+              r *= b;
+            return r;
+          };
+          dofs_per_cell = ipow(n, dim);
+          dofs_per_face = ipow(n, dim - 1);
+          // subspace table: cell index (inside the subspace) of face entry l
+          const auto sub = [&](const int dim_s, const unsigned int f, const unsigned int l) {
+            const unsigned int e = f / 2, layer = (f % 2) * (n - 1);
+            unsigned int       digit[3] = {0, 0, 0};
+            if (dim_s == 3 && e == 1)
+              {
+                digit[2] = l % n; // z fastest
+                digit[0] = l / n;
+              }
+            else
+              {
+                unsigned int r = l;
+                for (int k = 0; k < dim_s; ++k)
+                  if (k != int(e))
+                    {
+                      digit[k] = r % n;
+                      r /= n;
+                    }
+              }
+            digit[e] = layer;
+            unsigned int idx = 0;
+            for (int k = dim_s - 1; k >= 0; --k)
+              idx = idx * n + digit[k];
+            return idx;
+          };
+          const unsigned int nx = ipow(n, dim_x), nfx = ipow(n, dim_x - 1), nfv = ipow(n, dim_v - 1);
+          face_to_cell_index_nodal.assign(2 * dim, std::vector<unsigned int>(dofs_per_face));
+          for (unsigned int f = 0; f < 2 * dim; ++f)
+            for (unsigned int k = 0; k < dofs_per_face; ++k)
+              {
+                if (f < 2 * (unsigned int)dim_x)
+                  face_to_cell_index_nodal[f][k] = sub(dim_x, f, k % nfx) + nx * (k / nfx);
+                else
+                  face_to_cell_index_nodal[f][k] = (k % nx) + nx * sub(dim_v, f - 2 * dim_x, (k / nx) % nfv);
+              }
+          // the 2 x 8 orientations of a quadrilateral face of a 3-D subspace (x-faces: tables 0-7, v-faces: 8-15).  Entry c
+          // of a table = where face value c goes; (orientation, flip, rotation) swap and mirror the two in-face indices.
+          // A Cartesian lattice only ever uses the identity (tables 0 and 8).
+          if (dim_x == 3 || dim_v == 3)
+            {
+              face_orientations.assign(16, std::vector<unsigned int>(dofs_per_face));
+              // {first index: 0 = take k, 1 = take j; mirrored?}, {second index ...} for tables 0..7
+              static const int pick[8][4] = {{0, 0, 1, 0}, {1, 0, 0, 0}, {0, 1, 1, 1}, {1, 1, 0, 1}, {1, 0, 0, 1}, {0, 0, 1, 1}, {1, 1, 0, 0}, {0, 1, 1, 0}};
+              const auto     entry = [&](const int t, const unsigned int j, const unsigned int k) {
+                const unsigned int a = pick[t][0] ? j : k, b = pick[t][2] ? j : k;
+                return (pick[t][1] ? n - 1 - a : a) + (pick[t][3] ? n - 1 - b : b) * n;
+              };
+              for (int t = 0; t < 8; ++t)
+                for (unsigned int c = 0; c < dofs_per_face; ++c)
+                  {
+                    // x-face: c = i * n^2 + j * n + k (i over the v-digits); v-face: c = (j * n + k) * n^dim_x + i
+                    if (dim_x == 3)
+                      face_orientations[t][c] = entry(t, (c / n) % n, c % n) + (c / (n * n)) * n * n;
+                    else
+                      face_orientations[t][c] = c;
+                    if (dim_v == 3)
+                      face_orientations[8 + t][c] = entry(t, (c / nx) / n, (c / nx) % n) * nx + c % nx;
+                    else
+                      face_orientations[8 + t][c] = c;
+                  }
+            }
+        }
+        std::size_t
+        memory_consumption() const
+        {
+          std::size_t b = 0;
+          for (const auto &v : face_to_cell_index_nodal)
+            b += v.size() * sizeof(unsigned int);
+          return b;
+        }
+        unsigned int                           dofs_per_cell = 0, dofs_per_face = 0;
+        std::vector<std::vector<unsigned int>> face_to_cell_index_nodal;
+        std::vector<std::vector<unsigned int>> face_orientations;
+      };
+    } // namespace MatrixFreeFunctions
+
+    // boundary id of face `face` (2 * direction + side) of local cell `cell`, or internal_face_boundary_id
+    // (MatrixFree::get_faces_by_cells_boundary_id, matrix_free.h:279): only the outer layer of a non-periodic direction
+    // has boundary faces; 1-D subspaces number their two end points 0 and 1 (see get_boundary_id)
+    inline dealii_compat::types::boundary_id
+    face_boundary_id(const hd_mesh_desc &d, std::int64_t cell, const unsigned int face)
+    {
+      const int dim = d.dim_x + d.dim_v, dir = int(face / 2), side = int(face % 2);
+      int       c   = 0;
+      for (int e = 0; e < dim; ++e)
+        {
+          if (e == dir)
+            c = int(cell % d.n_cells[e]);
+          cell /= d.n_cells[e];
+        }
+      const bool outer = side ? (c + d.cell_offset[dir] == d.n_cells_global[dir] - 1) : (c + d.cell_offset[dir] == 0);
+      const int  kind  = d.side_kind[dir][side];
+      if (!outer || (kind != HD_SIDE_DIRICHLET && kind != HD_SIDE_DIRICHLET_HOM))
+        return dealii_compat::numbers::internal_face_boundary_id;
+      const bool one_d = dir < d.dim_x ? d.dim_x == 1 : d.dim_v == 1;
+      return one_d ? side : 0;
+    }
+  } // namespace internal
 
   // ---- low-dimensional lattice: what the two dealii::MatrixFree arguments describe on this path ----
   // (subdivided_hyper_rectangle, grid/grid_generator.cc:235, with FE_DGQ(degree) and QGauss(n_points) or the
@@ -300,13 +430,28 @@ namespace hyperdeal
       const bool one_d = direction < (unsigned int)dim_x ? dim_x == 1 : dim_v == 1;
       return one_d ? side : 0;
     }
+    // matrix_free.h:279: boundary id of a face of a local cell, numbers::internal_face_boundary_id for interior faces
+    dealii_compat::types::boundary_id
+    get_faces_by_cells_boundary_id(const std::int64_t cell, const unsigned int face) const
+    {
+      return internal::face_boundary_id(desc, cell, face);
+    }
+    // matrix_free.h:308: the face tables of the phase-space element (host side)
+    const internal::MatrixFreeFunctions::ShapeInfo<Number> &
+    get_shape_info() const
+    {
+      if (shape_info.dofs_per_cell == 0)
+        shape_info.template reinit<dim_x, dim_v>(lattice_x.degree);
+      return shape_info;
+    }
     std::size_t
     memory_consumption() const
     {
-      return sizeof(*this);
+      return sizeof(*this) + shape_info.memory_consumption();
     }
 
   private:
+    mutable internal::MatrixFreeFunctions::ShapeInfo<Number> shape_info;
     const DeviceCommunicator &comm;
     CartesianLattice<dim_x>   lattice_x;
     CartesianLattice<dim_v>   lattice_v;
@@ -362,6 +507,18 @@ namespace hyperdeal
     void          zero_out_ghost_values() const {}
     std::size_t   memory_consumption() const { return std::size_t(n) * sizeof(Number); }
     hd_mesh *     get_mesh() const { return mesh; }
+    // element access from the host (one device -> host copy per call: for inspection, not for loops)
+    Number
+    operator()(const std::int64_t i) const
+    {
+      if (i < 0 || i >= n)
+        throw ExcMessage("DeviceVector: index out of range");
+      Number v;
+      HD_CALL(hd_vector_copy_out(mesh, static_cast<const Number *>(ptr) + i, &v, 1));
+      return v;
+    }
+    // the vectors of all ranks of the shared-memory domain (LinearAlgebra::SharedMPI::Vector): one process = one GPU here
+    std::vector<Number *> shared_vector_data() { return std::vector<Number *>(1, begin()); }
     DeviceVector &
     operator=(const Number s)
     {
