@@ -145,6 +145,24 @@ def test_cpp_operators_advection_driver(drivers, golden_dir):
     assert float(rows["throughput [GDoFs/s]"]) > 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("px,pv,velocity", [(2, 1, True), (1, 2, True), (2, 1, False), (2, 2, True)])
+def test_cpp_operators_advection_driver_multi_gpu(drivers, golden_dir, px, pv, velocity):
+    """the reference's performance driver on PartitionX x PartitionV GPUs of one process (with and without transport velocity:
+    the reference benchmark uses a = 0, i.e. no face term reads a neighbour)"""
+    if _n_gpus() < px * pv:
+        pytest.skip("needs %d GPUs" % (px * pv))
+    env = dict(os.environ, HD_PARTITION_X=str(px), HD_PARTITION_V=str(pv))
+    if velocity:
+        env["HD_BENCH_VELOCITY"] = "1"
+    r = subprocess.run([drivers["operators_advection"], os.path.join(golden_dir, "operators_advection_small.json")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    rows = dict(line.rsplit(None, 1) for line in r.stdout.splitlines() if line.startswith(("info", "throughput")))
+    assert float(rows["info->size [DoFs]"]) == 2 * 4 * 2 * 2 * 2 * 4 * 4096
+    assert float(rows["info->procs"]) == px * pv
+    assert float(rows["throughput [GDoFs/s]"]) > 0
+
+
 def test_json_parameter_reader(tmp_path, golden_dir):
     """the ParameterHandler-style JSON reader of the drivers: nested sections, quoted and bare values, booleans"""
     src = tmp_path / "j.cc"
