@@ -195,10 +195,35 @@ namespace
 #ifndef HD_VP_HOST_EMULATION
 namespace
 {
-  template <typename T, int N>
-  __global__ void __launch_bounds__(256) k_apply_tile_global(const __grid_constant__ TgParams<T> p, const __grid_constant__ TgCoef<T, N> cf)
+  template <typename T, int N, int THREADS>
+  __global__ void __launch_bounds__(THREADS) k_apply_tile_global(const __grid_constant__ TgParams<T> p, const __grid_constant__ TgCoef<T, N> cf)
   {
     tg_cell<T, N>(p, cf, blockIdx.x, threadIdx.x, blockDim.x);
+  }
+
+  // Experiment knobs (profiles/r02_tile_global_residency_ab.txt).  A resident CTA works on one cell = 2 x nd values (degree 5
+  // FP32: 364 KiB), and ncu measured 16.8 GB of DRAM traffic per launch for 5.2 GB algorithmic
+  // (profiles/r02x_tile_global_ncu_summary.json), which suggested that too many cells in flight thrash L2.  Capping the CTAs
+  // per SM (HD_TG_CTAS_PER_SM = n: a dynamic shared-memory request nobody uses; HD_TG_THREADS = 256 | 512) does NOT help:
+  // 1 CTA x 512 threads 10.1 ms, 2 x 512 7.3 ms, 3 or 4 x 256 6.85 ms, no cap 6.78 ms — the kernel needs the parallelism more
+  // than the locality (long-scoreboard stalls 48 %).  Default: no cap.
+  inline void
+  tg_launch_shape(const hd_mesh *m, int *threads, size_t *smem)
+  {
+    static const int env_threads = [] {
+      const char *e = getenv("HD_TG_THREADS");
+      return e ? atoi(e) : 0;
+    }();
+    static const int env_ctas = [] {
+      const char *e = getenv("HD_TG_CTAS_PER_SM");
+      return e ? atoi(e) : -1;
+    }();
+    const int ctas = env_ctas > 0 ? env_ctas : 0;
+    *threads = env_threads == 512 ? 512 : 256;
+    // an SM has 228 KiB of shared memory and reserves 1 KiB per resident CTA: with this request exactly `ctas` CTAs fit
+    *smem = (ctas > 0 && ctas < 8) ? (size_t)233472 / ctas - 1024 : 0;
+    if (*smem > m->ctx->smem_optin)
+      *smem = m->ctx->smem_optin;
   }
 
   template <typename T, int N>
@@ -234,7 +259,21 @@ namespace
     p.fb      = T(fu.fb);
     p.fa      = T(fu.fa);
     p.fused   = fu.enabled;
-    k_apply_tile_global<T, N><<<(unsigned)m->ncells, 256, 0, m->ctx->stream>>>(p, cf);
+    int    threads;
+    size_t smem;
+    tg_launch_shape(m, &threads, &smem);
+    if (threads == 512)
+      {
+        if (smem > 48 * 1024)
+          HD_CUDA(cudaFuncSetAttribute(k_apply_tile_global<T, N, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_apply_tile_global<T, N, 512><<<(unsigned)m->ncells, 512, smem, m->ctx->stream>>>(p, cf);
+      }
+    else
+      {
+        if (smem > 48 * 1024)
+          HD_CUDA(cudaFuncSetAttribute(k_apply_tile_global<T, N, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_apply_tile_global<T, N, 256><<<(unsigned)m->ncells, 256, smem, m->ctx->stream>>>(p, cf);
+      }
     HD_CUDA(cudaGetLastError());
     op->launches++;
     op->last_kernel = "tile_global";
