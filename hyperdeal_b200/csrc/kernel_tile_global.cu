@@ -68,13 +68,15 @@ namespace
 
   template <typename T, int N>
   HD_TG_FN void
-  tg_cell(const TgParams<T> &p, const TgCoef<T, N> &cf, const long long cell, const int tid, const int nthr)
+  tg_cell(const TgParams<T> &p, const TgCoef<T, N> &cf, const long long cell, const int tid, const int nthr, T *part = nullptr)
   {
+    // part != nullptr: the partial sums of the rounds live in a CTA-private buffer of nd values (shared memory) instead
+    // of dst; only the last round touches dst (or sol / Ti_next)
     const int dim = p.dim;
-    long long nd = 1;
+    int       nd  = 1; // (indices inside a cell fit 32 bits: N^6 = 46656 for degree 5)
     for (int d = 0; d < dim; ++d)
       nd *= N;
-    const long long nt = nd / (N * N); // tiles per round
+    const int nt = nd / (N * N); // tiles per round
     int             c[HD_MAX_DIM];
     long long       cstr[HD_MAX_DIM];
     {
@@ -87,19 +89,20 @@ namespace
           m *= p.ncell[d];
         }
     }
-    const T *uc = p.src + cell * nd;
-    T *      oc = p.dst + cell * nd;
+    const T *uc = p.src + cell * (long long)nd;
+    T *      oc = p.dst + cell * (long long)nd;
+    T *      pc = part ? part : oc; // where the partial sums of the earlier rounds are
     for (int r = 0; r < dim / 2; ++r)
       {
         const int dA = 2 * r, dB = 2 * r + 1;
-        long long sA = 1;
+        int sA = 1;
         for (int k = 0; k < dA; ++k)
           sA *= N;
-        const long long sB   = sA * N;
+        const int       sB   = sA * N;
         const bool      last = r == dim / 2 - 1;
-        for (long long tt = tid; tt < nt; tt += nthr)
+        for (int tt = tid; tt < nt; tt += nthr)
           {
-            const long long base = (tt % sA) + (tt / sA) * (sA * N * N); // dof index of the tile's (a, b) = (0, 0) entry
+            const int base = (tt % sA) + (tt / sA) * (sA * N * N); // dof index of the tile's (a, b) = (0, 0) entry
             T               U[N][N], out[N][N];
             HD_TG_UNROLL
             for (int b = 0; b < N; ++b)
@@ -107,7 +110,7 @@ namespace
               for (int a = 0; a < N; ++a)
                 {
                   U[b][a]   = HD_TG_LDG(uc + base + a * sA + b * sB);
-                  out[b][a] = r == 0 ? T(0) : oc[base + a * sA + b * sB];
+                  out[b][a] = r == 0 ? T(0) : pc[base + a * sA + b * sB];
                 }
             HD_TG_UNROLL
             for (int b = 0; b < N; ++b)
@@ -125,8 +128,8 @@ namespace
                 }
             for (int which = 0; which < 2; ++which)
               {
-                const int       d  = which ? dB : dA;
-                const long long sd = which ? sB : sA, so = which ? sA : sB;
+                const int d  = which ? dB : dA;
+                const int sd = which ? sB : sA, so = which ? sA : sB;
                 for (int side = 0; side < 2; ++side)
                   {
                     if (!((p.nb_mask[d] >> side) & 1))
@@ -143,11 +146,11 @@ namespace
                               fc += c[e] * m;
                               m *= p.ncell[e];
                             }
-                        const T *g = p.ghost + p.ghost_off[d][side] + fc * (nd / N);
+                        const T *g = p.ghost + p.ghost_off[d][side] + fc * (long long)(nd / N);
                         HD_TG_UNROLL
                         for (int x = 0; x < N; ++x)
                           {
-                            const long long o = base + x * so; // dof index with digit d = 0
+                            const int o = base + x * so; // dof index with digit d = 0
                             tv[x]             = HD_TG_LDG(g + (o % sd) + (o / (sd * N)) * sd);
                           }
                       }
@@ -156,7 +159,7 @@ namespace
                         long long nb = cell + (side ? cstr[d] : -cstr[d]);
                         if (at_edge) // periodic inside the brick
                           nb = cell + (side ? -(long long)(p.ncell[d] - 1) * cstr[d] : (long long)(p.ncell[d] - 1) * cstr[d]);
-                        const T *g = p.src + nb * nd + base + layer * sd;
+                        const T *g = p.src + nb * (long long)nd + base + layer * sd;
                         HD_TG_UNROLL
                         for (int x = 0; x < N; ++x)
                           tv[x] = HD_TG_LDG(g + x * so);
@@ -174,17 +177,17 @@ namespace
               HD_TG_UNROLL
               for (int a = 0; a < N; ++a)
                 {
-                  const long long i = base + a * sA + b * sB;
+                  const int i = base + a * sA + b * sB;
                   if (last && p.fused)
                     {
-                      const long long g = cell * nd + i;
+                      const long long g = cell * (long long)nd + i;
                       const T         s = p.sol[g];
                       p.sol[g]          = s + p.fb * out[b][a];
                       if (p.fa != T(0))
                         p.ti_next[g] = s + p.fa * out[b][a];
                     }
                   else
-                    oc[i] = out[b][a];
+                    (last ? oc : pc)[i] = out[b][a];
                 }
           }
         HD_TG_SYNC(); // the next round reads the partial sums other threads of this CTA have written
@@ -199,6 +202,20 @@ namespace
   __global__ void __launch_bounds__(THREADS) k_apply_tile_global(const __grid_constant__ TgParams<T> p, const __grid_constant__ TgCoef<T, N> cf)
   {
     tg_cell<T, N>(p, cf, blockIdx.x, threadIdx.x, blockDim.x);
+  }
+
+  // Variant with the partial sums in shared memory (one CTA per SM, the cell's nd values = 182 KiB for degree 5 in FP32): the
+  // rounds re-read only src (L1/L2), dst is written once.  No padding needed: a tile of round 0 is 36 contiguous values, i.e.
+  // consecutive threads are 144 B apart (conflict-free 16-byte accesses), the later rounds are contiguous across the lanes.
+  template <typename T, int N, int THREADS>
+  __global__ void __launch_bounds__(THREADS, 1) k_apply_tile_global_sp(const __grid_constant__ TgParams<T> p, const __grid_constant__ TgCoef<T, N> cf)
+  {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    for (long long cell = blockIdx.x; cell < p.ncells; cell += gridDim.x)
+      {
+        tg_cell<T, N>(p, cf, cell, threadIdx.x, blockDim.x, reinterpret_cast<T *>(tg_smem));
+        __syncthreads(); // (the last round still reads `part` while the next cell's round 0 would overwrite it)
+      }
   }
 
   // Experiment knobs (profiles/r02_tile_global_residency_ab.txt).  A resident CTA works on one cell = 2 x nd values (degree 5
@@ -259,6 +276,42 @@ namespace
     p.fb      = T(fu.fb);
     p.fa      = T(fu.fa);
     p.fused   = fu.enabled;
+    // partial sums in shared memory where a cell fits (HD_TG_SMEM_PARTIALS=0: in dst as before)
+    static const int env_sp = [] {
+      const char *e = getenv("HD_TG_SMEM_PARTIALS");
+      return e ? atoi(e) : 1;
+    }();
+    const size_t part_bytes = (size_t)m->nd * sizeof(T);
+    if (env_sp && N == 6 && part_bytes <= m->ctx->smem_optin)
+      {
+        // 1296 tiles per round: 448 threads (14 warps, 106 registers) take three tiles each; measured 448: 4.57 ms, 512: 4.62, 672 (two tiles
+        // each, 96 registers with spills): 4.81
+        // (HD_TG_SP_THREADS; profiles/r02tg_*.txt)
+        static const int env_thr = [] {
+          const char *e = getenv("HD_TG_SP_THREADS");
+          return e ? atoi(e) : 448;
+        }();
+        const long long grid = m->ncells < m->ctx->sm_count ? m->ncells : m->ctx->sm_count;
+        if (env_thr == 448)
+          {
+            HD_CUDA(cudaFuncSetAttribute(k_apply_tile_global_sp<T, N, 448>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
+            k_apply_tile_global_sp<T, N, 448><<<(unsigned)grid, 448, part_bytes, m->ctx->stream>>>(p, cf);
+          }
+        else if (env_thr == 512)
+          {
+            HD_CUDA(cudaFuncSetAttribute(k_apply_tile_global_sp<T, N, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
+            k_apply_tile_global_sp<T, N, 512><<<(unsigned)grid, 512, part_bytes, m->ctx->stream>>>(p, cf);
+          }
+        else
+          {
+            HD_CUDA(cudaFuncSetAttribute(k_apply_tile_global_sp<T, N, 672>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_bytes));
+            k_apply_tile_global_sp<T, N, 672><<<(unsigned)grid, 672, part_bytes, m->ctx->stream>>>(p, cf);
+          }
+        HD_CUDA(cudaGetLastError());
+        op->launches++;
+        op->last_kernel = "tile_global"; // (same kernel family; HD_TG_SMEM_PARTIALS=0 selects the variant with the partial sums in dst)
+        return HD_OK;
+      }
     int    threads;
     size_t smem;
     tg_launch_shape(m, &threads, &smem);

@@ -21,6 +21,7 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(so)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
     lib.hd_tg_emulate.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ip, dp, dp, dp, ctypes.c_double]
+    lib.hd_tg_sp_emulate.argtypes = lib.hd_tg_emulate.argtypes
     return lib
 
 
@@ -29,7 +30,8 @@ VEL = (1.0, 0.15, -0.05, 0.1, -0.15, 0.5)
 
 @pytest.mark.parametrize("dx,dv,nc,k,skew", [(3, 3, (2, 1, 1, 1, 1, 2), 5, 0.5), (2, 2, (2, 3, 2, 2), 5, 0.0), (1, 1, (3, 2), 5, 0.5), (3, 3, (2, 2, 1, 2, 1, 2), 3, 0.5),
                                              (2, 2, (3, 2, 2, 3), 3, 0.0)])
-def test_tile_global_body_matches_literal_oracle(emu, dx, dv, nc, k, skew):
+@pytest.mark.parametrize("smem_partials", [False, True], ids=["partials_in_dst", "partials_in_shared_memory"])
+def test_tile_global_body_matches_literal_oracle(emu, dx, dv, nc, k, skew, smem_partials):
     dim = dx + dv
     left, right = (-1.0,) * dim, (1.0,) * dim
     mesh = O.Mesh(dx, dv, nc, left, right, (True,) * dim)
@@ -39,7 +41,9 @@ def test_tile_global_body_matches_literal_oracle(emu, dx, dv, nc, k, skew):
     out = np.zeros_like(f)
     dp = ctypes.POINTER(ctypes.c_double)
     vel = np.array(VEL[:dim])
-    rc = emu.hd_tg_emulate(f.ctypes.data_as(dp), out.ctypes.data_as(dp), dim, k, (ctypes.c_int * dim)(*nc), (ctypes.c_double * dim)(*left), (ctypes.c_double * dim)(*right),
+    fn = emu.hd_tg_sp_emulate if smem_partials else emu.hd_tg_emulate
+    out[:] = np.nan
+    rc = fn(f.ctypes.data_as(dp), out.ctypes.data_as(dp), dim, k, (ctypes.c_int * dim)(*nc), (ctypes.c_double * dim)(*left), (ctypes.c_double * dim)(*right),
                            vel.ctypes.data_as(dp), float(skew))
     assert rc == 0
     assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))

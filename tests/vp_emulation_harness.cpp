@@ -364,7 +364,8 @@ namespace
 {
   template <int N>
   int
-  tg_emulate_n(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew)
+  tg_emulate_n(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew,
+               bool smem_partials = false)
   {
     hd::Basis1D b;
     b.init(degree, degree + 1, false);
@@ -406,11 +407,39 @@ namespace
     p.sol = p.ti_next = nullptr;
     p.fb = p.fa = 0.0;
     p.fused = 0;
+    if (smem_partials)
+      {
+        // the variant that keeps the partial sums of the rounds in a CTA-private buffer (shared memory on the device)
+        long long nd = 1;
+        for (int d = 0; d < dim; ++d)
+          nd *= N;
+        std::vector<double> part((size_t)nd, std::nan(""));
+        for (long long cell = 0; cell < p.ncells; ++cell)
+          tg_cell<double, N>(p, cf, cell, 0, 1, part.data());
+        return 0;
+      }
     for (long long cell = 0; cell < p.ncells; ++cell)
       tg_cell<double, N>(p, cf, cell, 0, 1);
     return 0;
   }
 } // namespace
+
+extern "C" int
+hd_tg_sp_emulate(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew)
+{
+  try
+    {
+      if (degree == 5)
+        return tg_emulate_n<6>(src, dst, dim, degree, ncell, left, right, velocity, skew, true);
+      if (degree == 3)
+        return tg_emulate_n<4>(src, dst, dim, degree, ncell, left, right, velocity, skew, true);
+      return -2;
+    }
+  catch (const std::exception &)
+    {
+      return -1;
+    }
+}
 
 extern "C" int
 hd_tg_emulate(const double *src, double *dst, int dim, int degree, const int *ncell, const double *left, const double *right, const double *velocity, double skew)
