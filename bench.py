@@ -239,6 +239,8 @@ def run_aux_workload(args):
          k5f32  — configs[2]: 3D3V advection, degree 5, FP32, periodic, 6x6x6x4x4x4 cells (6.4e8 DoFs)
          vp2d2v — configs[3]: one Vlasov-Poisson LSRK stage in 2D2V (degree 3, FP64, 32^4 cells): rho = int f dv, Poisson solve
                   (CG), grad(phi) table, general-velocity operator + stage update in ONE kernel
+         lsrk   — the headline lattice (3D3V, degree 3, FP64, 8^6 cells) inside its time integrator: one low-storage Runge-Kutta
+                  stage = operator + both vector updates in ONE kernel (hd_lsrk_step, rk45; a step = one stage, 32 B/DoF)
     `value` = device-resident throughput; `e2e` = the same step with the vectors starting and ending in pinned host memory."""
     import numpy as np
     import torch
@@ -251,7 +253,12 @@ def run_aux_workload(args):
     ctx = api.Context(0)
     peak, peak_src = _peaks()
     vp = args.workload == "vp2d2v"
-    if vp:
+    lsrk = args.workload == "lsrk"
+    if lsrk:
+        dx, k, nc, np_dtype, t_dtype = 3, DEGREE, (CELLS_PER_DIR,) * 6, np.float64, torch.float64
+        left, right = (0.0,) * 6, (1.0,) * 6
+        bytes_per_dof, skew = 32, SKEW
+    elif vp:
         dx, k, nc, np_dtype, t_dtype = 2, 3, (32, 32, 32, 32), np.float64, torch.float64
         left, right = (0.0,) * 2 + (-6.0,) * 2, (4.0 * np.pi,) * 2 + (6.0,) * 2
         bytes_per_dof, skew = 32, 0.0  # read Ti and sol, write sol and Ti_next (the rho pass re-reads Ti: + 8, counted as overhead)
@@ -281,11 +288,19 @@ def run_aux_workload(args):
             api.VectorTools.velocity_space_integration(mf, d_rho, src.data_ptr())
             cg.append(ps.solve(d_rho, a_v.data_ptr(), rel_tol=1e-7, max_iterations=10000))
             api._check(L.hd_lsrk_stage_fused(rk._h, op._h, 1, api.c_void_p(sol.data_ptr()), api.c_void_p(src.data_ptr()), api.c_void_p(ti_next.data_ptr()), None, 0.0, 1e-9))
+    elif lsrk:
+        ki = torch.zeros_like(src)
+        rk = api.LowStorageRungeKuttaIntegrator(mf, ki.data_ptr(), dst.data_ptr(), "rk45")
+        n_stages = rk.n_stages()
+
+        def step():  # one complete rk45 step = n_stages fused stages; reported per stage below
+            rk.perform_time_step(src.data_ptr(), 0.0, 1e-6, op)
     else:
 
         def step():
             op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
 
+    per_step = n_stages if lsrk else 1
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -299,20 +314,22 @@ def run_aux_workload(args):
     ev1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms = ev0.elapsed_time(ev1) / args.steps / per_step
     # the dominant kernel alone (events on the library's stream)
     k_ms = []
     for _ in range(5):
         ctx.timer_start()
-        if vp:
+        if lsrk:
+            step()
+        elif vp:
             api._check(L.hd_lsrk_stage_fused(rk._h, op._h, 1, api.c_void_p(sol.data_ptr()), api.c_void_p(src.data_ptr()), api.c_void_p(ti_next.data_ptr()), None, 0.0, 1e-9))
         else:
             op.apply(dst.data_ptr(), src.data_ptr(), 0.0)
-        k_ms.append(ctx.timer_stop())
+        k_ms.append(ctx.timer_stop() / per_step)
     k_ms = sum(k_ms) / len(k_ms)
     launches = op.launch_count - launches0
     name = op.kernel_name
-    result = sol if vp else dst
+    result = sol if vp else (src if lsrk else dst)
     checksum = float(result[:: max(1, n // 65536)].double().abs().sum().item())
     # end to end: vectors start and end in pinned host memory
     es = src.element_size()
@@ -327,21 +344,23 @@ def run_aux_workload(args):
         step()
         h_out.copy_(result, non_blocking=True)
         torch.cuda.synchronize()
-    el = time.perf_counter() - t0
+    el = (time.perf_counter() - t0) / per_step
     achieved = n * bytes_per_dof / (k_ms * 1e-3) / 1e9
     out = {
-        "metric": "Vlasov-Poisson LSRK stage throughput (2D2V, k=3, FP64)" if vp else "advection operator throughput (3D3V, k=5, FP32)",
+        "metric": "Vlasov-Poisson LSRK stage throughput (2D2V, k=3, FP64)" if vp else ("fused LSRK stage throughput (3D3V, k=3, FP64)" if lsrk else "advection operator throughput (3D3V, k=5, FP32)"),
         "value": n / (ms * 1e-3) / 1e9, "unit": "GDoF/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if vp else "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if (vp or lsrk) else "f32", "data": "synthetic",
         "config": {"workload": ("2D2V k=3 FP64 Vlasov-Poisson stage (rho, CG field solve, general-velocity operator + LSRK update), %s cells (%.3g DoFs)" if vp else
-                                "3D3V k=5 FP32 advection apply, Cartesian periodic, %s cells (%.3g DoFs), skew 0.5, ECL") % ("x".join(map(str, nc)), n),
+                                ("3D3V k=3 FP64 low-storage Runge-Kutta stage (rk45; operator + both vector updates in one kernel), %s cells (%.3g DoFs), skew 0.5; a step = one stage" if lsrk else
+                                 "3D3V k=5 FP32 advection apply, Cartesian periodic, %s cells (%.3g DoFs), skew 0.5, ECL")) % ("x".join(map(str, nc)), n),
                    "kernel": name, "l2": "vectors (%.1f GiB each) are larger than L2; no flush needed" % (n * es / 2**30)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(name, 1), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": n * bytes_per_dof, "kernel_ms": k_ms,
                      "note": ("FP64-bound, not HBM-bound: ~77 DFMA per DoF (velocity varies inside the cell), see DESIGN.md" if vp else
-                              "global-memory tile kernel (kernel_tile_global.cu): shared memory cannot hold a degree-5 cell plus partial sums, see DESIGN.md")},
+                              ("32 B/DoF: Ti read, sol read + written, Ti_next written; K is never stored (DESIGN.md section 5)" if lsrk else
+                               "global-memory tile kernel (kernel_tile_global.cu): a degree-5 cell and its partial sums do not fit into shared memory together, see DESIGN.md"))},
         "clocks": clocks, "gpu_launches": int(launches) + (args.steps * 2 if vp else 0), "checksum": checksum,
-        "e2e": {"value": n * e_steps / el / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": n * es, "d2h_bytes_per_step": n * es, "steps": e_steps},
+        "e2e": {"value": n * e_steps / el / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": n * es / per_step, "d2h_bytes_per_step": n * es / per_step, "steps": e_steps * per_step},
     }
     if vp:
         out["config"]["cg_iterations_per_solve"] = sum(cg[-args.steps:]) / max(1, args.steps)
@@ -350,8 +369,9 @@ def run_aux_workload(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="headline", choices=["headline", "k5f32", "vp2d2v"],
-                    help="headline = the BASELINE.json metric (default); k5f32 / vp2d2v = secondary lines for configs[2] / configs[3] (N = 1)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "k5f32", "vp2d2v", "lsrk"],
+                    help="headline = the BASELINE.json metric (default); k5f32 / vp2d2v = secondary lines for configs[2] / configs[3]; lsrk = one fused "
+                         "Runge-Kutta stage on the headline lattice (N = 1)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)

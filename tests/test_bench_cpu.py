@@ -38,7 +38,7 @@ def test_product_arm_needs_a_gpu():
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
-@pytest.mark.parametrize("workload", ["k5f32", "vp2d2v"])
+@pytest.mark.parametrize("workload", ["k5f32", "vp2d2v", "lsrk"])
 def test_secondary_workloads_need_a_gpu(workload):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0
