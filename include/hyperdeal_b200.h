@@ -325,7 +325,9 @@ int hd_lsrk_stage_overlapped(hd_lsrk *rk, hd_advection *op, int stage, void *sol
  * left/right, degree..., side_kind = kind of the DOMAIN boundary per direction: HD_SIDE_PERIODIC_LOCAL or a Dirichlet kind;
  * n_cells / cell_offset are ignored) is cut into grid[d] equal bricks per direction, brick i (coordinates: i in mixed radix
  * over grid, direction 0 fastest) lives on devices[i] (NULL: device i), peer access is enabled between all of them, ghost
- * faces travel as direct stores of the sender's pack kernel into the receiver's ghost buffer, ordered by CUDA events.
+ * faces travel as direct stores over NVLink into the receiver's ghost buffer — from inside the operator kernel on 3D3V
+ * degree-3 FP64 lattices (arrival counters in peer memory, as hd_advection_apply_overlapped), from a pack kernel otherwise
+ * (HD_MULTI_FUSED=0 forces the latter) — and the reuse of the two ghost buffers per brick is ordered by CUDA events.
  * Vectors are arrays of n_gpus device pointers (one per brick, the brick's own lattice layout). */
 typedef struct hd_multi           hd_multi;
 typedef struct hd_multi_advection hd_multi_advection;
