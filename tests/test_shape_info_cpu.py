@@ -35,6 +35,18 @@ int main()
   e.dim_x = 1; e.dim_v = 1;
   for (int i = 0; i < 2; ++i) { e.n_cells[i] = e.n_cells_global[i] = 3; e.cell_offset[i] = 0; e.side_kind[i][0] = e.side_kind[i][1] = HD_SIDE_DIRICHLET; }
   for (long long c = 0; c < 9; ++c) { std::printf("E"); for (unsigned f = 0; f < 4; ++f) std::printf(" %d", int(internal::face_boundary_id(e, c, f))); std::printf("\n"); }
+  // multi::brick_grid: how PartitionX / PartitionV ranks cut a Cartesian lattice (slowest direction first)
+  {
+    CartesianLattice<3> l3; l3.n_cells = {{8, 8, 8}};
+    for (int parts : {1, 2, 4, 8, 16, 64, 512}) { auto g = multi::brick_grid<3>(l3, parts); std::printf("G 3 %d %d %d %d\n", parts, g[0], g[1], g[2]); }
+    CartesianLattice<2> l2; l2.n_cells = {{4, 6}};
+    for (int parts : {1, 2, 3, 4, 6, 12, 24}) { auto g = multi::brick_grid<2>(l2, parts); std::printf("G 2 %d %d %d\n", parts, g[0], g[1]); }
+    CartesianLattice<1> l1; l1.n_cells = {{6}};
+    for (int parts : {1, 2, 3, 6}) { auto g = multi::brick_grid<1>(l1, parts); std::printf("G 1 %d %d\n", parts, g[0]); }
+    bool threw = false;
+    try { multi::brick_grid<2>(l2, 5); } catch (const ExcMessage &) { threw = true; }
+    std::printf("G throw %d\n", int(threw));
+  }
   return 0;
 }
 '''
@@ -166,3 +178,31 @@ def test_face_boundary_ids(dump):
             d, side = f // 2, f % 2
             outer = c[d] == (2 if side else 0)
             assert r[f] == (side if outer else -1)
+
+
+def test_brick_grid_of_the_multi_gpu_shim(dump):
+    """hyperdeal::multi::brick_grid: the product of the grid is the number of ranks, every extent divides its direction, the
+    slowest direction is cut first (rows of cells along x_0 stay whole as long as possible), impossible requests throw"""
+    cells = {3: (8, 8, 8), 2: (4, 6), 1: (6,)}
+    seen = 0
+    for l in dump:
+        if not l.startswith("G ") or l.startswith("G throw"):
+            continue
+        f = [int(x) for x in l.split()[1:]]
+        dim, parts, g = f[0], f[1], f[2:]
+        assert len(g) == dim and np_prod(g) == parts
+        assert all(c % e == 0 for c, e in zip(cells[dim], g))
+        if parts > 1:
+            assert g[-1] > 1  # slowest direction first
+        if dim == 3 and parts <= 8:
+            assert g[0] == 1  # x_0 is cut last
+        seen += 1
+    assert seen == 7 + 7 + 4
+    assert "G throw 1" in dump
+
+
+def np_prod(v):
+    r = 1
+    for x in v:
+        r *= x
+    return r
