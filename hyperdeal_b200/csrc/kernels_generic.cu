@@ -1236,7 +1236,13 @@ namespace hd
                 return hd::fail(HD_ERR_UNSUPPORTED, "face does not fit into shared memory");
               HD_CUDA(cudaFuncSetAttribute(k_dirichlet_source<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
-          k_dirichlet_source<T><<<(unsigned)nfc, 256, smem, m->ctx->stream>>>(p);
+          // one CTA per boundary face cell; as many threads as the face has quadrature points / nodal values (64 in 2D2V,
+          // 1024 in 3D3V), at most 256
+          long long work = 1;
+          for (int e = 0; e < m->dim - 1; ++e)
+            work *= mx;
+          const int threads = work >= 256 ? 256 : int((work + 31) / 32 * 32);
+          k_dirichlet_source<T><<<(unsigned)nfc, threads, smem, m->ctx->stream>>>(p);
           HD_CUDA(cudaGetLastError());
           op->launches++;
         }
