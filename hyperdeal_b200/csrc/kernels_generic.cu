@@ -319,8 +319,41 @@ namespace
             fac[i]         = e == 0 ? sin(2.0 * (x - p.time * adv[e]) * PI) : cos(2.0 * (x - p.time * adv[e]) * PI);
           }
         __syncthreads();
+        // The projection of a product of 1-D factors is the product of the 1-D projections: ghat[i] = prod_e (Sinv f_e)[i_e].
+        // So the dim - 1 transverse sweeps over the whole face (with a block barrier each) reduce to dim - 1 tiny
+        // matrix-vector products and one product per nodal face value.
+        double *pf = fac + HD_MAX_DIM * mx; // [dim][n]
+        for (int i = threadIdx.x; i < dim * n; i += blockDim.x)
+          {
+            const int e = i / n, r = i % n;
+            double    acc = 0.0;
+            if (e == p.dir)
+              acc = fac[e * nq]; // the factor at the face coordinate (no projection along the face normal)
+            else
+              for (int k = 0; k < nq; ++k)
+                acc += Sinv[r * nq + k] * fac[e * nq + k];
+            pf[i] = acc;
+          }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nf; i += blockDim.x)
+          {
+            int    rr = i;
+            double r  = 1.0;
+            for (int e = 0; e < dim; ++e)
+              {
+                int ie = 0;
+                if (e != p.dir)
+                  {
+                    ie = rr % n;
+                    rr /= n;
+                  }
+                r = e == 0 ? pf[ie] : r * pf[e * n + ie];
+              }
+            A[i] = r;
+          }
+        __syncthreads();
       }
-    for (int q = threadIdx.x; q < nqf; q += blockDim.x)
+    for (int q = threadIdx.x; q < nqf && !separable; q += blockDim.x)
       {
         double val;
         if (p.homogeneous)
@@ -365,7 +398,7 @@ namespace
     __syncthreads();
     // transverse Sinv sweeps, last face direction first (extents: nq for not-yet-swept dirs, n for swept)
     double *in = A, *out = B;
-    for (int e = fd - 1; e >= 0; --e)
+    for (int e = fd - 1; e >= 0 && !separable; --e)
       {
         int stride = 1;
         for (int k = 0; k < e; ++k)
@@ -1229,7 +1262,7 @@ namespace hd
           int mx = m->n > m->nq ? m->n : m->nq, cap = 1;
           for (int e = 0; e < m->dim - 1; ++e)
             cap *= mx;
-          const size_t smem = 2 * sizeof(double) * cap + sizeof(double) * HD_MAX_DIM * mx;
+          const size_t smem = 2 * sizeof(double) * cap + 2 * sizeof(double) * HD_MAX_DIM * mx;
           if (smem > 48 * 1024)
             {
               if (smem > m->ctx->smem_optin)
