@@ -5,7 +5,8 @@
 //
 //   vlasov_poisson <file.json>      (DIM_X, DIM_V, DEGREE, N_POINTS from <name>.configuration beside the json)
 //
-// STATUS: the field solve and the diagnostics behind it have not run on a GPU yet.
+// Reproduces examples/vlasov_poisson/tests/vp_2D_2D_k3.hyperrectangle_01.out on the GPU (tests/test_zz_vp_device_gpu.py), with
+// fused stages (field refresh, then ONE kernel for operator + stage update) or, HD_DRIVER_UNFUSED=1, the reference's call structure.
 #include <cstdlib>
 #include <cstring>
 #include <fstream>

@@ -1,16 +1,20 @@
 // Tile kernel for cells that do not fit into shared memory twice — first of all 3D3V degree 5 in FP32 (BASELINE.json
-// configs[2]: 6^6 = 46 656 values = 182 KiB per cell), which today runs on the generic kernel at 10 % of the HBM roofline.
+// configs[2]: 6^6 = 46 656 values = 182 KiB per cell), where the generic kernel reaches 10 % of the HBM roofline.
 //
 // Same rounds as the shared-memory tile kernel (kernels_generic.cu: two directions per round, an N x N tile per thread in
-// registers), but nothing is staged: a CTA owns one cell, reads its tiles straight from global memory (the cell is re-read in
-// every round and stays in L1/L2) and keeps the partial sums of the rounds in `dst` itself (written in round 0, read-modified-
-// written in the later rounds; a block-wide barrier separates the rounds).  HBM traffic stays at read src + write dst; the
-// extra passes are L2 traffic on a per-SM working set of two cells (148 x 364 KiB = 54 MB, inside the 126 MB L2).
-// The fused LSRK update is applied in the last round.  Periodic and ghost sides (no Dirichlet), even dim_x + dim_v.
+// registers), but the cell is not staged: a CTA owns one cell at a time and reads its tiles straight from global memory (the
+// cell is re-read in every round and stays in L1/L2); a block-wide barrier separates the rounds.  The partial sums of the
+// rounds live
+//   * in shared memory (k_apply_tile_global_sp, the shipped variant for degree 5: one persistent CTA per SM, 182 KiB;
+//     dst is written once, DRAM traffic 6.7 GB per launch on the configs[2] lattice, 141 GDoF/s), or
+//   * in `dst` itself (k_apply_tile_global: written in round 0, read-modified-written in the later rounds; 16.8 GB of DRAM
+//     traffic, 95 GDoF/s — the partial sums of all resident CTAs do not stay in L2; HD_TG_SMEM_PARTIALS=0, and degree 3).
+// The fused LSRK update is applied in the last round.  Periodic and ghost sides (Dirichlet lattices arrive here as ghost
+// sides, capi.cu: apply_dirichlet_as_ghosts), even dim_x + dim_v.
 //
-// STATUS: written after the GPU budget of round 1 was spent; the body is checked on the CPU against the oracle through
-// tests/vp_emulation_harness.cpp (tests/test_tile_global_emulation.py); not yet run on a GPU, never selected automatically
-// (hd_advection_set_kernel(op, 5)).
+// The body is host/device code: tests/vp_emulation_harness.cpp runs it on the CPU against the oracle
+// (tests/test_tile_global_emulation.py, both variants); GPU parity in tests/tile_global_check.py and tests/test_apply_gpu.py.
+// Automatic choice for degree 5; hd_advection_set_kernel(op, 5) elsewhere.
 #ifdef HD_VP_HOST_EMULATION
 #  ifndef HD_MAX_DIM
 #    include <cmath>

@@ -2,9 +2,10 @@
 //   a_x = v at the v-space quadrature points, a_v = a table per (x-cell, x-quadrature point), typically grad(phi)
 // (examples/vlasov_poisson/include/velocity_field_view.h:111-175 — PhaseSpaceVelocityFieldView).
 //
-// STATUS: parity with the literal oracle at round-off on B200 (tests/test_vp_gpu.py, profiles/r01n_vp_kernel_gpu.txt:
-// 1D1V, 2D2V incl. over-integration, 3D3V, FP32); not optimised and not yet timed.  Reachable only through
-// hd_advection_set_phase_space_velocity.
+// Two families behind hd_advection_set_phase_space_velocity: the register-tile kernels of kernel_vp_tile.cuh (degree 3 with 4
+// quadrature points: 1D1V, 2D2V, 3D3V — the automatic choice there) and the generic kernel of this file (every other degree /
+// quadrature, and the cross-check: hd_advection_set_kernel(op, 1)).  Parity of both with the literal oracle at round-off on
+// B200: tests/test_vp_gpu.py (1D1V, 2D2V incl. over-integration, 3D3V, FP32); timings in profiles/r02*_vp_*.
 //
 // Collapsed form: with C = a C_a + |a| C_abs and L_f = a L_a,f + |a| L_abs,f the speed-independent parts of
 // the constant-velocity matrices (basis.hpp), direction d contributes

@@ -7,9 +7,9 @@
 // residual 1e-7, poisson.h:575-610).  On a Cartesian lattice every integrand is integrated exactly by the (k+1)-point Gauss
 // rule, so K = sum_d (mass in the other directions) (x) (1-D SIP operator along d) with three (k+1)x(k+1) blocks per direction.
 //
-// STATUS: like kernel_vp.cu this file was written after the GPU budget of round 1 was spent.  The per-cell bodies are
-// checked on the CPU against the oracle's dense operator (tests/test_poisson_emulation.py, via tests/vp_emulation_harness.cpp);
-// nothing here has run on a GPU yet.  Reachable only through hd_poisson_*.
+// The per-cell bodies are checked on the CPU against the oracle's dense operator (tests/test_poisson_emulation.py, via
+// tests/vp_emulation_harness.cpp) and on the GPU through the Vlasov-Poisson right-hand side and the reference's Landau-damping
+// golden (tests/test_zz_vp_device_gpu.py).  Reachable only through hd_poisson_*.
 #ifdef HD_VP_HOST_EMULATION
 #  ifndef HD_MAX_DIM
 #    include <cmath>

@@ -2,8 +2,8 @@
 //   phase_space_diagnostics (:34-86)   mass, squared L2 norm, kinetic energy, momentum of f at the Gauss points
 //   compute_electric_energy (:88-143)  sum_q (d_d phi)^2 JxW per x-direction, from the gradient table of hd_poisson_solve
 //
-// STATUS: written after the GPU budget of round 1 was spent; bodies checked on the CPU through tests/vp_emulation_harness.cpp
-// (tests/test_vp_diagnostics_emulation.py), not yet run on a GPU.
+// Bodies checked on the CPU through tests/vp_emulation_harness.cpp (tests/test_vp_diagnostics_emulation.py) and on the GPU
+// against the oracle's diagnostics during the Landau-damping golden run (tests/vp_step_check.py).
 #ifdef HD_VP_HOST_EMULATION
 #  ifndef HD_MAX_DIM
 #    include <cmath>

@@ -109,7 +109,7 @@ if sel in ("levels",):
         del src, dst
         op.close(); mf.close()
         torch.cuda.empty_cache()
-if sel in ("tg",):  # the not yet validated global-memory tile kernel on BASELINE.json configs[2]
+if sel in ("tg",):  # the global-memory tile kernel on BASELINE.json configs[2] against the generic kernel
     apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), global-memory tile kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=5)
     torch.cuda.empty_cache()
     apply_case("apply 3D3V k=5 f32, 6x6x6x4x4x4 cells (configs[2]), generic kernel", 3, 3, 5, [6, 6, 6, 4, 4, 4], np.float32, kernel=1)
