@@ -1,4 +1,9 @@
-// Pipelined 3D3V, degree-3, FP64 advection kernel for sm_100a (the BASELINE.json headline case).
+// The two 3D3V, degree-3, FP64 advection kernels for sm_100a (the BASELINE.json headline case) and everything they share:
+// tensor maps, row scheduler, work lists of the interior/boundary phases, halo sender CTAs, launch code.
+//   * k_rounds_3d3v_k3 (kernel_rounds6d.cuh, included below; round 2; the default): three light compute warpgroups, one
+//     round of two directions each, traces read through L2 — see the header of that file;
+//   * k_advect_3d3v_k3 (this file; round 1; hd_advection_set_kernel(op, 2) or HD_FAST_VARIANT=pipe): two heavy compute
+//     warpgroups, face layers staged by TMA — described in the rest of this comment.
 //
 // What it computes (same collapsed form as kernels_generic.cu, basis.hpp):
 //   dst_cell = sum_{d=0..5} (I x .. C_d .. x I) u_cell + L_d(i_d) * trace_d(upwind neighbour)
